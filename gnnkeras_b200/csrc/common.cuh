@@ -1,0 +1,148 @@
+// common.cuh - shared types of libgnnfp (sm_100a).  See DESIGN.md for the kernel inventory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "gnnfp.h"
+
+#define GNNFP_MAXP 6        // max input pieces of one net application
+#define GNNFP_JC 16         // output columns per thread chunk in the tile MLP
+#define GNNFP_NSM_FALLBACK 148
+
+// ---- error plumbing (never throw across the C ABI) -------------------------------------------
+void gnnfp_set_error(const char* fmt, ...);
+#define GNNFP_CHECK_CUDA(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      gnnfp_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                      cudaGetErrorString(_e));                                              \
+      return GNNFP_E_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+#define GNNFP_FAIL(code, ...)      \
+  do {                             \
+    gnnfp_set_error(__VA_ARGS__);  \
+    return (code);                 \
+  } while (0)
+
+extern long long g_gnnfp_launches;
+#define GNNFP_COUNT_LAUNCH() (++g_gnnfp_launches)
+
+// ---- a "piece": one column block of a net's input, read straight from where the data lives ---
+// The reference materialises tf.concat([...]) every iteration (GNN.py:231); here the concat only
+// ever exists as a shared-memory tile.
+enum { PK_DIRECT = 0, PK_GATHER = 1 };
+enum { GM_NONE = 0, GM_STORE = 1, GM_ADD = 2, GM_ATOMIC = 3 };
+
+struct Piece {
+  const float* ptr;        // source matrix (row-major)
+  int ld;                  // its leading dimension
+  int width;               // columns taken
+  int col0;                // first column in the concatenated net input
+  int kind;                // PK_DIRECT | PK_GATHER
+  int accumulate;          // staging adds into the tile instead of overwriting (sum of pieces)
+  unsigned magic;          // ceil(2^32/width) for the flat-index division
+  const int* map;          // DIRECT: source row = map[gr] (arc focus: src/dst of the arc; un-pool: node2graph)
+  const float* rowscale;   // DIRECT: value *= rowscale[gr]  (un-pooling by NodeGraph values)
+  const int* rowptr;       // GATHER: CSR over the global row id gr
+  const int* idx;          //         source row of each entry
+  const float* wgt;        //         weight of each entry (NULL = 1)
+  const double* st_sum;    // BN batch statistics of these columns (sum over rows) or NULL
+  const double* st_sq;     //                                     (sum of squares)
+  const int* gate;         // piece enabled iff gate==NULL || ((*gate != 0) == gate_pol)
+  int gate_pol;
+  // backward: where the gradient w.r.t. these columns goes
+  float* gptr;
+  int gld;
+  int gmode;               // GM_*
+};
+
+struct TileSrc {
+  int n_rows;              // rows of the row set
+  const int* rowlist;      // global row id of row r (NULL = identity)
+  int n_pieces;
+  int in_dim;
+  Piece p[GNNFP_MAXP];
+};
+
+struct NetDev {
+  int n_layers;
+  int in_dim;
+  int widths[GNNFP_MAX_LAYERS];
+  int acts[GNNFP_MAX_LAYERS];
+  const float* W[GNNFP_MAX_LAYERS];
+  const float* b[GNNFP_MAX_LAYERS];
+  int bn_mode;             // 0 none, 1 batch statistics (training), 2 moving statistics
+  float bn_eps, bn_momentum;
+  const float* gamma;
+  const float* beta;
+  float* mmean;
+  float* mvar;
+  double inv_n;            // 1 / rows of the BN batch
+};
+
+// ---- tile geometry chosen on the host ------------------------------------------------------------
+struct TileCfg {
+  int RG;                  // row-group warps
+  int CG;                  // column-group warps
+  int R;                   // rows per tile = 64 * RG  (2 rows per lane)
+  int XS0, XS1;            // odd row strides of the two activation buffers
+  int threads;
+  size_t smem_bytes;
+  int grid;
+};
+
+struct FwdArgs {
+  TileSrc src;
+  NetDev net;
+  TileCfg tc;
+  float* out;              // output rows
+  int ld_out;
+  int out_compact;         // 1: row r of the row set -> out[r]; 0: -> out[gr]
+  double* ost_sum;         // column statistics of the output (next iteration's BN) or NULL
+  double* ost_sq;
+  const float* prev;       // convergence test against this matrix (rows gr), or NULL
+  int ld_prev;
+  float thr;
+  int* flag_next;          // set to 1 when any row is not converged
+  const int* gate;         // whole kernel runs only if *gate != 0 (NULL = always)
+  int update_moving;       // CTA 0 applies the Keras moving-average update
+};
+
+struct PassArgs {           // tile pass without a net: materialise pieces and/or column statistics
+  TileSrc src;
+  TileCfg tc;
+  float* out;              // [n_rows, in_dim] or NULL
+  int ld_out;
+  double* st_sum;          // [in_dim] or NULL
+  double* st_sq;
+  const int* gate;
+};
+
+struct BwdArgs {
+  TileSrc src;             // the net's input pieces (with gradient destinations)
+  TileSrc gsrc;            // pieces that assemble dL/d(out) of this application (width = last layer)
+  NetDev net;
+  TileCfg tc;
+  const float* saved_out;  // the forward output rows (rows gr or compact), for act' of the last layer
+  int ld_saved;
+  int saved_compact;
+  float* partial;          // [grid, n_params] per-CTA partial sums, accumulated across launches
+  int n_params;
+  float* bn_partial;       // [grid, 2*in_dim] per-CTA sum(dy), sum(dy*xhat0) of THIS launch
+  const int* gate;
+};
+
+// launchers (kernels.cu)
+int launch_tile_fwd(const FwdArgs& a, cudaStream_t s);
+int launch_tile_pass(const PassArgs& a, cudaStream_t s);
+int launch_tile_bwd(const BwdArgs& a, cudaStream_t s);
+int tile_cfg_fwd(const NetDev& net, int n_rows, TileCfg* tc);
+int tile_cfg_pass(int in_dim, int n_rows, TileCfg* tc);
+int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc);
+int net_param_count(const gnnfp_net_desc& d);   // W,b of all layers (+ 2*in_dim for BN gamma/beta at the end)
+
+int gnnfp_num_sms();

@@ -1,0 +1,32 @@
+// graph.h - the opaque graph handle of gnnfp.h
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct gnnfp_graph {
+  int N = 0, A = 0, G = 0, n_types = 0, mode = 0, mask_len = 0, M = 0;
+  int* src = nullptr;          // [A] arcs[:,0]
+  int* dst = nullptr;          // [A] arcs[:,1]
+  int* dst_rowptr = nullptr;   // [N+1] destination-grouped CSR
+  int* dst_arc = nullptr;      // [A]  arc id per entry (ascending inside a row)
+  int* dst_src = nullptr;      // [A]  source node per entry
+  float* dst_w = nullptr;      // [A]  value per entry
+  int* src_rowptr = nullptr;   // [N+1] source-grouped CSR
+  int* src_arc = nullptr;
+  int* src_dst = nullptr;
+  float* src_w = nullptr;
+  float* arc_val = nullptr;    // [A] in arc order
+  uint8_t* mask = nullptr;     // [mask_len] set_mask & output_mask
+  int* mask_idx = nullptr;     // [M]
+  uint8_t* type_mask = nullptr;             // [n_types, N]
+  int* type_rows[GNNFP_MAX_TYPES] = {};     // rows of each type, ascending
+  int type_count[GNNFP_MAX_TYPES] = {};
+  float* typed_w[GNNFP_MAX_TYPES] = {};     // dst-CSR weights of CompositeAdjacencies[t]
+  int types_ok = 1;                         // every node in exactly one type
+  int* node2graph = nullptr;   // [N]
+  float* ng_val = nullptr;     // [N]
+  int* graph_ptr = nullptr;    // [G+1]
+  std::vector<void*> allocs;
+  size_t device_bytes = 0;
+};

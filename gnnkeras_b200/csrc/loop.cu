@@ -1,0 +1,538 @@
+// loop.cu - host orchestration of the fixed-point loop behind the C ABI (gnnfp.h).
+//
+// Forward  = reference GNN.py:245-274 Loop (+341-346 pooling, +317-330 arc focus) and
+//            CompositeGNN.py:242-272: prologue (loop-invariant aggregates), max_iteration gated
+//            iteration kernels (the while_loop of GNN.py:265 without any host round trip: kernel t
+//            runs only if the device flag written by kernel t-1 is set), final state, net_output,
+//            NodeGraph pooling.
+// Backward = the BPTT that tf.GradientTape performs in train_step (GNN.py:284-295), hand written:
+//            see loop_bwd.cu.
+#include <stdarg.h>
+
+#include "loop.h"
+#include "tile.cuh"
+
+// ---- error / misc -------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+long long g_gnnfp_launches = 0;
+void gnnfp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* gnnfp_last_error(void) { return g_err; }
+extern "C" int gnnfp_abi_version(void) { return GNNFP_ABI_VERSION; }
+extern "C" long long gnnfp_launch_count(int reset) {
+  long long v = g_gnnfp_launches;
+  if (reset) g_gnnfp_launches = 0;
+  return v;
+}
+int gnnfp_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = GNNFP_NSM_FALLBACK;
+  }
+  return n;
+}
+
+int net_param_count(const gnnfp_net_desc& d) {
+  int n = 0, in_l = d.in_dim;
+  for (int l = 0; l < d.n_layers; ++l) {
+    n += in_l * d.widths[l] + d.widths[l];
+    in_l = d.widths[l];
+  }
+  return n;
+}
+
+// ---- small kernels ------------------------------------------------------------------------------
+// condition() before the first iteration: state_old = ones (GNN.py:261), k = 0 < max_iteration
+static __global__ void k_cond0(const float* s0, int ld, int n, int D, float thr, int max_iter, int* flag0) {
+  int notconv = 0;
+  const float normp = thr * sqrtf((float)D);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float sd = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float d = s0[(size_t)i * ld + j] - 1.0f;
+      sd = fmaf(d, d, sd);
+    }
+    if (sqrtf(sd) > normp) notconv = 1;
+  }
+  const int any = __syncthreads_or(notconv);
+  if (threadIdx.x == 0 && any && max_iter > 0) atomicOr(flag0, 1);
+}
+
+__device__ __forceinline__ int count_k(const int* flags, int max_iter) {
+  int k = 0;
+  for (int t = 0; t < max_iter; ++t) k += flags[t] != 0;   // flags[t] set => iteration t+1 executed
+  return k;
+}
+
+// state_out = S_k ; k_out = k
+static __global__ void k_finalize(const int* flags, int max_iter, const float* s0, int ld0, const float* slots,
+                                  size_t slot_stride, int training, int n, int D, float* state_out, int* k_out) {
+  const int k = count_k(flags, max_iter);
+  const float* src;
+  int ld;
+  if (k == 0) { src = s0; ld = ld0; }
+  else { src = slots + (training ? (size_t)(k - 1) : (size_t)(k & 1)) * slot_stride; ld = D; }
+  const size_t total = (size_t)n * D;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / D;
+    const int j = (int)(e - r * D);
+    state_out[e] = src[r * ld + j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && k_out) *k_out = k;
+}
+
+// out[g, :] = sum_{i in graph g} NodeGraph[i, g] * out_nodes[i, :]  (GNN.py:345), sequential in node order
+static __global__ void k_pool(const float* out_nodes, const int* graph_ptr, const float* ng_val, int G, int T, float* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= G * T) return;
+  const int gi = e / T, j = e - gi * T;
+  float acc = 0.f;
+  for (int i = graph_ptr[gi]; i < graph_ptr[gi + 1]; ++i) acc = fmaf(ng_val[i], out_nodes[(size_t)i * T + j], acc);
+  out[e] = acc;
+}
+
+// ---- piece builders -----------------------------------------------------------------------------
+static Piece mk_piece(int kind, const float* ptr, int ld, int width, int col0) {
+  Piece p;
+  memset(&p, 0, sizeof(p));
+  p.kind = kind; p.ptr = ptr; p.ld = ld; p.width = width; p.col0 = col0;
+  p.magic = width > 0 ? (unsigned)((0x100000000ull + (unsigned)width - 1) / (unsigned)width) : 0u;
+  return p;
+}
+Piece mk_direct(const float* ptr, int ld, int width, int col0) { return mk_piece(PK_DIRECT, ptr, ld, width, col0); }
+Piece mk_gather(const float* ptr, int ld, int width, int col0, const int* rowptr, const int* idx, const float* wgt) {
+  Piece p = mk_piece(PK_GATHER, ptr, ld, width, col0);
+  p.rowptr = rowptr; p.idx = idx; p.wgt = wgt;
+  return p;
+}
+static void add_piece(TileSrc& ts, const Piece& p) {
+  if (p.width <= 0) return;
+  ts.p[ts.n_pieces++] = p;
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- per-call context ---------------------------------------------------------------------------
+struct Ctx {
+  gnnfp_loop* L;
+  const gnnfp_loop_io* io;
+  char* ws;
+  cudaStream_t s;
+  int* flags() const { return (int*)(ws + L->ws.flags); }
+  float* Xs() const { return (float*)(ws + L->ws.Xs); }
+  float* slots() const { return (float*)(ws + L->ws.slots); }
+  size_t slot_stride() const { return (size_t)L->N * L->D; }
+  const float* S(int t) const {   // state after t iterations
+    if (t == 0) return L->S > 0 ? io->state0 : io->nodes;
+    return slots() + (L->cfg.training ? (size_t)(t - 1) : (size_t)(t & 1)) * slot_stride();
+  }
+  int ldS(int t) const { return t == 0 ? (L->S > 0 ? L->S : io->ld_nodes) : L->D; }
+  int stXw() const {
+    if (!L->composite) return L->LsM;
+    int m = 0;
+    for (int t = 0; t < L->nt; ++t) m = L->dt[t] > m ? L->dt[t] : m;
+    return m + L->sum_dt + L->AL;
+  }
+  double* stS(int ty, int t) const { return (double*)(ws + L->ws.stS) + ((size_t)ty * (L->cfg.max_iteration + 1) + t) * 2 * L->D; }
+  double* stA(int ty, int t) const { return (double*)(ws + L->ws.stA) + ((size_t)ty * (L->cfg.max_iteration + 1) + t) * 2 * L->D; }
+  double* stX(int ty) const { return (double*)(ws + L->ws.stX) + (size_t)ty * 2 * stXw(); }
+  double* stO() const { return (double*)(ws + L->ws.stO); }
+};
+
+static void set_rows(const gnnfp_loop* L, int ty, TileSrc& ts) {
+  if (L->composite) { ts.n_rows = L->g->type_count[ty]; ts.rowlist = L->g->type_rows[ty]; }
+  else { ts.n_rows = L->N; ts.rowlist = nullptr; }
+}
+
+// input of net_state[ty] at iteration t (1-based): GNN.py:222-231 / CompositeGNN.py:224
+void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts) {
+  const gnnfp_loop* L = c.L;
+  const gnnfp_graph* g = L->g;
+  memset(&ts, 0, sizeof(ts));
+  set_rows(L, ty, ts);
+  ts.in_dim = L->snet[ty].in_dim;
+  const int D = L->D;
+  const float* Sp = c.S(t - 1);
+  const int ld = c.ldS(t - 1);
+  const float* wgt = g->mode == GNNFP_AGG_SUM ? nullptr : g->dst_w;
+  const bool bn = L->bn_train_state;
+  const int xw = c.stXw();
+  if (!L->composite) {
+    const int NLp = L->S > 0 ? L->NLw : 0;
+    Piece p0 = mk_direct(Sp, ld, D, 0);
+    if (bn) { p0.st_sum = c.stS(0, t - 1); p0.st_sq = p0.st_sum + D; }
+    add_piece(ts, p0);
+    if (NLp) {
+      Piece p1 = mk_direct(c.Xs(), L->LsM, NLp, D);
+      if (bn) { p1.st_sum = c.stX(0); p1.st_sq = c.stX(0) + xw; }
+      add_piece(ts, p1);
+    }
+    Piece p2 = mk_gather(Sp, ld, D, D + NLp, g->dst_rowptr, g->dst_src, wgt);
+    if (bn) { p2.st_sum = c.stA(0, t - 1); p2.st_sq = p2.st_sum + D; }
+    add_piece(ts, p2);
+    Piece p3 = mk_direct(c.Xs() + NLp, L->LsM, NLp + L->AL, 2 * D + NLp);
+    if (bn) { p3.st_sum = c.stX(0) + NLp; p3.st_sq = c.stX(0) + xw + NLp; }
+    add_piece(ts, p3);
+  } else {
+    const int d = L->dt[ty];
+    Piece p0 = mk_direct(c.io->nodes, c.io->ld_nodes, d, 0);
+    if (bn) { p0.st_sum = c.stX(ty); p0.st_sq = c.stX(ty) + xw; }
+    add_piece(ts, p0);
+    Piece p1 = mk_direct(Sp, ld, D, d);
+    if (bn) { p1.st_sum = c.stS(ty, t - 1); p1.st_sq = p1.st_sum + D; }
+    add_piece(ts, p1);
+    Piece p2 = mk_gather(Sp, ld, D, d + D, g->dst_rowptr, g->dst_src, wgt);
+    if (bn) { p2.st_sum = c.stA(ty, t - 1); p2.st_sq = p2.st_sum + D; }
+    add_piece(ts, p2);
+    Piece p3 = mk_direct(c.Xs(), L->LsM, L->sum_dt + L->AL, d + 2 * D);
+    if (bn) { p3.st_sum = c.stX(ty) + d; p3.st_sq = c.stX(ty) + xw + d; }
+    add_piece(ts, p3);
+  }
+}
+
+// input of net_output: apply_filters (GNN.py:239-242, 317-330; CompositeGNN.py:237-239, 315-327)
+void build_out_src(const Ctx& c, TileSrc& ts) {
+  const gnnfp_loop* L = c.L;
+  const gnnfp_graph* g = L->g;
+  memset(&ts, 0, sizeof(ts));
+  ts.n_rows = L->M;
+  ts.rowlist = (L->M == g->mask_len) ? nullptr : g->mask_idx;
+  ts.in_dim = L->out_in;
+  const int D = L->D;
+  const int NLp = (!L->composite && L->S > 0) ? L->NLw : 0;
+  const bool bn = L->bn_train_out;
+  double* st = c.stO();
+  auto with_stats = [&](Piece p) {
+    if (bn) { p.st_sum = st + p.col0; p.st_sq = st + L->out_in + p.col0; }
+    return p;
+  };
+  if (L->cfg.kind == GNNFP_KIND_ARC) {
+    const int w = D + NLp;
+    Piece a = mk_direct(c.io->state_out, D, D, 0); a.map = g->src; add_piece(ts, with_stats(a));
+    if (NLp) { Piece b = mk_direct(c.io->nodes, c.io->ld_nodes, NLp, D); b.map = g->src; add_piece(ts, with_stats(b)); }
+    Piece d = mk_direct(c.io->state_out, D, D, w); d.map = g->dst; add_piece(ts, with_stats(d));
+    if (NLp) { Piece e = mk_direct(c.io->nodes, c.io->ld_nodes, NLp, w + D); e.map = g->dst; add_piece(ts, with_stats(e)); }
+    add_piece(ts, with_stats(mk_direct(c.io->arc_labels, c.io->ld_arcs, L->AL, 2 * w)));
+  } else {
+    add_piece(ts, with_stats(mk_direct(c.io->state_out, D, D, 0)));
+    if (NLp) add_piece(ts, with_stats(mk_direct(c.io->nodes, c.io->ld_nodes, NLp, D)));
+  }
+}
+
+void fill_netdev(const gnnfp_net_desc& d, const gnnfp_net_params& p, int training, int n_rows, NetDev& nd) {
+  memset(&nd, 0, sizeof(nd));
+  nd.n_layers = d.n_layers;
+  nd.in_dim = d.in_dim;
+  for (int l = 0; l < d.n_layers; ++l) {
+    nd.widths[l] = d.widths[l];
+    nd.acts[l] = d.acts[l];
+    nd.W[l] = p.W[l];
+    nd.b[l] = p.b[l];
+  }
+  nd.bn_mode = d.has_bn ? (training ? 1 : 2) : 0;
+  nd.bn_eps = d.bn_eps;
+  nd.bn_momentum = d.bn_momentum;
+  nd.gamma = p.bn_gamma; nd.beta = p.bn_beta; nd.mmean = p.bn_moving_mean; nd.mvar = p.bn_moving_var;
+  nd.inv_n = n_rows > 0 ? 1.0 / (double)n_rows : 0.0;
+}
+
+static int check_params(const gnnfp_net_desc& d, const gnnfp_net_params& p, const char* what) {
+  for (int l = 0; l < d.n_layers; ++l)
+    if (!p.W[l] || !p.b[l]) GNNFP_FAIL(GNNFP_E_INVALID, "%s: missing Dense parameters of layer %d", what, l);
+  if (d.has_bn && (!p.bn_gamma || !p.bn_beta || !p.bn_moving_mean || !p.bn_moving_var))
+    GNNFP_FAIL(GNNFP_E_INVALID, "%s: missing BatchNormalization parameters", what);
+  return GNNFP_OK;
+}
+
+static int check_desc(const gnnfp_net_desc& d, const char* what, bool is_out) {
+  if (d.n_layers < 1 || d.n_layers > GNNFP_MAX_LAYERS) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "%s: %d Dense layers (1..%d supported)", what, d.n_layers, GNNFP_MAX_LAYERS);
+  for (int l = 0; l < d.n_layers; ++l) {
+    if (d.widths[l] < 1) GNNFP_FAIL(GNNFP_E_INVALID, "%s: layer %d has width %d", what, l, d.widths[l]);
+    if (d.acts[l] < 0 || d.acts[l] > GNNFP_ACT_SOFTMAX) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "%s: unknown activation %d", what, d.acts[l]);
+  }
+  (void)is_out;
+  return GNNFP_OK;
+}
+
+// ---- plan ----------------------------------------------------------------------------------------
+extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const gnnfp_loop_cfg* cfg,
+                                 const gnnfp_net_desc* state_nets, const gnnfp_net_desc* out_net) {
+  if (!out || !g || !cfg || !state_nets || !out_net) GNNFP_FAIL(GNNFP_E_INVALID, "loop_create: null argument");
+  *out = nullptr;
+  // the reference's constructor asserts (GNN.py:26-28, CompositeGNN.py:26-28)
+  if (cfg->state_vect_dim < 0) GNNFP_FAIL(GNNFP_E_INVALID, "assert state_vect_dim >= 0");
+  if (cfg->max_iteration < 0) GNNFP_FAIL(GNNFP_E_INVALID, "assert max_iteration >= 0");
+  if (cfg->state_threshold < 0) GNNFP_FAIL(GNNFP_E_INVALID, "assert state_threshold >= 0");
+  if (cfg->n_types != 0 && cfg->max_iteration == 0) GNNFP_FAIL(GNNFP_E_INVALID, "assert max_iteration > 0 (composite)");
+  if (cfg->n_types != g->n_types) GNNFP_FAIL(GNNFP_E_INVALID, "loop_create: cfg.n_types=%d but the graph has %d node types", cfg->n_types, g->n_types);
+  if (cfg->kind < 0 || cfg->kind > GNNFP_KIND_GRAPH) GNNFP_FAIL(GNNFP_E_INVALID, "loop_create: kind=%d", cfg->kind);
+  gnnfp_loop* L = new gnnfp_loop();
+  L->g = g; L->cfg = *cfg;
+  L->composite = cfg->n_types > 0;
+  L->nt = L->composite ? cfg->n_types : 1;
+  L->N = g->N; L->A = g->A; L->M = g->M;
+  L->S = cfg->state_vect_dim; L->NLw = cfg->nodes_width; L->AL = cfg->arc_label_width;
+  L->D = L->S > 0 ? L->S : L->NLw;
+  int rc = GNNFP_OK;
+#define PLAN_FAIL(code, ...) do { gnnfp_set_error(__VA_ARGS__); delete L; return (code); } while (0)
+  if (L->NLw <= 0) PLAN_FAIL(GNNFP_E_INVALID, "loop_create: nodes_width=%d", L->NLw);
+  if (L->composite && !g->types_ok)
+    PLAN_FAIL(GNNFP_E_UNSUPPORTED, "composite: every node must belong to exactly one type (one-hot type_mask)");
+  for (int t = 0; t < L->nt; ++t) {
+    L->snet[t] = state_nets[t];
+    if ((rc = check_desc(L->snet[t], "net_state", false))) { delete L; return rc; }
+  }
+  L->onet = *out_net;
+  if ((rc = check_desc(L->onet, "net_output", true))) { delete L; return rc; }
+  L->T = L->onet.widths[L->onet.n_layers - 1];
+  // widths (MLP.py:112-124 get_inout_dims)
+  const int NLp = (!L->composite && L->S > 0) ? L->NLw : 0;
+  if (!L->composite) {
+    L->LsM = 2 * NLp + L->AL;
+    const int din = 2 * L->D + L->LsM;
+    if (L->snet[0].in_dim != din) PLAN_FAIL(GNNFP_E_INVALID, "net_state expects %d inputs but the loop feeds %d ([state|nodes?|agg_state|agg_nodes|agg_arcs])", L->snet[0].in_dim, din);
+  } else {
+    L->sum_dt = 0;
+    for (int t = 0; t < L->nt; ++t) {
+      int d = cfg->dim_node_label[t];
+      if (d < 0) PLAN_FAIL(GNNFP_E_INVALID, "dim_node_label[%d]=%d", t, d);
+      L->dt[t] = d > L->NLw ? L->NLw : d;   // python slicing nodes[:, :d] clamps
+      L->sum_dt += L->dt[t];
+    }
+    L->LsM = L->sum_dt + L->AL;
+    for (int t = 0; t < L->nt; ++t) {
+      const int din = L->dt[t] + 2 * L->D + L->LsM;
+      if (L->snet[t].in_dim != din) PLAN_FAIL(GNNFP_E_INVALID, "net_state[%d] expects %d inputs but the loop feeds %d", t, L->snet[t].in_dim, din);
+    }
+  }
+  for (int t = 0; t < L->nt; ++t)
+    if (L->snet[t].widths[L->snet[t].n_layers - 1] != L->D)
+      PLAN_FAIL(GNNFP_E_INVALID, "net_state[%d] outputs %d columns but the state has %d", t, L->snet[t].widths[L->snet[t].n_layers - 1], L->D);
+  if (cfg->kind == GNNFP_KIND_ARC) {
+    if (g->mask_len != g->A) PLAN_FAIL(GNNFP_E_INVALID, "arc focus: masks must have one entry per arc");
+    L->out_in = 2 * (L->D + NLp) + L->AL;
+  } else {
+    if (g->mask_len != g->N) PLAN_FAIL(GNNFP_E_INVALID, "node/graph focus: masks must have one entry per node");
+    L->out_in = L->D + NLp;
+  }
+  if (L->onet.in_dim != L->out_in) PLAN_FAIL(GNNFP_E_INVALID, "net_output expects %d inputs but apply_filters yields %d", L->onet.in_dim, L->out_in);
+  L->pool = cfg->pool < 0 ? (cfg->kind == GNNFP_KIND_GRAPH) : (cfg->pool != 0);
+  if (L->pool) {
+    if (g->G <= 0) PLAN_FAIL(GNNFP_E_INVALID, "graph focus needs a NodeGraph (n_graphs > 0)");
+    if (L->M != L->N) PLAN_FAIL(GNNFP_E_INVALID, "graph focus: NodeGraph pooling needs every node unmasked (M=%d, N=%d)", L->M, L->N);
+  }
+  L->out_rows = L->pool ? g->G : L->M;
+  L->bn_train_state = cfg->training;
+  for (int t = 0; t < L->nt; ++t) L->bn_train_state = L->bn_train_state && L->snet[t].has_bn;
+  for (int t = 0; t < L->nt; ++t)
+    if (L->snet[t].has_bn != L->snet[0].has_bn) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "composite: all state nets must agree on BatchNormalization");
+  L->bn_train_out = cfg->training && L->onet.has_bn;
+  for (int t = 0; t < L->nt; ++t) L->nparam_s[t] = net_param_count(L->snet[t]);
+  L->nparam_o = net_param_count(L->onet);
+  L->grid_cap = gnnfp_num_sms() * 8;
+
+  // ---- workspace layout ---------------------------------------------------------------------
+  WsLayout& w = L->ws;
+  const int MI = cfg->max_iteration;
+  size_t off = 0;
+  w.ctrl = off;
+  w.flags = off; off = align_up(off + sizeof(int) * (MI + 4));
+  const size_t st_per = (size_t)L->nt * (MI + 1) * 2 * L->D * sizeof(double);
+  w.stS = off; off = align_up(off + st_per);
+  w.stA = off; off = align_up(off + st_per);
+  int xw = L->LsM;
+  if (L->composite) { int m = 0; for (int t = 0; t < L->nt; ++t) m = L->dt[t] > m ? L->dt[t] : m; xw = m + L->sum_dt + L->AL; }
+  w.stX = off; off = align_up(off + (size_t)L->nt * 2 * (xw > 0 ? xw : 1) * sizeof(double));
+  w.stO = off; off = align_up(off + (size_t)2 * L->out_in * sizeof(double));
+  w.ctrl_bytes = off - w.ctrl;
+  w.Xs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float));
+  L->slot_count = cfg->training ? MI : (MI > 0 ? 2 : 0);
+  w.slots = off; off = align_up(off + (size_t)L->slot_count * L->N * L->D * sizeof(float));
+  w.out_nodes = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
+  if (cfg->training) {
+    const size_t ND = (size_t)L->N * L->D * sizeof(float);
+    w.dSfin = off; off = align_up(off + ND);
+    w.dOwn = off; off = align_up(off + 2 * ND);
+    w.dAgg = off; off = align_up(off + 2 * ND);
+    w.dXs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float));
+    w.dOutN = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
+    size_t ps = 0;
+    int din_max = L->onet.in_dim;
+    for (int t = 0; t < L->nt; ++t) { ps += (size_t)L->nparam_s[t]; din_max = L->snet[t].in_dim > din_max ? L->snet[t].in_dim : din_max; }
+    w.part_state = off; off = align_up(off + (size_t)L->grid_cap * ps * sizeof(float));
+    w.part_out = off; off = align_up(off + (size_t)L->grid_cap * L->nparam_o * sizeof(float));
+    w.bn_part = off; off = align_up(off + (size_t)L->grid_cap * 2 * din_max * sizeof(float));
+    w.bn_const = off; off = align_up(off + (size_t)4 * din_max * sizeof(float));
+  }
+  w.total = off;
+  *out = L;
+  return GNNFP_OK;
+}
+
+extern "C" void gnnfp_loop_free(gnnfp_loop* L) { delete L; }
+extern "C" size_t gnnfp_loop_workspace_bytes(const gnnfp_loop* L) { return L ? L->ws.total : 0; }
+extern "C" int gnnfp_loop_out_rows(const gnnfp_loop* L) { return L ? L->out_rows : -1; }
+extern "C" int gnnfp_loop_state_dim(const gnnfp_loop* L) { return L ? L->D : -1; }
+
+int check_io(const gnnfp_loop* L, const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes) {
+  if (!L || !io) GNNFP_FAIL(GNNFP_E_INVALID, "loop: null argument");
+  if (!workspace || workspace_bytes < L->ws.total) GNNFP_FAIL(GNNFP_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, L->ws.total);
+  if (((uintptr_t)workspace & 255) != 0) GNNFP_FAIL(GNNFP_E_INVALID, "workspace must be 256-byte aligned");
+  if (!io->nodes || io->ld_nodes < L->NLw) GNNFP_FAIL(GNNFP_E_INVALID, "loop: nodes missing or ld_nodes < nodes_width");
+  if (L->AL > 0 && (!io->arc_labels || io->ld_arcs < L->AL)) GNNFP_FAIL(GNNFP_E_INVALID, "loop: arc_labels missing or ld_arcs < AL");
+  if (L->S > 0 && !io->state0) GNNFP_FAIL(GNNFP_E_INVALID, "loop: state0 must be passed explicitly when state_vect_dim > 0 (GNN.py:257 draws it unseeded)");
+  if (!io->state_out || !io->out) GNNFP_FAIL(GNNFP_E_INVALID, "loop: state_out / out missing");
+  return GNNFP_OK;
+}
+
+// ---- forward ---------------------------------------------------------------------------------------
+extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                                  const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_io(L, io, workspace, workspace_bytes))) return rc;
+  if (!sp || !op) GNNFP_FAIL(GNNFP_E_INVALID, "loop_forward: parameters missing");
+  for (int t = 0; t < L->nt; ++t) if ((rc = check_params(L->snet[t], sp[t], "net_state"))) return rc;
+  if ((rc = check_params(L->onet, *op, "net_output"))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  Ctx c{L, io, (char*)workspace, s};
+  const gnnfp_graph* g = L->g;
+  const int MI = L->cfg.max_iteration, D = L->D, N = L->N;
+  const int training = L->cfg.training;
+  const float* wgt = g->mode == GNNFP_AGG_SUM ? nullptr : g->dst_w;
+
+  GNNFP_CHECK_CUDA(cudaMemsetAsync(c.ws + L->ws.ctrl, 0, L->ws.ctrl_bytes, s));
+
+  // ---- prologue: loop-invariant aggregates (GNN.py:254-258, CompositeGNN.py:251-253) -----------
+  if (L->LsM > 0) {
+    PassArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.src.n_rows = N; pa.src.in_dim = L->LsM;
+    if (!L->composite) {
+      const int NLp = L->S > 0 ? L->NLw : 0;
+      if (NLp) {
+        add_piece(pa.src, mk_direct(io->nodes, io->ld_nodes, NLp, 0));
+        add_piece(pa.src, mk_gather(io->nodes, io->ld_nodes, NLp, NLp, g->dst_rowptr, g->dst_src, wgt));
+      }
+      add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, 2 * NLp, g->dst_rowptr, g->dst_arc, wgt));
+      if (L->bn_train_state) { pa.st_sum = c.stX(0); pa.st_sq = c.stX(0) + c.stXw(); }
+    } else {
+      int col = 0;
+      for (int t = 0; t < L->nt; ++t) {
+        add_piece(pa.src, mk_gather(io->nodes, io->ld_nodes, L->dt[t], col, g->dst_rowptr, g->dst_src, g->typed_w[t]));
+        col += L->dt[t];
+      }
+      add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, col, g->dst_rowptr, g->dst_arc, wgt));
+    }
+    pa.out = c.Xs(); pa.ld_out = L->LsM;
+    if ((rc = tile_cfg_pass(L->LsM, N, &pa.tc))) return rc;
+    if ((rc = launch_tile_pass(pa, s))) return rc;
+  }
+  if (L->composite && L->bn_train_state) {   // per-type statistics of the static columns
+    for (int ty = 0; ty < L->nt; ++ty) {
+      PassArgs pa;
+      memset(&pa, 0, sizeof(pa));
+      set_rows(L, ty, pa.src);
+      pa.src.in_dim = L->dt[ty] + L->LsM;
+      add_piece(pa.src, mk_direct(io->nodes, io->ld_nodes, L->dt[ty], 0));
+      add_piece(pa.src, mk_direct(c.Xs(), L->LsM, L->LsM, L->dt[ty]));
+      // stX(ty) is laid out [d_t | LsM] with stride stXw: the pass writes sums to [0,in_dim) and squares
+      // to [stXw, stXw+in_dim)
+      pa.st_sum = c.stX(ty); pa.st_sq = c.stX(ty) + c.stXw();
+      if ((rc = tile_cfg_pass(pa.src.in_dim, pa.src.n_rows, &pa.tc))) return rc;
+      if ((rc = launch_tile_pass(pa, s))) return rc;
+    }
+  }
+  // ---- condition before the first iteration ------------------------------------------------------
+  {
+    const int blocks = (N + 255) / 256 < 1184 ? (N + 255) / 256 : 1184;
+    k_cond0<<<blocks, 256, 0, s>>>(c.S(0), c.ldS(0), N, D, L->cfg.state_threshold, MI, c.flags());
+    GNNFP_COUNT_LAUNCH();
+  }
+  if (L->bn_train_state && MI > 0) {   // statistics of S_0 per type
+    for (int ty = 0; ty < L->nt; ++ty) {
+      PassArgs pa;
+      memset(&pa, 0, sizeof(pa));
+      set_rows(L, ty, pa.src);
+      pa.src.in_dim = D;
+      add_piece(pa.src, mk_direct(c.S(0), c.ldS(0), D, 0));
+      pa.st_sum = c.stS(ty, 0); pa.st_sq = pa.st_sum + D;
+      if ((rc = tile_cfg_pass(D, pa.src.n_rows, &pa.tc))) return rc;
+      if ((rc = launch_tile_pass(pa, s))) return rc;
+    }
+  }
+  // ---- the fixed-point iterations (GNN.py:265) -----------------------------------------------------
+  for (int t = 1; t <= MI; ++t) {
+    const int* gate = c.flags() + (t - 1);
+    if (L->bn_train_state) {
+      for (int ty = 0; ty < L->nt; ++ty) {   // batch statistics of Adj^T.state
+        PassArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        set_rows(L, ty, pa.src);
+        pa.src.in_dim = D;
+        add_piece(pa.src, mk_gather(c.S(t - 1), c.ldS(t - 1), D, 0, g->dst_rowptr, g->dst_src, wgt));
+        pa.st_sum = c.stA(ty, t - 1); pa.st_sq = pa.st_sum + D;
+        pa.gate = gate;
+        if ((rc = tile_cfg_pass(D, pa.src.n_rows, &pa.tc))) return rc;
+        if ((rc = launch_tile_pass(pa, s))) return rc;
+      }
+    }
+    for (int ty = 0; ty < L->nt; ++ty) {
+      FwdArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      build_state_src(c, ty, t, fa.src);
+      fill_netdev(L->snet[ty], sp[ty], training, fa.src.n_rows, fa.net);
+      if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;
+      fa.out = (float*)c.S(t); fa.ld_out = D; fa.out_compact = 0;
+      if (L->bn_train_state && t < MI) { fa.ost_sum = c.stS(ty, t); fa.ost_sq = fa.ost_sum + D; }
+      if (t < MI) { fa.prev = c.S(t - 1); fa.ld_prev = c.ldS(t - 1); fa.thr = L->cfg.state_threshold; fa.flag_next = c.flags() + t; }
+      fa.gate = gate;
+      fa.update_moving = training;
+      if ((rc = launch_tile_fwd(fa, s))) return rc;
+    }
+  }
+  // ---- converged state, iteration count --------------------------------------------------------------
+  {
+    const size_t total = (size_t)N * D;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 2368) blocks = 2368;
+    k_finalize<<<blocks, 256, 0, s>>>(c.flags(), MI, c.S(0), c.ldS(0), c.slots(), c.slot_stride(), training, N, D,
+                                      io->state_out, io->k_out);
+    GNNFP_COUNT_LAUNCH();
+  }
+  // ---- net_output (+ pooling) ----------------------------------------------------------------------------
+  {
+    FwdArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    build_out_src(c, fa.src);
+    if (L->bn_train_out) {
+      PassArgs pa;
+      memset(&pa, 0, sizeof(pa));
+      pa.src = fa.src;
+      for (int p = 0; p < pa.src.n_pieces; ++p) { pa.src.p[p].st_sum = nullptr; pa.src.p[p].st_sq = nullptr; }
+      pa.st_sum = c.stO(); pa.st_sq = c.stO() + L->out_in;
+      if ((rc = tile_cfg_pass(L->out_in, pa.src.n_rows, &pa.tc))) return rc;
+      if ((rc = launch_tile_pass(pa, s))) return rc;
+    }
+    fill_netdev(L->onet, *op, training, fa.src.n_rows, fa.net);
+    if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;
+    float* on = L->pool ? (float*)(c.ws + L->ws.out_nodes) : io->out;
+    fa.out = on; fa.ld_out = L->T; fa.out_compact = 1;
+    fa.update_moving = training;
+    if ((rc = launch_tile_fwd(fa, s))) return rc;
+    if (L->pool) {
+      const int tot = g->G * L->T;
+      k_pool<<<(tot + 255) / 256, 256, 0, s>>>(on, g->graph_ptr, g->ng_val, g->G, L->T, io->out);
+      GNNFP_COUNT_LAUNCH();
+    }
+    if (io->out_nodes && io->out_nodes != on)
+      GNNFP_CHECK_CUDA(cudaMemcpyAsync(io->out_nodes, on, (size_t)L->M * L->T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
