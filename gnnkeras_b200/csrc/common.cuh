@@ -36,6 +36,7 @@ extern long long g_gnnfp_launches;
 // ever exists as a shared-memory tile.
 enum { PK_DIRECT = 0, PK_GATHER = 1 };
 enum { GM_NONE = 0, GM_STORE = 1, GM_ADD = 2, GM_ATOMIC = 3 };
+enum { TAG_NONE = 0, TAG_STATE = 1, TAG_NODES = 2, TAG_AGG_STATE = 3, TAG_STATIC = 4, TAG_ARC_LABELS = 5 };
 
 struct Piece {
   const float* ptr;        // source matrix (row-major)
@@ -44,6 +45,8 @@ struct Piece {
   int col0;                // first column in the concatenated net input
   int kind;                // PK_DIRECT | PK_GATHER
   int accumulate;          // staging adds into the tile instead of overwriting (sum of pieces)
+  int compact;             // DIRECT: source row = position in the row set (not the global row id)
+  int tag;                 // TAG_*: what the columns are (host-side bookkeeping for the backward)
   unsigned magic;          // ceil(2^32/width) for the flat-index division
   const int* map;          // DIRECT: source row = map[gr] (arc focus: src/dst of the arc; un-pool: node2graph)
   const float* rowscale;   // DIRECT: value *= rowscale[gr]  (un-pooling by NodeGraph values)

@@ -111,39 +111,12 @@ Piece mk_gather(const float* ptr, int ld, int width, int col0, const int* rowptr
   p.rowptr = rowptr; p.idx = idx; p.wgt = wgt;
   return p;
 }
-static void add_piece(TileSrc& ts, const Piece& p) {
+void add_piece(TileSrc& ts, const Piece& p) {
   if (p.width <= 0) return;
   ts.p[ts.n_pieces++] = p;
 }
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-
-// ---- per-call context ---------------------------------------------------------------------------
-struct Ctx {
-  gnnfp_loop* L;
-  const gnnfp_loop_io* io;
-  char* ws;
-  cudaStream_t s;
-  int* flags() const { return (int*)(ws + L->ws.flags); }
-  float* Xs() const { return (float*)(ws + L->ws.Xs); }
-  float* slots() const { return (float*)(ws + L->ws.slots); }
-  size_t slot_stride() const { return (size_t)L->N * L->D; }
-  const float* S(int t) const {   // state after t iterations
-    if (t == 0) return L->S > 0 ? io->state0 : io->nodes;
-    return slots() + (L->cfg.training ? (size_t)(t - 1) : (size_t)(t & 1)) * slot_stride();
-  }
-  int ldS(int t) const { return t == 0 ? (L->S > 0 ? L->S : io->ld_nodes) : L->D; }
-  int stXw() const {
-    if (!L->composite) return L->LsM;
-    int m = 0;
-    for (int t = 0; t < L->nt; ++t) m = L->dt[t] > m ? L->dt[t] : m;
-    return m + L->sum_dt + L->AL;
-  }
-  double* stS(int ty, int t) const { return (double*)(ws + L->ws.stS) + ((size_t)ty * (L->cfg.max_iteration + 1) + t) * 2 * L->D; }
-  double* stA(int ty, int t) const { return (double*)(ws + L->ws.stA) + ((size_t)ty * (L->cfg.max_iteration + 1) + t) * 2 * L->D; }
-  double* stX(int ty) const { return (double*)(ws + L->ws.stX) + (size_t)ty * 2 * stXw(); }
-  double* stO() const { return (double*)(ws + L->ws.stO); }
-};
 
 static void set_rows(const gnnfp_loop* L, int ty, TileSrc& ts) {
   if (L->composite) { ts.n_rows = L->g->type_count[ty]; ts.rowlist = L->g->type_rows[ty]; }
@@ -166,31 +139,39 @@ void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts) {
   if (!L->composite) {
     const int NLp = L->S > 0 ? L->NLw : 0;
     Piece p0 = mk_direct(Sp, ld, D, 0);
+    p0.tag = TAG_STATE;
     if (bn) { p0.st_sum = c.stS(0, t - 1); p0.st_sq = p0.st_sum + D; }
     add_piece(ts, p0);
     if (NLp) {
       Piece p1 = mk_direct(c.Xs(), L->LsM, NLp, D);
+      p1.tag = TAG_STATIC;
       if (bn) { p1.st_sum = c.stX(0); p1.st_sq = c.stX(0) + xw; }
       add_piece(ts, p1);
     }
     Piece p2 = mk_gather(Sp, ld, D, D + NLp, g->dst_rowptr, g->dst_src, wgt);
+    p2.tag = TAG_AGG_STATE;
     if (bn) { p2.st_sum = c.stA(0, t - 1); p2.st_sq = p2.st_sum + D; }
     add_piece(ts, p2);
     Piece p3 = mk_direct(c.Xs() + NLp, L->LsM, NLp + L->AL, 2 * D + NLp);
+    p3.tag = TAG_STATIC;
     if (bn) { p3.st_sum = c.stX(0) + NLp; p3.st_sq = c.stX(0) + xw + NLp; }
     add_piece(ts, p3);
   } else {
     const int d = L->dt[ty];
     Piece p0 = mk_direct(c.io->nodes, c.io->ld_nodes, d, 0);
+    p0.tag = TAG_NODES;
     if (bn) { p0.st_sum = c.stX(ty); p0.st_sq = c.stX(ty) + xw; }
     add_piece(ts, p0);
     Piece p1 = mk_direct(Sp, ld, D, d);
+    p1.tag = TAG_STATE;
     if (bn) { p1.st_sum = c.stS(ty, t - 1); p1.st_sq = p1.st_sum + D; }
     add_piece(ts, p1);
     Piece p2 = mk_gather(Sp, ld, D, d + D, g->dst_rowptr, g->dst_src, wgt);
+    p2.tag = TAG_AGG_STATE;
     if (bn) { p2.st_sum = c.stA(ty, t - 1); p2.st_sq = p2.st_sum + D; }
     add_piece(ts, p2);
     Piece p3 = mk_direct(c.Xs(), L->LsM, L->sum_dt + L->AL, d + 2 * D);
+    p3.tag = TAG_STATIC;
     if (bn) { p3.st_sum = c.stX(ty) + d; p3.st_sq = c.stX(ty) + xw + d; }
     add_piece(ts, p3);
   }
@@ -214,14 +195,14 @@ void build_out_src(const Ctx& c, TileSrc& ts) {
   };
   if (L->cfg.kind == GNNFP_KIND_ARC) {
     const int w = D + NLp;
-    Piece a = mk_direct(c.io->state_out, D, D, 0); a.map = g->src; add_piece(ts, with_stats(a));
-    if (NLp) { Piece b = mk_direct(c.io->nodes, c.io->ld_nodes, NLp, D); b.map = g->src; add_piece(ts, with_stats(b)); }
-    Piece d = mk_direct(c.io->state_out, D, D, w); d.map = g->dst; add_piece(ts, with_stats(d));
-    if (NLp) { Piece e = mk_direct(c.io->nodes, c.io->ld_nodes, NLp, w + D); e.map = g->dst; add_piece(ts, with_stats(e)); }
-    add_piece(ts, with_stats(mk_direct(c.io->arc_labels, c.io->ld_arcs, L->AL, 2 * w)));
+    Piece a = mk_direct(c.io->state_out, D, D, 0); a.map = g->src; a.tag = TAG_STATE; add_piece(ts, with_stats(a));
+    if (NLp) { Piece b = mk_direct(c.io->nodes, c.io->ld_nodes, NLp, D); b.map = g->src; b.tag = TAG_NODES; add_piece(ts, with_stats(b)); }
+    Piece d = mk_direct(c.io->state_out, D, D, w); d.map = g->dst; d.tag = TAG_STATE; add_piece(ts, with_stats(d));
+    if (NLp) { Piece e = mk_direct(c.io->nodes, c.io->ld_nodes, NLp, w + D); e.map = g->dst; e.tag = TAG_NODES; add_piece(ts, with_stats(e)); }
+    { Piece al = mk_direct(c.io->arc_labels, c.io->ld_arcs, L->AL, 2 * w); al.tag = TAG_ARC_LABELS; add_piece(ts, with_stats(al)); }
   } else {
-    add_piece(ts, with_stats(mk_direct(c.io->state_out, D, D, 0)));
-    if (NLp) add_piece(ts, with_stats(mk_direct(c.io->nodes, c.io->ld_nodes, NLp, D)));
+    { Piece a = mk_direct(c.io->state_out, D, D, 0); a.tag = TAG_STATE; add_piece(ts, with_stats(a)); }
+    if (NLp) { Piece b = mk_direct(c.io->nodes, c.io->ld_nodes, NLp, D); b.tag = TAG_NODES; add_piece(ts, with_stats(b)); }
   }
 }
 
@@ -242,7 +223,7 @@ void fill_netdev(const gnnfp_net_desc& d, const gnnfp_net_params& p, int trainin
   nd.inv_n = n_rows > 0 ? 1.0 / (double)n_rows : 0.0;
 }
 
-static int check_params(const gnnfp_net_desc& d, const gnnfp_net_params& p, const char* what) {
+int check_params(const gnnfp_net_desc& d, const gnnfp_net_params& p, const char* what) {
   for (int l = 0; l < d.n_layers; ++l)
     if (!p.W[l] || !p.b[l]) GNNFP_FAIL(GNNFP_E_INVALID, "%s: missing Dense parameters of layer %d", what, l);
   if (d.has_bn && (!p.bn_gamma || !p.bn_beta || !p.bn_moving_mean || !p.bn_moving_var))
@@ -335,7 +316,20 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   L->bn_train_out = cfg->training && L->onet.has_bn;
   for (int t = 0; t < L->nt; ++t) L->nparam_s[t] = net_param_count(L->snet[t]);
   L->nparam_o = net_param_count(L->onet);
-  L->grid_cap = gnnfp_num_sms() * 8;
+  L->grid_cap = 1;
+  if (cfg->training) {   // exact grids of the backward tile kernels (they are a pure function of the shapes)
+    gnnfp_net_params none;
+    memset(&none, 0, sizeof(none));
+    for (int t = 0; t <= L->nt; ++t) {
+      NetDev nd;
+      const gnnfp_net_desc& dsc = t < L->nt ? L->snet[t] : L->onet;
+      const int rows = t < L->nt ? (L->composite ? g->type_count[t] : L->N) : L->M;
+      fill_netdev(dsc, none, 1, rows, nd);
+      TileCfg tcb;
+      if ((rc = tile_cfg_bwd(nd, rows > 0 ? rows : 1, 0, &tcb))) { delete L; return rc; }
+      L->grid_cap = tcb.grid > L->grid_cap ? tcb.grid : L->grid_cap;
+    }
+  }
 
   // ---- workspace layout ---------------------------------------------------------------------
   WsLayout& w = L->ws;
@@ -360,15 +354,22 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     w.dSfin = off; off = align_up(off + ND);
     w.dOwn = off; off = align_up(off + 2 * ND);
     w.dAgg = off; off = align_up(off + 2 * ND);
-    w.dXs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float));
     w.dOutN = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
-    size_t ps = 0;
+    size_t ps = 0, bg = 2 * (size_t)L->onet.in_dim;
     int din_max = L->onet.in_dim;
-    for (int t = 0; t < L->nt; ++t) { ps += (size_t)L->nparam_s[t]; din_max = L->snet[t].in_dim > din_max ? L->snet[t].in_dim : din_max; }
-    w.part_state = off; off = align_up(off + (size_t)L->grid_cap * ps * sizeof(float));
-    w.part_out = off; off = align_up(off + (size_t)L->grid_cap * L->nparam_o * sizeof(float));
+    for (int t = 0; t < L->nt; ++t) {
+      ps += (size_t)L->nparam_s[t];
+      bg += 2 * (size_t)L->snet[t].in_dim;
+      din_max = L->snet[t].in_dim > din_max ? L->snet[t].in_dim : din_max;
+    }
     w.bn_part = off; off = align_up(off + (size_t)L->grid_cap * 2 * din_max * sizeof(float));
     w.bn_const = off; off = align_up(off + (size_t)4 * din_max * sizeof(float));
+    w.bwd_zero = off;
+    w.dXs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float) * (cfg->want_input_grads ? 1 : 0) + 4);
+    w.part_state = off; off = align_up(off + (size_t)L->grid_cap * ps * sizeof(float));
+    w.part_out = off; off = align_up(off + (size_t)L->grid_cap * L->nparam_o * sizeof(float));
+    w.bn_grad = off; off = align_up(off + bg * sizeof(float));
+    w.bwd_zero_bytes = off - w.bwd_zero;
   }
   w.total = off;
   *out = L;

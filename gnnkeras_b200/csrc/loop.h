@@ -11,7 +11,8 @@ struct WsLayout {
   size_t out_nodes = 0;                     // float [M, T]
   // backward
   size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0;
-  size_t part_state = 0, part_out = 0, bn_part = 0, bn_const = 0;
+  size_t part_state = 0, part_out = 0, bn_part = 0, bn_const = 0, bn_grad = 0;
+  size_t bwd_zero = 0, bwd_zero_bytes = 0;   // region zeroed at the start of every backward
   size_t total = 0;
 };
 
@@ -31,6 +32,45 @@ struct gnnfp_loop {
   int slot_count = 0;
   int bn_train_state = 0, bn_train_out = 0;
   int nparam_s[GNNFP_MAX_TYPES]{}, nparam_o = 0;
-  int grid_cap = 0;      // upper bound of any tile kernel grid (partials are sized by it)
+  int grid_cap = 0;      // upper bound of any backward tile kernel grid (partials are sized by it)
   WsLayout ws;
 };
+
+// ---- per-call context (loop.cu / loop_bwd.cu) ---------------------------------------------------
+struct Ctx {
+  gnnfp_loop* L;
+  const gnnfp_loop_io* io;
+  char* ws;
+  cudaStream_t s;
+  int* flags() const { return (int*)(ws + L->ws.flags); }
+  float* Xs() const { return (float*)(ws + L->ws.Xs); }
+  float* slots() const { return (float*)(ws + L->ws.slots); }
+  size_t slot_stride() const { return (size_t)L->N * L->D; }
+  const float* S(int t) const {   // state after t iterations
+    if (t == 0) return L->S > 0 ? io->state0 : io->nodes;
+    return slots() + (L->cfg.training ? (size_t)(t - 1) : (size_t)(t & 1)) * slot_stride();
+  }
+  int ldS(int t) const { return t == 0 ? (L->S > 0 ? L->S : io->ld_nodes) : L->D; }
+  int stXw() const {
+    if (!L->composite) return L->LsM;
+    int m = 0;
+    for (int t = 0; t < L->nt; ++t) m = L->dt[t] > m ? L->dt[t] : m;
+    return m + L->sum_dt + L->AL;
+  }
+  double* stS(int ty, int t) const { return (double*)(ws + L->ws.stS) + ((size_t)ty * (L->cfg.max_iteration + 1) + t) * 2 * L->D; }
+  double* stA(int ty, int t) const { return (double*)(ws + L->ws.stA) + ((size_t)ty * (L->cfg.max_iteration + 1) + t) * 2 * L->D; }
+  double* stX(int ty) const { return (double*)(ws + L->ws.stX) + (size_t)ty * 2 * stXw(); }
+  double* stO() const { return (double*)(ws + L->ws.stO); }
+};
+
+Piece mk_direct(const float* ptr, int ld, int width, int col0);
+Piece mk_gather(const float* ptr, int ld, int width, int col0, const int* rowptr, const int* idx, const float* wgt);
+void add_piece(TileSrc& ts, const Piece& p);
+void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts);
+void build_out_src(const Ctx& c, TileSrc& ts);
+void fill_netdev(const gnnfp_net_desc& d, const gnnfp_net_params& p, int training, int n_rows, NetDev& nd);
+int check_io(const gnnfp_loop* L, const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes);
+int check_params(const gnnfp_net_desc& d, const gnnfp_net_params& p, const char* what);
+int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream_t s);
+int launch_reduce_params(const NetDev& net, const float* partial, int grid, int n_params, const float* bn_grad,
+                         const gnnfp_net_params& d, const int* flags, int max_iter, int average, cudaStream_t s);

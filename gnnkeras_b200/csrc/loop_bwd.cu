@@ -1,0 +1,258 @@
+// loop_bwd.cu - hand-written BPTT over the k executed iterations (replaces tf.GradientTape in
+// train_step, reference GNN.py:284-295 / LGNN.py:259-272 / CompositeGNN.py:282-293).
+//
+//   1. net_output backward (un-pooling through NodeGraph fused into the gradient staging)
+//      -> dL/ds_final (+ d_nodes through the [state|nodes] concat, GNN.py:241)
+//   2. for t = max_iteration .. 1, gated on the same device flags as the forward (no host sync):
+//        G_t = (t is the last executed) ? dL/ds_final : dOwn_{t+1} + Adj . dAgg_{t+1}
+//        tile_bwd_kernel -> dW/db partials, dOwn_t, dAgg_t (+ static-column gradients)
+//        BN training: bn_reduce + tile_bnfix
+//   3. input gradients (LGNN chaining): d_state0 / d_nodes / d_arc_labels
+//   4. deterministic reduction of the per-CTA partials, optional /k (average_st_grads)
+#include "loop.h"
+#include "tile.cuh"
+
+// G0 and the loop-invariant aggregates' gradients -> d_state0 / d_nodes
+struct InGradArgs {
+  int N, D, S, NLp, NLw, AL, LsM, composite, nt;
+  int dt[GNNFP_MAX_TYPES], doff[GNNFP_MAX_TYPES];
+  const uint8_t* type_mask;          // [nt, N]
+  const int* flags;
+  const float* dSfin; const float* dOwn1; const float* dAgg1; const float* dXs;
+  const int* src_rowptr; const int* src_dst; const float* src_w;
+  float* d_nodes; float* d_state0;
+  int want;
+};
+static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a) {
+  const int W = a.D > a.NLw ? a.D : a.NLw;
+  const size_t total = (size_t)a.N * W;
+  const bool ran = a.flags[0] != 0;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / W), j = (int)(e - (size_t)i * W);
+    const int a0 = a.src_rowptr[i], a1 = a.src_rowptr[i + 1];
+    if (j < a.D) {   // G0 = dL/d state0
+      float g0;
+      if (ran) {
+        g0 = a.dOwn1[(size_t)i * a.D + j];
+        for (int p = a0; p < a1; ++p) g0 = fmaf(a.src_w ? a.src_w[p] : 1.0f, a.dAgg1[(size_t)a.src_dst[p] * a.D + j], g0);
+      } else {
+        g0 = a.dSfin[(size_t)i * a.D + j];
+      }
+      if (a.S > 0) { if (a.d_state0) a.d_state0[(size_t)i * a.S + j] = g0; }
+      else if (a.d_nodes) a.d_nodes[(size_t)i * a.NLw + j] += g0;           // state0 = nodes (GNN.py:259)
+    }
+    if (a.d_nodes && a.dXs && j < a.NLw) {
+      float g = 0.f;
+      if (!a.composite) {
+        if (a.NLp) {   // own-label columns + Adj . d(agg_nodes)
+          g = a.dXs[(size_t)i * a.LsM + j];
+          for (int p = a0; p < a1; ++p) g = fmaf(a.src_w ? a.src_w[p] : 1.0f, a.dXs[(size_t)a.src_dst[p] * a.LsM + a.NLp + j], g);
+        }
+      } else {
+        for (int t = 0; t < a.nt; ++t) {
+          if (j < a.dt[t] && a.type_mask[(size_t)t * a.N + i]) {   // CompositeAdjacencies[t] keeps arcs whose source is type t
+            for (int p = a0; p < a1; ++p) g = fmaf(a.src_w ? a.src_w[p] : 1.0f, a.dXs[(size_t)a.src_dst[p] * a.LsM + a.doff[t] + j], g);
+          }
+        }
+      }
+      a.d_nodes[(size_t)i * a.NLw + j] += g;
+    }
+  }
+}
+// d_arc_labels[a] += v_a * d(agg_arcs)[dst_a]   (ArcNode . dInp[:, agg_arcs cols])
+static __global__ void k_input_grads_arcs(int A, int AL, int LsM, int col0, const int* dst, const float* val,
+                                          const float* dXs, float* d_arcs) {
+  const size_t total = (size_t)A * AL;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int ar = (int)(e / AL), c = (int)(e - (size_t)ar * AL);
+    d_arcs[e] += val[ar] * dXs[(size_t)dst[ar] * LsM + col0 + c];
+  }
+}
+
+extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                                   const gnnfp_loop_io* io, const gnnfp_loop_grads* gr, gnnfp_net_params* dsp,
+                                   gnnfp_net_params* dop, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_io(L, io, workspace, workspace_bytes))) return rc;
+  if (!sp || !op || !gr || !dsp || !dop) GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward: null argument");
+  if (!L->cfg.training) GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward needs a plan created with training=1 (states are not saved otherwise)");
+  for (int t = 0; t < L->nt; ++t) {
+    if ((rc = check_params(L->snet[t], sp[t], "net_state"))) return rc;
+    gnnfp_net_desc nd = L->snet[t]; nd.has_bn = 0;
+    if ((rc = check_params(nd, dsp[t], "d net_state"))) return rc;
+    if (L->snet[t].has_bn && (!dsp[t].bn_gamma || !dsp[t].bn_beta)) GNNFP_FAIL(GNNFP_E_INVALID, "d net_state: BN gradient buffers missing");
+  }
+  if ((rc = check_params(L->onet, *op, "net_output"))) return rc;
+  { gnnfp_net_desc nd = L->onet; nd.has_bn = 0; if ((rc = check_params(nd, *dop, "d net_output"))) return rc; }
+  if (L->onet.has_bn && (!dop->bn_gamma || !dop->bn_beta)) GNNFP_FAIL(GNNFP_E_INVALID, "d net_output: BN gradient buffers missing");
+  for (int l = 1; l < L->onet.n_layers; ++l)
+    if (L->onet.acts[l - 1] == GNNFP_ACT_SOFTMAX) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "softmax is only supported as the last activation in the backward");
+  for (int t = 0; t < L->nt; ++t)
+    for (int l = 1; l < L->snet[t].n_layers; ++l)
+      if (L->snet[t].acts[l - 1] == GNNFP_ACT_SOFTMAX) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "softmax is only supported as the last activation in the backward");
+  const int want = L->cfg.want_input_grads;
+  if ((want & 1) && !gr->d_nodes) GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward: d_nodes missing");
+  if ((want & 2) && L->AL > 0 && !gr->d_arc_labels) GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward: d_arc_labels missing");
+  if ((want & 4) && L->S > 0 && !gr->d_state0) GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward: d_state0 missing");
+
+  cudaStream_t s = (cudaStream_t)stream;
+  Ctx c{L, io, (char*)workspace, s};
+  const gnnfp_graph* g = L->g;
+  const int MI = L->cfg.max_iteration, D = L->D, N = L->N;
+  const size_t ND = (size_t)N * D;
+  float* dSfin = (float*)(c.ws + L->ws.dSfin);
+  float* dOwn[2] = {(float*)(c.ws + L->ws.dOwn), (float*)(c.ws + L->ws.dOwn) + ND};
+  float* dAgg[2] = {(float*)(c.ws + L->ws.dAgg), (float*)(c.ws + L->ws.dAgg) + ND};
+  float* dXs = want ? (float*)(c.ws + L->ws.dXs) : nullptr;
+  float* part_state = (float*)(c.ws + L->ws.part_state);
+  float* part_out = (float*)(c.ws + L->ws.part_out);
+  float* bn_part = (float*)(c.ws + L->ws.bn_part);
+  float* bn_const = (float*)(c.ws + L->ws.bn_const);
+  float* bn_grad = (float*)(c.ws + L->ws.bn_grad);
+  const float* src_w = g->mode == GNNFP_AGG_SUM ? nullptr : g->src_w;
+
+  GNNFP_CHECK_CUDA(cudaMemsetAsync(c.ws + L->ws.bwd_zero, 0, L->ws.bwd_zero_bytes, s));
+  if (gr->d_state) GNNFP_CHECK_CUDA(cudaMemcpyAsync(dSfin, gr->d_state, ND * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  else GNNFP_CHECK_CUDA(cudaMemsetAsync(dSfin, 0, ND * sizeof(float), s));
+  if ((want & 1)) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_nodes, 0, (size_t)N * L->NLw * sizeof(float), s));
+  if ((want & 2) && L->AL > 0) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_arc_labels, 0, (size_t)L->A * L->AL * sizeof(float), s));
+
+  // bn_grad layout: [state net 0 | state net 1 | ... | out net]
+  size_t bg_off[GNNFP_MAX_TYPES + 1];
+  {
+    size_t o = 0;
+    for (int t = 0; t < L->nt; ++t) { bg_off[t] = o; o += 2 * (size_t)L->snet[t].in_dim; }
+    bg_off[L->nt] = o;
+  }
+  size_t ps_off[GNNFP_MAX_TYPES];
+  {
+    size_t o = 0;
+    for (int t = 0; t < L->nt; ++t) { ps_off[t] = o; o += (size_t)L->grid_cap * L->nparam_s[t]; }
+  }
+  int grid_state[GNNFP_MAX_TYPES] = {0};
+  int grid_out = 0;
+  const int NLp = (!L->composite && L->S > 0) ? L->NLw : 0;
+
+  // ---- 1. net_output backward -----------------------------------------------------------------
+  NetDev ond;
+  fill_netdev(L->onet, *op, 1, L->M, ond);
+  if (gr->d_out || gr->d_out_nodes) {
+    BwdArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    build_out_src(c, ba.src);
+    const bool arc = L->cfg.kind == GNNFP_KIND_ARC;
+    for (int p = 0; p < ba.src.n_pieces; ++p) {
+      Piece& pc = ba.src.p[p];
+      if (pc.tag == TAG_STATE) { pc.gptr = dSfin; pc.gld = D; pc.gmode = arc ? GM_ATOMIC : GM_ADD; }
+      else if (pc.tag == TAG_NODES) { if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = arc ? GM_ATOMIC : GM_ADD; } }
+      else if (pc.tag == TAG_ARC_LABELS) { if ((want & 2) && L->AL > 0) { pc.gptr = gr->d_arc_labels; pc.gld = L->AL; pc.gmode = GM_ADD; } }
+    }
+    ba.gsrc.n_rows = ba.src.n_rows; ba.gsrc.rowlist = ba.src.rowlist; ba.gsrc.in_dim = L->T;
+    if (gr->d_out) {
+      Piece p = mk_direct(gr->d_out, L->T, L->T, 0);
+      if (L->pool) { p.map = g->node2graph; p.rowscale = g->ng_val; }   // d out_nodes[i] = NodeGraph[i,g(i)] * d out[g(i)]
+      else p.compact = 1;
+      add_piece(ba.gsrc, p);
+    }
+    if (gr->d_out_nodes) {
+      Piece p = mk_direct(gr->d_out_nodes, L->T, L->T, 0);
+      p.compact = 1;
+      p.accumulate = gr->d_out ? 1 : 0;
+      add_piece(ba.gsrc, p);
+    }
+    ba.net = ond;
+    if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, L->T, &ba.tc))) return rc;
+    grid_out = ba.tc.grid;
+    ba.saved_out = L->pool ? (const float*)(c.ws + L->ws.out_nodes) : io->out;
+    ba.ld_saved = L->T; ba.saved_compact = 1;
+    ba.partial = part_out; ba.n_params = L->nparam_o;
+    ba.bn_partial = bn_part;
+    if ((rc = launch_tile_bwd(ba, s))) return rc;
+    if (L->onet.has_bn && (rc = launch_bn_tail(ba, bn_grad + bg_off[L->nt], bn_const, s))) return rc;
+  }
+
+  // ---- 2. iterations, newest first ---------------------------------------------------------------
+  for (int t = MI; t >= 1; --t) {
+    const int* gate = c.flags() + (t - 1);
+    const int wb = t & 1, rb = (t + 1) & 1;
+    for (int ty = 0; ty < L->nt; ++ty) {
+      BwdArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      build_state_src(c, ty, t, ba.src);
+      for (int p = 0; p < ba.src.n_pieces; ++p) {
+        Piece& pc = ba.src.p[p];
+        if (pc.tag == TAG_AGG_STATE) { pc.gptr = dAgg[wb]; pc.gld = D; pc.gmode = GM_STORE; }
+        else if (pc.tag == TAG_STATE) { pc.gptr = dOwn[wb]; pc.gld = D; pc.gmode = GM_STORE; }
+        else if (want) {
+          if (pc.tag == TAG_NODES) { if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = GM_ADD; } }   // composite nodes[:, :d_t]
+          else if (pc.tag == TAG_STATIC) { pc.gptr = dXs + (pc.ptr - c.Xs()); pc.gld = L->LsM; pc.gmode = GM_ADD; }  // static block columns
+        }
+      }
+      ba.gsrc.n_rows = ba.src.n_rows; ba.gsrc.rowlist = ba.src.rowlist; ba.gsrc.in_dim = D;
+      {
+        Piece pa = mk_direct(dSfin, D, D, 0);
+        if (t < MI) { pa.gate = c.flags() + t; pa.gate_pol = 0; }   // enabled iff iteration t+1 did not run
+        add_piece(ba.gsrc, pa);
+        if (t < MI) {
+          Piece pb = mk_direct(dOwn[rb], D, D, 0);
+          pb.accumulate = 1; pb.gate = c.flags() + t; pb.gate_pol = 1;
+          add_piece(ba.gsrc, pb);
+          Piece pc2 = mk_gather(dAgg[rb], D, D, 0, g->src_rowptr, g->src_dst, src_w);
+          pc2.accumulate = 1; pc2.gate = c.flags() + t; pc2.gate_pol = 1;
+          add_piece(ba.gsrc, pc2);
+        }
+      }
+      fill_netdev(L->snet[ty], sp[ty], 1, ba.src.n_rows, ba.net);
+      if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc))) return rc;
+      grid_state[ty] = ba.tc.grid;
+      ba.saved_out = c.S(t); ba.ld_saved = D; ba.saved_compact = 0;
+      ba.partial = part_state + ps_off[ty]; ba.n_params = L->nparam_s[ty];
+      ba.bn_partial = bn_part;
+      ba.gate = gate;
+      if ((rc = launch_tile_bwd(ba, s))) return rc;
+      if (L->snet[ty].has_bn && (rc = launch_bn_tail(ba, bn_grad + bg_off[ty], bn_const, s))) return rc;
+    }
+  }
+
+  // ---- 3. input gradients --------------------------------------------------------------------------
+  if (want) {
+    InGradArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    ia.N = N; ia.D = D; ia.S = L->S; ia.NLp = NLp; ia.NLw = L->NLw; ia.AL = L->AL; ia.LsM = L->LsM;
+    ia.composite = L->composite; ia.nt = L->nt;
+    int o = 0;
+    for (int t = 0; t < L->nt; ++t) { ia.dt[t] = L->dt[t]; ia.doff[t] = o; o += L->dt[t]; }
+    ia.type_mask = g->type_mask; ia.flags = c.flags();
+    ia.dSfin = dSfin; ia.dOwn1 = dOwn[1]; ia.dAgg1 = dAgg[1]; ia.dXs = L->LsM > 0 ? dXs : nullptr;
+    ia.src_rowptr = g->src_rowptr; ia.src_dst = g->src_dst; ia.src_w = src_w;
+    ia.d_nodes = (want & 1) ? gr->d_nodes : nullptr;
+    ia.d_state0 = ((want & 4) && L->S > 0) ? gr->d_state0 : nullptr;
+    ia.want = want;
+    const size_t tot = (size_t)N * (D > L->NLw ? D : L->NLw);
+    int blocks = (int)((tot + 255) / 256);
+    if (blocks > 4736) blocks = 4736;
+    if (ia.d_nodes || ia.d_state0) {
+      k_input_grads_nodes<<<blocks, 256, 0, s>>>(ia);
+      GNNFP_COUNT_LAUNCH();
+    }
+    if ((want & 2) && L->AL > 0 && L->A > 0) {
+      const int col0 = L->composite ? L->sum_dt : 2 * NLp;
+      const size_t ta = (size_t)L->A * L->AL;
+      int b2 = (int)((ta + 255) / 256);
+      if (b2 > 4736) b2 = 4736;
+      k_input_grads_arcs<<<b2, 256, 0, s>>>(L->A, L->AL, L->LsM, col0, g->dst, g->arc_val, dXs, gr->d_arc_labels);
+      GNNFP_COUNT_LAUNCH();
+    }
+  }
+
+  // ---- 4. parameter gradients ------------------------------------------------------------------------
+  for (int ty = 0; ty < L->nt; ++ty) {
+    NetDev nd;
+    fill_netdev(L->snet[ty], sp[ty], 1, 1, nd);
+    if ((rc = launch_reduce_params(nd, part_state + ps_off[ty], grid_state[ty], L->nparam_s[ty], bn_grad + bg_off[ty],
+                                   dsp[ty], c.flags(), MI, gr->average_st_grads, s))) return rc;
+  }
+  if ((rc = launch_reduce_params(ond, part_out, grid_out, L->nparam_o, bn_grad + bg_off[L->nt], *dop, c.flags(), MI, 0, s))) return rc;
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}

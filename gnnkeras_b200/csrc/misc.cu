@@ -1,7 +1,167 @@
-#include "loop.h"
-extern "C" int gnnfp_loop_backward(gnnfp_loop*, const gnnfp_net_params*, const gnnfp_net_params*, const gnnfp_loop_io*,
-                        const gnnfp_loop_grads*, gnnfp_net_params*, gnnfp_net_params*, void*, size_t, void*) { GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "backward not built yet"); }
-extern "C" int gnnfp_update_graph_forward(const gnnfp_graph*, int32_t, const float*, int32_t, const float*, int32_t, const float*, int32_t, int32_t, float*, void*) { GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "nyi"); }
-extern "C" int gnnfp_update_graph_backward(const gnnfp_graph*, int32_t, const float*, float*, int32_t, float*, int32_t, float*, int32_t, int32_t, void*) { GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "nyi"); }
-extern "C" int gnnfp_cce_loss(const float*, const float*, const float*, int32_t, int32_t, float, float*, float*, void*) { GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "nyi"); }
-extern "C" int gnnfp_adam_step(float*, const float*, float*, float*, size_t, float, float, float, float, int32_t, float, void*) { GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "nyi"); }
+// misc.cu - small device ops around the loop: LGNN.update_graph (reference LGNN.py:175-214) and the
+// fused train-step tail (Keras categorical_crossentropy + Adam).
+#include "graph.h"
+
+static __global__ void k_update_graph_fwd(int n, const float* state, int sw, int ow, const float* base, int bw, int ldb, float* dst) {
+  const int W = sw + ow + bw;
+  const size_t total = (size_t)n * W;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / W;
+    const int c = (int)(e - r * W);
+    float v;
+    if (c < sw) v = state[r * sw + c];
+    else if (c < sw + ow) v = 0.0f;                       // tf.scatter_nd zero fill (LGNN.py:203)
+    else v = base[r * ldb + (c - sw - ow)];
+    dst[e] = v;
+  }
+}
+static __global__ void k_scatter_rows(int m, const int* idx, const float* rows, int ow, float* dst, int W, int col0) {
+  const size_t total = (size_t)m * ow;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / ow;
+    const int c = (int)(e - r * ow);
+    const size_t row = idx ? (size_t)idx[r] : r;
+    dst[row * W + col0 + c] = rows[e];
+  }
+}
+static __global__ void k_update_graph_bwd(int n, const float* d_dst, float* d_state, int sw, int ow, float* d_base, int bw, int accumulate) {
+  const int W = sw + ow + bw;
+  const size_t total = (size_t)n * W;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / W;
+    const int c = (int)(e - r * W);
+    const float v = d_dst[e];
+    if (c < sw) { if (d_state) d_state[r * sw + c] = v; }
+    else if (c >= sw + ow) {
+      if (d_base) { float* d = d_base + r * bw + (c - sw - ow); if (accumulate) *d += v; else *d = v; }
+    }
+  }
+}
+static __global__ void k_gather_rows(int m, const int* idx, const float* src, int W, int col0, int ow, float* rows) {
+  const size_t total = (size_t)m * ow;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / ow;
+    const int c = (int)(e - r * ow);
+    const size_t row = idx ? (size_t)idx[r] : r;
+    rows[e] = src[row * W + col0 + c];
+  }
+}
+
+static int blocks_for(size_t total) {
+  size_t b = (total + 255) / 256;
+  if (b > 4736) b = 4736;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int gnnfp_update_graph_forward(const gnnfp_graph* g, int32_t n_rows, const float* state, int32_t state_w,
+                                          const float* out_rows, int32_t out_w, const float* base, int32_t base_w,
+                                          int32_t ld_base, float* dst, void* stream) {
+  if (!g || !dst || !base) GNNFP_FAIL(GNNFP_E_INVALID, "update_graph: null argument");
+  if (n_rows != g->mask_len) GNNFP_FAIL(GNNFP_E_INVALID, "update_graph: n_rows must equal the mask length");
+  if ((state_w > 0 && !state) || (out_w > 0 && !out_rows)) GNNFP_FAIL(GNNFP_E_INVALID, "update_graph: state / out rows missing");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int W = state_w + out_w + base_w;
+  k_update_graph_fwd<<<blocks_for((size_t)n_rows * W), 256, 0, s>>>(n_rows, state, state_w, out_w, base, base_w, ld_base, dst);
+  GNNFP_COUNT_LAUNCH();
+  if (out_w > 0 && g->M > 0) {
+    const int* idx = g->M == g->mask_len ? nullptr : g->mask_idx;
+    k_scatter_rows<<<blocks_for((size_t)g->M * out_w), 256, 0, s>>>(g->M, idx, out_rows, out_w, dst, W, state_w);
+    GNNFP_COUNT_LAUNCH();
+  }
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
+extern "C" int gnnfp_update_graph_backward(const gnnfp_graph* g, int32_t n_rows, const float* d_dst, float* d_state,
+                                           int32_t state_w, float* d_out_rows, int32_t out_w, float* d_base,
+                                           int32_t base_w, int32_t accumulate_base, void* stream) {
+  if (!g || !d_dst) GNNFP_FAIL(GNNFP_E_INVALID, "update_graph_backward: null argument");
+  if (n_rows != g->mask_len) GNNFP_FAIL(GNNFP_E_INVALID, "update_graph_backward: n_rows must equal the mask length");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int W = state_w + out_w + base_w;
+  k_update_graph_bwd<<<blocks_for((size_t)n_rows * W), 256, 0, s>>>(n_rows, d_dst, d_state, state_w, out_w, d_base, base_w, accumulate_base);
+  GNNFP_COUNT_LAUNCH();
+  if (out_w > 0 && d_out_rows && g->M > 0) {
+    const int* idx = g->M == g->mask_len ? nullptr : g->mask_idx;
+    k_gather_rows<<<blocks_for((size_t)g->M * out_w), 256, 0, s>>>(g->M, idx, d_dst, W, state_w, out_w, d_out_rows);
+    GNNFP_COUNT_LAUNCH();
+  }
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
+// Keras categorical_crossentropy on probabilities: p/sum(p), clip to [1e-7, 1-1e-7],
+// -sum y log p; reduction SUM_OVER_BATCH_SIZE with sample weights: sum_i w_i l_i / rows.
+static __global__ void k_cce(const float* y, const float* p, const float* w, int rows, int cols, float scale,
+                             float* loss, float* dp) {
+  float local = 0.f;
+  const float eps = 1e-7f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+    const float* pi = p + (size_t)i * cols;
+    const float* yi = y + (size_t)i * cols;
+    float s = 0.f;
+    for (int c = 0; c < cols; ++c) s += pi[c];
+    const float wi = (w ? w[i] : 1.0f) * scale / (float)rows;
+    float li = 0.f, dot = 0.f;
+    for (int c = 0; c < cols; ++c) {
+      const float q = pi[c] / s;
+      const float qc = fminf(fmaxf(q, eps), 1.0f - eps);
+      li -= yi[c] * logf(qc);
+      if (q >= eps && q <= 1.0f - eps) dot += (-yi[c] / qc) * q;
+    }
+    local += wi * li;
+    if (dp) {
+      for (int c = 0; c < cols; ++c) {
+        const float q = pi[c] / s;
+        const float qc = fminf(fmaxf(q, eps), 1.0f - eps);
+        const float dq = (q >= eps && q <= 1.0f - eps) ? (-yi[c] / qc) : 0.0f;
+        dp[(size_t)i * cols + c] = wi * (dq - dot) / s;
+      }
+    }
+  }
+  // block reduction, one atomic per block
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, v);
+  }
+}
+
+extern "C" int gnnfp_cce_loss(const float* y_true, const float* y_pred, const float* sample_weight, int32_t rows,
+                              int32_t cols, float scale, float* loss_out, float* d_pred, void* stream) {
+  if (!y_true || !y_pred || rows <= 0 || cols <= 0) GNNFP_FAIL(GNNFP_E_INVALID, "cce_loss: bad arguments");
+  int blocks = (rows + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  k_cce<<<blocks, 256, 0, (cudaStream_t)stream>>>(y_true, y_pred, sample_weight, rows, cols, scale, loss_out, d_pred);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
+// Keras-2 Adam (non-amsgrad): alpha = lr*sqrt(1-b2^t)/(1-b1^t); m,v updates; p -= alpha*m/(sqrt(v)+eps)
+static __global__ void k_adam(float* p, const float* g, float* m, float* v, size_t n, float alpha, float b1, float b2,
+                              float eps, float gscale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.0f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (mi * alpha) / (sqrtf(vi) + eps);
+  }
+}
+extern "C" int gnnfp_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                               float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+  if (!params || !grads || !m || !v || step < 1) GNNFP_FAIL(GNNFP_E_INVALID, "adam_step: bad arguments");
+  if (n == 0) return GNNFP_OK;
+  const double alpha = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  k_adam<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, (float)alpha, beta1, beta2, eps, grad_scale);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}

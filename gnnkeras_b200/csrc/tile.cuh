@@ -58,7 +58,7 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
         float v = 0.0f;
         if (on && r < nr) {
           const int gr = ts.rowlist ? ts.rowlist[row0 + r] : row0 + r;
-          const int sr = pc.map ? pc.map[gr] : gr;
+          const int sr = pc.compact ? (row0 + r) : (pc.map ? pc.map[gr] : gr);
           v = pc.ptr[(size_t)sr * pc.ld + c];
           if (pc.rowscale) v *= pc.rowscale[gr];
           if (bnA) v = fmaf(v, bnA[c0 + c], bnB[c0 + c]);
