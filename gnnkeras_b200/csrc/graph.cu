@@ -96,16 +96,19 @@ static __global__ void k_nodegraph_values(const int* node2graph, const int* cnt,
 
 #define GRID(n) (((n) + 255) / 256), 256
 
+// Stream-ordered allocations from the device's default memory pool (kept warm: release threshold
+// = max), so building the structures of every batch costs no cudaMalloc after the first few steps.
 struct DevAlloc {
   std::vector<void*>* list;
   size_t* bytes;
+  cudaStream_t s;
   template <typename T>
   int get(T** p, size_t n) {
     void* q = nullptr;
     size_t b = (n ? n : 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(&q, b);
+    cudaError_t e = cudaMallocAsync(&q, b, s);
     if (e != cudaSuccess) {
-      gnnfp_set_error("cudaMalloc(%zu) failed: %s", b, cudaGetErrorString(e));
+      gnnfp_set_error("cudaMallocAsync(%zu) failed: %s", b, cudaGetErrorString(e));
       return GNNFP_E_CUDA;
     }
     list->push_back(q);
@@ -195,7 +198,20 @@ extern "C" int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* d, v
   g->N = d->n_nodes; g->A = d->n_arcs; g->G = d->n_graphs; g->n_types = d->n_types;
   g->mode = d->aggregation_mode;
   g->mask_len = d->mask_len ? d->mask_len : d->n_nodes;
-  DevAlloc A{&g->allocs, &g->device_bytes};
+  DevAlloc A{&g->allocs, &g->device_bytes, s};
+  g->stream = s;
+  {
+    static bool pool_set = false;
+    if (!pool_set) {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_set = true;
+    }
+  }
   const int N = g->N, NA = g->A;
   int rc = 0;
   void* tmp = nullptr;
@@ -242,7 +258,9 @@ extern "C" int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* d, v
     k_gather_f<<<GRID(NA), 0, s>>>(g->arc_val, g->src_arc, g->src_w, NA);
   }
   // masks -> index list
-  {
+  if (!d->set_mask && !d->output_mask) {
+    g->M = g->mask_len;             // all rows selected: no index list needed
+  } else {
     uint8_t* m = nullptr;
     BUILD_TRY(A.get(&m, (size_t)g->mask_len));
     k_mask_and<<<GRID(g->mask_len), 0, s>>>(d->set_mask, d->output_mask, m, g->mask_len);
@@ -307,7 +325,7 @@ extern "C" int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* d, v
 
 extern "C" void gnnfp_graph_free(gnnfp_graph* g) {
   if (!g) return;
-  for (void* p : g->allocs) cudaFree(p);
+  for (void* p : g->allocs) cudaFreeAsync(p, g->stream);
   delete g;
 }
 
@@ -334,7 +352,13 @@ extern "C" int gnnfp_graph_export(const gnnfp_graph* g, int which, void* host_ds
     case GNNFP_X_SRC_DST: p = g->src_dst; n = sizeof(int) * (size_t)g->A; break;
     case GNNFP_X_SRC_ARC: p = g->src_arc; n = sizeof(int) * (size_t)g->A; break;
     case GNNFP_X_ARC_VALUE: p = g->arc_val; n = sizeof(float) * (size_t)g->A; break;
-    case GNNFP_X_MASK_INDEX: p = g->mask_idx; n = sizeof(int) * (size_t)g->M; break;
+    case GNNFP_X_MASK_INDEX:
+      if (!g->mask_idx) {   // all rows selected
+        if (sizeof(int) * (size_t)g->M > bytes) GNNFP_FAIL(GNNFP_E_INVALID, "graph_export: buffer too small");
+        for (int i = 0; i < g->M; ++i) ((int*)host_dst)[i] = i;
+        return GNNFP_OK;
+      }
+      p = g->mask_idx; n = sizeof(int) * (size_t)g->M; break;
     case GNNFP_X_GRAPH_PTR: p = g->graph_ptr; n = g->G ? sizeof(int) * ((size_t)g->G + 1) : 0; break;
     case GNNFP_X_NODEGRAPH_VALUE: p = g->ng_val; n = g->G ? sizeof(float) * (size_t)g->N : 0; break;
     case GNNFP_X_TYPE_ROWS: {

@@ -27,6 +27,7 @@ struct gnnfp_graph {
   int* node2graph = nullptr;   // [N]
   float* ng_val = nullptr;     // [N]
   int* graph_ptr = nullptr;    // [G+1]
+  cudaStream_t stream = nullptr;   // stream the device arrays were allocated on (stream-ordered pool)
   std::vector<void*> allocs;
   size_t device_bytes = 0;
 };

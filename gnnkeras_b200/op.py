@@ -205,7 +205,7 @@ class LoopPlan:
     def __init__(self, graph: DeviceGraph, nets_state: Sequence[Net], net_output: Net, kind: str,
                  state_vect_dim: int, max_iteration: int, state_threshold: float, training: bool,
                  nodes_width: int, arc_label_width: int, dim_node_label: Optional[Sequence[int]] = None,
-                 pool: Optional[bool] = None, want_input_grads: int = 0):
+                 pool: Optional[bool] = None, want_input_grads: int = 0, workspace: Optional[torch.Tensor] = None):
         L = B.lib()
         # the reference's constructor asserts (GNN.py:26-28)
         assert state_vect_dim >= 0
@@ -238,7 +238,10 @@ class LoopPlan:
         self.T = net_output.widths[-1]
         self.S = int(state_vect_dim)
         self.nodes_width, self.AL = int(nodes_width), int(arc_label_width)
-        self.workspace = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8, device=graph.device)
+        if workspace is not None and workspace.numel() >= self.workspace_bytes + 256:
+            self.workspace = workspace           # grow-only buffer owned by the model
+        else:
+            self.workspace = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8, device=graph.device)
 
     def _ws_ptr(self):
         p = self.workspace.data_ptr()
@@ -285,7 +288,7 @@ class LoopPlan:
         return k, state, out
 
     def backward(self, d_out=None, d_out_nodes=None, d_state=None, average_st_grads=False,
-                 state_tensors=None, out_tensors=None):
+                 state_tensors=None, out_tensors=None, grad_state=None, grad_out=None):
         """BPTT of the last forward (same workspace).  Returns (state_grads[list per net][Keras order],
         out_grads, d_nodes, d_arc_labels, d_state0)."""
         nodes, arc_labels, ld_arcs, state0, state, out, out_nodes, k = self._last
@@ -293,15 +296,15 @@ class LoopPlan:
         dev = g.device
         io = self._io(nodes, arc_labels, ld_arcs, state0, state, out, out_nodes, k)
         sp, op = self._param_arrays(state_tensors, out_tensors)
-        gs = [[torch.zeros_like(t) for t in n.trainable()] for n in self.nets_state]
-        go = [torch.zeros_like(t) for t in self.net_output.trainable()]
+        gs = grad_state if grad_state is not None else [[torch.empty_like(t) for t in n.trainable()] for n in self.nets_state]
+        go = grad_out if grad_out is not None else [torch.empty_like(t) for t in self.net_output.trainable()]
         dsp = (B.NetParams * len(self.nets_state))(*[n.params(gs[i]) for i, n in enumerate(self.nets_state)])
         dop = self.net_output.params(go)
         gr = B.LoopGrads()
         want = self.cfg.want_input_grads
-        d_nodes = torch.zeros((g.n_nodes, self.nodes_width), dtype=torch.float32, device=dev) if want & 1 else None
-        d_arcs = torch.zeros((g.n_arcs, max(self.AL, 1)), dtype=torch.float32, device=dev) if want & 2 else None
-        d_state0 = torch.zeros((g.n_nodes, self.S), dtype=torch.float32, device=dev) if (want & 4 and self.S > 0) else None
+        d_nodes = torch.empty((g.n_nodes, self.nodes_width), dtype=torch.float32, device=dev) if want & 1 else None
+        d_arcs = torch.empty((g.n_arcs, max(self.AL, 1)), dtype=torch.float32, device=dev) if want & 2 else None
+        d_state0 = torch.empty((g.n_nodes, self.S), dtype=torch.float32, device=dev) if (want & 4 and self.S > 0) else None
         keep = []
         for nm, t in (("d_out", d_out), ("d_out_nodes", d_out_nodes), ("d_state", d_state)):
             if t is not None:

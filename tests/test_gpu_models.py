@@ -1,0 +1,163 @@
+"""GPU parity at the model level: composite GNN, arc focus, LGNN chaining (+ gradients across layers),
+train_step (loss + Adam) against the torch-CPU oracle."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from gnnkeras_b200 import models as M
+from gnnkeras_b200.graph import GraphTensor
+from gnnkeras_b200.op import Net
+from gnnkeras_b200.synthetic import make_net, mutag_shaped_batch
+from oracle import loop_numpy as LN
+from oracle import loop_torch as LT
+from oracle.adapt import copy_net, ograph_from_batch
+
+from test_gpu_backward import oracle_grads
+from util import DEV, nets_for, relerr, run_cuda, tol_vs64
+
+pytestmark = pytest.mark.gpu
+
+
+def gt_from_ograph(g, focus):
+    return GraphTensor.from_host_arrays(g.nodes, g.arcs, g.targets, g.sample_weight.astype(np.float32), g.set_mask,
+                                        g.output_mask, g.dim_node_label, focus, g.aggregation_mode,
+                                        g.node2graph.astype(np.int32), g.nodegraph_values, g.n_graphs, g.type_mask,
+                                        None, DEV)
+
+
+@pytest.mark.parametrize("S_,kind,bn,mode", [(0, "graph", False, "composite_average"), (5, "graph", True, "average"),
+                                             (4, "node", False, "sum"), (3, "arc", False, "average")])
+def test_composite_forward_backward(S_, kind, bn, mode):
+    b = mutag_shaped_batch(250, seed=5, n_types=2)
+    rng = np.random.default_rng(3)
+    if kind == "arc":
+        b.set_mask = np.ones(b.n_arcs, bool)
+        b.output_mask = rng.random(b.n_arcs) < 0.5
+    dnl = [14, 14] if S_ == 0 else [14, 9]
+    g = ograph_from_batch(b, {"graph": "g", "node": "n", "arc": "a"}[kind], mode, dim_node_label=dnl)
+    ns, no = nets_for(rng, 14, 3, 2, S_, kind, bn, "tanh", (), n_types=2, dnl=dnl)
+    s0 = (0.1 * rng.standard_normal((g.n_nodes, S_))).astype(np.float32) if S_ else None
+    D = S_ if S_ else 14
+    k64, s64, o64 = LN.loop_composite(g, [copy_net(n) for n in ns], copy_net(no), S_, 4, 0.01, True, s0, np.float64, kind)
+    k32, s32, o32 = LN.loop_composite(g, [copy_net(n) for n in ns], copy_net(no), S_, 4, 0.01, True, s0, np.float32, kind)
+    plan, nets, onet, (k, state, out) = run_cuda(g, ns, no, S_, 4, 0.01, True, s0, kind, want_input_grads=7)
+    assert int(k.item()) == k64
+    assert tol_vs64(relerr(state.cpu().numpy(), s64), relerr(s32, s64))
+    assert tol_vs64(relerr(out.cpu().numpy(), o64), relerr(o32, o64))
+    r_out = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    r_state = rng.standard_normal((g.n_nodes, D)).astype(np.float32)
+    gs, go, d_nodes, d_arcs, d_s0 = plan.backward(torch.as_tensor(r_out).to(DEV), None, torch.as_tensor(r_state).to(DEV), False)
+    torch.cuda.synchronize()
+    _, gs64, go64, gi64, _, _ = oracle_grads(g, ns, no, S_, 4, 0.01, s0, kind, r_out, r_state, torch.float64, composite=True, want_inputs=True)
+    _, gs32, go32, gi32, _, _ = oracle_grads(g, ns, no, S_, 4, 0.01, s0, kind, r_out, r_state, torch.float32, composite=True, want_inputs=True)
+    flat = lambda gsl, gol: [a for n in gsl for a in n] + list(gol)
+    for a, b64, b32 in zip(flat(gs, go), flat(gs64, go64), flat(gs32, go32)):
+        a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+        assert relerr(a, b64) <= max(2e-5, 8 * relerr(b32, b64)), (relerr(a, b64), relerr(b32, b64), a.shape)
+    assert relerr(d_nodes.cpu().numpy(), gi64[0]) <= max(2e-5, 8 * relerr(gi32[0], gi64[0]))
+    assert relerr(d_arcs.cpu().numpy(), gi64[1]) <= max(2e-5, 8 * relerr(gi32[1], gi64[1]))
+    if S_:
+        assert relerr(d_s0.cpu().numpy(), gi64[2]) <= max(2e-5, 8 * relerr(gi32[2], gi64[2]))
+
+
+@pytest.mark.parametrize("S_,bn", [(0, False), (4, True)])
+def test_arc_focus_homogeneous(S_, bn):
+    b = mutag_shaped_batch(200, seed=9)
+    rng = np.random.default_rng(4)
+    b.set_mask = np.ones(b.n_arcs, bool)
+    b.output_mask = rng.random(b.n_arcs) < 0.6
+    g = ograph_from_batch(b, "a", "average")
+    ns, no = nets_for(rng, 14, 3, 3, S_, "arc", bn, "tanh", ())
+    s0 = (0.1 * rng.standard_normal((g.n_nodes, S_))).astype(np.float32) if S_ else None
+    k64, s64, o64 = LN.loop_homogeneous(g, copy_net(ns), copy_net(no), S_, 3, 0.01, True, s0, np.float64, "arc")
+    k32, s32, o32 = LN.loop_homogeneous(g, copy_net(ns), copy_net(no), S_, 3, 0.01, True, s0, np.float32, "arc")
+    plan, nets, onet, (k, state, out) = run_cuda(g, ns, no, S_, 3, 0.01, True, s0, "arc", want_input_grads=7)
+    assert int(k.item()) == k64 and out.shape[0] == int((g.set_mask & g.output_mask).sum())
+    assert tol_vs64(relerr(out.cpu().numpy(), o64), relerr(o32, o64))
+    r_out = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    gs, go, d_nodes, d_arcs, d_s0 = plan.backward(torch.as_tensor(r_out).to(DEV), None, None, False)
+    _, gs64, go64, gi64, _, _ = oracle_grads(g, ns, no, S_, 3, 0.01, s0, "arc", r_out, None, torch.float64, want_inputs=True)
+    _, gs32, go32, gi32, _, _ = oracle_grads(g, ns, no, S_, 3, 0.01, s0, "arc", r_out, None, torch.float32, want_inputs=True)
+    for a, b64, b32 in zip(gs[0] + go, gs64[0] + go64, gs32[0] + go32):
+        assert relerr(a.cpu().numpy(), b64) <= max(2e-5, 8 * relerr(b32, b64))
+    assert relerr(d_nodes.cpu().numpy(), gi64[0]) <= max(2e-5, 8 * relerr(gi32[0], gi64[0]))
+    assert relerr(d_arcs.cpu().numpy(), gi64[1]) <= max(2e-5, 8 * relerr(gi32[1], gi64[1]))
+
+
+def _lgnn_specs(rng, layers, S_, bn, act, kind="graph", NL=14, AL=3, T=2, get_state=True, get_output=True):
+    specs, nl = [], NL
+    for l in range(layers):
+        ns, no = nets_for(rng, nl, AL, T, S_, kind, bn, act, ())
+        specs.append({"net_state": ns, "net_output": no, "state_vect_dim": S_, "max_iteration": 3,
+                      "state_threshold": 0.01, "kind": kind})
+        D = S_ if S_ else nl
+        nl = NL + (D if get_state else 0) + (T if get_output else 0)
+    return specs
+
+
+@pytest.mark.parametrize("S_,bn,mode", [(0, True, "parallel"), (4, False, "residual"), (0, False, "parallel")])
+def test_lgnn_train_step_matches_oracle(S_, bn, mode):
+    """3-layer LGNN: forward outputs, loss, and one Adam step vs torch autograd on the oracle."""
+    layers = 3
+    b = mutag_shaped_batch(150, seed=13)
+    rng = np.random.default_rng(8)
+    g = ograph_from_batch(b, "g", "average")
+    specs = _lgnn_specs(rng, layers, S_, bn, "selu" if bn else "tanh")
+    s0s = [(0.1 * rng.standard_normal((g.n_nodes, S_))).astype(np.float32) if S_ else None for _ in range(layers)]
+    # ---- oracle (fp64 and fp32): loss + grads + Adam(0.01) update ----------------------------------------
+    def oracle(dtype):
+        tg = LT.TorchGraph(g, dtype)
+        tspecs = [dict(s, net_state=LT.net_to_torch(s["net_state"], dtype), net_output=LT.net_to_torch(s["net_output"], dtype)) for s in specs]
+        nodes = torch.tensor(g.nodes, dtype=dtype)
+        arcs = torch.tensor(g.arcs, dtype=dtype)
+        st = None if not S_ else [torch.tensor(s, dtype=dtype) for s in s0s]
+        K, states, outs = LT.loop_lgnn(tg, nodes, arcs, tspecs, True, True, True, st)
+        y = torch.tensor(g.targets, dtype=dtype)
+        sw = torch.tensor(g.sample_weight, dtype=dtype)
+        if mode == "parallel":
+            loss = torch.stack([LT.categorical_crossentropy(y, o, sw) for o in outs]).mean()
+        else:
+            loss = LT.categorical_crossentropy(y, torch.stack(outs).mean(dim=0), sw)
+        loss.backward()
+        params = [p for s in tspecs for p in LT.trainable(s["net_state"])] + [p for s in tspecs for p in LT.trainable(s["net_output"])]
+        # average_st_grads=True: state grads / k of their layer (LGNN.py:272)
+        ns_len = len(LT.trainable(tspecs[0]["net_state"]))
+        grads = []
+        for li, s in enumerate(tspecs):
+            grads += [p.grad / K[li] for p in LT.trainable(s["net_state"])]
+        for s in tspecs:
+            grads += [p.grad for p in LT.trainable(s["net_output"])]
+        return K, [o.detach().numpy() for o in outs], float(loss.detach()), [x.numpy() for x in grads]
+    K64, outs64, loss64, grads64 = oracle(torch.float64)
+    K32, outs32, loss32, grads32 = oracle(torch.float32)
+    # ---- CUDA ------------------------------------------------------------------------------------------
+    gnns = [M.GNNgraphBased(Net.from_dict(s["net_state"], DEV), Net.from_dict(s["net_output"], DEV), S_, 3, 0.01) for s in specs]
+    lgnn = M.LGNN(gnns, True, True)
+    lgnn.compile(optimizer=M.Adam(learning_rate=0.01), loss="categorical_crossentropy", average_st_grads=True, training_mode=mode)
+    gt = gt_from_ograph(g, "g")
+    x = [gt.nodes, gt.arcs, gt.DIM_NODE_LABEL, gt.set_mask, gt.output_mask, gt.graph, gt.graph, gt.graph]
+    st = None if not S_ else [torch.as_tensor(s).to(DEV) for s in s0s]
+    before = lgnn._store.flat.clone()
+    K, states, outs = lgnn.Loop(*x, training=True, state0s=st, _keep=True)
+    assert [int(k.item()) for k in K] == K64
+    for o, o64, o32 in zip(outs, outs64, outs32):
+        assert tol_vs64(relerr(o.cpu().numpy(), o64), relerr(o32, o64))
+    lgnn.fixed_state0s = st            # train_step re-runs the forward with the same initial states
+    res = lgnn.train_step((x, gt.targets, gt.sample_weight))
+    torch.cuda.synchronize()
+    assert abs(float(res["loss"].item()) - loss64) <= max(1e-5, 8 * abs(loss32 - loss64)) * max(1.0, abs(loss64))
+    gflat = lgnn._store.grad_flat.cpu().numpy()
+    off = 0
+    for g64, g32 in zip(grads64, grads32):
+        a = gflat[off: off + g64.size].reshape(g64.shape)
+        off += g64.size
+        assert relerr(a, g64) <= max(5e-5, 8 * relerr(g32, g64)), (relerr(a, g64), relerr(g32, g64), g64.shape)
+    # Keras Adam, step 1: alpha = lr*sqrt(1-b2)/(1-b1), m = (1-b1) g, v = (1-b2) g^2
+    #   => p -= lr * g / (|g| + eps / sqrt(1-b2))
+    after = lgnn._store.flat.cpu().numpy()
+    gcat = np.concatenate([x_.reshape(-1) for x_ in grads64])
+    expect = before.cpu().numpy() - 0.01 * gcat / (np.abs(gcat) + 1e-7 / np.sqrt(1 - 0.999))
+    big = np.abs(gcat) > 1e-4          # elements whose update direction is well-conditioned
+    assert np.abs(after[big] - expect[big]).max() < 2e-5
