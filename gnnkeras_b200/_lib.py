@@ -74,7 +74,7 @@ SYMBOLS = ["gnnfp_last_error", "gnnfp_abi_version", "gnnfp_graph_build", "gnnfp_
            "gnnfp_graph_export", "gnnfp_loop_create", "gnnfp_loop_free", "gnnfp_loop_workspace_bytes",
            "gnnfp_loop_out_rows", "gnnfp_loop_state_dim", "gnnfp_loop_forward", "gnnfp_loop_backward",
            "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step",
-           "gnnfp_launch_count"]
+           "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect"]
 
 
 def lib():
@@ -114,6 +114,8 @@ def lib():
                                   C.c_int32, C.c_float, _vp]
     L.gnnfp_launch_count.argtypes = [C.c_int]
     L.gnnfp_launch_count.restype = C.c_longlong
+    L.gnnfp_profile_enable.argtypes = [C.c_int]
+    L.gnnfp_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     if L.gnnfp_abi_version() != 1:
         raise GnnfpError("libgnnfp.so ABI version mismatch")
     _LIB = L

@@ -31,6 +31,18 @@ void gnnfp_set_error(const char* fmt, ...);
 extern long long g_gnnfp_launches;
 #define GNNFP_COUNT_LAUNCH() (++g_gnnfp_launches)
 
+// optional per-category kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
+enum { PC_OTHER = 0, PC_FWD_ITER = 1, PC_BWD_ITER = 2, PC_PASS = 3, PC_FWD_OUT = 4, PC_BWD_OUT = 5, PC_BNFIX = 6,
+       PC_COUNT = 8 };
+extern int g_gnnfp_prof;
+void gnnfp_prof_begin(int cat, cudaStream_t s);
+void gnnfp_prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(int cat, cudaStream_t st) : s(st), on(g_gnnfp_prof != 0) { if (on) gnnfp_prof_begin(cat, s); }
+  ~ProfScope() { if (on) gnnfp_prof_end(s); }
+};
+
 // ---- a "piece": one column block of a net's input, read straight from where the data lives ---
 // The reference materialises tf.concat([...]) every iteration (GNN.py:231); here the concat only
 // ever exists as a shared-memory tile.
@@ -113,6 +125,7 @@ struct FwdArgs {
   int* flag_next;          // set to 1 when any row is not converged
   const int* gate;         // whole kernel runs only if *gate != 0 (NULL = always)
   int update_moving;       // CTA 0 applies the Keras moving-average update
+  int prof_cat;
 };
 
 struct PassArgs {           // tile pass without a net: materialise pieces and/or column statistics
@@ -123,6 +136,7 @@ struct PassArgs {           // tile pass without a net: materialise pieces and/o
   double* st_sum;          // [in_dim] or NULL
   double* st_sq;
   const int* gate;
+  int prof_cat;
 };
 
 struct BwdArgs {
@@ -137,6 +151,7 @@ struct BwdArgs {
   int n_params;
   float* bn_partial;       // [grid, 2*in_dim] per-CTA sum(dy), sum(dy*xhat0) of THIS launch
   const int* gate;
+  int prof_cat;
 };
 
 // launchers (kernels.cu)

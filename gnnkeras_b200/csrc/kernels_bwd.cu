@@ -19,7 +19,8 @@ struct BwdLayout {
   int L, recompute, bn;
   int inw[GNNFP_MAX_LAYERS + 1];    // width of activation l (0 = input)
   int XSa[GNNFP_MAX_LAYERS + 1];
-  int XSd;
+  int XSdA, XSdB;                   // dz ping-pong buffers: A holds widths inw[L], inw[L-2]..; B holds inw[L-1], inw[L-3]..
+  int regacc;                       // single big layer: dW accumulators live in registers (no smem copy)
   int groups[GNNFP_MAX_LAYERS];
   size_t oWT[GNNFP_MAX_LAYERS], oWf[GNNFP_MAX_LAYERS], obf[GNNFP_MAX_LAYERS], oAct[GNNFP_MAX_LAYERS + 1];
   size_t oAccW[GNNFP_MAX_LAYERS], oAccb[GNNFP_MAX_LAYERS];
@@ -27,19 +28,22 @@ struct BwdLayout {
   size_t total;   // floats
 };
 
-__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, BwdLayout& y) {
+__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int regacc, BwdLayout& y) {
   y.L = net.n_layers;
+  y.regacc = regacc;
   y.recompute = net.n_layers > 1;
   y.bn = net.bn_mode != 0;
   y.inw[0] = net.in_dim;
   for (int l = 0; l < y.L; ++l) y.inw[l + 1] = net.widths[l];
-  int dmax = 0;
+  int dmax = 0, dA = 0, dB = 0;
   for (int l = 0; l <= y.L; ++l) {
     y.XSa[l] = odd_stride(ceil_to(y.inw[l], 16));
     const int p = ceil_to(y.inw[l], 16);
     dmax = p > dmax ? p : dmax;
+    if (((y.L - l) & 1) == 0) dA = p > dA ? p : dA; else dB = p > dB ? p : dB;
   }
-  y.XSd = odd_stride(dmax);
+  y.XSdA = odd_stride(dA);
+  y.XSdB = odd_stride(dB > 0 ? dB : 16);
   size_t o = 0;
   for (int l = 0; l < y.L; ++l) {
     const int in_l = y.inw[l], H = y.inw[l + 1];
@@ -52,7 +56,7 @@ __host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, BwdL
     int g = U >= T ? 1 : T / U;
     if (g > 16) g = 16;
     y.groups[l] = g;
-    y.oAccW[l] = o; o += (size_t)ceil_to(g * in_l * H, 4);
+    y.oAccW[l] = o; o += regacc ? 0 : (size_t)ceil_to(g * in_l * H, 4);
     y.oAccb[l] = o; o += ceil_to(H, 4);
   }
   y.obnA = o; o += ceil_to(net.in_dim, 4);
@@ -61,8 +65,8 @@ __host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, BwdL
   y.oAccBN = o; o += 2 * (size_t)ceil_to(net.in_dim, 4);
   y.oZero = o; o += dmax;
   for (int l = 0; l <= y.L; ++l) { y.oAct[l] = o; o += (size_t)R * y.XSa[l]; }
-  y.odzA = o; o += (size_t)R * y.XSd;
-  y.odzB = o; o += (size_t)R * y.XSd;
+  y.odzA = o; o += (size_t)R * y.XSdA;
+  y.odzB = o; o += (size_t)R * y.XSdB;
   y.total = o;
 }
 
@@ -108,7 +112,8 @@ __device__ __forceinline__ void dense_tile(const float* __restrict__ Ain, int XS
   }
 }
 
-__global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ BwdArgs a) {
+template <bool REGACC>
+__global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __grid_constant__ BwdArgs a) {
   if (a.gate && *a.gate == 0) return;
   extern __shared__ __align__(16) float smem[];
   const NetDev& net = a.net;
@@ -117,8 +122,17 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
   const int lane = tid & 31, warp = tid >> 5;
   const int rg = warp % tc.RG, cg = warp / tc.RG;
   BwdLayout y;
-  bwd_layout(net, tc.R, T, y);
+  bwd_layout(net, tc.R, T, REGACC ? 1 : 0, y);
   const int L = y.L;
+  float racc[2][8][4];
+  if (REGACC) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) racc[q][i][jj] = 0.f;
+  }
   float* bnA = y.bn ? smem + y.obnA : nullptr;
   float* bnB = y.bn ? smem + y.obnB : nullptr;
   float* bnS = smem + y.obnS;
@@ -149,8 +163,10 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
         bf[j] = b;
       }
     }
-    float* aw = smem + y.oAccW[l];
-    for (int e = tid; e < y.groups[l] * in_l * H; e += T) aw[e] = 0.0f;
+    if (!REGACC) {
+      float* aw = smem + y.oAccW[l];
+      for (int e = tid; e < y.groups[l] * in_l * H; e += T) aw[e] = 0.0f;
+    }
     float* ab = smem + y.oAccb[l];
     for (int j = tid; j < H; j += T) ab[j] = 0.0f;
   }
@@ -175,7 +191,7 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
     stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], bnA, bnB);
-    stage_tile(a.gsrc, row0, nr, tc.R, dzA, y.XSd, nullptr, nullptr);
+    stage_tile(a.gsrc, row0, nr, tc.R, dzA, y.XSdA, nullptr, nullptr);
     if (!y.recompute) {
       float* aL = smem + y.oAct[L];
       for (int e = tid; e < tc.R * HL; e += T) {
@@ -220,20 +236,21 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
       if (actL == GNNFP_ACT_SOFTMAX) {
         for (int r = tid; r < tc.R; r += T) {
           float dot = 0.f;
-          for (int j = 0; j < HL; ++j) dot = fmaf(dzA[r * y.XSd + j], aL[r * XS + j], dot);
-          for (int j = 0; j < HL; ++j) dzA[r * y.XSd + j] = aL[r * XS + j] * (dzA[r * y.XSd + j] - dot);
+          for (int j = 0; j < HL; ++j) dot = fmaf(dzA[r * y.XSdA + j], aL[r * XS + j], dot);
+          for (int j = 0; j < HL; ++j) dzA[r * y.XSdA + j] = aL[r * XS + j] * (dzA[r * y.XSdA + j] - dot);
         }
       } else {
         for (int e = tid; e < tc.R * HL; e += T) {
           const int r = (int)__umulhi((unsigned)e, magicHL);
           const int j = e - r * HL;
-          dzA[r * y.XSd + j] = act_bwd(actL, aL[r * XS + j], dzA[r * y.XSd + j]);
+          dzA[r * y.XSdA + j] = act_bwd(actL, aL[r * XS + j], dzA[r * y.XSdA + j]);
         }
       }
     }
     __syncthreads();
     float* cur = dzA;
     float* oth = dzB;
+    int XSc = y.XSdA, XSo = y.XSdB;
     for (int l = L - 1; l >= 0; --l) {
       const int in_l = y.inw[l], H = y.inw[l + 1];
       const float* al = smem + y.oAct[l];
@@ -245,8 +262,9 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
         int u0, g, ustride;
         if (groups == 1) { u0 = tid; g = 0; ustride = T; }
         else { u0 = tid % U; g = tid / U; ustride = U; if (g >= groups) u0 = U; }
-        float* aw = smem + y.oAccW[l] + (size_t)g * in_l * H;
-        for (int u = u0; u < U; u += ustride) {
+        float* aw = REGACC ? nullptr : smem + y.oAccW[l] + (size_t)g * in_l * H;
+        int q = 0;
+        for (int u = u0; u < U; u += ustride, ++q) {
           const int cu = u / h4, ju = u - cu * h4;
           const int c0 = cu * 8, j0 = ju * 4;
           float acc[8][4];
@@ -259,23 +277,37 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
 #pragma unroll
             for (int i = 0; i < 8; ++i) av[i] = al[r * XSl + c0 + i];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) dv[jj] = cur[r * y.XSd + j0 + jj];
+            for (int jj = 0; jj < 4; ++jj) dv[jj] = cur[r * XSc + j0 + jj];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(av[i], dv[jj], acc[i][jj]);
           }
+          if (REGACC) {
+            if (q == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              if (c0 + i < in_l && j0 + jj < H) aw[(c0 + i) * H + j0 + jj] += acc[i][jj];
+                for (int jj = 0; jj < 4; ++jj) racc[0][i][jj] += acc[i][jj];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) racc[1][i][jj] += acc[i][jj];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (c0 + i < in_l && j0 + jj < H) aw[(c0 + i) * H + j0 + jj] += acc[i][jj];
+          }
           if (groups > 1) break;
         }
         float* ab = smem + y.oAccb[l];
         for (int j = tid; j < H; j += T) {
           float s = 0.f;
-          for (int r = 0; r < nr; ++r) s += cur[r * y.XSd + j];
+          for (int r = 0; r < nr; ++r) s += cur[r * XSc + j];
           ab[j] += s;
         }
       }
@@ -283,7 +315,7 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
       {
         const int inpad = ceil_to(in_l, 16);
         if (cg < inpad / GNNFP_JC)
-          dense_tile(cur, y.XSd, oth, y.XSd, smem + y.oWT[l], zero, H, inpad, GNNFP_ACT_LINEAR, rg, cg, tc.CG, lane);
+          dense_tile(cur, XSc, oth, XSo, smem + y.oWT[l], zero, H, inpad, GNNFP_ACT_LINEAR, rg, cg, tc.CG, lane);
       }
       __syncthreads();
       if (l > 0) {
@@ -292,11 +324,12 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
         for (int e = tid; e < tc.R * in_l; e += T) {
           const int r = (int)__umulhi((unsigned)e, magic);
           const int c = e - r * in_l;
-          oth[r * y.XSd + c] = act_bwd(actp, al[r * XSl + c], oth[r * y.XSd + c]);
+          oth[r * XSo + c] = act_bwd(actp, al[r * XSl + c], oth[r * XSo + c]);
         }
         __syncthreads();
       }
       float* t2 = cur; cur = oth; oth = t2;
+      const int t3 = XSc; XSc = XSo; XSo = t3;
     }
     // ---- cur = dy (gradient w.r.t. the BN output / the raw input) ---------------------------------
     if (y.bn) {
@@ -305,7 +338,7 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
       for (int c = tid; c < net.in_dim; c += T) {
         float p = 0.f, q = 0.f;
         for (int r = 0; r < nr; ++r) {
-          const float dy = cur[r * y.XSd + c];
+          const float dy = cur[r * XSc + c];
           p += dy;
           q = fmaf(dy, a0[r * y.XSa[0] + c], q);
         }
@@ -320,7 +353,7 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
       for (int e = tid; e < nr * w; e += T) {
         const int r = (int)__umulhi((unsigned)e, pc.magic);
         const int c = e - r * w;
-        float v = cur[r * y.XSd + pc.col0 + c];
+        float v = cur[r * XSc + pc.col0 + c];
         if (y.bn) v *= bnS[pc.col0 + c];
         const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
         const int drow = pc.map ? pc.map[gr] : gr;
@@ -338,11 +371,25 @@ __global__ void __launch_bounds__(256) tile_bwd_kernel(const __grid_constant__ B
     size_t off = 0;
     for (int l = 0; l < L; ++l) {
       const int in_l = y.inw[l], H = y.inw[l + 1];
-      const float* aw = smem + y.oAccW[l];
-      for (int e = tid; e < in_l * H; e += T) {
-        float s = 0.f;
-        for (int g = 0; g < y.groups[l]; ++g) s += aw[(size_t)g * in_l * H + e];
-        part[off + e] += s;
+      if (REGACC) {
+        const int h4 = (H + 3) / 4, U = ((in_l + 7) / 8) * h4;
+        int q = 0;
+        for (int u = tid; u < U && q < 2; u += T, ++q) {
+          const int cu = u / h4, ju = u - cu * h4;
+          const int c0 = cu * 8, j0 = ju * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if (c0 + i < in_l && j0 + jj < H) part[off + (size_t)(c0 + i) * H + j0 + jj] += (q == 0 ? racc[0][i][jj] : racc[1][i][jj]);
+        }
+      } else {
+        const float* aw = smem + y.oAccW[l];
+        for (int e = tid; e < in_l * H; e += T) {
+          float s = 0.f;
+          for (int g = 0; g < y.groups[l]; ++g) s += aw[(size_t)g * in_l * H + e];
+          part[off + e] += s;
+        }
       }
       off += (size_t)in_l * H;
       const float* ab = smem + y.oAccb[l];
@@ -518,16 +565,22 @@ int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc) {
   int RG = 8 / CG;
   const int nsm = gnnfp_num_sms();
   BwdLayout y;
-  const size_t cap = 200 * 1024, want = 100 * 1024;
+  const size_t cap = 216 * 1024, want = 100 * 1024;
+  int regacc = 0;
   for (;;) {
-    bwd_layout(net, 64 * RG, 256, y);
+    bwd_layout(net, 64 * RG, 256, 0, y);
     const bool too_big = y.total * 4 > want;
     const bool underfill = (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm;
     if (RG > 1 && (too_big || underfill)) { RG /= 2; CG = 8 / RG; continue; }
     break;
   }
+  if (y.total * 4 > want && net.n_layers == 1) {
+    // one big Dense layer: keep the dW accumulators in registers (2 units of 8x4 per thread)
+    const int U = ((net.in_dim + 7) / 8) * ((net.widths[0] + 3) / 4);
+    if (U >= 256 && U <= 512) { regacc = 1; bwd_layout(net, 64 * RG, 256, 1, y); }
+  }
   tc->RG = RG; tc->CG = CG; tc->R = 64 * RG; tc->threads = 256;
-  tc->XS0 = y.XSa[0]; tc->XS1 = y.XSd;
+  tc->XS0 = y.XSa[0]; tc->XS1 = regacc;   // XS1 doubles as the register-accumulation switch of the backward kernel
   tc->smem_bytes = y.total * 4;
   if (tc->smem_bytes > cap)
     GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "net too large for the shared-memory backward tile kernel (%zu bytes needed)", tc->smem_bytes);
@@ -544,11 +597,14 @@ int launch_tile_bwd(const BwdArgs& a, cudaStream_t s) {
   if (a.src.n_rows <= 0) return GNNFP_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(tile_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(tile_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(tile_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     GNNFP_CHECK_CUDA(cudaFuncSetAttribute(tile_bnfix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
     attr_set = true;
   }
-  tile_bwd_kernel<<<a.tc.grid, a.tc.threads, a.tc.smem_bytes, s>>>(a);
+  ProfScope ps(a.prof_cat ? a.prof_cat : PC_OTHER, s);
+  if (a.tc.XS1) tile_bwd_kernel<true><<<a.tc.grid, a.tc.threads, a.tc.smem_bytes, s>>>(a);
+  else tile_bwd_kernel<false><<<a.tc.grid, a.tc.threads, a.tc.smem_bytes, s>>>(a);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;
@@ -574,6 +630,7 @@ int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream
   int rc = tile_cfg_pass(a.net.in_dim, a.src.n_rows, &fa.tc);
   if (rc) return rc;
   fa.tc.smem_bytes += 4 * (size_t)ceil_to(a.net.in_dim, 4) * sizeof(float);
+  ProfScope ps(PC_BNFIX, s);
   tile_bnfix_kernel<<<fa.tc.grid, fa.tc.threads, fa.tc.smem_bytes, s>>>(fa);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());

@@ -376,6 +376,7 @@ int launch_tile_fwd(const FwdArgs& a, cudaStream_t s) {
                                           (int)(220 * 1024)));
     attr_set = 220 * 1024;
   }
+  ProfScope ps(a.prof_cat ? a.prof_cat : PC_OTHER, s);
   tile_fwd_kernel<<<a.tc.grid, a.tc.threads, a.tc.smem_bytes, s>>>(a);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
@@ -390,6 +391,7 @@ int launch_tile_pass(const PassArgs& a, cudaStream_t s) {
                                           (int)(100 * 1024)));
     attr_set = true;
   }
+  ProfScope ps(PC_PASS, s);
   tile_pass_kernel<<<a.tc.grid, a.tc.threads, a.tc.smem_bytes, s>>>(a);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());

@@ -23,6 +23,38 @@ void gnnfp_set_error(const char* fmt, ...) {
 }
 extern "C" const char* gnnfp_last_error(void) { return g_err; }
 extern "C" int gnnfp_abi_version(void) { return GNNFP_ABI_VERSION; }
+// ---- optional kernel timing ---------------------------------------------------------------------------
+#include <vector>
+int g_gnnfp_prof = 0;
+struct ProfRec { int cat; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+void gnnfp_prof_begin(int cat, cudaStream_t s) {
+  ProfRec r;
+  r.cat = cat;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  g_prof_recs.push_back(r);
+}
+void gnnfp_prof_end(cudaStream_t s) { cudaEventRecord(g_prof_recs.back().b, s); }
+extern "C" int gnnfp_profile_enable(int on) {
+  g_gnnfp_prof = on;
+  return GNNFP_OK;
+}
+extern "C" int gnnfp_profile_collect(double* ms_by_cat, long long* count_by_cat, int ncat) {
+  for (int i = 0; i < ncat; ++i) { ms_by_cat[i] = 0.0; count_by_cat[i] = 0; }
+  for (auto& r : g_prof_recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.cat >= 0 && r.cat < ncat) { ms_by_cat[r.cat] += ms; count_by_cat[r.cat] += 1; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+  return GNNFP_OK;
+}
+
 extern "C" long long gnnfp_launch_count(int reset) {
   long long v = g_gnnfp_launches;
   if (reset) g_gnnfp_launches = 0;
@@ -494,6 +526,7 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       if (t < MI) { fa.prev = c.S(t - 1); fa.ld_prev = c.ldS(t - 1); fa.thr = L->cfg.state_threshold; fa.flag_next = c.flags() + t; }
       fa.gate = gate;
       fa.update_moving = training;
+      fa.prof_cat = PC_FWD_ITER;
       if ((rc = launch_tile_fwd(fa, s))) return rc;
     }
   }
@@ -525,6 +558,7 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
     float* on = L->pool ? (float*)(c.ws + L->ws.out_nodes) : io->out;
     fa.out = on; fa.ld_out = L->T; fa.out_compact = 1;
     fa.update_moving = training;
+    fa.prof_cat = PC_FWD_OUT;
     if ((rc = launch_tile_fwd(fa, s))) return rc;
     if (L->pool) {
       const int tot = g->G * L->T;

@@ -167,6 +167,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     ba.ld_saved = L->T; ba.saved_compact = 1;
     ba.partial = part_out; ba.n_params = L->nparam_o;
     ba.bn_partial = bn_part;
+    ba.prof_cat = PC_BWD_OUT;
     if ((rc = launch_tile_bwd(ba, s))) return rc;
     if (L->onet.has_bn && (rc = launch_bn_tail(ba, bn_grad + bg_off[L->nt], bn_const, s))) return rc;
   }
@@ -209,6 +210,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
       ba.partial = part_state + ps_off[ty]; ba.n_params = L->nparam_s[ty];
       ba.bn_partial = bn_part;
       ba.gate = gate;
+      ba.prof_cat = PC_BWD_ITER;
       if ((rc = launch_tile_bwd(ba, s))) return rc;
       if (L->snet[ty].has_bn && (rc = launch_bn_tail(ba, bn_grad + bg_off[ty], bn_const, s))) return rc;
     }
