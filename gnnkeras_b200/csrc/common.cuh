@@ -104,7 +104,9 @@ struct TileCfg {
   int RG;                  // row-group warps
   int CG;                  // column-group warps
   int R;                   // rows per tile = 64 * RG  (2 rows per lane)
-  int XS0, XS1;            // odd row strides of the two activation buffers
+  int XS0, XS1;            // row strides (% 8 == 4) of the two activation buffers
+  int cap;                 // arcs of one tile the CSR scratch can hold (fast gather path)
+  int cap_per_row;         // in: scratch capacity per tile row (0 = default 4), set by the caller from A/N
   int threads;
   size_t smem_bytes;
   int grid;
@@ -121,6 +123,7 @@ struct FwdArgs {
   double* ost_sq;
   const float* prev;       // convergence test against this matrix (rows gr), or NULL
   int ld_prev;
+  int prev_col0;           // column of the raw previous state inside the staged input tile (-1: read `prev`)
   float thr;
   int* flag_next;          // set to 1 when any row is not converged
   const int* gate;         // whole kernel runs only if *gate != 0 (NULL = always)

@@ -22,13 +22,13 @@ struct BwdLayout {
   int XSdA, XSdB;                   // dz ping-pong buffers: A holds widths inw[L], inw[L-2]..; B holds inw[L-1], inw[L-3]..
   int regacc;                       // single big layer: dW accumulators live in registers (no smem copy)
   int groups[GNNFP_MAX_LAYERS];
-  size_t oWT[GNNFP_MAX_LAYERS], oWf[GNNFP_MAX_LAYERS], obf[GNNFP_MAX_LAYERS], oAct[GNNFP_MAX_LAYERS + 1];
-  size_t oAccW[GNNFP_MAX_LAYERS], oAccb[GNNFP_MAX_LAYERS];
-  size_t obnA, obnB, obnS, oZero, odzA, odzB, oAccBN;
-  size_t total;   // floats
+  int oWT[GNNFP_MAX_LAYERS], oWf[GNNFP_MAX_LAYERS], obf[GNNFP_MAX_LAYERS], oAct[GNNFP_MAX_LAYERS + 1];
+  int oAccW[GNNFP_MAX_LAYERS], oAccb[GNNFP_MAX_LAYERS];
+  int obnA, obnB, obnS, oZero, odzA, odzB, oAccBN, oScr;
+  int total;   // floats
 };
 
-__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int regacc, BwdLayout& y) {
+__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int regacc, int cap, BwdLayout& y) {
   y.L = net.n_layers;
   y.regacc = regacc;
   y.recompute = net.n_layers > 1;
@@ -37,79 +37,38 @@ __host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int 
   for (int l = 0; l < y.L; ++l) y.inw[l + 1] = net.widths[l];
   int dmax = 0, dA = 0, dB = 0;
   for (int l = 0; l <= y.L; ++l) {
-    y.XSa[l] = odd_stride(ceil_to(y.inw[l], 16));
     const int p = ceil_to(y.inw[l], 16);
+    y.XSa[l] = tile_stride(p);
     dmax = p > dmax ? p : dmax;
     if (((y.L - l) & 1) == 0) dA = p > dA ? p : dA; else dB = p > dB ? p : dB;
   }
-  y.XSdA = odd_stride(dA);
-  y.XSdB = odd_stride(dB > 0 ? dB : 16);
-  size_t o = 0;
+  y.XSdA = tile_stride(dA);
+  y.XSdB = tile_stride(dB > 0 ? dB : 16);
+  int o = 0;
   for (int l = 0; l < y.L; ++l) {
     const int in_l = y.inw[l], H = y.inw[l + 1];
-    y.oWT[l] = o; o += (size_t)H * ceil_to(in_l, 16);
+    y.oWT[l] = o; o += ceil_to(H, 4) * ceil_to(in_l, 16);           // W^T: [ceil4(H)][ceil16(in)]
     if (y.recompute) {
-      y.oWf[l] = o; o += (size_t)in_l * ceil_to(H, 16);
+      y.oWf[l] = o; o += ceil_to(in_l, 4) * ceil_to(H, 16);         // forward weights [ceil4(in)][ceil16(H)]
       y.obf[l] = o; o += ceil_to(H, 16);
     } else { y.oWf[l] = 0; y.obf[l] = 0; }
     const int U = ((in_l + 7) / 8) * ((H + 3) / 4);
     int g = U >= T ? 1 : T / U;
     if (g > 16) g = 16;
     y.groups[l] = g;
-    y.oAccW[l] = o; o += regacc ? 0 : (size_t)ceil_to(g * in_l * H, 4);
+    y.oAccW[l] = o; o += regacc ? 0 : ceil_to(g * in_l * H, 4);
     y.oAccb[l] = o; o += ceil_to(H, 4);
   }
   y.obnA = o; o += ceil_to(net.in_dim, 4);
   y.obnB = o; o += ceil_to(net.in_dim, 4);
   y.obnS = o; o += ceil_to(net.in_dim, 4);
-  y.oAccBN = o; o += 2 * (size_t)ceil_to(net.in_dim, 4);
+  y.oAccBN = o; o += 2 * ceil_to(net.in_dim, 4);
   y.oZero = o; o += dmax;
-  for (int l = 0; l <= y.L; ++l) { y.oAct[l] = o; o += (size_t)R * y.XSa[l]; }
-  y.odzA = o; o += (size_t)R * y.XSdA;
-  y.odzB = o; o += (size_t)R * y.XSdB;
+  y.oScr = o; o += (int)scratch_floats(R, cap);
+  for (int l = 0; l <= y.L; ++l) { y.oAct[l] = o; o += R * y.XSa[l]; }
+  y.odzA = o; o += R * y.XSdA;
+  y.odzB = o; o += R * y.XSdB;
   y.total = o;
-}
-
-// forward-style dense layer used for both the recompute and dprev = dz . W^T (no activation, bias from `bl`)
-__device__ __forceinline__ void dense_tile(const float* __restrict__ Ain, int XSin, float* __restrict__ Aout, int XSout,
-                                           const float* __restrict__ Wl, const float* __restrict__ bl, int in_l, int Hpad,
-                                           int act, int rg, int cg, int CG, int lane) {
-  const int nch = Hpad / GNNFP_JC;
-  const float* x0p = Ain + (rg * 64 + lane) * XSin;
-  const float* x1p = x0p + 32 * XSin;
-  for (int ch = cg; ch < nch; ch += CG) {
-    float acc0[GNNFP_JC], acc1[GNNFP_JC];
-#pragma unroll
-    for (int j = 0; j < GNNFP_JC; ++j) { const float bj = bl[ch * GNNFP_JC + j]; acc0[j] = bj; acc1[j] = bj; }
-    const float4* wp = reinterpret_cast<const float4*>(Wl + ch * GNNFP_JC);
-    const int wstride = Hpad / 4;
-#pragma unroll 2
-    for (int c = 0; c < in_l; ++c) {
-      const float x0 = x0p[c], x1 = x1p[c];
-      const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-      wp += wstride;
-      acc0[0] = fmaf(x0, w0.x, acc0[0]);   acc1[0] = fmaf(x1, w0.x, acc1[0]);
-      acc0[1] = fmaf(x0, w0.y, acc0[1]);   acc1[1] = fmaf(x1, w0.y, acc1[1]);
-      acc0[2] = fmaf(x0, w0.z, acc0[2]);   acc1[2] = fmaf(x1, w0.z, acc1[2]);
-      acc0[3] = fmaf(x0, w0.w, acc0[3]);   acc1[3] = fmaf(x1, w0.w, acc1[3]);
-      acc0[4] = fmaf(x0, w1.x, acc0[4]);   acc1[4] = fmaf(x1, w1.x, acc1[4]);
-      acc0[5] = fmaf(x0, w1.y, acc0[5]);   acc1[5] = fmaf(x1, w1.y, acc1[5]);
-      acc0[6] = fmaf(x0, w1.z, acc0[6]);   acc1[6] = fmaf(x1, w1.z, acc1[6]);
-      acc0[7] = fmaf(x0, w1.w, acc0[7]);   acc1[7] = fmaf(x1, w1.w, acc1[7]);
-      acc0[8] = fmaf(x0, w2.x, acc0[8]);   acc1[8] = fmaf(x1, w2.x, acc1[8]);
-      acc0[9] = fmaf(x0, w2.y, acc0[9]);   acc1[9] = fmaf(x1, w2.y, acc1[9]);
-      acc0[10] = fmaf(x0, w2.z, acc0[10]); acc1[10] = fmaf(x1, w2.z, acc1[10]);
-      acc0[11] = fmaf(x0, w2.w, acc0[11]); acc1[11] = fmaf(x1, w2.w, acc1[11]);
-      acc0[12] = fmaf(x0, w3.x, acc0[12]); acc1[12] = fmaf(x1, w3.x, acc1[12]);
-      acc0[13] = fmaf(x0, w3.y, acc0[13]); acc1[13] = fmaf(x1, w3.y, acc1[13]);
-      acc0[14] = fmaf(x0, w3.z, acc0[14]); acc1[14] = fmaf(x1, w3.z, acc1[14]);
-      acc0[15] = fmaf(x0, w3.w, acc0[15]); acc1[15] = fmaf(x1, w3.w, acc1[15]);
-    }
-    float* o0 = Aout + (rg * 64 + lane) * XSout + ch * GNNFP_JC;
-    float* o1 = o0 + 32 * XSout;
-#pragma unroll
-    for (int j = 0; j < GNNFP_JC; ++j) { o0[j] = act_fwd(act, acc0[j]); o1[j] = act_fwd(act, acc1[j]); }
-  }
 }
 
 template <bool REGACC>
@@ -121,8 +80,9 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
   const int tid = threadIdx.x, T = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int rg = warp % tc.RG, cg = warp / tc.RG;
-  BwdLayout y;
-  bwd_layout(net, tc.R, T, REGACC ? 1 : 0, y);
+  __shared__ BwdLayout y;
+  if (tid == 0) bwd_layout(net, tc.R, T, REGACC ? 1 : 0, tc.cap, y);
+  __syncthreads();
   const int L = y.L;
   float racc[2][8][4];
   if (REGACC) {
@@ -133,33 +93,38 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) racc[q][i][jj] = 0.f;
   }
-  float* bnA = y.bn ? smem + y.obnA : nullptr;
-  float* bnB = y.bn ? smem + y.obnB : nullptr;
-  float* bnS = smem + y.obnS;
+  float* bnA = smem + y.obnA;     // rstd            (x~ = x*bnA + bnB)
+  float* bnB = smem + y.obnB;     // -mean*rstd
+  float* bnS = smem + y.obnS;     // gamma*rstd      (dx = bnS * dy - correction)
   float* accBN = smem + y.oAccBN;
   float* zero = smem + y.oZero;
+  const StageScratch sc = carve_scratch(smem + y.oScr, tc.R, tc.cap);
 
-  // ---- one-time staging: W^T (true weights), forward weights for the recompute, BN, accumulators ----
+  if (y.bn) bn_coefficients(a.src, net, 0, bnA, bnB, nullptr, nullptr);
+  __syncthreads();
+  // ---- one-time staging: W^T (true weights), forward weights for the recompute, accumulators --------
   for (int l = 0; l < L; ++l) {
     const int in_l = y.inw[l], H = y.inw[l + 1], inpad = ceil_to(in_l, 16), Hpad = ceil_to(H, 16);
     float* WT = smem + y.oWT[l];
-    for (int e = tid; e < H * inpad; e += T) {
+    for (int e = tid; e < ceil_to(H, 4) * inpad; e += T) {
       const int j = e / inpad, c = e - j * inpad;
-      WT[e] = c < in_l ? net.W[l][(size_t)c * H + j] : 0.0f;
+      WT[e] = (c < in_l && j < H) ? net.W[l][(size_t)c * H + j] : 0.0f;
     }
     if (y.recompute) {
+      // the tile holds RAW inputs: x_hat = (gamma*rstd) x + (gamma*(-mean*rstd) + beta) folded into layer 0
       float* Wf = smem + y.oWf[l];
-      for (int e = tid; e < in_l * Hpad; e += T) {
+      const bool fold = (l == 0 && y.bn);
+      for (int e = tid; e < ceil_to(in_l, 4) * Hpad; e += T) {
         const int c = e / Hpad, j = e - c * Hpad;
-        float w = j < H ? net.W[l][(size_t)c * H + j] : 0.0f;
-        if (l == 0 && y.bn) w *= net.gamma[c];               // act0 holds x~: fold gamma/beta into layer 0
+        float w = (j < H && c < in_l) ? net.W[l][(size_t)c * H + j] : 0.0f;
+        if (fold && c < in_l) w *= net.gamma[c] * bnA[c];
         Wf[e] = w;
       }
       float* bf = smem + y.obf[l];
       for (int j = tid; j < Hpad; j += T) {
         float b = j < H ? net.b[l][j] : 0.0f;
-        if (l == 0 && y.bn && j < H)
-          for (int c = 0; c < in_l; ++c) b = fmaf(net.beta[c], net.W[l][(size_t)c * H + j], b);
+        if (fold && j < H)
+          for (int c = 0; c < in_l; ++c) b = fmaf(fmaf(net.gamma[c], bnB[c], net.beta[c]), net.W[l][(size_t)c * H + j], b);
         bf[j] = b;
       }
     }
@@ -170,14 +135,11 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
     float* ab = smem + y.oAccb[l];
     for (int j = tid; j < H; j += T) ab[j] = 0.0f;
   }
-  if (y.bn) {
-    bn_coefficients(a.src, net, 0, bnA, bnB, nullptr, nullptr);
-  }
   for (int c = tid; c < 2 * ceil_to(net.in_dim, 4); c += T) accBN[c] = 0.0f;
-  for (int c = tid; c < (int)(y.oAct[0] - y.oZero); c += T) zero[c] = 0.0f;
-  __syncthreads();
+  for (int c = tid; c < y.oScr - y.oZero; c += T) zero[c] = 0.0f;
+  for (int c = tid; c < y.total - y.oAct[0]; c += T) smem[y.oAct[0] + c] = 0.0f;   // activation + dz tiles
   if (y.bn)
-    for (int c = tid; c < net.in_dim; c += T) bnS[c] = net.gamma[c] * bnA[c];   // a_c = gamma * rstd
+    for (int c = tid; c < net.in_dim; c += T) bnS[c] = net.gamma[c] * bnA[c];
   __syncthreads();
 
   const int n = a.src.n_rows;
@@ -186,14 +148,16 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
   const unsigned magicHL = (unsigned)((0x100000000ull + (unsigned)HL - 1) / (unsigned)HL);
   float* dzA = smem + y.odzA;
   float* dzB = smem + y.odzB;
+  const int XSdA = y.XSdA, XSdB = y.XSdB;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
-    stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], bnA, bnB);
-    stage_tile(a.gsrc, row0, nr, tc.R, dzA, y.XSdA, nullptr, nullptr);
+    stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], sc);
+    stage_tile(a.gsrc, row0, nr, tc.R, dzA, XSdA, sc);
     if (!y.recompute) {
       float* aL = smem + y.oAct[L];
+      const int XS = y.XSa[L];
       for (int e = tid; e < tc.R * HL; e += T) {
         const int r = (int)__umulhi((unsigned)e, magicHL);
         const int j = e - r * HL;
@@ -202,7 +166,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           const int srow = a.saved_compact ? (row0 + r) : (a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r);
           v = a.saved_out[(size_t)srow * a.ld_saved + j];
         }
-        aL[r * y.XSa[L] + j] = v;
+        aL[r * XS + j] = v;
       }
     }
     __syncthreads();
@@ -211,19 +175,10 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         const int Hpad = ceil_to(y.inw[l + 1], 16);
         if (cg < Hpad / GNNFP_JC)
           dense_tile(smem + y.oAct[l], y.XSa[l], smem + y.oAct[l + 1], y.XSa[l + 1], smem + y.oWf[l], smem + y.obf[l],
-                     y.inw[l], Hpad, net.acts[l], rg, cg, tc.CG, lane);
+                     (y.inw[l] + 3) / 4, Hpad, net.acts[l], rg, cg, tc.CG, lane);
         __syncthreads();
         if (net.acts[l] == GNNFP_ACT_SOFTMAX) {
-          float* A = smem + y.oAct[l + 1];
-          const int XS = y.XSa[l + 1], H = y.inw[l + 1];
-          for (int r = tid; r < tc.R; r += T) {
-            float* row = A + r * XS;
-            float m = row[0];
-            for (int j = 1; j < H; ++j) m = fmaxf(m, row[j]);
-            float s = 0.f;
-            for (int j = 0; j < H; ++j) { const float e2 = expf(row[j] - m); row[j] = e2; s += e2; }
-            for (int j = 0; j < H; ++j) row[j] = row[j] / s;
-          }
+          softmax_rows(smem + y.oAct[l + 1], y.XSa[l + 1], y.inw[l + 1], tc.R);
           __syncthreads();
         }
       }
@@ -236,21 +191,21 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       if (actL == GNNFP_ACT_SOFTMAX) {
         for (int r = tid; r < tc.R; r += T) {
           float dot = 0.f;
-          for (int j = 0; j < HL; ++j) dot = fmaf(dzA[r * y.XSdA + j], aL[r * XS + j], dot);
-          for (int j = 0; j < HL; ++j) dzA[r * y.XSdA + j] = aL[r * XS + j] * (dzA[r * y.XSdA + j] - dot);
+          for (int j = 0; j < HL; ++j) dot = fmaf(dzA[r * XSdA + j], aL[r * XS + j], dot);
+          for (int j = 0; j < HL; ++j) dzA[r * XSdA + j] = aL[r * XS + j] * (dzA[r * XSdA + j] - dot);
         }
       } else {
         for (int e = tid; e < tc.R * HL; e += T) {
           const int r = (int)__umulhi((unsigned)e, magicHL);
           const int j = e - r * HL;
-          dzA[r * y.XSdA + j] = act_bwd(actL, aL[r * XS + j], dzA[r * y.XSdA + j]);
+          dzA[r * XSdA + j] = act_bwd(actL, aL[r * XS + j], dzA[r * XSdA + j]);
         }
       }
     }
     __syncthreads();
     float* cur = dzA;
     float* oth = dzB;
-    int XSc = y.XSdA, XSo = y.XSdB;
+    int XSc = XSdA, XSo = XSdB;
     for (int l = L - 1; l >= 0; --l) {
       const int in_l = y.inw[l], H = y.inw[l + 1];
       const float* al = smem + y.oAct[l];
@@ -262,7 +217,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         int u0, g, ustride;
         if (groups == 1) { u0 = tid; g = 0; ustride = T; }
         else { u0 = tid % U; g = tid / U; ustride = U; if (g >= groups) u0 = U; }
-        float* aw = REGACC ? nullptr : smem + y.oAccW[l] + (size_t)g * in_l * H;
+        float* aw = REGACC ? nullptr : smem + y.oAccW[l] + g * in_l * H;
         int q = 0;
         for (int u = u0; u < U; u += ustride, ++q) {
           const int cu = u / h4, ju = u - cu * h4;
@@ -272,12 +227,15 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.f;
+          const float* ap = al + c0;
+          const float* dp = cur + j0;
+#pragma unroll 2
           for (int r = g; r < nr; r += groups) {
-            float av[8], dv[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) av[i] = al[r * XSl + c0 + i];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) dv[jj] = cur[r * XSc + j0 + jj];
+            const float4 a0 = *reinterpret_cast<const float4*>(ap + r * XSl);
+            const float4 a1 = *reinterpret_cast<const float4*>(ap + r * XSl + 4);
+            const float4 d4 = *reinterpret_cast<const float4*>(dp + r * XSc);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -304,18 +262,28 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           }
           if (groups > 1) break;
         }
+        // db_l += column sums of dz (all threads: column x row group, shared float atomics)
         float* ab = smem + y.oAccb[l];
-        for (int j = tid; j < H; j += T) {
-          float s = 0.f;
-          for (int r = 0; r < nr; ++r) s += cur[r * XSc + j];
-          ab[j] += s;
+        if (T >= H) {
+          const int ngr = T / H, j = tid % H, gg = tid / H;
+          if (gg < ngr) {
+            float s2 = 0.f;
+            for (int r = gg; r < nr; r += ngr) s2 += cur[r * XSc + j];
+            atomicAdd(ab + j, s2);
+          }
+        } else {
+          for (int j = tid; j < H; j += T) {
+            float s2 = 0.f;
+            for (int r = 0; r < nr; ++r) s2 += cur[r * XSc + j];
+            ab[j] += s2;
+          }
         }
       }
       // (b) dprev = dz . W_l^T
       {
         const int inpad = ceil_to(in_l, 16);
         if (cg < inpad / GNNFP_JC)
-          dense_tile(cur, XSc, oth, XSo, smem + y.oWT[l], zero, H, inpad, GNNFP_ACT_LINEAR, rg, cg, tc.CG, lane);
+          dense_tile(cur, XSc, oth, XSo, smem + y.oWT[l], zero, (H + 3) / 4, inpad, GNNFP_ACT_LINEAR, rg, cg, tc.CG, lane);
       }
       __syncthreads();
       if (l > 0) {
@@ -332,18 +300,32 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       const int t3 = XSc; XSc = XSo; XSo = t3;
     }
     // ---- cur = dy (gradient w.r.t. the BN output / the raw input) ---------------------------------
-    if (y.bn) {
+    if (y.bn) {   // P_c = sum dy, Qraw_c = sum dy * x  (all threads: column x row group)
       const float* a0 = smem + y.oAct[0];
-      const int pin = ceil_to(net.in_dim, 4);
-      for (int c = tid; c < net.in_dim; c += T) {
-        float p = 0.f, q = 0.f;
-        for (int r = 0; r < nr; ++r) {
-          const float dy = cur[r * XSc + c];
-          p += dy;
-          q = fmaf(dy, a0[r * y.XSa[0] + c], q);
+      const int pin = ceil_to(net.in_dim, 4), ind = net.in_dim, XS0 = y.XSa[0];
+      if (T >= ind) {
+        const int ngr = T / ind, c = tid % ind, gg = tid / ind;
+        if (gg < ngr) {
+          float p = 0.f, q = 0.f;
+          for (int r = gg; r < nr; r += ngr) {
+            const float dy = cur[r * XSc + c];
+            p += dy;
+            q = fmaf(dy, a0[r * XS0 + c], q);
+          }
+          atomicAdd(accBN + c, p);
+          atomicAdd(accBN + pin + c, q);
         }
-        accBN[c] += p;
-        accBN[pin + c] += q;
+      } else {
+        for (int c = tid; c < ind; c += T) {
+          float p = 0.f, q = 0.f;
+          for (int r = 0; r < nr; ++r) {
+            const float dy = cur[r * XSc + c];
+            p += dy;
+            q = fmaf(dy, a0[r * XS0 + c], q);
+          }
+          accBN[c] += p;
+          accBN[pin + c] += q;
+        }
       }
     }
     for (int p = 0; p < a.src.n_pieces; ++p) {
@@ -366,11 +348,16 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
     __syncthreads();
   }
   // ---- flush per-CTA accumulators to this CTA's partial slot (plain +=: the slot is private) ----
+  // With BN the layer-0 accumulators were taken on RAW inputs x; the gradient w.r.t. the Dense kernel is
+  //   dW0[c][j] = sum x_hat dz = gamma_c*(rstd_c*acc[c][j] - mean_c*rstd_c*db[j]) + beta_c*db[j]
+  // and sum dy*x~ = rstd_c*Qraw_c - mean_c*rstd_c*P_c  (this launch's batch statistics).
   {
     float* part = a.partial + (size_t)blockIdx.x * a.n_params;
-    size_t off = 0;
+    int off = 0;
     for (int l = 0; l < L; ++l) {
       const int in_l = y.inw[l], H = y.inw[l + 1];
+      const float* ab = smem + y.oAccb[l];
+      const bool fix = (l == 0 && y.bn);
       if (REGACC) {
         const int h4 = (H + 3) / 4, U = ((in_l + 7) / 8) * h4;
         int q = 0;
@@ -381,18 +368,26 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-              if (c0 + i < in_l && j0 + jj < H) part[off + (size_t)(c0 + i) * H + j0 + jj] += (q == 0 ? racc[0][i][jj] : racc[1][i][jj]);
+              if (c0 + i < in_l && j0 + jj < H) {
+                const int c = c0 + i, j = j0 + jj;
+                float v = (q == 0 ? racc[0][i][jj] : racc[1][i][jj]);
+                if (fix) v = net.gamma[c] * fmaf(bnA[c], v, bnB[c] * ab[j]) + net.beta[c] * ab[j];
+                part[off + c * H + j] += v;
+              }
         }
       } else {
         const float* aw = smem + y.oAccW[l];
         for (int e = tid; e < in_l * H; e += T) {
-          float s = 0.f;
-          for (int g = 0; g < y.groups[l]; ++g) s += aw[(size_t)g * in_l * H + e];
-          part[off + e] += s;
+          float v = 0.f;
+          for (int g = 0; g < y.groups[l]; ++g) v += aw[g * in_l * H + e];
+          if (fix) {
+            const int c = e / H, j = e - c * H;
+            v = net.gamma[c] * fmaf(bnA[c], v, bnB[c] * ab[j]) + net.beta[c] * ab[j];
+          }
+          part[off + e] += v;
         }
       }
-      off += (size_t)in_l * H;
-      const float* ab = smem + y.oAccb[l];
+      off += in_l * H;
       for (int j = tid; j < H; j += T) part[off + j] += ab[j];
       off += H;
     }
@@ -400,8 +395,9 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       const int pin = ceil_to(net.in_dim, 4);
       float* bp = a.bn_partial + (size_t)blockIdx.x * 2 * net.in_dim;
       for (int c = tid; c < net.in_dim; c += T) {
-        bp[c] = accBN[c];
-        bp[net.in_dim + c] = accBN[pin + c];
+        const float P = accBN[c], Qraw = accBN[pin + c];
+        bp[c] = P;
+        bp[net.in_dim + c] = fmaf(bnA[c], Qraw, bnB[c] * P);
       }
     }
   }
@@ -463,7 +459,8 @@ __global__ void __launch_bounds__(256) tile_bnfix_kernel(const __grid_constant__
   float* bnB = smem + pin;
   float* c0 = smem + 2 * pin;
   float* c1 = smem + 3 * pin;
-  float* X = smem + 4 * pin;
+  const StageScratch sc = carve_scratch(smem + 4 * pin, tc.R, tc.cap);
+  float* X = smem + 4 * pin + scratch_floats(tc.R, tc.cap);
   const int tid = threadIdx.x, T = blockDim.x;
   bn_coefficients(a.src, a.net, 0, bnA, bnB, nullptr, nullptr);
   for (int c = tid; c < in; c += T) { c0[c] = a.bn_const[c]; c1[c] = a.bn_const[in + c]; }
@@ -473,7 +470,7 @@ __global__ void __launch_bounds__(256) tile_bnfix_kernel(const __grid_constant__
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
-    stage_tile(a.src, row0, nr, tc.R, X, tc.XS0, bnA, bnB);
+    stage_tile(a.src, row0, nr, tc.R, X, tc.XS0, sc);
     __syncthreads();
     for (int p = 0; p < a.src.n_pieces; ++p) {
       const Piece& pc = a.src.p[p];
@@ -483,7 +480,7 @@ __global__ void __launch_bounds__(256) tile_bnfix_kernel(const __grid_constant__
         const int r = (int)__umulhi((unsigned)e, pc.magic);
         const int c = e - r * w;
         const int cc = pc.col0 + c;
-        const float corr = c0[cc] + X[r * tc.XS0 + cc] * c1[cc];
+        const float corr = c0[cc] + fmaf(X[r * tc.XS0 + cc], bnA[cc], bnB[cc]) * c1[cc];
         const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
         const int drow = pc.map ? pc.map[gr] : gr;
         float* d = pc.gptr + (size_t)drow * pc.gld + c;
@@ -529,14 +526,8 @@ __global__ void reduce_params_kernel(const __grid_constant__ ReduceArgs a) {
       const int H = a.net.widths[l];
       if (i < off + in_l * H) {
         const int e = i - off, c = e / H, j = e - c * H;
-        float v = (float)s;
-        if (l == 0 && bn) {
-          double sb = 0.0;
-          const int ib = off + in_l * H + j;
-          for (int b = 0; b < a.grid; ++b) sb += (double)a.partial[(size_t)b * a.n_params + ib];
-          v = (float)((double)a.net.gamma[c] * s + (double)a.net.beta[c] * sb);
-        }
-        a.dW[l][e] = v * scale;
+        (void)c; (void)j;
+        a.dW[l][e] = (float)s * scale;
         break;
       }
       off += in_l * H;
@@ -566,22 +557,24 @@ int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc) {
   const int nsm = gnnfp_num_sms();
   BwdLayout y;
   const size_t cap = 216 * 1024, want = 100 * 1024;
+  const int cap_per_row = tc->cap_per_row > 0 ? tc->cap_per_row : 4;
   int regacc = 0;
   for (;;) {
-    bwd_layout(net, 64 * RG, 256, 0, y);
-    const bool too_big = y.total * 4 > want;
+    bwd_layout(net, 64 * RG, 256, 0, 64 * RG * cap_per_row, y);
+    const bool too_big = (size_t)y.total * 4 > want;
     const bool underfill = (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm;
     if (RG > 1 && (too_big || underfill)) { RG /= 2; CG = 8 / RG; continue; }
     break;
   }
-  if (y.total * 4 > want && net.n_layers == 1) {
+  if ((size_t)y.total * 4 > want && net.n_layers == 1) {
     // one big Dense layer: keep the dW accumulators in registers (2 units of 8x4 per thread)
     const int U = ((net.in_dim + 7) / 8) * ((net.widths[0] + 3) / 4);
-    if (U >= 256 && U <= 512) { regacc = 1; bwd_layout(net, 64 * RG, 256, 1, y); }
+    if (U >= 256 && U <= 512) { regacc = 1; bwd_layout(net, 64 * RG, 256, 1, 64 * RG * cap_per_row, y); }
   }
   tc->RG = RG; tc->CG = CG; tc->R = 64 * RG; tc->threads = 256;
   tc->XS0 = y.XSa[0]; tc->XS1 = regacc;   // XS1 doubles as the register-accumulation switch of the backward kernel
-  tc->smem_bytes = y.total * 4;
+  tc->cap = tc->R * cap_per_row;
+  tc->smem_bytes = (size_t)y.total * 4 + 64;
   if (tc->smem_bytes > cap)
     GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "net too large for the shared-memory backward tile kernel (%zu bytes needed)", tc->smem_bytes);
   int per_sm = (int)((220 * 1024) / (tc->smem_bytes + 1024));
@@ -627,6 +620,7 @@ int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream
   BnFixArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.src = a.src; fa.net = a.net; fa.bn_const = bn_const; fa.gate = a.gate;
+  fa.tc.cap_per_row = a.tc.cap_per_row;
   int rc = tile_cfg_pass(a.net.in_dim, a.src.n_rows, &fa.tc);
   if (rc) return rc;
   fa.tc.smem_bytes += 4 * (size_t)ceil_to(a.net.in_dim, 4) * sizeof(float);

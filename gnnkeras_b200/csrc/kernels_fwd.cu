@@ -15,74 +15,6 @@
 // weight reads are 128-bit broadcasts.
 #include "tile.cuh"
 
-// ------------------------------------------------------------------------------------------------
-// one Dense layer on the tile: each warp (rg, cg) owns 64 rows x 16-column chunks
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dense_layer_tile(const float* __restrict__ Ain, int XSin,
-                                                 float* __restrict__ Aout, int XSout,
-                                                 const float* __restrict__ Wl, const float* __restrict__ bl,
-                                                 int in_l, int Hpad, int act, int rg, int cg, int CG, int lane) {
-  const int nch = Hpad / GNNFP_JC;
-  const float* x0p = Ain + (rg * 64 + lane) * XSin;
-  const float* x1p = x0p + 32 * XSin;
-  for (int ch = cg; ch < nch; ch += CG) {
-    float acc0[GNNFP_JC], acc1[GNNFP_JC];
-#pragma unroll
-    for (int j = 0; j < GNNFP_JC; ++j) {
-      const float bj = bl[ch * GNNFP_JC + j];
-      acc0[j] = bj;
-      acc1[j] = bj;
-    }
-    const float4* wp = reinterpret_cast<const float4*>(Wl + ch * GNNFP_JC);
-    const int wstride = Hpad / 4;
-#pragma unroll 2
-    for (int c = 0; c < in_l; ++c) {
-      const float x0 = x0p[c], x1 = x1p[c];
-      const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-      wp += wstride;
-      acc0[0] = fmaf(x0, w0.x, acc0[0]);   acc1[0] = fmaf(x1, w0.x, acc1[0]);
-      acc0[1] = fmaf(x0, w0.y, acc0[1]);   acc1[1] = fmaf(x1, w0.y, acc1[1]);
-      acc0[2] = fmaf(x0, w0.z, acc0[2]);   acc1[2] = fmaf(x1, w0.z, acc1[2]);
-      acc0[3] = fmaf(x0, w0.w, acc0[3]);   acc1[3] = fmaf(x1, w0.w, acc1[3]);
-      acc0[4] = fmaf(x0, w1.x, acc0[4]);   acc1[4] = fmaf(x1, w1.x, acc1[4]);
-      acc0[5] = fmaf(x0, w1.y, acc0[5]);   acc1[5] = fmaf(x1, w1.y, acc1[5]);
-      acc0[6] = fmaf(x0, w1.z, acc0[6]);   acc1[6] = fmaf(x1, w1.z, acc1[6]);
-      acc0[7] = fmaf(x0, w1.w, acc0[7]);   acc1[7] = fmaf(x1, w1.w, acc1[7]);
-      acc0[8] = fmaf(x0, w2.x, acc0[8]);   acc1[8] = fmaf(x1, w2.x, acc1[8]);
-      acc0[9] = fmaf(x0, w2.y, acc0[9]);   acc1[9] = fmaf(x1, w2.y, acc1[9]);
-      acc0[10] = fmaf(x0, w2.z, acc0[10]); acc1[10] = fmaf(x1, w2.z, acc1[10]);
-      acc0[11] = fmaf(x0, w2.w, acc0[11]); acc1[11] = fmaf(x1, w2.w, acc1[11]);
-      acc0[12] = fmaf(x0, w3.x, acc0[12]); acc1[12] = fmaf(x1, w3.x, acc1[12]);
-      acc0[13] = fmaf(x0, w3.y, acc0[13]); acc1[13] = fmaf(x1, w3.y, acc1[13]);
-      acc0[14] = fmaf(x0, w3.z, acc0[14]); acc1[14] = fmaf(x1, w3.z, acc1[14]);
-      acc0[15] = fmaf(x0, w3.w, acc0[15]); acc1[15] = fmaf(x1, w3.w, acc1[15]);
-    }
-    float* o0 = Aout + (rg * 64 + lane) * XSout + ch * GNNFP_JC;
-    float* o1 = o0 + 32 * XSout;
-#pragma unroll
-    for (int j = 0; j < GNNFP_JC; ++j) {
-      o0[j] = act_fwd(act, acc0[j]);
-      o1[j] = act_fwd(act, acc1[j]);
-    }
-  }
-}
-
-// row-wise softmax over the first H columns of the tile (Keras softmax, last axis)
-__device__ __forceinline__ void softmax_rows(float* A, int XS, int H, int R) {
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
-    float* row = A + r * XS;
-    float m = row[0];
-    for (int j = 1; j < H; ++j) m = fmaxf(m, row[j]);
-    float s = 0.f;
-    for (int j = 0; j < H; ++j) {
-      const float e = expf(row[j] - m);
-      row[j] = e;
-      s += e;
-    }
-    for (int j = 0; j < H; ++j) row[j] = row[j] / s;
-  }
-}
-
 struct FwdSmem {
   float* W[GNNFP_MAX_LAYERS];
   float* b[GNNFP_MAX_LAYERS];
@@ -91,8 +23,10 @@ struct FwdSmem {
   float* buf0;
   float* buf1;
   double* ost;   // [2*H] output statistics accumulators
+  StageScratch sc;
 };
 
+// shared-memory layout (floats); must match fwd_smem_floats()
 __device__ __forceinline__ void carve_fwd(const NetDev& net, const TileCfg& tc, float* base, FwdSmem& s) {
   float* p = base;
   s.ost = reinterpret_cast<double*>(p);
@@ -101,7 +35,7 @@ __device__ __forceinline__ void carve_fwd(const NetDev& net, const TileCfg& tc, 
   for (int l = 0; l < net.n_layers; ++l) {
     const int Hpad = ceil_to(net.widths[l], GNNFP_JC);
     s.W[l] = p;
-    p += in_l * Hpad;
+    p += ceil_to(in_l, 4) * Hpad;
     s.b[l] = p;
     p += Hpad;
     in_l = net.widths[l];
@@ -110,6 +44,8 @@ __device__ __forceinline__ void carve_fwd(const NetDev& net, const TileCfg& tc, 
   p += ceil_to(net.in_dim, 4);
   s.bnB = p;
   p += ceil_to(net.in_dim, 4);
+  s.sc = carve_scratch(p, tc.R, tc.cap);
+  p += scratch_floats(tc.R, tc.cap);
   s.buf0 = p;
   p += tc.R * tc.XS0;
   s.buf1 = p;
@@ -128,25 +64,9 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
   const int L = net.n_layers;
   const int H = net.widths[L - 1];
 
-  // ---- weights (zero padded to 16 columns), BN coefficients, statistics accumulators ----------
-  {
-    int in_l = net.in_dim;
-    for (int l = 0; l < L; ++l) {
-      const int Hl = net.widths[l], Hpad = ceil_to(Hl, GNNFP_JC);
-      for (int e = tid; e < in_l * Hpad; e += T) {
-        const int c = e / Hpad, j = e - c * Hpad;
-        s.W[l][e] = j < Hl ? net.W[l][(size_t)c * Hl + j] : 0.0f;
-      }
-      for (int j = tid; j < Hpad; j += T) s.b[l][j] = j < Hl ? net.b[l][j] : 0.0f;
-      in_l = Hl;
-    }
-  }
-  float* bnA = nullptr;
-  float* bnB = nullptr;
+  // ---- BN coefficients (x_hat = x*a + b), moving-average update -------------------------------------
   if (net.bn_mode) {
-    bnA = s.bnA;
-    bnB = s.bnB;
-    bn_coefficients(a.src, net, 1, bnA, bnB, nullptr, nullptr);
+    bn_coefficients(a.src, net, 1, s.bnA, s.bnB, nullptr, nullptr);
     if (a.update_moving && net.bn_mode == 1 && blockIdx.x == 0) {
       // Keras BatchNormalization._assign_moving_average: var -= (var - value) * (1 - momentum)
       const float decay = (float)(1.0 - (double)net.bn_momentum);
@@ -166,8 +86,32 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
         net.mvar[cc] -= (net.mvar[cc] - var) * decay;
       }
     }
+    __syncthreads();
+  }
+  // ---- weights: zero padded to [ceil4(in)][ceil16(H)]; BN affine folded into layer 0 -------------------
+  //      x_hat . W + b = x . (a (.) W) + (b + bnB . W)
+  {
+    int in_l = net.in_dim;
+    for (int l = 0; l < L; ++l) {
+      const int Hl = net.widths[l], Hpad = ceil_to(Hl, GNNFP_JC), inp = ceil_to(in_l, 4);
+      const bool fold = (l == 0 && net.bn_mode != 0);
+      for (int e = tid; e < inp * Hpad; e += T) {
+        const int c = e / Hpad, j = e - c * Hpad;
+        float w = (j < Hl && c < in_l) ? net.W[l][(size_t)c * Hl + j] : 0.0f;
+        if (fold && c < in_l) w *= s.bnA[c];
+        s.W[l][e] = w;
+      }
+      for (int j = tid; j < Hpad; j += T) {
+        float bj = j < Hl ? net.b[l][j] : 0.0f;
+        if (fold && j < Hl)
+          for (int c = 0; c < in_l; ++c) bj = fmaf(s.bnB[c], net.W[l][(size_t)c * Hl + j], bj);
+        s.b[l][j] = bj;
+      }
+      in_l = Hl;
+    }
   }
   for (int j = tid; j < 2 * H; j += T) s.ost[j] = 0.0;
+  for (int e = tid; e < tc.R * (tc.XS0 + tc.XS1); e += T) s.buf0[e] = 0.0f;   // buf0 and buf1 are adjacent
   __syncthreads();
 
   const int n = a.src.n_rows;
@@ -178,7 +122,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
-    stage_tile(a.src, row0, nr, tc.R, s.buf0, tc.XS0, bnA, bnB);
+    stage_tile(a.src, row0, nr, tc.R, s.buf0, tc.XS0, s.sc);
     __syncthreads();
     // ---- the MLP --------------------------------------------------------------------------
     float* cur = s.buf0;
@@ -188,7 +132,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
     for (int l = 0; l < L; ++l) {
       const int Hl = net.widths[l], Hpad = ceil_to(Hl, GNNFP_JC);
       if (cg < Hpad / GNNFP_JC)
-        dense_layer_tile(cur, XSc, nxt, XSn, s.W[l], s.b[l], in_l, Hpad, net.acts[l], rg, cg, tc.CG, lane);
+        dense_tile(cur, XSc, nxt, XSn, s.W[l], s.b[l], (in_l + 3) / 4, Hpad, net.acts[l], rg, cg, tc.CG, lane);
       __syncthreads();
       if (net.acts[l] == GNNFP_ACT_SOFTMAX) {
         softmax_rows(nxt, XSn, Hl, tc.R);
@@ -206,31 +150,31 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
       a.out[(size_t)orow * a.ld_out + j] = cur[r * XSc + j];
     }
     if (a.prev) {   // GNN.py:200-209: sqrt(sum (s-s_old)^2) > thr * sqrt(sum s_old^2), strict
+      const bool from_tile = (L == 1 && a.prev_col0 >= 0);   // the raw previous state still sits in buf0
       for (int r = tid; r < nr; r += T) {
-        const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
-        const float* pv = a.prev + (size_t)gr * a.ld_prev;
         float sd = 0.f, sp = 0.f;
-        for (int j = 0; j < H; ++j) {
-          const float p = pv[j];
-          const float d = cur[r * XSc + j] - p;
-          sd = fmaf(d, d, sd);
-          sp = fmaf(p, p, sp);
+        if (from_tile) {
+          const float* pv = s.buf0 + r * tc.XS0 + a.prev_col0;
+          for (int j = 0; j < H; ++j) {
+            const float p = pv[j];
+            const float d = cur[r * XSc + j] - p;
+            sd = fmaf(d, d, sd);
+            sp = fmaf(p, p, sp);
+          }
+        } else {
+          const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
+          const float* pv = a.prev + (size_t)gr * a.ld_prev;
+          for (int j = 0; j < H; ++j) {
+            const float p = pv[j];
+            const float d = cur[r * XSc + j] - p;
+            sd = fmaf(d, d, sd);
+            sp = fmaf(p, p, sp);
+          }
         }
         if (sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
       }
     }
-    if (a.ost_sum) {
-      for (int j = tid; j < H; j += T) {
-        double su = 0.0, sq = 0.0;
-        for (int r = 0; r < nr; ++r) {
-          const double v = (double)cur[r * XSc + j];
-          su += v;
-          sq += v * v;
-        }
-        s.ost[j] += su;
-        s.ost[H + j] += sq;
-      }
-    }
+    if (a.ost_sum) tile_col_stats(cur, XSc, H, nr, s.ost);
     __syncthreads();
   }
   if (a.flag_next) {
@@ -238,6 +182,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
     if (tid == 0 && any) atomicOr(a.flag_next, 1);
   }
   if (a.ost_sum) {
+    __syncthreads();
     for (int j = tid; j < H; j += T) {
       atomicAdd(a.ost_sum + j, s.ost[j]);
       atomicAdd(a.ost_sq + j, s.ost[H + j]);
@@ -252,7 +197,9 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
   const TileCfg& tc = a.tc;
   const int W = a.src.in_dim;
   double* acc = reinterpret_cast<double*>(smem);          // [2*W]
-  float* X = smem + 4 * ceil_to(W, 4);
+  float* p = smem + 4 * ceil_to(W, 4);
+  StageScratch sc = carve_scratch(p, tc.R, tc.cap);
+  float* X = p + scratch_floats(tc.R, tc.cap);
   const int tid = threadIdx.x, T = blockDim.x;
   for (int j = tid; j < 2 * W; j += T) acc[j] = 0.0;
   __syncthreads();
@@ -262,7 +209,7 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
-    stage_tile(a.src, row0, nr, tc.R, X, tc.XS0, nullptr, nullptr);
+    stage_tile(a.src, row0, nr, tc.R, X, tc.XS0, sc);
     __syncthreads();
     if (a.out) {
       for (int e = tid; e < nr * W; e += T) {
@@ -271,18 +218,7 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
         a.out[(size_t)(row0 + r) * a.ld_out + j] = X[r * tc.XS0 + j];
       }
     }
-    if (a.st_sum) {
-      for (int j = tid; j < W; j += T) {
-        double su = 0.0, sq = 0.0;
-        for (int r = 0; r < nr; ++r) {
-          const double v = (double)X[r * tc.XS0 + j];
-          su += v;
-          sq += v * v;
-        }
-        acc[j] += su;
-        acc[W + j] += sq;
-      }
-    }
+    if (a.st_sum) tile_col_stats(X, tc.XS0, W, nr, acc);
     __syncthreads();
   }
   if (a.st_sum) {
@@ -296,15 +232,16 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side: tile geometry + launch
 // ------------------------------------------------------------------------------------------------
-static size_t fwd_smem_floats(const NetDev& net, int R, int XS0, int XS1) {
+static size_t fwd_smem_floats(const NetDev& net, int R, int XS0, int XS1, int cap) {
   size_t f = 4 * (size_t)ceil_to(net.widths[net.n_layers - 1], 4);
   int in_l = net.in_dim;
   for (int l = 0; l < net.n_layers; ++l) {
     const int Hpad = ceil_to(net.widths[l], GNNFP_JC);
-    f += (size_t)in_l * Hpad + Hpad;
+    f += (size_t)ceil_to(in_l, 4) * Hpad + Hpad;
     in_l = net.widths[l];
   }
   f += 2 * (size_t)ceil_to(net.in_dim, 4);
+  f += scratch_floats(R, cap);
   f += (size_t)R * XS0 + (size_t)R * XS1;
   return f;
 }
@@ -316,8 +253,9 @@ int tile_cfg_fwd(const NetDev& net, int n_rows, TileCfg* tc) {
     hpmax = Hpad > hpmax ? Hpad : hpmax;
     if (l % 2 == 0) w1 = Hpad > w1 ? Hpad : w1; else w0 = Hpad > w0 ? Hpad : w0;
   }
-  tc->XS0 = odd_stride(w0);
-  tc->XS1 = odd_stride(w1);
+  tc->XS0 = tile_stride(w0);
+  tc->XS1 = tile_stride(w1);
+  const int cap_per_row = tc->cap_per_row > 0 ? tc->cap_per_row : 4;
   int CG = hpmax / GNNFP_JC;
   if (CG > 8) CG = 8;
   int RG = 8 / CG;
@@ -326,14 +264,15 @@ int tile_cfg_fwd(const NetDev& net, int n_rows, TileCfg* tc) {
   const int nsm = gnnfp_num_sms();
   const size_t cap = 200 * 1024, want = 100 * 1024;
   // shrink the tile until it fits twice per SM (or at all), and until the grid fills the GPU
-  while (RG > 1 && (fwd_smem_floats(net, 64 * RG, tc->XS0, tc->XS1) * 4 > want ||
+  while (RG > 1 && (fwd_smem_floats(net, 64 * RG, tc->XS0, tc->XS1, 64 * RG * cap_per_row) * 4 > want ||
                     (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm))
     RG /= 2;
   tc->RG = RG;
   tc->CG = CG;
   tc->R = 64 * RG;
   tc->threads = 32 * RG * CG;
-  tc->smem_bytes = fwd_smem_floats(net, tc->R, tc->XS0, tc->XS1) * 4;
+  tc->cap = tc->R * cap_per_row;
+  tc->smem_bytes = fwd_smem_floats(net, tc->R, tc->XS0, tc->XS1, tc->cap) * 4;
   if (tc->smem_bytes > cap)
     GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "net too large for the shared-memory tile kernel (%zu bytes needed)",
                tc->smem_bytes);
@@ -351,13 +290,16 @@ int tile_cfg_fwd(const NetDev& net, int n_rows, TileCfg* tc) {
 int tile_cfg_pass(int in_dim, int n_rows, TileCfg* tc) {
   tc->RG = 1;
   tc->CG = 1;
-  tc->XS0 = odd_stride(in_dim);
-  tc->XS1 = 1;
+  tc->XS0 = tile_stride(in_dim);
+  tc->XS1 = 4;
   tc->threads = 256;
+  const int cap_per_row = tc->cap_per_row > 0 ? tc->cap_per_row : 4;
   int R = 128;
-  while (R > 16 && ((size_t)R * tc->XS0 + 4 * (size_t)ceil_to(in_dim, 4)) * 4 > 48 * 1024) R /= 2;
+  auto bytes = [&](int r) { return ((size_t)r * tc->XS0 + 4 * (size_t)ceil_to(in_dim, 4) + scratch_floats(r, r * cap_per_row)) * 4; };
+  while (R > 16 && bytes(R) > 48 * 1024) R /= 2;
   tc->R = R;
-  tc->smem_bytes = ((size_t)R * tc->XS0 + 4 * (size_t)ceil_to(in_dim, 4)) * 4;
+  tc->cap = R * cap_per_row;
+  tc->smem_bytes = bytes(R);
   const int nsm = gnnfp_num_sms();
   int per_sm = (int)((200 * 1024) / (tc->smem_bytes + 1024));
   if (per_sm > 8) per_sm = 8;

@@ -348,6 +348,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   L->bn_train_out = cfg->training && L->onet.has_bn;
   for (int t = 0; t < L->nt; ++t) L->nparam_s[t] = net_param_count(L->snet[t]);
   L->nparam_o = net_param_count(L->onet);
+  { long long cpr = g->N > 0 ? (2ll * g->A + g->N - 1) / g->N : 4; L->cap_per_row = cpr < 4 ? 4 : (cpr > 16 ? 16 : (int)cpr); }
   L->grid_cap = 1;
   if (cfg->training) {   // exact grids of the backward tile kernels (they are a pure function of the shapes)
     gnnfp_net_params none;
@@ -358,6 +359,8 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
       const int rows = t < L->nt ? (L->composite ? g->type_count[t] : L->N) : L->M;
       fill_netdev(dsc, none, 1, rows, nd);
       TileCfg tcb;
+      memset(&tcb, 0, sizeof(tcb));
+      tcb.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_bwd(nd, rows > 0 ? rows : 1, 0, &tcb))) { delete L; return rc; }
       L->grid_cap = tcb.grid > L->grid_cap ? tcb.grid : L->grid_cap;
     }
@@ -463,6 +466,7 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, col, g->dst_rowptr, g->dst_arc, wgt));
     }
     pa.out = c.Xs(); pa.ld_out = L->LsM;
+    pa.tc.cap_per_row = L->cap_per_row;
     if ((rc = tile_cfg_pass(L->LsM, N, &pa.tc))) return rc;
     if ((rc = launch_tile_pass(pa, s))) return rc;
   }
@@ -477,6 +481,7 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       // stX(ty) is laid out [d_t | LsM] with stride stXw: the pass writes sums to [0,in_dim) and squares
       // to [stXw, stXw+in_dim)
       pa.st_sum = c.stX(ty); pa.st_sq = c.stX(ty) + c.stXw();
+      pa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_pass(pa.src.in_dim, pa.src.n_rows, &pa.tc))) return rc;
       if ((rc = launch_tile_pass(pa, s))) return rc;
     }
@@ -495,6 +500,7 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       pa.src.in_dim = D;
       add_piece(pa.src, mk_direct(c.S(0), c.ldS(0), D, 0));
       pa.st_sum = c.stS(ty, 0); pa.st_sq = pa.st_sum + D;
+      pa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_pass(D, pa.src.n_rows, &pa.tc))) return rc;
       if ((rc = launch_tile_pass(pa, s))) return rc;
     }
@@ -511,7 +517,8 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
         add_piece(pa.src, mk_gather(c.S(t - 1), c.ldS(t - 1), D, 0, g->dst_rowptr, g->dst_src, wgt));
         pa.st_sum = c.stA(ty, t - 1); pa.st_sq = pa.st_sum + D;
         pa.gate = gate;
-        if ((rc = tile_cfg_pass(D, pa.src.n_rows, &pa.tc))) return rc;
+        pa.tc.cap_per_row = L->cap_per_row;
+      if ((rc = tile_cfg_pass(D, pa.src.n_rows, &pa.tc))) return rc;
         if ((rc = launch_tile_pass(pa, s))) return rc;
       }
     }
@@ -520,7 +527,9 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       memset(&fa, 0, sizeof(fa));
       build_state_src(c, ty, t, fa.src);
       fill_netdev(L->snet[ty], sp[ty], training, fa.src.n_rows, fa.net);
+      fa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;
+      fa.prev_col0 = L->composite ? L->dt[ty] : 0;
       fa.out = (float*)c.S(t); fa.ld_out = D; fa.out_compact = 0;
       if (L->bn_train_state && t < MI) { fa.ost_sum = c.stS(ty, t); fa.ost_sq = fa.ost_sum + D; }
       if (t < MI) { fa.prev = c.S(t - 1); fa.ld_prev = c.ldS(t - 1); fa.thr = L->cfg.state_threshold; fa.flag_next = c.flags() + t; }
@@ -550,11 +559,14 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       pa.src = fa.src;
       for (int p = 0; p < pa.src.n_pieces; ++p) { pa.src.p[p].st_sum = nullptr; pa.src.p[p].st_sq = nullptr; }
       pa.st_sum = c.stO(); pa.st_sq = c.stO() + L->out_in;
+      pa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_pass(L->out_in, pa.src.n_rows, &pa.tc))) return rc;
       if ((rc = launch_tile_pass(pa, s))) return rc;
     }
     fill_netdev(L->onet, *op, training, fa.src.n_rows, fa.net);
+    fa.tc.cap_per_row = L->cap_per_row;
     if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;
+    fa.prev_col0 = -1;
     float* on = L->pool ? (float*)(c.ws + L->ws.out_nodes) : io->out;
     fa.out = on; fa.ld_out = L->T; fa.out_compact = 1;
     fa.update_moving = training;

@@ -161,6 +161,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
       add_piece(ba.gsrc, p);
     }
     ba.net = ond;
+    ba.tc.cap_per_row = L->cap_per_row;
     if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, L->T, &ba.tc))) return rc;
     grid_out = ba.tc.grid;
     ba.saved_out = L->pool ? (const float*)(c.ws + L->ws.out_nodes) : io->out;
@@ -204,6 +205,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
         }
       }
       fill_netdev(L->snet[ty], sp[ty], 1, ba.src.n_rows, ba.net);
+      ba.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc))) return rc;
       grid_state[ty] = ba.tc.grid;
       ba.saved_out = c.S(t); ba.ld_saved = D; ba.saved_compact = 0;

@@ -1,6 +1,12 @@
 // tile.cuh - device helpers shared by the tile kernels: staging of input pieces into a
-// shared-memory tile (row-major, odd row stride => conflict-free for lane==row access),
-// activations and their derivatives, BN coefficient set-up.
+// shared-memory tile, activations and their derivatives, BN coefficient set-up.
+//
+// Tile layout: row-major [R][XS] floats with XS % 8 == 4, so that
+//   * lane==row LDS.128 / STS.128 of 4 consecutive columns are bank-conflict free
+//     (8 lanes per phase hit 8 distinct 16-byte bank groups because XS/4 is odd),
+//   * staging writes (consecutive columns of one row) are conflict free.
+// Staging never applies BatchNormalization: the forward folds the BN affine into the first Dense
+// layer once per CTA, the backward works on raw inputs and corrects its reductions at flush time.
 #pragma once
 #include "common.cuh"
 
@@ -30,16 +36,94 @@ __device__ __forceinline__ float act_bwd(int act, float y, float g) {
   }
 }
 
+__host__ __device__ __forceinline__ int ceil_to(int x, int m) { return (x + m - 1) / m * m; }
+// smallest stride >= w with stride % 8 == 4
+__host__ __device__ __forceinline__ int tile_stride(int w) {
+  const int p = ceil_to(w < 1 ? 1 : w, 4);
+  return (p % 8 == 4) ? p : p + 4;
+}
+
 __device__ __forceinline__ bool piece_enabled(const Piece& pc) {
   if (pc.gate == nullptr) return true;
   return ((*pc.gate) != 0) == (pc.gate_pol != 0);
 }
 
-// Stage every piece of `ts` for tile rows [row0, row0+nr) into X[r*XS + col].  Rows nr..R-1 are
-// zero-filled.  bnA/bnB (nullable): per-column affine applied while staging (BN as x*a+b,
-// tf.nn.batch_normalization's own form).
+// shared-memory scratch for the CSR slice of one tile (identity row sets only)
+struct StageScratch {
+  int* rp;      // [R + 1]
+  int* sidx;    // [cap]
+  float* sw;    // [cap]
+  int cap;
+};
+__host__ __device__ __forceinline__ size_t scratch_floats(int R, int cap) { return (size_t)ceil_to(R + 1, 4) + 2 * (size_t)ceil_to(cap, 4); }
+__device__ __forceinline__ StageScratch carve_scratch(float* base, int R, int cap) {
+  StageScratch s;
+  s.rp = reinterpret_cast<int*>(base);
+  s.sidx = s.rp + ceil_to(R + 1, 4);
+  s.sw = reinterpret_cast<float*>(s.sidx + ceil_to(cap, 4));
+  s.cap = cap;
+  return s;
+}
+
+// ---- gather with the tile's CSR slice resident in shared memory ---------------------------------
+// one item = (row r, VEC-wide column chunk q): all source addresses are known from shared memory, so
+// the (up to 4) neighbour-row loads of an item are issued back to back; accumulation stays sequential
+// in arc order (the order TF-CPU SparseTensorDenseMatMul uses).
+template <int VEC>
+__device__ __forceinline__ void gather_items(const Piece& pc, const StageScratch& sc, int abase, int nr, int R,
+                                             float* X, int XS, bool has_w) {
+  const int w = pc.width, nq = w / VEC;
+  const int items = R * nq;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int r = it / nq, q = it - r * nq;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    if (r < nr) {
+      const int a0 = sc.rp[r] - abase, a1 = sc.rp[r + 1] - abase;
+      for (int a = a0; a < a1; a += 4) {
+        float val[4][VEC];
+        float wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = a + u < a1;
+          const int ai = ok ? a + u : a;
+          const float* sp = pc.ptr + (size_t)sc.sidx[ai] * pc.ld + q * VEC;
+          wv[u] = ok ? (has_w ? sc.sw[ai] : 1.0f) : 0.0f;
+          if (VEC == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(sp);
+            val[u][0] = t.x; val[u][1 % VEC] = t.y; val[u][2 % VEC] = t.z; val[u][3 % VEC] = t.w;
+          } else if (VEC == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(sp);
+            val[u][0] = t.x; val[u][1 % VEC] = t.y;
+          } else {
+            val[u][0] = *sp;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (a + u < a1) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], val[u][v], acc[v]);
+          }
+      }
+    }
+    float* d = X + r * XS + pc.col0 + q * VEC;
+    if (pc.accumulate) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) d[v] += acc[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) d[v] = acc[v];
+    }
+  }
+}
+
+// Stage every piece of `ts` for tile rows [row0, row0+nr) into X[r*XS + col] (raw values).  Rows
+// nr..R-1 are zero-filled.  Ends WITHOUT a trailing __syncthreads (callers sync).
 __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, int R, float* X, int XS,
-                                           const float* bnA, const float* bnB) {
+                                           const StageScratch& sc) {
+  const int tid = threadIdx.x, T = blockDim.x;
   for (int p = 0; p < ts.n_pieces; ++p) {
     const Piece& pc = ts.p[p];
     const bool on = piece_enabled(pc);
@@ -51,38 +135,72 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
     const int total = R * w;
     const int c0 = pc.col0;
     if (pc.kind == PK_DIRECT) {
-#pragma unroll 4
-      for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int r = (int)__umulhi((unsigned)e, pc.magic);
-        const int c = e - r * w;
-        float v = 0.0f;
-        if (on && r < nr) {
-          const int gr = ts.rowlist ? ts.rowlist[row0 + r] : row0 + r;
-          const int sr = pc.compact ? (row0 + r) : (pc.map ? pc.map[gr] : gr);
-          v = pc.ptr[(size_t)sr * pc.ld + c];
-          if (pc.rowscale) v *= pc.rowscale[gr];
-          if (bnA) v = fmaf(v, bnA[c0 + c], bnB[c0 + c]);
+      // 4 independent loads in flight per thread, then the 4 stores
+      for (int e0 = tid; e0 < total; e0 += 4 * T) {
+        float v[4];
+        int off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * T;
+          v[u] = 0.f;
+          off[u] = -1;
+          if (e < total) {
+            const int r = (int)__umulhi((unsigned)e, pc.magic);
+            const int c = e - r * w;
+            off[u] = r * XS + c0 + c;
+            if (on && r < nr) {
+              const int gr = ts.rowlist ? ts.rowlist[row0 + r] : row0 + r;
+              const int sr = pc.compact ? (row0 + r) : (pc.map ? pc.map[gr] : gr);
+              v[u] = pc.ptr[(size_t)sr * pc.ld + c];
+              if (pc.rowscale) v[u] *= pc.rowscale[gr];
+            }
+          }
         }
-        float* d = X + r * XS + c0 + c;
-        if (pc.accumulate) *d += v; else *d = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (off[u] >= 0) { if (pc.accumulate) X[off[u]] += v[u]; else X[off[u]] = v[u]; }
       }
     } else {
-      for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int r = (int)__umulhi((unsigned)e, pc.magic);
-        const int c = e - r * w;
-        float v = 0.0f;
-        if (on && r < nr) {
-          const int gr = ts.rowlist ? ts.rowlist[row0 + r] : row0 + r;
-          const int a0 = pc.rowptr[gr], a1 = pc.rowptr[gr + 1];
-          // sequential in arc order: the order TF-CPU SparseTensorDenseMatMul accumulates in
-          for (int a = a0; a < a1; ++a) {
-            const float wv = pc.wgt ? pc.wgt[a] : 1.0f;
-            v = fmaf(wv, pc.ptr[(size_t)pc.idx[a] * pc.ld + c], v);
+      // ---- gather: fast path = identity rows and the tile's arcs fit the scratch ----------------
+      bool fast = on && ts.rowlist == nullptr && sc.cap > 0;
+      int abase = 0;
+      if (fast) {
+        __syncthreads();                               // scratch may still be read by a previous piece
+        for (int i = tid; i <= nr; i += T) sc.rp[i] = pc.rowptr[row0 + i];
+        __syncthreads();
+        abase = sc.rp[0];
+        const int na = sc.rp[nr] - abase;
+        fast = na <= sc.cap;                           // uniform across the CTA
+        if (fast) {
+          for (int i = tid; i < na; i += T) {
+            sc.sidx[i] = pc.idx[abase + i];
+            if (pc.wgt) sc.sw[i] = pc.wgt[abase + i];
           }
-          if (bnA) v = fmaf(v, bnA[c0 + c], bnB[c0 + c]);
+          __syncthreads();
         }
-        float* d = X + r * XS + c0 + c;
-        if (pc.accumulate) *d += v; else *d = v;
+      }
+      if (fast) {
+        const bool al16 = ((reinterpret_cast<uintptr_t>(pc.ptr) & 15) == 0) && (pc.ld % 4 == 0) && (w % 4 == 0) && (c0 % 4 == 0);
+        const bool al8 = ((reinterpret_cast<uintptr_t>(pc.ptr) & 7) == 0) && (pc.ld % 2 == 0) && (w % 2 == 0) && (c0 % 2 == 0);
+        if (al16) gather_items<4>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
+        else if (al8) gather_items<2>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
+        else gather_items<1>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
+      } else {
+        for (int e = tid; e < total; e += T) {
+          const int r = (int)__umulhi((unsigned)e, pc.magic);
+          const int c = e - r * w;
+          float v = 0.0f;
+          if (on && r < nr) {
+            const int gr = ts.rowlist ? ts.rowlist[row0 + r] : row0 + r;
+            const int a0 = pc.rowptr[gr], a1 = pc.rowptr[gr + 1];
+            for (int a = a0; a < a1; ++a) {
+              const float wv = pc.wgt ? pc.wgt[a] : 1.0f;
+              v = fmaf(wv, pc.ptr[(size_t)pc.idx[a] * pc.ld + c], v);
+            }
+          }
+          float* d = X + r * XS + c0 + c;
+          if (pc.accumulate) *d += v; else *d = v;
+        }
       }
     }
   }
@@ -91,8 +209,7 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
 // Per-column BN coefficients: x_hat = x*a + b.
 //   affine=1: a = gamma*rsqrt(var+eps), b = beta - mean*a      (what the forward applies)
 //   affine=0: a = rsqrt(var+eps),       b = -mean*a            (x_tilde, for the backward)
-// Also returns mean/var through optional arrays.  bn_mode 1 = batch stats from the pieces'
-// st_sum/st_sq (double sums), 2 = moving statistics.
+// bn_mode 1 = batch stats from the pieces' st_sum/st_sq (double sums), 2 = moving statistics.
 __device__ __forceinline__ void bn_coefficients(const TileSrc& ts, const NetDev& net, int affine, float* A,
                                                 float* B, float* meanOut, float* varOut) {
   for (int cc = threadIdx.x; cc < net.in_dim; cc += blockDim.x) {
@@ -122,5 +239,105 @@ __device__ __forceinline__ void bn_coefficients(const TileSrc& ts, const NetDev&
   }
 }
 
-__host__ __device__ __forceinline__ int ceil_to(int x, int m) { return (x + m - 1) / m * m; }
-__host__ __device__ __forceinline__ int odd_stride(int w) { return (w | 1); }
+// ---- one Dense layer on the tile -----------------------------------------------------------------
+// warp (rg, cg) owns rows [rg*64, rg*64+64) (lane -> rows rg*64+lane and +32) and 16-column chunks
+// ch = cg, cg+CG, ...  Inputs are read as LDS.128 (4 columns at a time), weights as 128-bit broadcasts
+// from Wl[in_pad4][Hpad]; outputs are written as STS.128.  in4 = ceil(in/4) (padding columns of the tile
+// and padding rows of Wl are zero).
+__device__ __forceinline__ void dense_tile(const float* __restrict__ Ain, int XSin, float* __restrict__ Aout, int XSout,
+                                           const float* __restrict__ Wl, const float* __restrict__ bl, int in4, int Hpad,
+                                           int act, int rg, int cg, int CG, int lane) {
+  const int nch = Hpad / GNNFP_JC;
+  const float4* x0p = reinterpret_cast<const float4*>(Ain + (rg * 64 + lane) * XSin);
+  const float4* x1p = reinterpret_cast<const float4*>(Ain + (rg * 64 + lane + 32) * XSin);
+  const int wstride = Hpad / 4;
+  for (int ch = cg; ch < nch; ch += CG) {
+    float acc0[GNNFP_JC], acc1[GNNFP_JC];
+#pragma unroll
+    for (int j = 0; j < GNNFP_JC; ++j) { const float bj = bl[ch * GNNFP_JC + j]; acc0[j] = bj; acc1[j] = bj; }
+    const float4* wp = reinterpret_cast<const float4*>(Wl + ch * GNNFP_JC);
+#pragma unroll 1
+    for (int c4 = 0; c4 < in4; ++c4) {
+      const float4 xa = x0p[c4], xb = x1p[c4];
+      const float xs0[4] = {xa.x, xa.y, xa.z, xa.w};
+      const float xs1[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+        wp += wstride;
+        const float x0 = xs0[k], x1 = xs1[k];
+        acc0[0] = fmaf(x0, w0.x, acc0[0]);   acc1[0] = fmaf(x1, w0.x, acc1[0]);
+        acc0[1] = fmaf(x0, w0.y, acc0[1]);   acc1[1] = fmaf(x1, w0.y, acc1[1]);
+        acc0[2] = fmaf(x0, w0.z, acc0[2]);   acc1[2] = fmaf(x1, w0.z, acc1[2]);
+        acc0[3] = fmaf(x0, w0.w, acc0[3]);   acc1[3] = fmaf(x1, w0.w, acc1[3]);
+        acc0[4] = fmaf(x0, w1.x, acc0[4]);   acc1[4] = fmaf(x1, w1.x, acc1[4]);
+        acc0[5] = fmaf(x0, w1.y, acc0[5]);   acc1[5] = fmaf(x1, w1.y, acc1[5]);
+        acc0[6] = fmaf(x0, w1.z, acc0[6]);   acc1[6] = fmaf(x1, w1.z, acc1[6]);
+        acc0[7] = fmaf(x0, w1.w, acc0[7]);   acc1[7] = fmaf(x1, w1.w, acc1[7]);
+        acc0[8] = fmaf(x0, w2.x, acc0[8]);   acc1[8] = fmaf(x1, w2.x, acc1[8]);
+        acc0[9] = fmaf(x0, w2.y, acc0[9]);   acc1[9] = fmaf(x1, w2.y, acc1[9]);
+        acc0[10] = fmaf(x0, w2.z, acc0[10]); acc1[10] = fmaf(x1, w2.z, acc1[10]);
+        acc0[11] = fmaf(x0, w2.w, acc0[11]); acc1[11] = fmaf(x1, w2.w, acc1[11]);
+        acc0[12] = fmaf(x0, w3.x, acc0[12]); acc1[12] = fmaf(x1, w3.x, acc1[12]);
+        acc0[13] = fmaf(x0, w3.y, acc0[13]); acc1[13] = fmaf(x1, w3.y, acc1[13]);
+        acc0[14] = fmaf(x0, w3.z, acc0[14]); acc1[14] = fmaf(x1, w3.z, acc1[14]);
+        acc0[15] = fmaf(x0, w3.w, acc0[15]); acc1[15] = fmaf(x1, w3.w, acc1[15]);
+      }
+    }
+    float4* o0 = reinterpret_cast<float4*>(Aout + (rg * 64 + lane) * XSout + ch * GNNFP_JC);
+    float4* o1 = reinterpret_cast<float4*>(Aout + (rg * 64 + lane + 32) * XSout + ch * GNNFP_JC);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      o0[j4] = make_float4(act_fwd(act, acc0[4 * j4]), act_fwd(act, acc0[4 * j4 + 1]), act_fwd(act, acc0[4 * j4 + 2]), act_fwd(act, acc0[4 * j4 + 3]));
+      o1[j4] = make_float4(act_fwd(act, acc1[4 * j4]), act_fwd(act, acc1[4 * j4 + 1]), act_fwd(act, acc1[4 * j4 + 2]), act_fwd(act, acc1[4 * j4 + 3]));
+    }
+  }
+}
+
+// row-wise softmax over the first H columns of the tile (Keras softmax, last axis)
+__device__ __forceinline__ void softmax_rows(float* A, int XS, int H, int R) {
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float* row = A + r * XS;
+    float m = row[0];
+    for (int j = 1; j < H; ++j) m = fmaxf(m, row[j]);
+    float s = 0.f;
+    for (int j = 0; j < H; ++j) {
+      const float e = expf(row[j] - m);
+      row[j] = e;
+      s += e;
+    }
+    for (int j = 0; j < H; ++j) row[j] = row[j] / s;
+  }
+}
+
+// column statistics of a tile (first H columns, nr rows) accumulated into shared double accumulators
+// acc[0..H) (sum) and acc[H..2H) (sum of squares) by ALL threads: thread -> (column, row group).
+__device__ __forceinline__ void tile_col_stats(const float* A, int XS, int H, int nr, double* acc) {
+  const int T = blockDim.x;
+  const int ng = T / H > 0 ? T / H : 1;              // row groups
+  const int tid = threadIdx.x;
+  if (T >= H) {
+    const int j = tid % H, g = tid / H;
+    if (g < ng) {
+      double su = 0.0, sq = 0.0;
+      for (int r = g; r < nr; r += ng) {
+        const double v = (double)A[r * XS + j];
+        su += v;
+        sq += v * v;
+      }
+      atomicAdd(acc + j, su);
+      atomicAdd(acc + H + j, sq);
+    }
+  } else {
+    for (int j = tid; j < H; j += T) {
+      double su = 0.0, sq = 0.0;
+      for (int r = 0; r < nr; ++r) {
+        const double v = (double)A[r * XS + j];
+        su += v;
+        sq += v * v;
+      }
+      acc[j] += su;
+      acc[H + j] += sq;
+    }
+  }
+}
