@@ -65,6 +65,7 @@ struct Piece {
   const int* rowptr;       // GATHER: CSR over the global row id gr
   const int* idx;          //         source row of each entry
   const float* wgt;        //         weight of each entry (NULL = 1)
+  int nnz;                 //         entries in idx/wgt (bounds the next-tile prefetch)
   const double* st_sum;    // BN batch statistics of these columns (sum over rows) or NULL
   const double* st_sq;     //                                     (sum of squares)
   const int* gate;         // piece enabled iff gate==NULL || ((*gate != 0) == gate_pol)
@@ -128,6 +129,8 @@ struct FwdArgs {
   int* flag_next;          // set to 1 when any row is not converged
   const int* gate;         // whole kernel runs only if *gate != 0 (NULL = always)
   int update_moving;       // CTA 0 applies the Keras moving-average update
+  float* agg_out;          // optional: save tile columns [agg_col0, agg_col0+agg_w) (Adj^T.state) for the backward
+  int agg_col0, agg_w;
   int prof_cat;
 };
 

@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
   float* dzB = smem + y.odzB;
   const int XSdA = y.XSdA, XSdB = y.XSdB;
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_end = min(n_tiles, ((int)blockIdx.x + 1) * tiles_per_cta);
+  for (int tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
     stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], sc);
@@ -467,7 +469,9 @@ __global__ void __launch_bounds__(256) tile_bnfix_kernel(const __grid_constant__
   __syncthreads();
   const int n = a.src.n_rows;
   const int n_tiles = (n + tc.R - 1) / tc.R;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_end = min(n_tiles, ((int)blockIdx.x + 1) * tiles_per_cta);
+  for (int tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
     stage_tile(a.src, row0, nr, tc.R, X, tc.XS0, sc);
@@ -476,16 +480,28 @@ __global__ void __launch_bounds__(256) tile_bnfix_kernel(const __grid_constant__
       const Piece& pc = a.src.p[p];
       if (pc.gmode == GM_NONE) continue;
       const int w = pc.width;
-      for (int e = tid; e < nr * w; e += T) {
-        const int r = (int)__umulhi((unsigned)e, pc.magic);
-        const int c = e - r * w;
-        const int cc = pc.col0 + c;
-        const float corr = c0[cc] + fmaf(X[r * tc.XS0 + cc], bnA[cc], bnB[cc]) * c1[cc];
-        const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
-        const int drow = pc.map ? pc.map[gr] : gr;
-        float* d = pc.gptr + (size_t)drow * pc.gld + c;
-        if (pc.gmode == GM_ATOMIC) atomicAdd(d, -corr);
-        else *d -= corr;
+      for (int e0 = tid; e0 < nr * w; e0 += 4 * T) {      // 4 read-modify-writes in flight per thread
+        float* dp[4];
+        float corr[4], old[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * T;
+          dp[u] = nullptr;
+          corr[u] = 0.f; old[u] = 0.f;
+          if (e < nr * w) {
+            const int r = (int)__umulhi((unsigned)e, pc.magic);
+            const int c = e - r * w;
+            const int cc = pc.col0 + c;
+            corr[u] = c0[cc] + fmaf(X[r * tc.XS0 + cc], bnA[cc], bnB[cc]) * c1[cc];
+            const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
+            const int drow = pc.map ? pc.map[gr] : gr;
+            dp[u] = pc.gptr + (size_t)drow * pc.gld + c;
+            if (pc.gmode != GM_ATOMIC) old[u] = *dp[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dp[u]) { if (pc.gmode == GM_ATOMIC) atomicAdd(dp[u], -corr[u]); else *dp[u] = old[u] - corr[u]; }
       }
     }
     __syncthreads();

@@ -15,40 +15,29 @@
 // weight reads are 128-bit broadcasts.
 #include "tile.cuh"
 
-struct FwdSmem {
-  float* W[GNNFP_MAX_LAYERS];
-  float* b[GNNFP_MAX_LAYERS];
-  float* bnA;
-  float* bnB;
-  float* buf0;
-  float* buf1;
-  double* ost;   // [2*H] output statistics accumulators
-  StageScratch sc;
+// shared-memory layout as integer offsets (floats from the start of dynamic shared memory).  Kept in
+// shared memory itself so that every access stays in the shared address space (LDS/STS, 32-bit addressing).
+struct FwdLayout {
+  int oW[GNNFP_MAX_LAYERS], ob[GNNFP_MAX_LAYERS];
+  int obnA, obnB, oScr, obuf0, obuf1, oOst;
+  int total;
 };
-
-// shared-memory layout (floats); must match fwd_smem_floats()
-__device__ __forceinline__ void carve_fwd(const NetDev& net, const TileCfg& tc, float* base, FwdSmem& s) {
-  float* p = base;
-  s.ost = reinterpret_cast<double*>(p);
-  p += 4 * ceil_to(net.widths[net.n_layers - 1], 4);   // 2*H doubles
+__host__ __device__ inline void fwd_layout(const NetDev& net, int R, int XS0, int XS1, int cap, FwdLayout& y) {
+  int o = 0;
+  y.oOst = o; o += 4 * ceil_to(net.widths[net.n_layers - 1], 4);   // 2*H doubles
   int in_l = net.in_dim;
   for (int l = 0; l < net.n_layers; ++l) {
     const int Hpad = ceil_to(net.widths[l], GNNFP_JC);
-    s.W[l] = p;
-    p += ceil_to(in_l, 4) * Hpad;
-    s.b[l] = p;
-    p += Hpad;
+    y.oW[l] = o; o += ceil_to(in_l, 4) * Hpad;
+    y.ob[l] = o; o += Hpad;
     in_l = net.widths[l];
   }
-  s.bnA = p;
-  p += ceil_to(net.in_dim, 4);
-  s.bnB = p;
-  p += ceil_to(net.in_dim, 4);
-  s.sc = carve_scratch(p, tc.R, tc.cap);
-  p += scratch_floats(tc.R, tc.cap);
-  s.buf0 = p;
-  p += tc.R * tc.XS0;
-  s.buf1 = p;
+  y.obnA = o; o += ceil_to(net.in_dim, 4);
+  y.obnB = o; o += ceil_to(net.in_dim, 4);
+  y.oScr = o; o += (int)scratch_floats(R, cap);
+  y.obuf0 = o; o += R * XS0;
+  y.obuf1 = o; o += R * XS1;
+  y.total = o;
 }
 
 __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ FwdArgs a) {
@@ -56,9 +45,16 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
   extern __shared__ __align__(16) float smem[];
   const NetDev& net = a.net;
   const TileCfg& tc = a.tc;
-  FwdSmem s;
-  carve_fwd(net, tc, smem, s);
+  __shared__ FwdLayout y;
+  if (threadIdx.x == 0) fwd_layout(net, tc.R, tc.XS0, tc.XS1, tc.cap, y);
+  __syncthreads();
   const int tid = threadIdx.x, T = blockDim.x;
+  float* const bnA_ = smem + y.obnA;
+  float* const bnB_ = smem + y.obnB;
+  double* const ost = reinterpret_cast<double*>(smem + y.oOst);
+  float* const buf0 = smem + y.obuf0;
+  float* const buf1 = smem + y.obuf1;
+  const StageScratch sc = carve_scratch(smem + y.oScr, tc.R, tc.cap);
   const int lane = tid & 31, warp = tid >> 5;
   const int rg = warp % tc.RG, cg = warp / tc.RG;
   const int L = net.n_layers;
@@ -66,7 +62,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
 
   // ---- BN coefficients (x_hat = x*a + b), moving-average update -------------------------------------
   if (net.bn_mode) {
-    bn_coefficients(a.src, net, 1, s.bnA, s.bnB, nullptr, nullptr);
+    bn_coefficients(a.src, net, 1, bnA_, bnB_, nullptr, nullptr);
     if (a.update_moving && net.bn_mode == 1 && blockIdx.x == 0) {
       // Keras BatchNormalization._assign_moving_average: var -= (var - value) * (1 - momentum)
       const float decay = (float)(1.0 - (double)net.bn_momentum);
@@ -98,20 +94,20 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
       for (int e = tid; e < inp * Hpad; e += T) {
         const int c = e / Hpad, j = e - c * Hpad;
         float w = (j < Hl && c < in_l) ? net.W[l][(size_t)c * Hl + j] : 0.0f;
-        if (fold && c < in_l) w *= s.bnA[c];
-        s.W[l][e] = w;
+        if (fold && c < in_l) w *= bnA_[c];
+        smem[y.oW[l] + e] = w;
       }
       for (int j = tid; j < Hpad; j += T) {
         float bj = j < Hl ? net.b[l][j] : 0.0f;
         if (fold && j < Hl)
-          for (int c = 0; c < in_l; ++c) bj = fmaf(s.bnB[c], net.W[l][(size_t)c * Hl + j], bj);
-        s.b[l][j] = bj;
+          for (int c = 0; c < in_l; ++c) bj = fmaf(bnB_[c], net.W[l][(size_t)c * Hl + j], bj);
+        smem[y.ob[l] + j] = bj;
       }
       in_l = Hl;
     }
   }
-  for (int j = tid; j < 2 * H; j += T) s.ost[j] = 0.0;
-  for (int e = tid; e < tc.R * (tc.XS0 + tc.XS1); e += T) s.buf0[e] = 0.0f;   // buf0 and buf1 are adjacent
+  for (int j = tid; j < 2 * H; j += T) ost[j] = 0.0;
+  for (int e = tid; e < tc.R * (tc.XS0 + tc.XS1); e += T) buf0[e] = 0.0f;   // buf0 and buf1 are adjacent
   __syncthreads();
 
   const int n = a.src.n_rows;
@@ -119,20 +115,31 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
   int notconv = 0;
   const unsigned magicH = (unsigned)((0x100000000ull + (unsigned)H - 1) / (unsigned)H);
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_end = min(n_tiles, ((int)blockIdx.x + 1) * tiles_per_cta);
+  for (int tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
-    stage_tile(a.src, row0, nr, tc.R, s.buf0, tc.XS0, s.sc);
+    stage_tile(a.src, row0, nr, tc.R, buf0, tc.XS0, sc);
     __syncthreads();
+    if (a.agg_out) {
+      const unsigned magicA = (unsigned)((0x100000000ull + (unsigned)a.agg_w - 1) / (unsigned)a.agg_w);
+      for (int e = tid; e < nr * a.agg_w; e += T) {
+        const int r = (int)__umulhi((unsigned)e, magicA);
+        const int j = e - r * a.agg_w;
+        const int orow = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
+        a.agg_out[(size_t)orow * a.agg_w + j] = buf0[r * tc.XS0 + a.agg_col0 + j];
+      }
+    }
     // ---- the MLP --------------------------------------------------------------------------
-    float* cur = s.buf0;
-    float* nxt = s.buf1;
+    float* cur = buf0;
+    float* nxt = buf1;
     int XSc = tc.XS0, XSn = tc.XS1;
     int in_l = net.in_dim;
     for (int l = 0; l < L; ++l) {
       const int Hl = net.widths[l], Hpad = ceil_to(Hl, GNNFP_JC);
       if (cg < Hpad / GNNFP_JC)
-        dense_tile(cur, XSc, nxt, XSn, s.W[l], s.b[l], (in_l + 3) / 4, Hpad, net.acts[l], rg, cg, tc.CG, lane);
+        dense_tile(cur, XSc, nxt, XSn, smem + y.oW[l], smem + y.ob[l], (in_l + 3) / 4, Hpad, net.acts[l], rg, cg, tc.CG, lane);
       __syncthreads();
       if (net.acts[l] == GNNFP_ACT_SOFTMAX) {
         softmax_rows(nxt, XSn, Hl, tc.R);
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
       for (int r = tid; r < nr; r += T) {
         float sd = 0.f, sp = 0.f;
         if (from_tile) {
-          const float* pv = s.buf0 + r * tc.XS0 + a.prev_col0;
+          const float* pv = buf0 + r * tc.XS0 + a.prev_col0;
           for (int j = 0; j < H; ++j) {
             const float p = pv[j];
             const float d = cur[r * XSc + j] - p;
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
         if (sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
       }
     }
-    if (a.ost_sum) tile_col_stats(cur, XSc, H, nr, s.ost);
+    if (a.ost_sum) tile_col_stats(cur, XSc, H, nr, ost);
     __syncthreads();
   }
   if (a.flag_next) {
@@ -184,8 +191,8 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
   if (a.ost_sum) {
     __syncthreads();
     for (int j = tid; j < H; j += T) {
-      atomicAdd(a.ost_sum + j, s.ost[j]);
-      atomicAdd(a.ost_sq + j, s.ost[H + j]);
+      atomicAdd(a.ost_sum + j, ost[j]);
+      atomicAdd(a.ost_sq + j, ost[H + j]);
     }
   }
 }
@@ -206,7 +213,9 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
   const int n = a.src.n_rows;
   const int n_tiles = (n + tc.R - 1) / tc.R;
   const unsigned magicW = (unsigned)((0x100000000ull + (unsigned)W - 1) / (unsigned)W);
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_end = min(n_tiles, ((int)blockIdx.x + 1) * tiles_per_cta);
+  for (int tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
     stage_tile(a.src, row0, nr, tc.R, X, tc.XS0, sc);
@@ -215,7 +224,8 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
       for (int e = tid; e < nr * W; e += T) {
         const int r = (int)__umulhi((unsigned)e, magicW);
         const int j = e - r * W;
-        a.out[(size_t)(row0 + r) * a.ld_out + j] = X[r * tc.XS0 + j];
+        const int orow = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
+        a.out[(size_t)orow * a.ld_out + j] = X[r * tc.XS0 + j];
       }
     }
     if (a.st_sum) tile_col_stats(X, tc.XS0, W, nr, acc);
@@ -232,18 +242,10 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side: tile geometry + launch
 // ------------------------------------------------------------------------------------------------
-static size_t fwd_smem_floats(const NetDev& net, int R, int XS0, int XS1, int cap) {
-  size_t f = 4 * (size_t)ceil_to(net.widths[net.n_layers - 1], 4);
-  int in_l = net.in_dim;
-  for (int l = 0; l < net.n_layers; ++l) {
-    const int Hpad = ceil_to(net.widths[l], GNNFP_JC);
-    f += (size_t)ceil_to(in_l, 4) * Hpad + Hpad;
-    in_l = net.widths[l];
-  }
-  f += 2 * (size_t)ceil_to(net.in_dim, 4);
-  f += scratch_floats(R, cap);
-  f += (size_t)R * XS0 + (size_t)R * XS1;
-  return f;
+static size_t fwd_smem_bytes(const NetDev& net, int R, int XS0, int XS1, int cap) {
+  FwdLayout y;
+  fwd_layout(net, R, XS0, XS1, cap, y);
+  return (size_t)y.total * 4 + sizeof(FwdLayout) + 64;
 }
 
 int tile_cfg_fwd(const NetDev& net, int n_rows, TileCfg* tc) {
@@ -258,29 +260,38 @@ int tile_cfg_fwd(const NetDev& net, int n_rows, TileCfg* tc) {
   const int cap_per_row = tc->cap_per_row > 0 ? tc->cap_per_row : 4;
   int CG = hpmax / GNNFP_JC;
   if (CG > 8) CG = 8;
-  int RG = 8 / CG;
-  if (RG < 1) RG = 1;
-  if (RG > 4) RG = 4;
   const int nsm = gnnfp_num_sms();
-  const size_t cap = 200 * 1024, want = 100 * 1024;
-  // shrink the tile until it fits twice per SM (or at all), and until the grid fills the GPU
-  while (RG > 1 && (fwd_smem_floats(net, 64 * RG, tc->XS0, tc->XS1, 64 * RG * cap_per_row) * 4 > want ||
-                    (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm))
-    RG /= 2;
+  const size_t cap = 216 * 1024, sm_budget = 224 * 1024;
+  // pick the row-group count that keeps the most warps resident per SM (ties: the smaller tile), then
+  // shrink further while the grid would not cover the GPU twice
+  int best = 0, best_warps = -1;
+  for (int RG = 1; RG <= 4; RG *= 2) {
+    if (32 * RG * CG > 512) break;
+    const size_t b = fwd_smem_bytes(net, 64 * RG, tc->XS0, tc->XS1, 64 * RG * cap_per_row);
+    if (b > cap) break;
+    int ctas = (int)(sm_budget / (b + 1024));
+    const int by_thr = 2048 / (32 * RG * CG);
+    if (ctas > by_thr) ctas = by_thr;
+    if (ctas > 16) ctas = 16;
+    const int warps = ctas * RG * CG;
+    if (warps > best_warps) { best_warps = warps; best = RG; }
+  }
+  if (best == 0)
+    GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "net too large for the shared-memory tile kernel (%zu bytes needed)",
+               fwd_smem_bytes(net, 64, tc->XS0, tc->XS1, 64 * cap_per_row));
+  int RG = best;
+  while (RG > 1 && (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm) RG /= 2;
   tc->RG = RG;
   tc->CG = CG;
   tc->R = 64 * RG;
   tc->threads = 32 * RG * CG;
   tc->cap = tc->R * cap_per_row;
-  tc->smem_bytes = fwd_smem_floats(net, tc->R, tc->XS0, tc->XS1, tc->cap) * 4;
-  if (tc->smem_bytes > cap)
-    GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "net too large for the shared-memory tile kernel (%zu bytes needed)",
-               tc->smem_bytes);
-  int per_sm = (int)((220 * 1024) / (tc->smem_bytes + 1024));
+  tc->smem_bytes = fwd_smem_bytes(net, tc->R, tc->XS0, tc->XS1, tc->cap);
+  int per_sm = (int)(sm_budget / (tc->smem_bytes + 1024));
   const int by_threads = 2048 / tc->threads;
   if (per_sm > by_threads) per_sm = by_threads;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 16) per_sm = 16;
   const int n_tiles = (n_rows + tc->R - 1) / tc->R;
   tc->grid = n_tiles < nsm * per_sm ? n_tiles : nsm * per_sm;
   if (tc->grid < 1) tc->grid = 1;

@@ -138,9 +138,9 @@ static Piece mk_piece(int kind, const float* ptr, int ld, int width, int col0) {
   return p;
 }
 Piece mk_direct(const float* ptr, int ld, int width, int col0) { return mk_piece(PK_DIRECT, ptr, ld, width, col0); }
-Piece mk_gather(const float* ptr, int ld, int width, int col0, const int* rowptr, const int* idx, const float* wgt) {
+Piece mk_gather(const float* ptr, int ld, int width, int col0, const int* rowptr, const int* idx, const float* wgt, int nnz) {
   Piece p = mk_piece(PK_GATHER, ptr, ld, width, col0);
-  p.rowptr = rowptr; p.idx = idx; p.wgt = wgt;
+  p.rowptr = rowptr; p.idx = idx; p.wgt = wgt; p.nnz = nnz;
   return p;
 }
 void add_piece(TileSrc& ts, const Piece& p) {
@@ -156,7 +156,7 @@ static void set_rows(const gnnfp_loop* L, int ty, TileSrc& ts) {
 }
 
 // input of net_state[ty] at iteration t (1-based): GNN.py:222-231 / CompositeGNN.py:224
-void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts) {
+void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts, int agg_direct) {
   const gnnfp_loop* L = c.L;
   const gnnfp_graph* g = L->g;
   memset(&ts, 0, sizeof(ts));
@@ -180,7 +180,7 @@ void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts) {
       if (bn) { p1.st_sum = c.stX(0); p1.st_sq = c.stX(0) + xw; }
       add_piece(ts, p1);
     }
-    Piece p2 = mk_gather(Sp, ld, D, D + NLp, g->dst_rowptr, g->dst_src, wgt);
+    Piece p2 = agg_direct ? mk_direct(c.AGG(t), D, D, D + NLp) : mk_gather(Sp, ld, D, D + NLp, g->dst_rowptr, g->dst_src, wgt, g->A);
     p2.tag = TAG_AGG_STATE;
     if (bn) { p2.st_sum = c.stA(0, t - 1); p2.st_sq = p2.st_sum + D; }
     add_piece(ts, p2);
@@ -198,7 +198,7 @@ void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts) {
     p1.tag = TAG_STATE;
     if (bn) { p1.st_sum = c.stS(ty, t - 1); p1.st_sq = p1.st_sum + D; }
     add_piece(ts, p1);
-    Piece p2 = mk_gather(Sp, ld, D, d + D, g->dst_rowptr, g->dst_src, wgt);
+    Piece p2 = agg_direct ? mk_direct(c.AGG(t), D, D, d + D) : mk_gather(Sp, ld, D, d + D, g->dst_rowptr, g->dst_src, wgt, g->A);
     p2.tag = TAG_AGG_STATE;
     if (bn) { p2.st_sum = c.stA(ty, t - 1); p2.st_sq = p2.st_sum + D; }
     add_piece(ts, p2);
@@ -382,10 +382,11 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   w.ctrl_bytes = off - w.ctrl;
   w.Xs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float));
   L->slot_count = cfg->training ? MI : (MI > 0 ? 2 : 0);
-  w.slots = off; off = align_up(off + (size_t)L->slot_count * L->N * L->D * sizeof(float));
+  w.slots = off; off = align_up(off + (size_t)L->slot_count * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float));
   w.out_nodes = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
+  w.agg = off; off = align_up(off + (cfg->training ? (size_t)MI : 0) * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float) + 4);
   if (cfg->training) {
-    const size_t ND = (size_t)L->N * L->D * sizeof(float);
+    const size_t ND = (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float);
     w.dSfin = off; off = align_up(off + ND);
     w.dOwn = off; off = align_up(off + 2 * ND);
     w.dAgg = off; off = align_up(off + 2 * ND);
@@ -453,17 +454,17 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       const int NLp = L->S > 0 ? L->NLw : 0;
       if (NLp) {
         add_piece(pa.src, mk_direct(io->nodes, io->ld_nodes, NLp, 0));
-        add_piece(pa.src, mk_gather(io->nodes, io->ld_nodes, NLp, NLp, g->dst_rowptr, g->dst_src, wgt));
+        add_piece(pa.src, mk_gather(io->nodes, io->ld_nodes, NLp, NLp, g->dst_rowptr, g->dst_src, wgt, g->A));
       }
-      add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, 2 * NLp, g->dst_rowptr, g->dst_arc, wgt));
+      add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, 2 * NLp, g->dst_rowptr, g->dst_arc, wgt, g->A));
       if (L->bn_train_state) { pa.st_sum = c.stX(0); pa.st_sq = c.stX(0) + c.stXw(); }
     } else {
       int col = 0;
       for (int t = 0; t < L->nt; ++t) {
-        add_piece(pa.src, mk_gather(io->nodes, io->ld_nodes, L->dt[t], col, g->dst_rowptr, g->dst_src, g->typed_w[t]));
+        add_piece(pa.src, mk_gather(io->nodes, io->ld_nodes, L->dt[t], col, g->dst_rowptr, g->dst_src, g->typed_w[t], g->A));
         col += L->dt[t];
       }
-      add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, col, g->dst_rowptr, g->dst_arc, wgt));
+      add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, col, g->dst_rowptr, g->dst_arc, wgt, g->A));
     }
     pa.out = c.Xs(); pa.ld_out = L->LsM;
     pa.tc.cap_per_row = L->cap_per_row;
@@ -514,8 +515,9 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
         memset(&pa, 0, sizeof(pa));
         set_rows(L, ty, pa.src);
         pa.src.in_dim = D;
-        add_piece(pa.src, mk_gather(c.S(t - 1), c.ldS(t - 1), D, 0, g->dst_rowptr, g->dst_src, wgt));
+        add_piece(pa.src, mk_gather(c.S(t - 1), c.ldS(t - 1), D, 0, g->dst_rowptr, g->dst_src, wgt, g->A));
         pa.st_sum = c.stA(ty, t - 1); pa.st_sq = pa.st_sum + D;
+        pa.out = c.AGG(t); pa.ld_out = D;            // saved for this iteration's net_state and for the backward
         pa.gate = gate;
         pa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_pass(D, pa.src.n_rows, &pa.tc))) return rc;
@@ -525,7 +527,12 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
     for (int ty = 0; ty < L->nt; ++ty) {
       FwdArgs fa;
       memset(&fa, 0, sizeof(fa));
-      build_state_src(c, ty, t, fa.src);
+      build_state_src(c, ty, t, fa.src, L->bn_train_state ? 1 : 0);
+      if (training && !L->bn_train_state) {          // no BN pass: the iteration kernel itself saves Adj^T.state
+        fa.agg_out = c.AGG(t);
+        fa.agg_col0 = (L->composite ? L->dt[ty] : 0) + D + ((!L->composite && L->S > 0) ? L->NLw : 0);
+        fa.agg_w = D;
+      }
       fill_netdev(L->snet[ty], sp[ty], training, fa.src.n_rows, fa.net);
       fa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;

@@ -8,6 +8,7 @@ struct WsLayout {
   size_t stS = 0, stA = 0, stX = 0, stO = 0;  // double blocks
   size_t Xs = 0;                            // float [N, LsM]
   size_t slots = 0;                         // float state slots
+  size_t agg = 0;                           // float [max_iter][N, D]: Adj^T.state of every iteration (training)
   size_t out_nodes = 0;                     // float [M, T]
   // backward
   size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0;
@@ -46,11 +47,12 @@ struct Ctx {
   int* flags() const { return (int*)(ws + L->ws.flags); }
   float* Xs() const { return (float*)(ws + L->ws.Xs); }
   float* slots() const { return (float*)(ws + L->ws.slots); }
-  size_t slot_stride() const { return (size_t)L->N * L->D; }
+  size_t slot_stride() const { return ((size_t)L->N * L->D + 31) / 32 * 32; }   // 128-byte aligned slots (vector staging)
   const float* S(int t) const {   // state after t iterations
     if (t == 0) return L->S > 0 ? io->state0 : io->nodes;
     return slots() + (L->cfg.training ? (size_t)(t - 1) : (size_t)(t & 1)) * slot_stride();
   }
+  float* AGG(int t) const { return (float*)(ws + L->ws.agg) + (size_t)(t - 1) * slot_stride(); }   // t = 1..max_iter
   int ldS(int t) const { return t == 0 ? (L->S > 0 ? L->S : io->ld_nodes) : L->D; }
   int stXw() const {
     if (!L->composite) return L->LsM;
@@ -65,9 +67,9 @@ struct Ctx {
 };
 
 Piece mk_direct(const float* ptr, int ld, int width, int col0);
-Piece mk_gather(const float* ptr, int ld, int width, int col0, const int* rowptr, const int* idx, const float* wgt);
+Piece mk_gather(const float* ptr, int ld, int width, int col0, const int* rowptr, const int* idx, const float* wgt, int nnz = 0);
 void add_piece(TileSrc& ts, const Piece& p);
-void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts);
+void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts, int agg_direct);
 void build_out_src(const Ctx& c, TileSrc& ts);
 void fill_netdev(const gnnfp_net_desc& d, const gnnfp_net_params& p, int training, int n_rows, NetDev& nd);
 int check_io(const gnnfp_loop* L, const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes);

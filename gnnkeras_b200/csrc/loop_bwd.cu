@@ -101,8 +101,9 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
   const int MI = L->cfg.max_iteration, D = L->D, N = L->N;
   const size_t ND = (size_t)N * D;
   float* dSfin = (float*)(c.ws + L->ws.dSfin);
-  float* dOwn[2] = {(float*)(c.ws + L->ws.dOwn), (float*)(c.ws + L->ws.dOwn) + ND};
-  float* dAgg[2] = {(float*)(c.ws + L->ws.dAgg), (float*)(c.ws + L->ws.dAgg) + ND};
+  const size_t NDa = (ND + 31) / 32 * 32;
+  float* dOwn[2] = {(float*)(c.ws + L->ws.dOwn), (float*)(c.ws + L->ws.dOwn) + NDa};
+  float* dAgg[2] = {(float*)(c.ws + L->ws.dAgg), (float*)(c.ws + L->ws.dAgg) + NDa};
   float* dXs = want ? (float*)(c.ws + L->ws.dXs) : nullptr;
   float* part_state = (float*)(c.ws + L->ws.part_state);
   float* part_out = (float*)(c.ws + L->ws.part_out);
@@ -180,7 +181,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     for (int ty = 0; ty < L->nt; ++ty) {
       BwdArgs ba;
       memset(&ba, 0, sizeof(ba));
-      build_state_src(c, ty, t, ba.src);
+      build_state_src(c, ty, t, ba.src, 1);
       for (int p = 0; p < ba.src.n_pieces; ++p) {
         Piece& pc = ba.src.p[p];
         if (pc.tag == TAG_AGG_STATE) { pc.gptr = dAgg[wb]; pc.gld = D; pc.gmode = GM_STORE; }
@@ -199,7 +200,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
           Piece pb = mk_direct(dOwn[rb], D, D, 0);
           pb.accumulate = 1; pb.gate = c.flags() + t; pb.gate_pol = 1;
           add_piece(ba.gsrc, pb);
-          Piece pc2 = mk_gather(dAgg[rb], D, D, 0, g->src_rowptr, g->src_dst, src_w);
+          Piece pc2 = mk_gather(dAgg[rb], D, D, 0, g->src_rowptr, g->src_dst, src_w, g->A);
           pc2.accumulate = 1; pc2.gate = c.flags() + t; pc2.gate_pol = 1;
           add_piece(ba.gsrc, pc2);
         }

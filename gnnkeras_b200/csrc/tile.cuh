@@ -70,60 +70,101 @@ __device__ __forceinline__ StageScratch carve_scratch(float* base, int R, int ca
 // the (up to 4) neighbour-row loads of an item are issued back to back; accumulation stays sequential
 // in arc order (the order TF-CPU SparseTensorDenseMatMul uses).
 template <int VEC>
+__device__ __forceinline__ void load_vec(const float* sp, float* out) {
+  if (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(sp);
+    out[0] = t.x; out[1 % VEC] = t.y; out[2 % VEC] = t.z; out[3 % VEC] = t.w;
+  } else if (VEC == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(sp);
+    out[0] = t.x; out[1 % VEC] = t.y;
+  } else {
+    out[0] = *sp;
+  }
+}
+
+// NI items (row, VEC-wide chunk) per thread are processed together: the first two arcs of every item are
+// loaded before anything is consumed (2*NI independent loads in flight), longer rows continue sequentially.
+template <int VEC, int NI>
 __device__ __forceinline__ void gather_items(const Piece& pc, const StageScratch& sc, int abase, int nr, int R,
                                              float* X, int XS, bool has_w) {
   const int w = pc.width, nq = w / VEC;
   const int items = R * nq;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int r = it / nq, q = it - r * nq;
-    float acc[VEC];
+  const int T = blockDim.x;
+  for (int it0 = threadIdx.x; it0 < items; it0 += NI * T) {
+    float acc[NI][VEC];
+    float v0[NI][VEC], v1[NI][VEC], w0[NI], w1[NI];
+    int a0[NI], a1[NI], q[NI], rr[NI];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-    if (r < nr) {
-      const int a0 = sc.rp[r] - abase, a1 = sc.rp[r + 1] - abase;
-      for (int a = a0; a < a1; a += 4) {
-        float val[4][VEC];
-        float wv[4];
+    for (int i = 0; i < NI; ++i) {
+      const int it = it0 + i * T;
+      rr[i] = -1; a0[i] = 0; a1[i] = 0; q[i] = 0; w0[i] = 0.f; w1[i] = 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool ok = a + u < a1;
-          const int ai = ok ? a + u : a;
-          const float* sp = pc.ptr + (size_t)sc.sidx[ai] * pc.ld + q * VEC;
-          wv[u] = ok ? (has_w ? sc.sw[ai] : 1.0f) : 0.0f;
-          if (VEC == 4) {
-            const float4 t = *reinterpret_cast<const float4*>(sp);
-            val[u][0] = t.x; val[u][1 % VEC] = t.y; val[u][2 % VEC] = t.z; val[u][3 % VEC] = t.w;
-          } else if (VEC == 2) {
-            const float2 t = *reinterpret_cast<const float2*>(sp);
-            val[u][0] = t.x; val[u][1 % VEC] = t.y;
-          } else {
-            val[u][0] = *sp;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (a + u < a1) {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], val[u][v], acc[v]);
-          }
+      for (int v = 0; v < VEC; ++v) { acc[i][v] = 0.f; v0[i][v] = 0.f; v1[i][v] = 0.f; }
+      if (it < items) {
+        const int r = it / nq;
+        rr[i] = r; q[i] = it - r * nq;
+        if (r < nr) { a0[i] = sc.rp[r] - abase; a1[i] = sc.rp[r + 1] - abase; }
       }
     }
-    float* d = X + r * XS + pc.col0 + q * VEC;
-    if (pc.accumulate) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) d[v] += acc[v];
-    } else {
+    for (int i = 0; i < NI; ++i) {
+      if (a0[i] < a1[i]) {
+        load_vec<VEC>(pc.ptr + (size_t)sc.sidx[a0[i]] * pc.ld + q[i] * VEC, v0[i]);
+        w0[i] = has_w ? sc.sw[a0[i]] : 1.0f;
+      }
+      if (a0[i] + 1 < a1[i]) {
+        load_vec<VEC>(pc.ptr + (size_t)sc.sidx[a0[i] + 1] * pc.ld + q[i] * VEC, v1[i]);
+        w1[i] = has_w ? sc.sw[a0[i] + 1] : 1.0f;
+      }
+    }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) d[v] = acc[v];
+    for (int i = 0; i < NI; ++i) {
+      if (a0[i] < a1[i]) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[i][v] = fmaf(w0[i], v0[i][v], acc[i][v]);
+      }
+      if (a0[i] + 1 < a1[i]) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[i][v] = fmaf(w1[i], v1[i][v], acc[i][v]);
+      }
+      for (int a = a0[i] + 2; a < a1[i]; ++a) {     // arcs beyond the second: sequential, still in arc order
+        float t[VEC];
+        load_vec<VEC>(pc.ptr + (size_t)sc.sidx[a] * pc.ld + q[i] * VEC, t);
+        const float wv = has_w ? sc.sw[a] : 1.0f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[i][v] = fmaf(wv, t[v], acc[i][v]);
+      }
+      if (rr[i] >= 0) {
+        float* d = X + rr[i] * XS + pc.col0 + q[i] * VEC;
+        if (pc.accumulate) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) d[v] += acc[i][v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) d[v] = acc[i][v];
+        }
+      }
     }
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// L2-prefetch the byte range [p, p+bytes) cooperatively (one 128-byte line per thread-iteration)
+__device__ __forceinline__ void prefetch_range(const void* p, size_t bytes) {
+  const char* base = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127);
+  const size_t lines = (bytes + (reinterpret_cast<uintptr_t>(p) & 127) + 127) / 128;
+  for (size_t i = threadIdx.x; i < lines; i += blockDim.x) prefetch_l2(base + i * 128);
+}
+
 // Stage every piece of `ts` for tile rows [row0, row0+nr) into X[r*XS + col] (raw values).  Rows
 // nr..R-1 are zero-filled.  Ends WITHOUT a trailing __syncthreads (callers sync).
+// CTAs walk CONSECUTIVE tiles, so while staging tile i the data of tile i+1 (the next R rows and the next
+// slice of the CSR) is prefetched into L2: its DRAM latency is then hidden behind tile i's compute.
 __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, int R, float* X, int XS,
-                                           const StageScratch& sc) {
+                                           const StageScratch& sc, bool prefetch_next = true) {
   const int tid = threadIdx.x, T = blockDim.x;
+  const int next0 = row0 + R;
+  const int next_nr = prefetch_next ? max(0, min(R, ts.n_rows - next0)) : 0;
   for (int p = 0; p < ts.n_pieces; ++p) {
     const Piece& pc = ts.p[p];
     const bool on = piece_enabled(pc);
@@ -135,30 +176,75 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
     const int total = R * w;
     const int c0 = pc.col0;
     if (pc.kind == PK_DIRECT) {
-      // 4 independent loads in flight per thread, then the 4 stores
-      for (int e0 = tid; e0 < total; e0 += 4 * T) {
-        float v[4];
-        int off[4];
+      const bool ident = ts.rowlist == nullptr && pc.map == nullptr;
+      const bool flat = on && ident && pc.rowscale == nullptr && pc.ld == w &&
+                        ((reinterpret_cast<uintptr_t>(pc.ptr + (size_t)row0 * w) & 15) == 0);
+      if (on && ident && next_nr > 0) prefetch_range(pc.ptr + (size_t)next0 * pc.ld, (size_t)next_nr * pc.ld * sizeof(float));
+      if (flat) {
+        // the tile's rows are one contiguous, 16-byte aligned run: 128-bit loads, 4 in flight per thread
+        const float* srcf = pc.ptr + (size_t)row0 * w;
+        const float4* src4 = reinterpret_cast<const float4*>(srcf);
+        const int nvalid = nr * w;
+        const int n4 = (total + 3) / 4;
+        for (int i0 = tid; i0 < n4; i0 += 4 * T) {
+          float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = e0 + u * T;
-          v[u] = 0.f;
-          off[u] = -1;
-          if (e < total) {
-            const int r = (int)__umulhi((unsigned)e, pc.magic);
-            const int c = e - r * w;
-            off[u] = r * XS + c0 + c;
-            if (on && r < nr) {
-              const int gr = ts.rowlist ? ts.rowlist[row0 + r] : row0 + r;
-              const int sr = pc.compact ? (row0 + r) : (pc.map ? pc.map[gr] : gr);
-              v[u] = pc.ptr[(size_t)sr * pc.ld + c];
-              if (pc.rowscale) v[u] *= pc.rowscale[gr];
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * T;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n4) {
+              if (4 * i + 3 < nvalid) v[u] = src4[i];
+              else {
+                if (4 * i < nvalid) v[u].x = srcf[4 * i];
+                if (4 * i + 1 < nvalid) v[u].y = srcf[4 * i + 1];
+                if (4 * i + 2 < nvalid) v[u].z = srcf[4 * i + 2];
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * T;
+            if (i < n4) {
+              const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              int r = (int)__umulhi((unsigned)(4 * i), pc.magic);
+              int c = 4 * i - r * w;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (4 * i + k < total) {
+                  float* d = X + r * XS + c0 + c;
+                  if (pc.accumulate) *d += vv[k]; else *d = vv[k];
+                }
+                if (++c == w) { c = 0; ++r; }
+              }
             }
           }
         }
+      } else {
+        // 4 independent loads in flight per thread, then the 4 stores
+        for (int e0 = tid; e0 < total; e0 += 4 * T) {
+          float v[4];
+          int off[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (off[u] >= 0) { if (pc.accumulate) X[off[u]] += v[u]; else X[off[u]] = v[u]; }
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * T;
+            v[u] = 0.f;
+            off[u] = -1;
+            if (e < total) {
+              const int r = (int)__umulhi((unsigned)e, pc.magic);
+              const int c = e - r * w;
+              off[u] = r * XS + c0 + c;
+              if (on && r < nr) {
+                const int gr = ts.rowlist ? ts.rowlist[row0 + r] : row0 + r;
+                const int sr = pc.compact ? (row0 + r) : (pc.map ? pc.map[gr] : gr);
+                v[u] = pc.ptr[(size_t)sr * pc.ld + c];
+                if (pc.rowscale) v[u] *= pc.rowscale[gr];
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (off[u] >= 0) { if (pc.accumulate) X[off[u]] += v[u]; else X[off[u]] = v[u]; }
+        }
       }
     } else {
       // ---- gather: fast path = identity rows and the tile's arcs fit the scratch ----------------
@@ -167,10 +253,19 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
       if (fast) {
         __syncthreads();                               // scratch may still be read by a previous piece
         for (int i = tid; i <= nr; i += T) sc.rp[i] = pc.rowptr[row0 + i];
+        if (next_nr > 0) prefetch_range(pc.rowptr + next0, (size_t)(next_nr + 1) * sizeof(int));
         __syncthreads();
         abase = sc.rp[0];
         const int na = sc.rp[nr] - abase;
         fast = na <= sc.cap;                           // uniform across the CTA
+        if (next_nr > 0 && pc.nnz > 0) {               // next tile's CSR slice follows this one
+          const int nb = abase + na;
+          const int len = min(na + 32, pc.nnz - nb);
+          if (len > 0) {
+            prefetch_range(pc.idx + nb, (size_t)len * sizeof(int));
+            if (pc.wgt) prefetch_range(pc.wgt + nb, (size_t)len * sizeof(float));
+          }
+        }
         if (fast) {
           for (int i = tid; i < na; i += T) {
             sc.sidx[i] = pc.idx[abase + i];
@@ -182,9 +277,9 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
       if (fast) {
         const bool al16 = ((reinterpret_cast<uintptr_t>(pc.ptr) & 15) == 0) && (pc.ld % 4 == 0) && (w % 4 == 0) && (c0 % 4 == 0);
         const bool al8 = ((reinterpret_cast<uintptr_t>(pc.ptr) & 7) == 0) && (pc.ld % 2 == 0) && (w % 2 == 0) && (c0 % 2 == 0);
-        if (al16) gather_items<4>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
-        else if (al8) gather_items<2>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
-        else gather_items<1>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
+        if (al16) gather_items<4, 4>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
+        else if (al8) gather_items<2, 4>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
+        else gather_items<1, 4>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
       } else {
         for (int e = tid; e < total; e += T) {
           const int r = (int)__umulhi((unsigned)e, pc.magic);
