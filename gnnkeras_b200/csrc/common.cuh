@@ -108,6 +108,7 @@ struct TileCfg {
   int XS0, XS1;            // row strides (% 8 == 4) of the two activation buffers
   int cap;                 // arcs of one tile the CSR scratch can hold (fast gather path)
   int cap_per_row;         // in: scratch capacity per tile row (0 = default 4), set by the caller from A/N
+  int dz_ready;            // in (backward): the launch consumes a precomputed dz (no saved-output tile)
   int threads;
   size_t smem_bytes;
   int grid;
@@ -155,10 +156,36 @@ struct BwdArgs {
   int saved_compact;
   float* partial;          // [grid, n_params] per-CTA partial sums, accumulated across launches
   int n_params;
-  float* bn_partial;       // [grid, 2*in_dim] per-CTA sum(dy), sum(dy*xhat0) of THIS launch
+  float* bn_partial;       // [grid, 2*bn_in_total] per-CTA sum(dy), sum(dy*x~) of THIS launch
   const int* gate;
   int prof_cat;
+  // column-split mode (single Dense layer): `gsrc` already holds dz = G * act'(s_t) (dz_kernel), this launch
+  // owns input columns [c_off, c_off + net.in_dim) of the full net
+  int dz_ready;
+  int skip_bias;           // only one split accumulates db
+  int bias_off;            // offset of the bias block inside this launch's (shifted) partial slot
+  int bn_in_total;         // in_dim of the full net (bn_partial row layout); 0 = net.in_dim
+  int bn_c_off;
 };
+
+struct DzArgs {             // dz[i] = act'(s_t[i]) * G_t[i],  G_t = last ? dSfin : dOwn + Adj . dAgg
+  int n_rows;
+  const int* rowlist;
+  int D, act;
+  const float* s_t;        // saved output rows (by global row id)
+  int ld_s;
+  const float* dSfin;
+  const float* dOwn;
+  const float* dAgg;
+  const int* rowptr;       // source-grouped CSR
+  const int* idx;
+  const float* wgt;
+  const int* last_flag;    // G = dSfin iff last_flag == NULL || *last_flag == 0
+  int always_last;
+  float* dz;               // [N, D] by global row id
+  const int* gate;
+};
+int launch_dz(const DzArgs& a, cudaStream_t s);
 
 // launchers (kernels.cu)
 int launch_tile_fwd(const FwdArgs& a, cudaStream_t s);

@@ -28,7 +28,7 @@ struct BwdLayout {
   int total;   // floats
 };
 
-__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int regacc, int cap, BwdLayout& y) {
+__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int regacc, int cap, int dz_ready, BwdLayout& y) {
   y.L = net.n_layers;
   y.regacc = regacc;
   y.recompute = net.n_layers > 1;
@@ -65,7 +65,7 @@ __host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int 
   y.oAccBN = o; o += 2 * ceil_to(net.in_dim, 4);
   y.oZero = o; o += dmax;
   y.oScr = o; o += (int)scratch_floats(R, cap);
-  for (int l = 0; l <= y.L; ++l) { y.oAct[l] = o; o += R * y.XSa[l]; }
+  for (int l = 0; l <= y.L; ++l) { y.oAct[l] = o; o += (dz_ready && l == y.L) ? 0 : R * y.XSa[l]; }   // dz path: the saved output is not needed
   y.odzA = o; o += R * y.XSdA;
   y.odzB = o; o += R * y.XSdB;
   y.total = o;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
   const int lane = tid & 31, warp = tid >> 5;
   const int rg = warp % tc.RG, cg = warp / tc.RG;
   __shared__ BwdLayout y;
-  if (tid == 0) bwd_layout(net, tc.R, T, REGACC ? 1 : 0, tc.cap, y);
+  if (tid == 0) bwd_layout(net, tc.R, T, REGACC ? 1 : 0, tc.cap, a.dz_ready, y);
   __syncthreads();
   const int L = y.L;
   float racc[2][8][4];
@@ -157,19 +157,14 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
     const int nr = min(tc.R, n - row0);
     stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], sc);
     stage_tile(a.gsrc, row0, nr, tc.R, dzA, XSdA, sc);
-    if (!y.recompute) {
-      float* aL = smem + y.oAct[L];
-      const int XS = y.XSa[L];
-      for (int e = tid; e < tc.R * HL; e += T) {
-        const int r = (int)__umulhi((unsigned)e, magicHL);
-        const int j = e - r * HL;
-        float v = 0.0f;
-        if (r < nr) {
-          const int srow = a.saved_compact ? (row0 + r) : (a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r);
-          v = a.saved_out[(size_t)srow * a.ld_saved + j];
-        }
-        aL[r * XS + j] = v;
-      }
+    if (!y.recompute && !a.dz_ready) {
+      TileSrc so;
+      so.n_rows = a.src.n_rows; so.rowlist = a.saved_compact ? nullptr : a.src.rowlist; so.n_pieces = 1; so.in_dim = HL;
+      Piece& sp = so.p[0];
+      sp = Piece();
+      sp.ptr = a.saved_out; sp.ld = a.ld_saved; sp.width = HL; sp.col0 = 0; sp.kind = PK_DIRECT; sp.magic = magicHL;
+      sp.compact = (a.saved_compact && a.src.rowlist) ? 1 : 0;
+      stage_tile(so, row0, nr, tc.R, smem + y.oAct[L], y.XSa[L], sc);
     }
     __syncthreads();
     if (y.recompute) {
@@ -186,7 +181,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       }
     }
     // ---- dz_L = G * act'(h_L) ----------------------------------------------------------------
-    {
+    if (!a.dz_ready) {
       const float* aL = smem + y.oAct[L];
       const int XS = y.XSa[L];
       const int actL = net.acts[L - 1];
@@ -197,10 +192,24 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           for (int j = 0; j < HL; ++j) dzA[r * XSdA + j] = aL[r * XS + j] * (dzA[r * XSdA + j] - dot);
         }
       } else {
-        for (int e = tid; e < tc.R * HL; e += T) {
-          const int r = (int)__umulhi((unsigned)e, magicHL);
-          const int j = e - r * HL;
-          dzA[r * XSdA + j] = act_bwd(actL, aL[r * XS + j], dzA[r * XSdA + j]);
+        for (int e0 = tid; e0 < tc.R * HL; e0 += 4 * T) {
+          float yv[4], gv[4];
+          int o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * T;
+            o[u] = -1; yv[u] = 0.f; gv[u] = 0.f;
+            if (e < tc.R * HL) {
+              const int r = (int)__umulhi((unsigned)e, magicHL);
+              const int j = e - r * HL;
+              o[u] = r * XSdA + j;
+              yv[u] = aL[r * XS + j];
+              gv[u] = dzA[o[u]];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (o[u] >= 0) dzA[o[u]] = act_bwd(actL, yv[u], gv[u]);
         }
       }
     }
@@ -266,7 +275,8 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         }
         // db_l += column sums of dz (all threads: column x row group, shared float atomics)
         float* ab = smem + y.oAccb[l];
-        if (T >= H) {
+        if (a.skip_bias && !y.bn) {
+        } else if (T >= H) {
           const int ngr = T / H, j = tid % H, gg = tid / H;
           if (gg < ngr) {
             float s2 = 0.f;
@@ -291,6 +301,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       if (l > 0) {
         const int actp = net.acts[l - 1];
         const unsigned magic = (unsigned)((0x100000000ull + (unsigned)in_l - 1) / (unsigned)in_l);
+#pragma unroll 4
         for (int e = tid; e < tc.R * in_l; e += T) {
           const int r = (int)__umulhi((unsigned)e, magic);
           const int c = e - r * in_l;
@@ -334,17 +345,31 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       const Piece& pc = a.src.p[p];
       if (pc.gmode == GM_NONE) continue;
       const int w = pc.width;
-      for (int e = tid; e < nr * w; e += T) {
-        const int r = (int)__umulhi((unsigned)e, pc.magic);
-        const int c = e - r * w;
-        float v = cur[r * XSc + pc.col0 + c];
-        if (y.bn) v *= bnS[pc.col0 + c];
-        const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
-        const int drow = pc.map ? pc.map[gr] : gr;
-        float* d = pc.gptr + (size_t)drow * pc.gld + c;
-        if (pc.gmode == GM_STORE) *d = v;
-        else if (pc.gmode == GM_ADD) *d += v;
-        else atomicAdd(d, v);
+      for (int e0 = tid; e0 < nr * w; e0 += 4 * T) {
+        float v[4], old[4];
+        float* d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * T;
+          d[u] = nullptr; v[u] = 0.f; old[u] = 0.f;
+          if (e < nr * w) {
+            const int r = (int)__umulhi((unsigned)e, pc.magic);
+            const int c = e - r * w;
+            v[u] = cur[r * XSc + pc.col0 + c];
+            if (y.bn) v[u] *= bnS[pc.col0 + c];
+            const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
+            const int drow = pc.map ? pc.map[gr] : gr;
+            d[u] = pc.gptr + (size_t)drow * pc.gld + c;
+            if (pc.gmode == GM_ADD) old[u] = *d[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (d[u]) {
+            if (pc.gmode == GM_STORE) *d[u] = v[u];
+            else if (pc.gmode == GM_ADD) *d[u] = old[u] + v[u];
+            else atomicAdd(d[u], v[u]);
+          }
       }
     }
     __syncthreads();
@@ -390,16 +415,19 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         }
       }
       off += in_l * H;
-      for (int j = tid; j < H; j += T) part[off + j] += ab[j];
+      if (a.dz_ready) off = a.bias_off;
+      if (!a.skip_bias)
+        for (int j = tid; j < H; j += T) part[off + j] += ab[j];
       off += H;
     }
     if (y.bn && a.bn_partial) {
       const int pin = ceil_to(net.in_dim, 4);
-      float* bp = a.bn_partial + (size_t)blockIdx.x * 2 * net.in_dim;
+      const int tot = a.bn_in_total > 0 ? a.bn_in_total : net.in_dim;
+      float* bp = a.bn_partial + (size_t)blockIdx.x * 2 * tot + a.bn_c_off;
       for (int c = tid; c < net.in_dim; c += T) {
         const float P = accBN[c], Qraw = accBN[pin + c];
         bp[c] = P;
-        bp[net.in_dim + c] = fmaf(bnA[c], Qraw, bnB[c] * P);
+        bp[tot + c] = fmaf(bnA[c], Qraw, bnB[c] * P);
       }
     }
   }
@@ -559,8 +587,70 @@ __global__ void reduce_params_kernel(const __grid_constant__ ReduceArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// dz = act'(s_t) * G_t as a streaming kernel (single-layer state nets): the gather over the source-grouped
+// CSR runs with thousands of independent threads instead of inside the persistent GEMM kernel.
+template <int VEC>
+__global__ void __launch_bounds__(256) dz_kernel(const __grid_constant__ DzArgs a) {
+  if (a.gate && *a.gate == 0) return;
+  const bool last = a.always_last || a.last_flag == nullptr || *a.last_flag == 0;
+  const int nq = a.D / VEC;
+  const long long items = (long long)a.n_rows * nq;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(it / nq), q = (int)(it - (long long)r * nq);
+    const int gr = a.rowlist ? a.rowlist[r] : r;
+    const size_t o = (size_t)gr * a.D + q * VEC;
+    float g[VEC], yv[VEC];
+    load_vec<VEC>(a.s_t + (size_t)gr * a.ld_s + q * VEC, yv);
+    if (last) {
+      load_vec<VEC>(a.dSfin + o, g);
+    } else {
+      load_vec<VEC>(a.dOwn + o, g);
+      const int a0 = a.rowptr[gr], a1 = a.rowptr[gr + 1];
+      for (int p = a0; p < a1; p += 4) {
+        float t[4][VEC], wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = p + u < a1;
+          const int pi = ok ? p + u : p;
+          wv[u] = ok ? (a.wgt ? a.wgt[pi] : 1.0f) : 0.0f;
+          load_vec<VEC>(a.dAgg + (size_t)a.idx[pi] * a.D + q * VEC, t[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (p + u < a1) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) g[v] = fmaf(wv[u], t[u][v], g[v]);
+          }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) a.dz[o + v] = act_bwd(a.act, yv[v], g[v]);
+  }
+}
+
+int launch_dz(const DzArgs& a, cudaStream_t s) {
+  if (a.n_rows <= 0) return GNNFP_OK;
+  auto al = [&](const void* p, int m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+  int vec = 1;
+  if (a.D % 4 == 0 && a.ld_s % 4 == 0 && al(a.s_t, 16) && al(a.dSfin, 16) && al(a.dOwn, 16) && al(a.dAgg, 16) && al(a.dz, 16)) vec = 4;
+  else if (a.D % 2 == 0 && a.ld_s % 2 == 0 && al(a.s_t, 8) && al(a.dSfin, 8) && al(a.dOwn, 8) && al(a.dAgg, 8) && al(a.dz, 8)) vec = 2;
+  const long long items = (long long)a.n_rows * (a.D / vec);
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)gnnfp_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  ProfScope ps(PC_OTHER, s);
+  if (vec == 4) dz_kernel<4><<<(int)blocks, 256, 0, s>>>(a);
+  else if (vec == 2) dz_kernel<2><<<(int)blocks, 256, 0, s>>>(a);
+  else dz_kernel<1><<<(int)blocks, 256, 0, s>>>(a);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc) {
   (void)gwidth;
+  const int dzr = tc->dz_ready;
   int maxch = 1;
   for (int l = 0; l < net.n_layers; ++l) {
     const int in_l = l == 0 ? net.in_dim : net.widths[l - 1];
@@ -576,16 +666,26 @@ int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc) {
   const int cap_per_row = tc->cap_per_row > 0 ? tc->cap_per_row : 4;
   int regacc = 0;
   for (;;) {
-    bwd_layout(net, 64 * RG, 256, 0, 64 * RG * cap_per_row, y);
+    bwd_layout(net, 64 * RG, 256, 0, 64 * RG * cap_per_row, dzr, y);
     const bool too_big = (size_t)y.total * 4 > want;
     const bool underfill = (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm;
     if (RG > 1 && (too_big || underfill)) { RG /= 2; CG = 8 / RG; continue; }
     break;
   }
-  if ((size_t)y.total * 4 > want && net.n_layers == 1) {
-    // one big Dense layer: keep the dW accumulators in registers (2 units of 8x4 per thread)
+  if (net.n_layers == 1) {
+    // one Dense layer with 128 < units <= 512: keep the dW accumulators in registers (<= 2 units of 8x4 per thread)
     const int U = ((net.in_dim + 7) / 8) * ((net.widths[0] + 3) / 4);
-    if (U >= 256 && U <= 512) { regacc = 1; bwd_layout(net, 64 * RG, 256, 1, 64 * RG * cap_per_row, y); }
+    if (U > 128 && U <= 512) {
+      regacc = 1;
+      RG = 8 / CG;
+      for (;;) {
+        bwd_layout(net, 64 * RG, 256, 1, 64 * RG * cap_per_row, dzr, y);
+        const bool too_big = (size_t)y.total * 4 > want;
+        const bool underfill = (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm;
+        if (RG > 1 && (too_big || underfill)) { RG /= 2; CG = 8 / RG; continue; }
+        break;
+      }
+    }
   }
   tc->RG = RG; tc->CG = CG; tc->R = 64 * RG; tc->threads = 256;
   tc->XS0 = y.XSa[0]; tc->XS1 = regacc;   // XS1 doubles as the register-accumulation switch of the backward kernel
@@ -593,8 +693,8 @@ int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc) {
   tc->smem_bytes = (size_t)y.total * 4 + 64;
   if (tc->smem_bytes > cap)
     GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "net too large for the shared-memory backward tile kernel (%zu bytes needed)", tc->smem_bytes);
-  int per_sm = (int)((220 * 1024) / (tc->smem_bytes + 1024));
-  if (per_sm > 8) per_sm = 8;
+  int per_sm = (int)((224 * 1024) / (tc->smem_bytes + 1024));
+  if (per_sm > 4) per_sm = 4;      // partial-sum slots are sized for 4 CTAs per SM (loop.cu grid_cap)
   if (per_sm < 1) per_sm = 1;
   const int n_tiles = (n_rows + tc->R - 1) / tc->R;
   tc->grid = n_tiles < nsm * per_sm ? n_tiles : nsm * per_sm;

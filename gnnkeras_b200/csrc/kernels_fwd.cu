@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
       in_l = Hl;
     }
     // ---- epilogue: `cur` holds the output tile [R][XSc], first H columns ------------------------
+#pragma unroll 4
     for (int e = tid; e < nr * H; e += T) {
       const int r = (int)__umulhi((unsigned)e, magicH);
       const int j = e - r * H;

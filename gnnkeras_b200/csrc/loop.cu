@@ -349,22 +349,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   for (int t = 0; t < L->nt; ++t) L->nparam_s[t] = net_param_count(L->snet[t]);
   L->nparam_o = net_param_count(L->onet);
   { long long cpr = g->N > 0 ? (2ll * g->A + g->N - 1) / g->N : 4; L->cap_per_row = cpr < 4 ? 4 : (cpr > 16 ? 16 : (int)cpr); }
-  L->grid_cap = 1;
-  if (cfg->training) {   // exact grids of the backward tile kernels (they are a pure function of the shapes)
-    gnnfp_net_params none;
-    memset(&none, 0, sizeof(none));
-    for (int t = 0; t <= L->nt; ++t) {
-      NetDev nd;
-      const gnnfp_net_desc& dsc = t < L->nt ? L->snet[t] : L->onet;
-      const int rows = t < L->nt ? (L->composite ? g->type_count[t] : L->N) : L->M;
-      fill_netdev(dsc, none, 1, rows, nd);
-      TileCfg tcb;
-      memset(&tcb, 0, sizeof(tcb));
-      tcb.cap_per_row = L->cap_per_row;
-      if ((rc = tile_cfg_bwd(nd, rows > 0 ? rows : 1, 0, &tcb))) { delete L; return rc; }
-      L->grid_cap = tcb.grid > L->grid_cap ? tcb.grid : L->grid_cap;
-    }
-  }
+  L->grid_cap = gnnfp_num_sms() * 4;   // backward tile kernels run at most 4 CTAs per SM (tile_cfg_bwd)
 
   // ---- workspace layout ---------------------------------------------------------------------
   WsLayout& w = L->ws;
@@ -390,6 +375,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     w.dSfin = off; off = align_up(off + ND);
     w.dOwn = off; off = align_up(off + 2 * ND);
     w.dAgg = off; off = align_up(off + 2 * ND);
+    w.dz = off; off = align_up(off + ND);
     w.dOutN = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
     size_t ps = 0, bg = 2 * (size_t)L->onet.in_dim;
     int din_max = L->onet.in_dim;

@@ -11,7 +11,7 @@ struct WsLayout {
   size_t agg = 0;                           // float [max_iter][N, D]: Adj^T.state of every iteration (training)
   size_t out_nodes = 0;                     // float [M, T]
   // backward
-  size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0;
+  size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0, dz = 0;
   size_t part_state = 0, part_out = 0, bn_part = 0, bn_const = 0, bn_grad = 0;
   size_t bwd_zero = 0, bwd_zero_bytes = 0;   // region zeroed at the start of every backward
   size_t total = 0;

@@ -175,15 +175,51 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
   }
 
   // ---- 2. iterations, newest first ---------------------------------------------------------------
+  // Single-Dense-layer state nets (the reference's default MLP) take the "dz path": a streaming kernel forms
+  // dz = act'(s_t) * G_t (with the Adj . dAgg gather), then the GEMM pair runs as 1..n column-split launches
+  // whose inputs are all plain matrices.  Other nets use the fused kernel.
+  float* dzbuf = (float*)(c.ws + L->ws.dz);
+  struct Split { int p0, p1, c_off, width; };
+  Split splits[GNNFP_MAX_TYPES][4];
+  int nsplit[GNNFP_MAX_TYPES];
+  bool dzpath[GNNFP_MAX_TYPES];
+  for (int ty = 0; ty < L->nt; ++ty) {
+    const gnnfp_net_desc& d = L->snet[ty];
+    dzpath[ty] = d.n_layers == 1 && d.acts[0] != GNNFP_ACT_SOFTMAX && MI > 0;
+    nsplit[ty] = 1;
+    if (!dzpath[ty]) continue;
+    TileSrc probe;
+    build_state_src(c, ty, 1, probe, 1);
+    NetDev nd;
+    fill_netdev(d, sp[ty], 1, probe.n_rows, nd);
+    TileCfg tcf;
+    memset(&tcf, 0, sizeof(tcf));
+    tcf.cap_per_row = L->cap_per_row;
+    int want_splits = 1;
+    if (tile_cfg_bwd(nd, probe.n_rows > 0 ? probe.n_rows : 1, D, &tcf) != GNNFP_OK || tcf.smem_bytes > 110 * 1024)
+      want_splits = probe.n_pieces >= 2 ? 2 : 1;
+    if (d.in_dim > 384 && probe.n_pieces >= 3) want_splits = 3;
+    // greedy cut at piece boundaries
+    const int target = (d.in_dim + want_splits - 1) / want_splits;
+    int ns = 0, p0 = 0, acc = 0, coff = 0;
+    for (int p = 0; p < probe.n_pieces; ++p) {
+      acc += probe.p[p].width;
+      const bool lastp = p == probe.n_pieces - 1;
+      if (lastp || (acc >= target && ns < want_splits - 1)) {
+        splits[ty][ns++] = Split{p0, p + 1, coff, acc};
+        coff += acc; acc = 0; p0 = p + 1;
+      }
+    }
+    nsplit[ty] = ns;
+  }
   for (int t = MI; t >= 1; --t) {
     const int* gate = c.flags() + (t - 1);
     const int wb = t & 1, rb = (t + 1) & 1;
     for (int ty = 0; ty < L->nt; ++ty) {
-      BwdArgs ba;
-      memset(&ba, 0, sizeof(ba));
-      build_state_src(c, ty, t, ba.src, 1);
-      for (int p = 0; p < ba.src.n_pieces; ++p) {
-        Piece& pc = ba.src.p[p];
+      TileSrc full;
+      build_state_src(c, ty, t, full, 1);
+      for (int p = 0; p < full.n_pieces; ++p) {
+        Piece& pc = full.p[p];
         if (pc.tag == TAG_AGG_STATE) { pc.gptr = dAgg[wb]; pc.gld = D; pc.gmode = GM_STORE; }
         else if (pc.tag == TAG_STATE) { pc.gptr = dOwn[wb]; pc.gld = D; pc.gmode = GM_STORE; }
         else if (want) {
@@ -191,31 +227,82 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
           else if (pc.tag == TAG_STATIC) { pc.gptr = dXs + (pc.ptr - c.Xs()); pc.gld = L->LsM; pc.gmode = GM_ADD; }  // static block columns
         }
       }
-      ba.gsrc.n_rows = ba.src.n_rows; ba.gsrc.rowlist = ba.src.rowlist; ba.gsrc.in_dim = D;
-      {
-        Piece pa = mk_direct(dSfin, D, D, 0);
-        if (t < MI) { pa.gate = c.flags() + t; pa.gate_pol = 0; }   // enabled iff iteration t+1 did not run
-        add_piece(ba.gsrc, pa);
-        if (t < MI) {
-          Piece pb = mk_direct(dOwn[rb], D, D, 0);
-          pb.accumulate = 1; pb.gate = c.flags() + t; pb.gate_pol = 1;
-          add_piece(ba.gsrc, pb);
-          Piece pc2 = mk_gather(dAgg[rb], D, D, 0, g->src_rowptr, g->src_dst, src_w, g->A);
-          pc2.accumulate = 1; pc2.gate = c.flags() + t; pc2.gate_pol = 1;
-          add_piece(ba.gsrc, pc2);
+      NetDev ndfull;
+      fill_netdev(L->snet[ty], sp[ty], 1, full.n_rows, ndfull);
+      BwdArgs last_ba;
+      memset(&last_ba, 0, sizeof(last_ba));
+      if (dzpath[ty]) {
+        DzArgs da;
+        memset(&da, 0, sizeof(da));
+        da.n_rows = full.n_rows; da.rowlist = full.rowlist; da.D = D; da.act = L->snet[ty].acts[0];
+        da.s_t = c.S(t); da.ld_s = D;
+        da.dSfin = dSfin; da.dOwn = dOwn[rb]; da.dAgg = dAgg[rb];
+        da.rowptr = g->src_rowptr; da.idx = g->src_dst; da.wgt = src_w;
+        da.last_flag = t < MI ? c.flags() + t : nullptr; da.always_last = t == MI;
+        da.dz = dzbuf; da.gate = gate;
+        if ((rc = launch_dz(da, s))) return rc;
+        if (L->snet[ty].has_bn)
+          GNNFP_CHECK_CUDA(cudaMemsetAsync(bn_part, 0, (size_t)L->grid_cap * 2 * L->snet[ty].in_dim * sizeof(float), s));
+        const int H0 = L->snet[ty].widths[0];
+        for (int si = 0; si < nsplit[ty]; ++si) {
+          const Split& sp_ = splits[ty][si];
+          BwdArgs ba;
+          memset(&ba, 0, sizeof(ba));
+          ba.src.n_rows = full.n_rows; ba.src.rowlist = full.rowlist; ba.src.in_dim = sp_.width;
+          for (int p = sp_.p0; p < sp_.p1; ++p) { Piece pc = full.p[p]; pc.col0 -= sp_.c_off; ba.src.p[ba.src.n_pieces++] = pc; }
+          ba.gsrc.n_rows = full.n_rows; ba.gsrc.rowlist = full.rowlist; ba.gsrc.in_dim = D;
+          add_piece(ba.gsrc, mk_direct(dzbuf, D, D, 0));
+          ba.net = ndfull;
+          ba.net.in_dim = sp_.width;
+          ba.net.W[0] = ndfull.W[0] + (size_t)sp_.c_off * H0;
+          if (ndfull.gamma) { ba.net.gamma = ndfull.gamma + sp_.c_off; ba.net.beta = ndfull.beta + sp_.c_off;
+                              ba.net.mmean = ndfull.mmean + sp_.c_off; ba.net.mvar = ndfull.mvar + sp_.c_off; }
+          ba.tc.cap_per_row = L->cap_per_row;
+          ba.tc.dz_ready = 1;
+          if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc))) return rc;
+          if (ba.tc.grid > L->grid_cap) ba.tc.grid = L->grid_cap;
+          grid_state[ty] = ba.tc.grid > grid_state[ty] ? ba.tc.grid : grid_state[ty];
+          ba.dz_ready = 1; ba.skip_bias = si > 0;
+          ba.partial = part_state + ps_off[ty] + (size_t)sp_.c_off * H0; ba.n_params = L->nparam_s[ty];
+          ba.bias_off = (L->snet[ty].in_dim - sp_.c_off) * H0;
+          ba.bn_partial = bn_part; ba.bn_in_total = L->snet[ty].in_dim; ba.bn_c_off = sp_.c_off;
+          ba.gate = gate; ba.prof_cat = PC_BWD_ITER;
+          if ((rc = launch_tile_bwd(ba, s))) return rc;
         }
+        // BN tail over the whole net (all splits wrote their columns of bn_partial)
+        last_ba.src = full; last_ba.net = ndfull; last_ba.tc.grid = L->grid_cap; last_ba.tc.cap_per_row = L->cap_per_row;
+        last_ba.bn_partial = bn_part; last_ba.gate = gate;
+      } else {
+        BwdArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        ba.src = full;
+        ba.gsrc.n_rows = ba.src.n_rows; ba.gsrc.rowlist = ba.src.rowlist; ba.gsrc.in_dim = D;
+        {
+          Piece pa = mk_direct(dSfin, D, D, 0);
+          if (t < MI) { pa.gate = c.flags() + t; pa.gate_pol = 0; }   // enabled iff iteration t+1 did not run
+          add_piece(ba.gsrc, pa);
+          if (t < MI) {
+            Piece pb = mk_direct(dOwn[rb], D, D, 0);
+            pb.accumulate = 1; pb.gate = c.flags() + t; pb.gate_pol = 1;
+            add_piece(ba.gsrc, pb);
+            Piece pc2 = mk_gather(dAgg[rb], D, D, 0, g->src_rowptr, g->src_dst, src_w, g->A);
+            pc2.accumulate = 1; pc2.gate = c.flags() + t; pc2.gate_pol = 1;
+            add_piece(ba.gsrc, pc2);
+          }
+        }
+        ba.net = ndfull;
+        ba.tc.cap_per_row = L->cap_per_row;
+        if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc))) return rc;
+        grid_state[ty] = ba.tc.grid > grid_state[ty] ? ba.tc.grid : grid_state[ty];
+        ba.saved_out = c.S(t); ba.ld_saved = D; ba.saved_compact = 0;
+        ba.partial = part_state + ps_off[ty]; ba.n_params = L->nparam_s[ty];
+        ba.bn_partial = bn_part;
+        ba.gate = gate;
+        ba.prof_cat = PC_BWD_ITER;
+        if ((rc = launch_tile_bwd(ba, s))) return rc;
+        last_ba = ba;
       }
-      fill_netdev(L->snet[ty], sp[ty], 1, ba.src.n_rows, ba.net);
-      ba.tc.cap_per_row = L->cap_per_row;
-      if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc))) return rc;
-      grid_state[ty] = ba.tc.grid;
-      ba.saved_out = c.S(t); ba.ld_saved = D; ba.saved_compact = 0;
-      ba.partial = part_state + ps_off[ty]; ba.n_params = L->nparam_s[ty];
-      ba.bn_partial = bn_part;
-      ba.gate = gate;
-      ba.prof_cat = PC_BWD_ITER;
-      if ((rc = launch_tile_bwd(ba, s))) return rc;
-      if (L->snet[ty].has_bn && (rc = launch_bn_tail(ba, bn_grad + bg_off[ty], bn_const, s))) return rc;
+      if (L->snet[ty].has_bn && (rc = launch_bn_tail(last_ba, bn_grad + bg_off[ty], bn_const, s))) return rc;
     }
   }
 
