@@ -1,0 +1,175 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The reference has no distributed code at all; what the path offers is:
+
+* **many small graphs** (configs C1-C4): whole reference batches are independent units -> data parallel,
+  one merged batch per GPU per step, ONE all-reduce of the flat gradient buffer per step
+  (``DataParallel``).  Batch-global quantities of the reference (the stop rule GNN.py:212, BN batch
+  statistics, the `normalized` weight 1/A) stay local to a rank's batch, so every per-batch result is still
+  comparable with the oracle.
+* **one large graph** (config C5): 1-D block partition of the node ids; a rank owns a contiguous range of
+  destination nodes and every arc into it.  Per iteration the states of remote source nodes ("halo") are
+  exchanged and the 1-word convergence flag is max-reduced (``HaloPlan`` / ``PartitionedLoop``).
+
+Everything here is host-side bookkeeping (NumPy) plus torch.distributed calls; it works with the gloo
+backend on CPU tensors for the tests and with NCCL on device tensors in production.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------------------------
+# data parallel over whole batches
+# ------------------------------------------------------------------------------------------------------
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum over ranks; the 1/world factor is applied by the optimizer's grad_scale."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+class DataParallel:
+    """Wrap a compiled model (models.GNN*/LGNN): broadcast rank 0's parameters, then all-reduce the flat
+    gradient buffer once per train_step (one NCCL call, latency bound: C2 has ~28 k floats)."""
+
+    def __init__(self, model, group=None):
+        if model._store is None:
+            raise RuntimeError("compile() the model before wrapping it")
+        self.model, self.group = model, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > 1:
+            dist.broadcast(model._store.flat, src=0, group=group)
+            model.grad_hook = lambda flat: allreduce_mean_(flat, group)
+            model.grad_scale = 1.0 / self.world
+
+    def train_step(self, data):
+        return self.model.train_step(data)
+
+    def __getattr__(self, name):
+        return getattr(self.model, name)
+
+
+def shard_batches(n_batches: int, rank: int, world: int) -> List[int]:
+    """Round-robin assignment of whole reference batches to ranks."""
+    return list(range(rank, n_batches, world))
+
+
+# ------------------------------------------------------------------------------------------------------
+# edge-cut partition of one large graph
+# ------------------------------------------------------------------------------------------------------
+@dataclass
+class HaloPlan:
+    """What rank `rank` needs to run the loop on its block of destination nodes."""
+    rank: int
+    world: int
+    lo: int                       # owned node range [lo, hi)
+    hi: int
+    local_src: np.ndarray         # [A_loc] source ids remapped: < n_own -> own row, else n_own + halo slot
+    local_dst: np.ndarray         # [A_loc] destination ids - lo
+    arc_ids: np.ndarray           # [A_loc] global arc ids (arc labels / explicit values are taken from these)
+    halo_global: np.ndarray       # [n_halo] global node id of each halo slot (sorted by owner, then id)
+    recv_counts: np.ndarray       # [world] halo rows received from each peer
+    send_rows: List[np.ndarray]   # per peer: OWN local row ids this rank must send (in the peer's halo order)
+
+    @property
+    def n_own(self):
+        return self.hi - self.lo
+
+    @property
+    def n_halo(self):
+        return len(self.halo_global)
+
+
+def block_ranges(n_nodes: int, world: int) -> np.ndarray:
+    """Contiguous, near-equal node blocks: bounds[r] .. bounds[r+1]."""
+    return (np.arange(world + 1, dtype=np.int64) * n_nodes) // world
+
+
+def build_halo_plans(src: np.ndarray, dst: np.ndarray, n_nodes: int, world: int) -> List[HaloPlan]:
+    """All ranks' plans (deterministic; every rank can compute it locally from the same inputs)."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    bounds = block_ranges(n_nodes, world)
+    owner_of = lambda ids: np.searchsorted(bounds, ids, side="right") - 1
+    plans, halos = [], []
+    for r in range(world):
+        lo, hi = int(bounds[r]), int(bounds[r + 1])
+        mine = np.flatnonzero((dst >= lo) & (dst < hi))            # arc order preserved -> same summation order
+        s, d = src[mine], dst[mine]
+        remote = (s < lo) | (s >= hi)
+        halo = np.unique(s[remote])                                 # sorted => grouped by owner block
+        slot = np.searchsorted(halo, s[remote])
+        local_src = np.where(remote, 0, s - lo)
+        local_src[remote] = (hi - lo) + slot
+        recv = np.bincount(owner_of(halo), minlength=world) if len(halo) else np.zeros(world, np.int64)
+        plans.append(HaloPlan(r, world, lo, hi, local_src.astype(np.int32), (d - lo).astype(np.int32),
+                              mine.astype(np.int64), halo, recv.astype(np.int64), []))
+        halos.append(halo)
+    for r in range(world):
+        lo, hi = plans[r].lo, plans[r].hi
+        plans[r].send_rows = [(h[(h >= lo) & (h < hi)] - lo).astype(np.int64) for h in halos]
+    return plans
+
+
+def exchange_halo(plan: HaloPlan, own_rows: torch.Tensor, group=None) -> torch.Tensor:
+    """Send the owned rows every peer needs and receive this rank's halo rows ([n_halo, D], halo-slot order).
+    One all-to-all-v per call (NCCL on device tensors, gloo on CPU tensors)."""
+    D = own_rows.shape[1]
+    send_idx = torch.as_tensor(np.concatenate(plan.send_rows) if plan.world else np.zeros(0, np.int64),
+                               device=own_rows.device)
+    send = own_rows.index_select(0, send_idx) if send_idx.numel() else own_rows.new_zeros((0, D))
+    recv = own_rows.new_empty((plan.n_halo, D))
+    in_splits = [int(len(x)) for x in plan.send_rows]
+    out_splits = [int(x) for x in plan.recv_counts]
+    if plan.world == 1:
+        return recv
+    if dist.get_backend(group) == "gloo":
+        # gloo has no all_to_all: emulate with point-to-point (tests only)
+        outs = list(recv.split(out_splits)) if plan.n_halo else [recv.new_zeros((0, D)) for _ in out_splits]
+        ins = list(send.split(in_splits))
+        reqs = []
+        for p in range(plan.world):
+            if p == plan.rank:
+                continue
+            if in_splits[p]:
+                reqs.append(dist.isend(ins[p].contiguous(), p, group=group))
+            if out_splits[p]:
+                reqs.append(dist.irecv(outs[p], p, group=group))
+        for q in reqs:
+            q.wait()
+        return recv
+    dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
+    return recv
+
+
+def reduce_halo_grads(plan: HaloPlan, d_halo: torch.Tensor, d_own: torch.Tensor, group=None) -> torch.Tensor:
+    """Backward of exchange_halo: gradients w.r.t. halo rows travel back to their owners and are summed
+    into d_own (rows may be needed by several peers)."""
+    D = d_own.shape[1]
+    in_splits = [int(x) for x in plan.recv_counts]          # what we send back (our halo, grouped by owner)
+    out_splits = [int(len(x)) for x in plan.send_rows]      # what we receive (our rows, per peer)
+    recv = d_own.new_empty((sum(out_splits), D))
+    if plan.world > 1:
+        if dist.get_backend(group) == "gloo":
+            outs, ins, reqs = list(recv.split(out_splits)), list(d_halo.split(in_splits)), []
+            for p in range(plan.world):
+                if p == plan.rank:
+                    continue
+                if in_splits[p]:
+                    reqs.append(dist.isend(ins[p].contiguous(), p, group=group))
+                if out_splits[p]:
+                    reqs.append(dist.irecv(outs[p], p, group=group))
+            for q in reqs:
+                q.wait()
+        else:
+            dist.all_to_all_single(recv, d_halo.contiguous(), out_splits, in_splits, group=group)
+    idx = torch.as_tensor(np.concatenate(plan.send_rows), device=d_own.device)
+    if idx.numel():
+        d_own.index_add_(0, idx, recv)
+    return d_own
