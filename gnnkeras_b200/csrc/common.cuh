@@ -184,8 +184,24 @@ struct DzArgs {             // dz[i] = act'(s_t[i]) * G_t[i],  G_t = last ? dSfi
   int always_last;
   float* dz;               // [N, D] by global row id
   const int* gate;
+  // BN training (homogeneous nets): constants [c0|c1|rstd|-mean*rstd] x in_dim of iteration t+1 and its saved Adj^T.s
+  const float* cn;
+  const float* agg_next;
+  int in_dim, own_col0, agg_col0;
 };
 int launch_dz(const DzArgs& a, cudaStream_t s);
+
+struct AggArgs {            // AGG = Adj^T . S (dst-CSR gather) as a streaming kernel + fp64 column statistics
+  int n_rows;
+  const int* rowlist;
+  int D;
+  const float* S; int ld;
+  const int* rowptr; const int* idx; const float* wgt;
+  float* out;              // [N, D] by global row id (may be NULL)
+  double* st_sum; double* st_sq;   // [D] each (may be NULL)
+  const int* gate;
+};
+int launch_agg_stats(const AggArgs& a, cudaStream_t s);
 
 // launchers (kernels.cu)
 int launch_tile_fwd(const FwdArgs& a, cudaStream_t s);

@@ -442,7 +442,8 @@ struct BnReduceArgs {
   const float* bn_partial;
   int grid;
   float* bn_grad;     // [2*in_dim] accumulators (gamma then beta)
-  float* bn_const;    // [2*in_dim] c0 then c1
+  float* bn_const;    // [4*in_dim] c0 | c1 | rstd | -mean*rstd
+  float* static_acc;  // optional [2*in_dim]: running sums of c0, c1 over the iterations (static columns)
   const int* gate;
 };
 __global__ void bn_reduce_kernel(const __grid_constant__ BnReduceArgs a) {
@@ -462,13 +463,16 @@ __global__ void bn_reduce_kernel(const __grid_constant__ BnReduceArgs a) {
     a.bn_grad[c] += (float)q;
     a.bn_grad[in + c] += (float)p;
     const float ac = a.net.gamma[c] * A[c];
+    float k0 = 0.f, k1 = 0.f;
     if (a.net.bn_mode == 1) {
-      a.bn_const[c] = (float)((double)ac * p * a.net.inv_n);
-      a.bn_const[in + c] = (float)((double)ac * q * a.net.inv_n);
-    } else {
-      a.bn_const[c] = 0.f;
-      a.bn_const[in + c] = 0.f;
+      k0 = (float)((double)ac * p * a.net.inv_n);
+      k1 = (float)((double)ac * q * a.net.inv_n);
     }
+    a.bn_const[c] = k0;
+    a.bn_const[in + c] = k1;
+    a.bn_const[2 * in + c] = A[c];
+    a.bn_const[3 * in + c] = Bc[c];
+    if (a.static_acc) { a.static_acc[c] += k0; a.static_acc[in + c] += k1; }
   }
 }
 
@@ -605,21 +609,39 @@ __global__ void __launch_bounds__(256) dz_kernel(const __grid_constant__ DzArgs 
       load_vec<VEC>(a.dSfin + o, g);
     } else {
       load_vec<VEC>(a.dOwn + o, g);
+      const float* cn = a.cn;
+      float k0a[VEC], k1a[VEC], Aa[VEC], Ba[VEC];
+      if (cn) {   // BN-training correction of iteration t+1's raw gradients, applied where they are consumed:
+                  // dx = a dy - (c0 + x~ c1),  x~ = x*rstd - mean*rstd
+        const int in = a.in_dim;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int oc = a.own_col0 + q * VEC + v, ac = a.agg_col0 + q * VEC + v;
+          g[v] -= cn[oc] + fmaf(yv[v], cn[2 * in + oc], cn[3 * in + oc]) * cn[in + oc];
+          k0a[v] = cn[ac]; k1a[v] = cn[in + ac]; Aa[v] = cn[2 * in + ac]; Ba[v] = cn[3 * in + ac];
+        }
+      }
       const int a0 = a.rowptr[gr], a1 = a.rowptr[gr + 1];
       for (int p = a0; p < a1; p += 4) {
-        float t[4][VEC], wv[4];
+        float t[4][VEC], xg[4][VEC], wv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const bool ok = p + u < a1;
           const int pi = ok ? p + u : p;
           wv[u] = ok ? (a.wgt ? a.wgt[pi] : 1.0f) : 0.0f;
-          load_vec<VEC>(a.dAgg + (size_t)a.idx[pi] * a.D + q * VEC, t[u]);
+          const size_t so = (size_t)a.idx[pi] * a.D + q * VEC;
+          load_vec<VEC>(a.dAgg + so, t[u]);
+          if (cn) load_vec<VEC>(a.agg_next + so, xg[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (p + u < a1) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) g[v] = fmaf(wv[u], t[u][v], g[v]);
+            for (int v = 0; v < VEC; ++v) {
+              float tv = t[u][v];
+              if (cn) tv -= k0a[v] + fmaf(xg[u][v], Aa[v], Ba[v]) * k1a[v];
+              g[v] = fmaf(wv[u], tv, g[v]);
+            }
           }
       }
     }
@@ -720,16 +742,16 @@ int launch_tile_bwd(const BwdArgs& a, cudaStream_t s) {
 }
 
 // BN tail of one backward application: reduce + fix
-int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream_t s) {
+int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream_t s, int no_fix, float* static_acc) {
   if (a.src.n_rows <= 0) return GNNFP_OK;
   BnReduceArgs ra;
   memset(&ra, 0, sizeof(ra));
   ra.src = a.src; ra.net = a.net; ra.bn_partial = a.bn_partial; ra.grid = a.tc.grid;
-  ra.bn_grad = bn_grad; ra.bn_const = bn_const; ra.gate = a.gate;
+  ra.bn_grad = bn_grad; ra.bn_const = bn_const; ra.gate = a.gate; ra.static_acc = static_acc;
   bn_reduce_kernel<<<1, 256, 2 * a.net.in_dim * sizeof(float), s>>>(ra);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
-  if (a.net.bn_mode != 1) return GNNFP_OK;
+  if (a.net.bn_mode != 1 || no_fix) return GNNFP_OK;
   bool any = false;
   for (int p = 0; p < a.src.n_pieces; ++p) any = any || a.src.p[p].gmode != GM_NONE;
   if (!any) return GNNFP_OK;

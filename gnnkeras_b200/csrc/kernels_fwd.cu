@@ -241,6 +241,92 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Adj^T . S with thousands of independent threads: thread (qx, ry) owns the VEC-wide column chunk qx of
+// rows ry, ry + rows_per_block * gridDim, ...; per-thread fp64 column partials, one block reduction, one
+// fp64 atomicAdd per column and block.  Arc order inside a row is preserved (sequential fmaf).
+template <int VEC>
+__global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ AggArgs a, int QX) {
+  if (a.gate && *a.gate == 0) return;
+  __shared__ double red[256 * 2];
+  const int nq = a.D / VEC;
+  const int qx = threadIdx.x % QX, ry = threadIdx.x / QX;
+  const int rpb = blockDim.x / QX;
+  double su[VEC], sq[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { su[v] = 0.0; sq[v] = 0.0; }
+  if (qx < nq) {
+    for (int r = blockIdx.x * rpb + ry; r < a.n_rows; r += gridDim.x * rpb) {
+      const int gr = a.rowlist ? a.rowlist[r] : r;
+      const int a0 = a.rowptr[gr], a1 = a.rowptr[gr + 1];
+      float acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+      for (int p = a0; p < a1; p += 4) {
+        float t[4][VEC], wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = p + u < a1;
+          const int pi = ok ? p + u : p;
+          wv[u] = ok ? (a.wgt ? a.wgt[pi] : 1.0f) : 0.0f;
+          load_vec<VEC>(a.S + (size_t)a.idx[pi] * a.ld + qx * VEC, t[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (p + u < a1) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], t[u][v], acc[v]);
+          }
+      }
+      if (a.out) {
+        float* o = a.out + (size_t)gr * a.D + qx * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+        else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1 % VEC]);
+        else o[0] = acc[0];
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { su[v] += (double)acc[v]; sq[v] += (double)acc[v] * (double)acc[v]; }
+    }
+  }
+  if (a.st_sum) {
+    for (int v = 0; v < VEC; ++v) {
+      red[threadIdx.x] = su[v];
+      red[256 + threadIdx.x] = sq[v];
+      __syncthreads();
+      if (ry == 0 && qx < nq) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int y2 = 0; y2 < rpb; ++y2) { s1 += red[y2 * QX + qx]; s2 += red[256 + y2 * QX + qx]; }
+        atomicAdd(a.st_sum + qx * VEC + v, s1);
+        atomicAdd(a.st_sq + qx * VEC + v, s2);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int launch_agg_stats(const AggArgs& a, cudaStream_t s) {
+  if (a.n_rows <= 0) return GNNFP_OK;
+  auto al = [&](const void* p, int m) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+  int vec = 1;
+  if (a.D % 4 == 0 && a.ld % 4 == 0 && al(a.S, 16) && al(a.out, 16)) vec = 4;
+  else if (a.D % 2 == 0 && a.ld % 2 == 0 && al(a.S, 8) && al(a.out, 8)) vec = 2;
+  const int nq = a.D / vec;
+  if (nq > 256) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "state width %d too large for the aggregation kernel", a.D);
+  int QX = 1;
+  while (QX < nq) QX *= 2;
+  const int rpb = 256 / QX;
+  long long blocks = ((long long)a.n_rows + rpb - 1) / rpb;
+  const long long cap = (long long)gnnfp_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  ProfScope ps(PC_PASS, s);
+  if (vec == 4) agg_stats_kernel<4><<<(int)blocks, 256, 0, s>>>(a, QX);
+  else if (vec == 2) agg_stats_kernel<2><<<(int)blocks, 256, 0, s>>>(a, QX);
+  else agg_stats_kernel<1><<<(int)blocks, 256, 0, s>>>(a, QX);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tile geometry + launch
 // ------------------------------------------------------------------------------------------------
 static size_t fwd_smem_bytes(const NetDev& net, int R, int XS0, int XS1, int cap) {

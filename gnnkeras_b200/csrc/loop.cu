@@ -386,11 +386,13 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     }
     w.bn_part = off; off = align_up(off + (size_t)L->grid_cap * 2 * din_max * sizeof(float));
     w.bn_const = off; off = align_up(off + (size_t)4 * din_max * sizeof(float));
+    w.bn_const_t = off; off = align_up(off + (size_t)(MI + 2) * 4 * din_max * sizeof(float));
     w.bwd_zero = off;
     w.dXs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float) * (cfg->want_input_grads ? 1 : 0) + 4);
     w.part_state = off; off = align_up(off + (size_t)L->grid_cap * ps * sizeof(float));
     w.part_out = off; off = align_up(off + (size_t)L->grid_cap * L->nparam_o * sizeof(float));
     w.bn_grad = off; off = align_up(off + bg * sizeof(float));
+    w.bn_static = off; off = align_up(off + (size_t)2 * din_max * sizeof(float));
     w.bwd_zero_bytes = off - w.bwd_zero;
   }
   w.total = off;
@@ -496,18 +498,19 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
   for (int t = 1; t <= MI; ++t) {
     const int* gate = c.flags() + (t - 1);
     if (L->bn_train_state) {
-      for (int ty = 0; ty < L->nt; ++ty) {   // batch statistics of Adj^T.state
-        PassArgs pa;
-        memset(&pa, 0, sizeof(pa));
-        set_rows(L, ty, pa.src);
-        pa.src.in_dim = D;
-        add_piece(pa.src, mk_gather(c.S(t - 1), c.ldS(t - 1), D, 0, g->dst_rowptr, g->dst_src, wgt, g->A));
-        pa.st_sum = c.stA(ty, t - 1); pa.st_sq = pa.st_sum + D;
-        pa.out = c.AGG(t); pa.ld_out = D;            // saved for this iteration's net_state and for the backward
-        pa.gate = gate;
-        pa.tc.cap_per_row = L->cap_per_row;
-      if ((rc = tile_cfg_pass(D, pa.src.n_rows, &pa.tc))) return rc;
-        if ((rc = launch_tile_pass(pa, s))) return rc;
+      for (int ty = 0; ty < L->nt; ++ty) {   // Adj^T.state of this iteration: saved + batch statistics
+        AggArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        TileSrc rows;
+        memset(&rows, 0, sizeof(rows));
+        set_rows(L, ty, rows);
+        aa.n_rows = rows.n_rows; aa.rowlist = rows.rowlist; aa.D = D;
+        aa.S = c.S(t - 1); aa.ld = c.ldS(t - 1);
+        aa.rowptr = g->dst_rowptr; aa.idx = g->dst_src; aa.wgt = wgt;
+        aa.out = c.AGG(t);
+        aa.st_sum = c.stA(ty, t - 1); aa.st_sq = aa.st_sum + D;
+        aa.gate = gate;
+        if ((rc = launch_agg_stats(aa, s))) return rc;
       }
     }
     for (int ty = 0; ty < L->nt; ++ty) {

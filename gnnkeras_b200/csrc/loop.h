@@ -13,6 +13,7 @@ struct WsLayout {
   // backward
   size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0, dz = 0;
   size_t part_state = 0, part_out = 0, bn_part = 0, bn_const = 0, bn_grad = 0;
+  size_t bn_const_t = 0, bn_static = 0;     // per-iteration BN constants, running static-column sums
   size_t bwd_zero = 0, bwd_zero_bytes = 0;   // region zeroed at the start of every backward
   size_t total = 0;
 };
@@ -74,6 +75,6 @@ void build_out_src(const Ctx& c, TileSrc& ts);
 void fill_netdev(const gnnfp_net_desc& d, const gnnfp_net_params& p, int training, int n_rows, NetDev& nd);
 int check_io(const gnnfp_loop* L, const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes);
 int check_params(const gnnfp_net_desc& d, const gnnfp_net_params& p, const char* what);
-int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream_t s);
+int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream_t s, int no_fix = 0, float* static_acc = nullptr);
 int launch_reduce_params(const NetDev& net, const float* partial, int grid, int n_params, const float* bn_grad,
                          const gnnfp_net_params& d, const int* flags, int max_iter, int average, cudaStream_t s);

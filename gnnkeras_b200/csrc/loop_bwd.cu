@@ -22,6 +22,9 @@ struct InGradArgs {
   const int* src_rowptr; const int* src_dst; const float* src_w;
   float* d_nodes; float* d_state0;
   int want;
+  // inline BN-training correction (homogeneous single-layer nets): constants of iteration 1 and static sums
+  const float* cn; const float* csum; int in_dim;
+  const float* s0; int ld0; const float* agg1; const float* Xs;
 };
 static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a) {
   const int W = a.D > a.NLw ? a.D : a.NLw;
@@ -34,7 +37,15 @@ static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a)
       float g0;
       if (ran) {
         g0 = a.dOwn1[(size_t)i * a.D + j];
-        for (int p = a0; p < a1; ++p) g0 = fmaf(a.src_w ? a.src_w[p] : 1.0f, a.dAgg1[(size_t)a.src_dst[p] * a.D + j], g0);
+        const float* cn = a.cn;
+        const int in = a.in_dim, ac = a.D + a.NLp + j;
+        if (cn) g0 -= cn[j] + fmaf(a.s0[(size_t)i * a.ld0 + j], cn[2 * in + j], cn[3 * in + j]) * cn[in + j];
+        for (int p = a0; p < a1; ++p) {
+          const size_t so = (size_t)a.src_dst[p] * a.D + j;
+          float tv = a.dAgg1[so];
+          if (cn) tv -= cn[ac] + fmaf(a.agg1[so], cn[2 * in + ac], cn[3 * in + ac]) * cn[in + ac];
+          g0 = fmaf(a.src_w ? a.src_w[p] : 1.0f, tv, g0);
+        }
       } else {
         g0 = a.dSfin[(size_t)i * a.D + j];
       }
@@ -45,8 +56,16 @@ static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a)
       float g = 0.f;
       if (!a.composite) {
         if (a.NLp) {   // own-label columns + Adj . d(agg_nodes)
+          const bool fixs = a.cn != nullptr && ran;
+          const int in = a.in_dim, ic0 = a.D + j, ic1 = 2 * a.D + a.NLp + j;      // input columns of Xs[:, j] and Xs[:, NLp + j]
           g = a.dXs[(size_t)i * a.LsM + j];
-          for (int p = a0; p < a1; ++p) g = fmaf(a.src_w ? a.src_w[p] : 1.0f, a.dXs[(size_t)a.src_dst[p] * a.LsM + a.NLp + j], g);
+          if (fixs) g -= a.csum[ic0] + fmaf(a.Xs[(size_t)i * a.LsM + j], a.cn[2 * in + ic0], a.cn[3 * in + ic0]) * a.csum[in + ic0];
+          for (int p = a0; p < a1; ++p) {
+            const size_t so = (size_t)a.src_dst[p] * a.LsM + a.NLp + j;
+            float tv = a.dXs[so];
+            if (fixs) tv -= a.csum[ic1] + fmaf(a.Xs[so], a.cn[2 * in + ic1], a.cn[3 * in + ic1]) * a.csum[in + ic1];
+            g = fmaf(a.src_w ? a.src_w[p] : 1.0f, tv, g);
+          }
         }
       } else {
         for (int t = 0; t < a.nt; ++t) {
@@ -61,11 +80,19 @@ static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a)
 }
 // d_arc_labels[a] += v_a * d(agg_arcs)[dst_a]   (ArcNode . dInp[:, agg_arcs cols])
 static __global__ void k_input_grads_arcs(int A, int AL, int LsM, int col0, const int* dst, const float* val,
-                                          const float* dXs, float* d_arcs) {
+                                          const float* dXs, float* d_arcs, const float* cn, const float* csum,
+                                          int in_dim, int in_col0, const float* Xs, const int* flags) {
   const size_t total = (size_t)A * AL;
+  const bool fixs = cn != nullptr && flags[0] != 0;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int ar = (int)(e / AL), c = (int)(e - (size_t)ar * AL);
-    d_arcs[e] += val[ar] * dXs[(size_t)dst[ar] * LsM + col0 + c];
+    const size_t so = (size_t)dst[ar] * LsM + col0 + c;
+    float tv = dXs[so];
+    if (fixs) {
+      const int ic = in_col0 + c;
+      tv -= csum[ic] + fmaf(Xs[so], cn[2 * in_dim + ic], cn[3 * in_dim + ic]) * csum[in_dim + ic];
+    }
+    d_arcs[e] += val[ar] * tv;
   }
 }
 
@@ -110,6 +137,10 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
   float* bn_part = (float*)(c.ws + L->ws.bn_part);
   float* bn_const = (float*)(c.ws + L->ws.bn_const);
   float* bn_grad = (float*)(c.ws + L->ws.bn_grad);
+  float* bn_static = (float*)(c.ws + L->ws.bn_static);
+  int din_max_ = L->onet.in_dim;
+  for (int t = 0; t < L->nt; ++t) din_max_ = L->snet[t].in_dim > din_max_ ? L->snet[t].in_dim : din_max_;
+  auto cn_t = [&](int t) { return (float*)(c.ws + L->ws.bn_const_t) + (size_t)t * 4 * din_max_; };
   const float* src_w = g->mode == GNNFP_AGG_SUM ? nullptr : g->src_w;
 
   GNNFP_CHECK_CUDA(cudaMemsetAsync(c.ws + L->ws.bwd_zero, 0, L->ws.bwd_zero_bytes, s));
@@ -240,6 +271,11 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
         da.rowptr = g->src_rowptr; da.idx = g->src_dst; da.wgt = src_w;
         da.last_flag = t < MI ? c.flags() + t : nullptr; da.always_last = t == MI;
         da.dz = dzbuf; da.gate = gate;
+        const bool inline_bn = L->snet[ty].has_bn && !L->composite;
+        if (inline_bn && t < MI) {
+          da.cn = cn_t(t + 1); da.agg_next = c.AGG(t + 1); da.in_dim = L->snet[ty].in_dim;
+          da.own_col0 = 0; da.agg_col0 = D + NLp;
+        }
         if ((rc = launch_dz(da, s))) return rc;
         if (L->snet[ty].has_bn)
           GNNFP_CHECK_CUDA(cudaMemsetAsync(bn_part, 0, (size_t)L->grid_cap * 2 * L->snet[ty].in_dim * sizeof(float), s));
@@ -302,7 +338,12 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
         if ((rc = launch_tile_bwd(ba, s))) return rc;
         last_ba = ba;
       }
-      if (L->snet[ty].has_bn && (rc = launch_bn_tail(last_ba, bn_grad + bg_off[ty], bn_const, s))) return rc;
+      if (L->snet[ty].has_bn) {
+        const bool inline_bn = dzpath[ty] && !L->composite;
+        if (inline_bn) rc = launch_bn_tail(last_ba, bn_grad + bg_off[ty], cn_t(t), s, 1, want ? bn_static : nullptr);
+        else rc = launch_bn_tail(last_ba, bn_grad + bg_off[ty], bn_const, s);
+        if (rc) return rc;
+      }
     }
   }
 
@@ -320,6 +361,10 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     ia.d_nodes = (want & 1) ? gr->d_nodes : nullptr;
     ia.d_state0 = ((want & 4) && L->S > 0) ? gr->d_state0 : nullptr;
     ia.want = want;
+    if (!L->composite && dzpath[0] && L->snet[0].has_bn) {
+      ia.cn = cn_t(1); ia.csum = bn_static; ia.in_dim = L->snet[0].in_dim;
+      ia.s0 = c.S(0); ia.ld0 = c.ldS(0); ia.agg1 = MI > 0 ? c.AGG(1) : nullptr; ia.Xs = c.Xs();
+    }
     const size_t tot = (size_t)N * (D > L->NLw ? D : L->NLw);
     int blocks = (int)((tot + 255) / 256);
     if (blocks > 4736) blocks = 4736;
@@ -332,7 +377,8 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
       const size_t ta = (size_t)L->A * L->AL;
       int b2 = (int)((ta + 255) / 256);
       if (b2 > 4736) b2 = 4736;
-      k_input_grads_arcs<<<b2, 256, 0, s>>>(L->A, L->AL, L->LsM, col0, g->dst, g->arc_val, dXs, gr->d_arc_labels);
+      k_input_grads_arcs<<<b2, 256, 0, s>>>(L->A, L->AL, L->LsM, col0, g->dst, g->arc_val, dXs, gr->d_arc_labels,
+                                            ia.cn, ia.csum, ia.in_dim, 2 * D + col0, c.Xs(), c.flags());
       GNNFP_COUNT_LAUNCH();
     }
   }
