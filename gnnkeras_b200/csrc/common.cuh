@@ -34,6 +34,14 @@ extern long long g_gnnfp_launches;
 // optional per-category kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
 enum { PC_OTHER = 0, PC_FWD_ITER = 1, PC_BWD_ITER = 2, PC_PASS = 3, PC_FWD_OUT = 4, PC_BWD_OUT = 5, PC_BNFIX = 6,
        PC_COUNT = 8 };
+// optional per-phase cycle counters inside the tile kernels (debug; thread 0 of every CTA, clock64)
+#ifdef GNNFP_PHASE_TIMING
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd((unsigned long long*)&g_phase_cycles[i], (unsigned long long)(_t - _pt)); _pt = _t; } } while (0)
+#define PHASE_INIT() long long _pt = clock64()
+#else
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_INIT() do { } while (0)
+#endif
 extern int g_gnnfp_prof;
 void gnnfp_prof_begin(int cat, cudaStream_t s);
 void gnnfp_prof_end(cudaStream_t s);
@@ -109,6 +117,10 @@ struct TileCfg {
   int cap;                 // arcs of one tile the CSR scratch can hold (fast gather path)
   int cap_per_row;         // in: scratch capacity per tile row (0 = default 4), set by the caller from A/N
   int dz_ready;            // in (backward): the launch consumes a precomputed dz (no saved-output tile)
+  int raw_per_row;         // in: floats per tile row of the TMA bulk-copy landing buffer (0 = synchronous staging only)
+  unsigned bulk_src, bulk_g; // in: bit p set = piece p of src / gsrc is staged by cp.async.bulk (full tiles)
+  unsigned bulk_out;       // in (backward): bit p set = gradient of src piece p leaves through a bulk store
+  int out_per_row;         // in: floats per tile row of the bulk-store staging buffer
   int threads;
   size_t smem_bytes;
   int grid;

@@ -15,6 +15,15 @@
 // dx -= a_c * (mean(dy) + x~ * mean(dy x~)).
 #include "tile.cuh"
 
+#ifdef GNNFP_PHASE_TIMING
+__device__ long long g_phase_cycles[32];
+extern "C" int gnnfp_debug_phases(long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(long long) * 32);
+  if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 struct BwdLayout {
   int L, recompute, bn;
   int inw[GNNFP_MAX_LAYERS + 1];    // width of activation l (0 = input)
@@ -24,11 +33,11 @@ struct BwdLayout {
   int groups[GNNFP_MAX_LAYERS];
   int oWT[GNNFP_MAX_LAYERS], oWf[GNNFP_MAX_LAYERS], obf[GNNFP_MAX_LAYERS], oAct[GNNFP_MAX_LAYERS + 1];
   int oAccW[GNNFP_MAX_LAYERS], oAccb[GNNFP_MAX_LAYERS];
-  int obnA, obnB, obnS, oZero, odzA, odzB, oAccBN, oScr;
+  int obnA, obnB, obnS, oZero, odzA, odzB, oAccBN, oScr, oRaw, oBar, oOutRaw;
   int total;   // floats
 };
 
-__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int regacc, int cap, int dz_ready, BwdLayout& y) {
+__host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int regacc, int cap, int dz_ready, int raw_per_row, int out_per_row, BwdLayout& y) {
   y.L = net.n_layers;
   y.regacc = regacc;
   y.recompute = net.n_layers > 1;
@@ -68,6 +77,9 @@ __host__ __device__ inline void bwd_layout(const NetDev& net, int R, int T, int 
   for (int l = 0; l <= y.L; ++l) { y.oAct[l] = o; o += (dz_ready && l == y.L) ? 0 : R * y.XSa[l]; }   // dz path: the saved output is not needed
   y.odzA = o; o += R * y.XSdA;
   y.odzB = o; o += R * y.XSdB;
+  y.oBar = o; o += 4;                                   // one 8-byte mbarrier (16-byte slot)
+  y.oRaw = o; o += ceil_to(R * raw_per_row, 4);         // landing buffer of the bulk copies
+  y.oOutRaw = o; o += ceil_to(R * out_per_row, 4);      // staging buffer of the bulk stores
   y.total = o;
 }
 
@@ -81,7 +93,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
   const int lane = tid & 31, warp = tid >> 5;
   const int rg = warp % tc.RG, cg = warp / tc.RG;
   __shared__ BwdLayout y;
-  if (tid == 0) bwd_layout(net, tc.R, T, REGACC ? 1 : 0, tc.cap, a.dz_ready, y);
+  if (tid == 0) bwd_layout(net, tc.R, T, REGACC ? 1 : 0, tc.cap, a.dz_ready, tc.raw_per_row, tc.out_per_row, y);
   __syncthreads();
   const int L = y.L;
   float racc[2][8][4];
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
   }
   for (int c = tid; c < 2 * ceil_to(net.in_dim, 4); c += T) accBN[c] = 0.0f;
   for (int c = tid; c < y.oScr - y.oZero; c += T) zero[c] = 0.0f;
-  for (int c = tid; c < y.total - y.oAct[0]; c += T) smem[y.oAct[0] + c] = 0.0f;   // activation + dz tiles
+  for (int c = tid; c < y.oBar - y.oAct[0]; c += T) smem[y.oAct[0] + c] = 0.0f;   // activation + dz tiles
   if (y.bn)
     for (int c = tid; c < net.in_dim; c += T) bnS[c] = net.gamma[c] * bnA[c];
   __syncthreads();
@@ -152,11 +164,37 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
 
   const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int tile_end = min(n_tiles, ((int)blockIdx.x + 1) * tiles_per_cta);
+  PHASE_INIT();
+  const bool use_bulk = tc.raw_per_row > 0;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + y.oBar);
+  float* raw = smem + y.oRaw;
+  uint32_t bar_phase = 0;
+  if (use_bulk) {
+    if (tid == 0) { mbar_init(bar, 1); fence_proxy_async(); }
+    __syncthreads();
+    const int t0 = blockIdx.x * tiles_per_cta;
+    if (tid == 0 && t0 < tile_end && n - t0 * tc.R >= tc.R) {
+      mbar_expect_tx(bar, bulk_bytes(a.src, tc.bulk_src, tc.R) + bulk_bytes(a.gsrc, tc.bulk_g, tc.R));
+      float* rp = bulk_issue(a.src, tc.bulk_src, t0 * tc.R, tc.R, raw, bar);
+      bulk_issue(a.gsrc, tc.bulk_g, t0 * tc.R, tc.R, rp, bar);
+    }
+  }
   for (int tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
     const int row0 = tile * tc.R;
     const int nr = min(tc.R, n - row0);
-    stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], sc);
-    stage_tile(a.gsrc, row0, nr, tc.R, dzA, XSdA, sc);
+    PHASE_MARK(0);
+    if (use_bulk && nr == tc.R) {
+      mbar_wait(bar, bar_phase);
+      bar_phase ^= 1u;
+      const float* rp = bulk_relayout(a.src, tc.bulk_src, tc.R, raw, smem + y.oAct[0], y.XSa[0]);
+      bulk_relayout(a.gsrc, tc.bulk_g, tc.R, rp, dzA, XSdA);
+      stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], sc, true, tc.bulk_src);
+      stage_tile(a.gsrc, row0, nr, tc.R, dzA, XSdA, sc, true, tc.bulk_g);
+    } else {
+      stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], sc);
+      stage_tile(a.gsrc, row0, nr, tc.R, dzA, XSdA, sc);
+    }
+    PHASE_MARK(1);
     if (!y.recompute && !a.dz_ready) {
       TileSrc so;
       so.n_rows = a.src.n_rows; so.rowlist = a.saved_compact ? nullptr : a.src.rowlist; so.n_pieces = 1; so.in_dim = HL;
@@ -167,6 +205,13 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       stage_tile(so, row0, nr, tc.R, smem + y.oAct[L], y.XSa[L], sc);
     }
     __syncthreads();
+    if (use_bulk && tid == 0 && tile + 1 < tile_end && n - (tile + 1) * tc.R >= tc.R) {
+      fence_proxy_async();                    // landing buffer: generic-proxy reads above, async-proxy writes below
+      mbar_expect_tx(bar, bulk_bytes(a.src, tc.bulk_src, tc.R) + bulk_bytes(a.gsrc, tc.bulk_g, tc.R));
+      float* rp = bulk_issue(a.src, tc.bulk_src, (tile + 1) * tc.R, tc.R, raw, bar);
+      bulk_issue(a.gsrc, tc.bulk_g, (tile + 1) * tc.R, tc.R, rp, bar);
+    }
+    PHASE_MARK(2);
     if (y.recompute) {
       for (int l = 0; l < L; ++l) {
         const int Hpad = ceil_to(y.inw[l + 1], 16);
@@ -214,6 +259,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       }
     }
     __syncthreads();
+    PHASE_MARK(3);
     float* cur = dzA;
     float* oth = dzB;
     int XSc = XSdA, XSo = XSdB;
@@ -291,13 +337,16 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           }
         }
       }
+      PHASE_MARK(4);
       // (b) dprev = dz . W_l^T
       {
         const int inpad = ceil_to(in_l, 16);
         if (cg < inpad / GNNFP_JC)
           dense_tile(cur, XSc, oth, XSo, smem + y.oWT[l], zero, (H + 3) / 4, inpad, GNNFP_ACT_LINEAR, rg, cg, tc.CG, lane);
       }
+      PHASE_MARK(5);
       __syncthreads();
+      PHASE_MARK(6);
       if (l > 0) {
         const int actp = net.acts[l - 1];
         const unsigned magic = (unsigned)((0x100000000ull + (unsigned)in_l - 1) / (unsigned)in_l);
@@ -313,6 +362,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       const int t3 = XSc; XSc = XSo; XSo = t3;
     }
     // ---- cur = dy (gradient w.r.t. the BN output / the raw input) ---------------------------------
+    PHASE_MARK(7);
     if (y.bn) {   // P_c = sum dy, Qraw_c = sum dy * x  (all threads: column x row group)
       const float* a0 = smem + y.oAct[0];
       const int pin = ceil_to(net.in_dim, 4), ind = net.in_dim, XS0 = y.XSa[0];
@@ -341,9 +391,51 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         }
       }
     }
+    PHASE_MARK(8);
+    const bool bulk_out = tc.bulk_out != 0u && nr == tc.R;
+    if (bulk_out) {
+      // dense staging buffer <- scaled dy columns of every bulk-stored piece; one bulk store per piece
+      if (tid == 0) bulk_wait_read0();              // the previous tile's stores have finished reading the buffer
+      __syncthreads();
+      float* ob = smem + y.oOutRaw;
+      for (int p = 0; p < a.src.n_pieces; ++p) {
+        if (!(tc.bulk_out & (1u << p))) continue;
+        const Piece& pc = a.src.p[p];
+        const int w = pc.width, n4 = tc.R * w / 4;
+        float4* o4 = reinterpret_cast<float4*>(ob);
+#pragma unroll 2
+        for (int i = tid; i < n4; i += T) {
+          int r = (int)__umulhi((unsigned)(4 * i), pc.magic);
+          int c = 4 * i - r * w;
+          float vv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float v = cur[r * XSc + pc.col0 + c];
+            if (y.bn) v *= bnS[pc.col0 + c];
+            vv[k] = v;
+            if (++c == w) { c = 0; ++r; }
+          }
+          o4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        }
+        ob += tc.R * w;
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        const float* ob2 = smem + y.oOutRaw;
+        for (int p = 0; p < a.src.n_pieces; ++p) {
+          if (!(tc.bulk_out & (1u << p))) continue;
+          const Piece& pc = a.src.p[p];
+          bulk_s2g(pc.gptr + (size_t)row0 * pc.width, ob2, (uint32_t)tc.R * pc.width * 4u);
+          ob2 += tc.R * pc.width;
+        }
+        bulk_commit();
+      }
+    }
     for (int p = 0; p < a.src.n_pieces; ++p) {
       const Piece& pc = a.src.p[p];
       if (pc.gmode == GM_NONE) continue;
+      if (bulk_out && (tc.bulk_out & (1u << p))) continue;
       const int w = pc.width;
       for (int e0 = tid; e0 < nr * w; e0 += 4 * T) {
         float v[4], old[4];
@@ -372,8 +464,11 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           }
       }
     }
+    PHASE_MARK(9);
     __syncthreads();
+    PHASE_MARK(10);
   }
+  if (tc.bulk_out != 0u && tid == 0) bulk_wait0();
   // ---- flush per-CTA accumulators to this CTA's partial slot (plain +=: the slot is private) ----
   // With BN the layer-0 accumulators were taken on RAW inputs x; the gradient w.r.t. the Dense kernel is
   //   dW0[c][j] = sum x_hat dz = gamma_c*(rstd_c*acc[c][j] - mean_c*rstd_c*db[j]) + beta_c*db[j]
@@ -446,20 +541,38 @@ struct BnReduceArgs {
   float* static_acc;  // optional [2*in_dim]: running sums of c0, c1 over the iterations (static columns)
   const int* gate;
 };
-__global__ void bn_reduce_kernel(const __grid_constant__ BnReduceArgs a) {
+// one block per 32 columns: thread (cx, gy) sums partial rows gy, gy+8, ... of column cx (4 loads in flight),
+// shared-memory reduction over gy in fixed order (deterministic).
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ BnReduceArgs a) {
   if (a.gate && *a.gate == 0) return;
   extern __shared__ float sm[];
+  __shared__ double redp[8][32], redq[8][32];
   const int in = a.net.in_dim;
   float* A = sm;
   float* Bc = sm + in;
   bn_coefficients(a.src, a.net, 0, A, Bc, nullptr, nullptr);
-  __syncthreads();
-  for (int c = threadIdx.x; c < in; c += blockDim.x) {
-    double p = 0.0, q = 0.0;
-    for (int b = 0; b < a.grid; ++b) {
-      p += (double)a.bn_partial[(size_t)b * 2 * in + c];
-      q += (double)a.bn_partial[(size_t)b * 2 * in + in + c];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double p = 0.0, q = 0.0;
+  if (c < in) {
+    for (int b0 = gy; b0 < a.grid; b0 += 32) {
+      float pv[4], qv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = b0 + 8 * u;
+        pv[u] = b < a.grid ? a.bn_partial[(size_t)b * 2 * in + c] : 0.f;
+        qv[u] = b < a.grid ? a.bn_partial[(size_t)b * 2 * in + in + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { p += (double)pv[u]; q += (double)qv[u]; }
     }
+  }
+  redp[gy][cx] = p;
+  redq[gy][cx] = q;
+  __syncthreads();
+  if (gy == 0 && c < in) {
+    p = 0.0; q = 0.0;
+    for (int g2 = 0; g2 < 8; ++g2) { p += redp[g2][cx]; q += redq[g2][cx]; }
     a.bn_grad[c] += (float)q;
     a.bn_grad[in + c] += (float)p;
     const float ac = a.net.gamma[c] * A[c];
@@ -688,7 +801,7 @@ int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc) {
   const int cap_per_row = tc->cap_per_row > 0 ? tc->cap_per_row : 4;
   int regacc = 0;
   for (;;) {
-    bwd_layout(net, 64 * RG, 256, 0, 64 * RG * cap_per_row, dzr, y);
+    bwd_layout(net, 64 * RG, 256, 0, 64 * RG * cap_per_row, dzr, tc->raw_per_row, tc->out_per_row, y);
     const bool too_big = (size_t)y.total * 4 > want;
     const bool underfill = (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm;
     if (RG > 1 && (too_big || underfill)) { RG /= 2; CG = 8 / RG; continue; }
@@ -701,7 +814,7 @@ int tile_cfg_bwd(const NetDev& net, int n_rows, int gwidth, TileCfg* tc) {
       regacc = 1;
       RG = 8 / CG;
       for (;;) {
-        bwd_layout(net, 64 * RG, 256, 1, 64 * RG * cap_per_row, dzr, y);
+        bwd_layout(net, 64 * RG, 256, 1, 64 * RG * cap_per_row, dzr, tc->raw_per_row, tc->out_per_row, y);
         const bool too_big = (size_t)y.total * 4 > want;
         const bool underfill = (n_rows + 64 * RG - 1) / (64 * RG) < 2 * nsm;
         if (RG > 1 && (too_big || underfill)) { RG /= 2; CG = 8 / RG; continue; }
@@ -748,7 +861,7 @@ int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream
   memset(&ra, 0, sizeof(ra));
   ra.src = a.src; ra.net = a.net; ra.bn_partial = a.bn_partial; ra.grid = a.tc.grid;
   ra.bn_grad = bn_grad; ra.bn_const = bn_const; ra.gate = a.gate; ra.static_acc = static_acc;
-  bn_reduce_kernel<<<1, 256, 2 * a.net.in_dim * sizeof(float), s>>>(ra);
+  bn_reduce_kernel<<<(a.net.in_dim + 31) / 32, 256, 2 * a.net.in_dim * sizeof(float), s>>>(ra);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   if (a.net.bn_mode != 1 || no_fix) return GNNFP_OK;

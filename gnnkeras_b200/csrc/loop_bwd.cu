@@ -230,16 +230,34 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     if (tile_cfg_bwd(nd, probe.n_rows > 0 ? probe.n_rows : 1, D, &tcf) != GNNFP_OK || tcf.smem_bytes > 110 * 1024)
       want_splits = probe.n_pieces >= 2 ? 2 : 1;
     if (d.in_dim > 384 && probe.n_pieces >= 3) want_splits = 3;
-    // greedy cut at piece boundaries
-    const int target = (d.in_dim + want_splits - 1) / want_splits;
-    int ns = 0, p0 = 0, acc = 0, coff = 0;
-    for (int p = 0; p < probe.n_pieces; ++p) {
-      acc += probe.p[p].width;
-      const bool lastp = p == probe.n_pieces - 1;
-      if (lastp || (acc >= target && ns < want_splits - 1)) {
-        splits[ty][ns++] = Split{p0, p + 1, coff, acc};
-        coff += acc; acc = 0; p0 = p + 1;
+    // cut at piece boundaries so that the widest split is as narrow as possible (<= 3 splits: brute force)
+    int pref[GNNFP_MAXP + 1];
+    pref[0] = 0;
+    for (int p = 0; p < probe.n_pieces; ++p) pref[p + 1] = pref[p] + probe.p[p].width;
+    const int np = probe.n_pieces;
+    int best_a = np, best_b = np, best_w = d.in_dim + 1;
+    if (want_splits == 1) { best_a = np; best_b = np; best_w = d.in_dim; }
+    else {
+      for (int ca = 1; ca < np; ++ca) {
+        if (want_splits == 2) {
+          const int w1 = pref[ca], w2 = pref[np] - pref[ca];
+          const int mw = w1 > w2 ? w1 : w2;
+          if (mw < best_w) { best_w = mw; best_a = ca; best_b = np; }
+        } else {
+          for (int cb = ca + 1; cb < np; ++cb) {
+            int mw = pref[ca];
+            if (pref[cb] - pref[ca] > mw) mw = pref[cb] - pref[ca];
+            if (pref[np] - pref[cb] > mw) mw = pref[np] - pref[cb];
+            if (mw < best_w) { best_w = mw; best_a = ca; best_b = cb; }
+          }
+        }
       }
+    }
+    int ns = 0;
+    const int cuts[4] = {0, best_a, best_b, np};
+    for (int k2 = 0; k2 < 3; ++k2) {
+      if (cuts[k2] >= cuts[k2 + 1]) continue;
+      splits[ty][ns++] = Split{cuts[k2], cuts[k2 + 1], pref[cuts[k2]], pref[cuts[k2 + 1]] - pref[cuts[k2]]};
     }
     nsplit[ty] = ns;
   }
@@ -295,6 +313,23 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
                               ba.net.mmean = ndfull.mmean + sp_.c_off; ba.net.mvar = ndfull.mvar + sp_.c_off; }
           ba.tc.cap_per_row = L->cap_per_row;
           ba.tc.dz_ready = 1;
+          // pieces that can be fetched by TMA bulk copies: plain contiguous 16-byte aligned matrices
+          auto eligible = [&](const TileSrc& ts2, const Piece& pc) {
+            return ts2.rowlist == nullptr && pc.kind == PK_DIRECT && !pc.map && !pc.rowscale && !pc.compact && !pc.gate &&
+                   pc.ld == pc.width && (reinterpret_cast<uintptr_t>(pc.ptr) & 15) == 0;
+          };
+          for (int p = 0; p < ba.src.n_pieces; ++p)
+            if (eligible(ba.src, ba.src.p[p])) { ba.tc.bulk_src |= 1u << p; ba.tc.raw_per_row += ba.src.p[p].width; }
+          if (eligible(ba.gsrc, ba.gsrc.p[0])) { ba.tc.bulk_g = 1u; ba.tc.raw_per_row += D; }
+          for (int p = 0; p < ba.src.n_pieces; ++p) {     // gradients that leave as plain dense matrices: bulk stores
+            const Piece& pc = ba.src.p[p];
+            if (ba.src.rowlist == nullptr && pc.gmode == GM_STORE && !pc.map && pc.gld == pc.width &&
+                (reinterpret_cast<uintptr_t>(pc.gptr) & 15) == 0) { ba.tc.bulk_out |= 1u << p; ba.tc.out_per_row += pc.width; }
+          }
+          if (tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc) != GNNFP_OK) {   // does not fit with both buffers
+            ba.tc.bulk_out = 0u; ba.tc.out_per_row = 0;
+            if (tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc) != GNNFP_OK) { ba.tc.bulk_src = ba.tc.bulk_g = 0u; ba.tc.raw_per_row = 0; }
+          }
           if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc))) return rc;
           if (ba.tc.grid > L->grid_cap) ba.tc.grid = L->grid_cap;
           grid_state[ty] = ba.tc.grid > grid_state[ty] ? ba.tc.grid : grid_state[ty];

@@ -161,12 +161,13 @@ __device__ __forceinline__ void prefetch_range(const void* p, size_t bytes) {
 // CTAs walk CONSECUTIVE tiles, so while staging tile i the data of tile i+1 (the next R rows and the next
 // slice of the CSR) is prefetched into L2: its DRAM latency is then hidden behind tile i's compute.
 __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, int R, float* X, int XS,
-                                           const StageScratch& sc, bool prefetch_next = true) {
+                                           const StageScratch& sc, bool prefetch_next = true, unsigned skip_mask = 0u) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int next0 = row0 + R;
   const int next_nr = prefetch_next ? max(0, min(R, ts.n_rows - next0)) : 0;
   for (int p = 0; p < ts.n_pieces; ++p) {
     const Piece& pc = ts.p[p];
+    if (skip_mask & (1u << p)) continue;      // staged by the asynchronous bulk path
     const bool on = piece_enabled(pc);
     if (pc.accumulate) {
       __syncthreads();          // the piece it adds to may have been staged with another mapping
@@ -299,6 +300,78 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
       }
     }
   }
+}
+
+// ---- asynchronous staging: TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier -----------------------
+// Direct pieces whose tile rows form one contiguous 16-byte aligned run are fetched by ONE bulk copy per piece
+// into a dense landing buffer while the previous tile is being computed; after the mbarrier flips, all threads
+// re-lay the landing buffer into the padded compute tile (shared -> shared, no global latency).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLAB_WAIT%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE%=;\n\tbra LAB_WAIT%=;\n\tDONE%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// thread 0: arm the barrier and issue one bulk copy per selected piece of `ts` (tile rows row0..row0+R, all valid)
+__device__ __forceinline__ uint32_t bulk_bytes(const TileSrc& ts, unsigned mask, int R) {
+  uint32_t b = 0;
+  for (int p = 0; p < ts.n_pieces; ++p)
+    if (mask & (1u << p)) b += (uint32_t)R * ts.p[p].width * 4u;
+  return b;
+}
+__device__ __forceinline__ float* bulk_issue(const TileSrc& ts, unsigned mask, int row0, int R, float* raw, uint64_t* bar) {
+  for (int p = 0; p < ts.n_pieces; ++p)
+    if (mask & (1u << p)) {
+      const Piece& pc = ts.p[p];
+      bulk_g2s(raw, pc.ptr + (size_t)row0 * pc.width, (uint32_t)R * pc.width * 4u, bar);
+      raw += R * pc.width;
+    }
+  return raw;
+}
+// all threads: landing buffer -> compute tile
+__device__ __forceinline__ const float* bulk_relayout(const TileSrc& ts, unsigned mask, int R, const float* raw, float* X, int XS) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int p = 0; p < ts.n_pieces; ++p)
+    if (mask & (1u << p)) {
+      const Piece& pc = ts.p[p];
+      const int w = pc.width, n4 = R * w / 4, c0 = pc.col0;
+      const float4* r4 = reinterpret_cast<const float4*>(raw);
+#pragma unroll 2
+      for (int i = tid; i < n4; i += T) {
+        const float4 v = r4[i];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        int r = (int)__umulhi((unsigned)(4 * i), pc.magic);
+        int c = 4 * i - r * w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float* d = X + r * XS + c0 + c;
+          if (pc.accumulate) *d += vv[k]; else *d = vv[k];
+          if (++c == w) { c = 0; ++r; }
+        }
+      }
+      raw += R * w;
+    }
+  return raw;
 }
 
 // Per-column BN coefficients: x_hat = x*a + b.
