@@ -9,6 +9,8 @@
 //        BN training: bn_reduce + tile_bnfix
 //   3. input gradients (LGNN chaining): d_state0 / d_nodes / d_arc_labels
 //   4. deterministic reduction of the per-CTA partials, optional /k (average_st_grads)
+#include <stdlib.h>
+
 #include "loop.h"
 #include "tile.cuh"
 
@@ -227,9 +229,11 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     memset(&tcf, 0, sizeof(tcf));
     tcf.cap_per_row = L->cap_per_row;
     int want_splits = 1;
-    if (tile_cfg_bwd(nd, probe.n_rows > 0 ? probe.n_rows : 1, D, &tcf) != GNNFP_OK || tcf.smem_bytes > 110 * 1024)
+    // measured on B200 (C2): one launch over all input columns beats column splits whenever it fits shared memory
+    if (tile_cfg_bwd(nd, probe.n_rows > 0 ? probe.n_rows : 1, D, &tcf) != GNNFP_OK)
       want_splits = probe.n_pieces >= 2 ? 2 : 1;
     if (d.in_dim > 384 && probe.n_pieces >= 3) want_splits = 3;
+    if (const char* ev = getenv("GNNFP_BWD_SPLITS")) { const int v = atoi(ev); if (v >= 1 && v <= 3 && v <= probe.n_pieces) want_splits = v; }
     // cut at piece boundaries so that the widest split is as narrow as possible (<= 3 splits: brute force)
     int pref[GNNFP_MAXP + 1];
     pref[0] = 0;
