@@ -49,7 +49,7 @@ class LoopCfg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("pool", C.c_int32), ("state_vect_dim", C.c_int32), ("max_iteration", C.c_int32),
                 ("state_threshold", C.c_float), ("training", C.c_int32), ("n_types", C.c_int32),
                 ("dim_node_label", C.c_int32 * MAX_TYPES), ("nodes_width", C.c_int32), ("arc_label_width", C.c_int32),
-                ("want_input_grads", C.c_int32)]
+                ("want_input_grads", C.c_int32), ("n_active_rows", C.c_int32)]
 
 
 class LoopIO(C.Structure):
@@ -72,7 +72,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnnfp.so
 # every symbol include/gnnfp.h declares
 SYMBOLS = ["gnnfp_last_error", "gnnfp_abi_version", "gnnfp_graph_build", "gnnfp_graph_free", "gnnfp_graph_get_info",
            "gnnfp_graph_export", "gnnfp_loop_create", "gnnfp_loop_free", "gnnfp_loop_workspace_bytes",
-           "gnnfp_loop_out_rows", "gnnfp_loop_state_dim", "gnnfp_loop_forward", "gnnfp_loop_backward",
+           "gnnfp_loop_out_rows", "gnnfp_loop_state_dim", "gnnfp_loop_forward", "gnnfp_loop_forward_begin", "gnnfp_loop_forward_iter",
+           "gnnfp_loop_forward_end", "gnnfp_loop_ws_offsets", "gnnfp_loop_backward",
            "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step",
            "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect"]
 
@@ -102,6 +103,12 @@ def lib():
     L.gnnfp_loop_state_dim.argtypes = [_vp]
     L.gnnfp_loop_forward.argtypes = [_vp, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(LoopIO), _vp,
                                      C.c_size_t, _vp]
+    L.gnnfp_loop_forward_begin.argtypes = L.gnnfp_loop_forward.argtypes
+    L.gnnfp_loop_forward_end.argtypes = L.gnnfp_loop_forward.argtypes
+    L.gnnfp_loop_forward_iter.argtypes = [_vp, C.c_int32, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(LoopIO), _vp,
+                                          C.c_size_t, _vp]
+    L.gnnfp_loop_ws_offsets.argtypes = [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_int32)]
     L.gnnfp_loop_backward.argtypes = [_vp, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(LoopIO),
                                       C.POINTER(LoopGrads), C.POINTER(NetParams), C.POINTER(NetParams), _vp,
                                       C.c_size_t, _vp]

@@ -152,7 +152,7 @@ static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 static void set_rows(const gnnfp_loop* L, int ty, TileSrc& ts) {
   if (L->composite) { ts.n_rows = L->g->type_count[ty]; ts.rowlist = L->g->type_rows[ty]; }
-  else { ts.n_rows = L->N; ts.rowlist = nullptr; }
+  else { ts.n_rows = L->Nact; ts.rowlist = nullptr; }
 }
 
 // input of net_state[ty] at iteration t (1-based): GNN.py:222-231 / CompositeGNN.py:224
@@ -292,6 +292,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   L->N = g->N; L->A = g->A; L->M = g->M;
   L->S = cfg->state_vect_dim; L->NLw = cfg->nodes_width; L->AL = cfg->arc_label_width;
   L->D = L->S > 0 ? L->S : L->NLw;
+  L->Nact = (cfg->n_active_rows > 0 && cfg->n_active_rows < g->N) ? cfg->n_active_rows : g->N;
   int rc = GNNFP_OK;
 #define PLAN_FAIL(code, ...) do { gnnfp_set_error(__VA_ARGS__); delete L; return (code); } while (0)
   if (L->NLw <= 0) PLAN_FAIL(GNNFP_E_INVALID, "loop_create: nodes_width=%d", L->NLw);
@@ -346,6 +347,11 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   for (int t = 0; t < L->nt; ++t)
     if (L->snet[t].has_bn != L->snet[0].has_bn) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "composite: all state nets must agree on BatchNormalization");
   L->bn_train_out = cfg->training && L->onet.has_bn;
+  if (L->Nact < L->N) {
+    if (L->composite) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) loops are homogeneous only");
+    if (cfg->training) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) loops are forward/inference only in this version");
+    if (L->snet[0].has_bn) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) loops do not support BatchNormalization in net_state (global batch statistics)");
+  }
   for (int t = 0; t < L->nt; ++t) L->nparam_s[t] = net_param_count(L->snet[t]);
   L->nparam_o = net_param_count(L->onet);
   { long long cpr = g->N > 0 ? (2ll * g->A + g->N - 1) / g->N : 4; L->cap_per_row = cpr < 4 ? 4 : (cpr > 16 ? 16 : (int)cpr); }
@@ -417,20 +423,16 @@ int check_io(const gnnfp_loop* L, const gnnfp_loop_io* io, void* workspace, size
 }
 
 // ---- forward ---------------------------------------------------------------------------------------
-extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
-                                  const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc;
-  if ((rc = check_io(L, io, workspace, workspace_bytes))) return rc;
-  if (!sp || !op) GNNFP_FAIL(GNNFP_E_INVALID, "loop_forward: parameters missing");
-  for (int t = 0; t < L->nt; ++t) if ((rc = check_params(L->snet[t], sp[t], "net_state"))) return rc;
-  if ((rc = check_params(L->onet, *op, "net_output"))) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  Ctx c{L, io, (char*)workspace, s};
+static int fwd_begin(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_params* op) {
+  cudaStream_t s = c.s;
+  gnnfp_loop* L = c.L;
+  const gnnfp_loop_io* io = c.io;
   const gnnfp_graph* g = L->g;
   const int MI = L->cfg.max_iteration, D = L->D, N = L->N;
   const int training = L->cfg.training;
   const float* wgt = g->mode == GNNFP_AGG_SUM ? nullptr : g->dst_w;
-
+  int rc = GNNFP_OK;
+  (void)MI; (void)D; (void)N; (void)training; (void)wgt; (void)io; (void)op; (void)sp;
   GNNFP_CHECK_CUDA(cudaMemsetAsync(c.ws + L->ws.ctrl, 0, L->ws.ctrl_bytes, s));
 
   // ---- prologue: loop-invariant aggregates (GNN.py:254-258, CompositeGNN.py:251-253) -----------
@@ -477,8 +479,8 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
   }
   // ---- condition before the first iteration ------------------------------------------------------
   {
-    const int blocks = (N + 255) / 256 < 1184 ? (N + 255) / 256 : 1184;
-    k_cond0<<<blocks, 256, 0, s>>>(c.S(0), c.ldS(0), N, D, L->cfg.state_threshold, MI, c.flags());
+    const int blocks = (L->Nact + 255) / 256 < 1184 ? (L->Nact + 255) / 256 : 1184;
+    k_cond0<<<blocks, 256, 0, s>>>(c.S(0), c.ldS(0), L->Nact, D, L->cfg.state_threshold, MI, c.flags());
     GNNFP_COUNT_LAUNCH();
   }
   if (L->bn_train_state && MI > 0) {   // statistics of S_0 per type
@@ -494,8 +496,22 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       if ((rc = launch_tile_pass(pa, s))) return rc;
     }
   }
-  // ---- the fixed-point iterations (GNN.py:265) -----------------------------------------------------
-  for (int t = 1; t <= MI; ++t) {
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return rc;
+}
+
+// iteration t (1-based), gated on the device flag written by iteration t-1 (GNN.py:265)
+static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp_net_params* op) {
+  cudaStream_t s = c.s;
+  gnnfp_loop* L = c.L;
+  const gnnfp_loop_io* io = c.io;
+  const gnnfp_graph* g = L->g;
+  const int MI = L->cfg.max_iteration, D = L->D, N = L->N;
+  const int training = L->cfg.training;
+  const float* wgt = g->mode == GNNFP_AGG_SUM ? nullptr : g->dst_w;
+  int rc = GNNFP_OK;
+  (void)MI; (void)D; (void)N; (void)training; (void)wgt; (void)io; (void)op; (void)sp;
+  {
     const int* gate = c.flags() + (t - 1);
     if (L->bn_train_state) {
       for (int ty = 0; ty < L->nt; ++ty) {   // Adj^T.state of this iteration: saved + batch statistics
@@ -535,6 +551,20 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       if ((rc = launch_tile_fwd(fa, s))) return rc;
     }
   }
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return rc;
+}
+
+static int fwd_end(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_params* op) {
+  cudaStream_t s = c.s;
+  gnnfp_loop* L = c.L;
+  const gnnfp_loop_io* io = c.io;
+  const gnnfp_graph* g = L->g;
+  const int MI = L->cfg.max_iteration, D = L->D, N = L->N;
+  const int training = L->cfg.training;
+  const float* wgt = g->mode == GNNFP_AGG_SUM ? nullptr : g->dst_w;
+  int rc = GNNFP_OK;
+  (void)MI; (void)D; (void)N; (void)training; (void)wgt; (void)io; (void)op; (void)sp;
   // ---- converged state, iteration count --------------------------------------------------------------
   {
     const size_t total = (size_t)N * D;
@@ -577,5 +607,60 @@ extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, con
       GNNFP_CHECK_CUDA(cudaMemcpyAsync(io->out_nodes, on, (size_t)L->M * L->T * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   GNNFP_CHECK_CUDA(cudaGetLastError());
+  return rc;
+}
+
+static int fwd_check(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op, const gnnfp_loop_io* io,
+                     void* workspace, size_t workspace_bytes) {
+  int rc;
+  if ((rc = check_io(L, io, workspace, workspace_bytes))) return rc;
+  if (!sp || !op) GNNFP_FAIL(GNNFP_E_INVALID, "loop_forward: parameters missing");
+  for (int t = 0; t < L->nt; ++t) if ((rc = check_params(L->snet[t], sp[t], "net_state"))) return rc;
+  if ((rc = check_params(L->onet, *op, "net_output"))) return rc;
+  return GNNFP_OK;
+}
+
+extern "C" int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                                  const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = fwd_check(L, sp, op, io, workspace, workspace_bytes))) return rc;
+  Ctx c{L, io, (char*)workspace, (cudaStream_t)stream};
+  if ((rc = fwd_begin(c, sp, op))) return rc;
+  for (int t = 1; t <= L->cfg.max_iteration; ++t)
+    if ((rc = fwd_iter(c, t, sp, op))) return rc;
+  return fwd_end(c, sp, op);
+}
+
+// ---- stepping API: the same forward, one phase per call, so that a multi-GPU driver can exchange halo rows
+// ---- and all-reduce the convergence flag between iterations (partitioned single graph) ----------
+extern "C" int gnnfp_loop_forward_begin(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                                        const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = fwd_check(L, sp, op, io, workspace, workspace_bytes))) return rc;
+  Ctx c{L, io, (char*)workspace, (cudaStream_t)stream};
+  return fwd_begin(c, sp, op);
+}
+extern "C" int gnnfp_loop_forward_iter(gnnfp_loop* L, int32_t t, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                                       const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = fwd_check(L, sp, op, io, workspace, workspace_bytes))) return rc;
+  if (t < 1 || t > L->cfg.max_iteration) GNNFP_FAIL(GNNFP_E_INVALID, "loop_forward_iter: t=%d outside 1..max_iteration", t);
+  Ctx c{L, io, (char*)workspace, (cudaStream_t)stream};
+  return fwd_iter(c, t, sp, op);
+}
+extern "C" int gnnfp_loop_forward_end(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                                      const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = fwd_check(L, sp, op, io, workspace, workspace_bytes))) return rc;
+  Ctx c{L, io, (char*)workspace, (cudaStream_t)stream};
+  return fwd_end(c, sp, op);
+}
+extern "C" int gnnfp_loop_ws_offsets(const gnnfp_loop* L, size_t* flags_off, size_t* slots_off, size_t* slot_stride_floats,
+                                     int32_t* slot_count) {
+  if (!L) GNNFP_FAIL(GNNFP_E_INVALID, "loop_ws_offsets: null plan");
+  if (flags_off) *flags_off = L->ws.flags;
+  if (slots_off) *slots_off = L->ws.slots;
+  if (slot_stride_floats) *slot_stride_floats = ((size_t)L->N * L->D + 31) / 32 * 32;
+  if (slot_count) *slot_count = L->slot_count;
   return GNNFP_OK;
 }

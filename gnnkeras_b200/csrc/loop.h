@@ -26,6 +26,7 @@ struct gnnfp_loop {
   int nt = 1;            // state nets
   int composite = 0;
   int N = 0, A = 0, M = 0, D = 0, S = 0, NLw = 0, AL = 0, T = 0;
+  int Nact = 0;          // rows net_state runs on (N, or the owned block of an edge-cut partition)
   int dt[GNNFP_MAX_TYPES]{};   // clamped d_t (composite)
   int sum_dt = 0;
   int LsM = 0;           // materialised static block width

@@ -173,3 +173,89 @@ def reduce_halo_grads(plan: HaloPlan, d_halo: torch.Tensor, d_own: torch.Tensor,
     if idx.numel():
         d_own.index_add_(0, idx, recv)
     return d_own
+
+
+# ------------------------------------------------------------------------------------------------------
+# partitioned fixed-point loop (forward / inference): device side through the stepping C ABI
+# ------------------------------------------------------------------------------------------------------
+class PartitionedLoop:
+    """One rank's share of GNNnodeBased.Loop on an edge-cut partitioned graph (BASELINE.json config 5).
+
+    The rank owns nodes [lo, hi) and every arc into them; its local graph has n_own + n_halo nodes, the halo
+    nodes being read-only copies of remote sources.  Per iteration t:
+        iteration kernel on the owned rows (gnnfp_loop_forward_iter, rows [0, n_own) only)
+        -> halo rows of state slot t <- owners (exchange_halo, all-to-all-v over NVLink)
+        -> flag[t] <- max over ranks (the reference's stop rule is global over the whole graph, GNN.py:212).
+    No host synchronisation: the flag all-reduce is a device collective, the next iteration kernel is gated
+    on the reduced flag.  `exchange` / `reduce_flag` are injectable so that tests can run several ranks in
+    lock-step inside one process."""
+
+    def __init__(self, plan: HaloPlan, nodes, arcs, net_state, net_output, state_vect_dim, max_iteration,
+                 state_threshold, aggregation_mode="sum", set_mask=None, output_mask=None, device="cuda",
+                 exchange=None, reduce_flag=None, group=None):
+        from .op import DeviceGraph, LoopPlan
+        if aggregation_mode not in ("sum", "average"):
+            raise ValueError("partitioned loop supports aggregation modes 'sum' and 'average' "
+                             "(normalized depends on the global arc count: pass explicit values instead)")
+        self.plan, self.group = plan, group
+        dev = torch.device(device)
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(np.asarray(a).astype(dt))).to(dev)
+        n_loc = plan.n_own + plan.n_halo
+        nodes = np.asarray(nodes, dtype=np.float32)
+        arcs = np.asarray(arcs, dtype=np.float32)
+        # local node labels: owned rows then halo rows (labels of halo nodes are needed by Adj^T.nodes)
+        self.nodes = t(np.concatenate([nodes[plan.lo:plan.hi], nodes[plan.halo_global]], axis=0), np.float32)
+        self.arc_labels = t(arcs[plan.arc_ids][:, 2:], np.float32)
+        sm = np.zeros(n_loc, np.uint8)
+        om = np.zeros(n_loc, np.uint8)
+        sm[:plan.n_own] = 1 if set_mask is None else np.asarray(set_mask)[plan.lo:plan.hi]
+        om[:plan.n_own] = 1 if output_mask is None else np.asarray(output_mask)[plan.lo:plan.hi]
+        self.graph = DeviceGraph(t(plan.local_src, np.int32), t(plan.local_dst, np.int32), n_loc, aggregation_mode,
+                                 set_mask=t(sm, np.uint8), output_mask=t(om, np.uint8))
+        self.loop = LoopPlan(self.graph, [net_state], net_output, "node", state_vect_dim, max_iteration, state_threshold,
+                             False, self.nodes.shape[1], self.arc_labels.shape[1], n_active_rows=plan.n_own)
+        self.S, self.max_iteration = int(state_vect_dim), int(max_iteration)
+        self.send_idx = torch.as_tensor(np.concatenate(plan.send_rows) if plan.world > 0 else np.zeros(0, np.int64)).to(dev)
+        self.exchange = exchange if exchange is not None else (lambda own: exchange_halo(plan, own, group))
+        self.reduce_flag = reduce_flag if reduce_flag is not None else self._allreduce_flag
+
+    def _allreduce_flag(self, flag):
+        if self.plan.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+
+    def local_state0(self, state0_global):
+        """[n_own + n_halo, S] initial state of this rank (explicit input: the reference draws it unseeded)."""
+        s = np.asarray(state0_global, dtype=np.float32)
+        return torch.as_tensor(np.concatenate([s[self.plan.lo:self.plan.hi], s[self.plan.halo_global]], axis=0)).to(self.nodes.device)
+
+    # the three phases are separate so that a lock-step emulation of several ranks can interleave them
+    def begin(self, state0=None):
+        self.loop.forward_begin(self.nodes, self.arc_labels, state0, ld_arcs=self.arc_labels.stride(0))
+        self.flags, self.slots = self.loop.ws_views()
+        self.reduce_flag(self.flags[0:1])
+
+    def iterate(self, t):
+        self.loop.forward_iter(t)
+
+    def own_rows(self, t):
+        return self.slots[t & 1][: self.plan.n_own]
+
+    def set_halo(self, t, rows):
+        if self.plan.n_halo:
+            self.slots[t & 1][self.plan.n_own:] = rows
+
+    def finish_iteration(self, t):
+        if t < self.max_iteration:          # the state of iteration max_iteration is final: nobody gathers it
+            self.set_halo(t, self.exchange(self.own_rows(t)))
+            self.reduce_flag(self.flags[t:t + 1])
+
+    def end(self):
+        k, state, out = self.loop.forward_end()
+        return k, state[: self.plan.n_own], out
+
+    def forward(self, state0=None):
+        self.begin(state0)
+        for t in range(1, self.max_iteration + 1):
+            self.iterate(t)
+            self.finish_iteration(t)
+        return self.end()

@@ -205,7 +205,8 @@ class LoopPlan:
     def __init__(self, graph: DeviceGraph, nets_state: Sequence[Net], net_output: Net, kind: str,
                  state_vect_dim: int, max_iteration: int, state_threshold: float, training: bool,
                  nodes_width: int, arc_label_width: int, dim_node_label: Optional[Sequence[int]] = None,
-                 pool: Optional[bool] = None, want_input_grads: int = 0, workspace: Optional[torch.Tensor] = None):
+                 pool: Optional[bool] = None, want_input_grads: int = 0, workspace: Optional[torch.Tensor] = None,
+                 n_active_rows: int = 0):
         L = B.lib()
         # the reference's constructor asserts (GNN.py:26-28)
         assert state_vect_dim >= 0
@@ -225,6 +226,7 @@ class LoopPlan:
                 cfg.dim_node_label[i] = int(dd)
         cfg.nodes_width, cfg.arc_label_width = int(nodes_width), int(arc_label_width)
         cfg.want_input_grads = int(want_input_grads)
+        cfg.n_active_rows = int(n_active_rows)
         descs = (B.NetDesc * len(nets_state))(*[n.desc() for n in nets_state])
         od = net_output.desc()
         h = C.c_void_p()
@@ -286,6 +288,47 @@ class LoopPlan:
         if want_out_nodes:
             return k, state, out, out_nodes
         return k, state, out
+
+    # ---- stepping form (multi-GPU partitioned driver) ---------------------------------------------------
+    def forward_begin(self, nodes, arc_labels, state0=None, ld_arcs=None):
+        g, dev = self.graph, self.graph.device
+        ld_arcs = int(arc_labels.stride(0)) if ld_arcs is None else ld_arcs
+        state = torch.empty((g.n_nodes, self.D), dtype=torch.float32, device=dev)
+        out = torch.empty((self.out_rows, self.T), dtype=torch.float32, device=dev)
+        k = torch.zeros((), dtype=torch.int32, device=dev)
+        self._step_io = self._io(nodes, arc_labels, ld_arcs, state0, state, out, None, k)
+        self._step_keep = (nodes, arc_labels, state0, state, out, k)
+        self._step_params = self._param_arrays()
+        sp, op = self._step_params
+        B.check(self._L.gnnfp_loop_forward_begin(self._h, sp, C.byref(op), C.byref(self._step_io), self._ws_ptr(),
+                                                 self.workspace_bytes, _stream()))
+
+    def forward_iter(self, t: int):
+        sp, op = self._step_params
+        B.check(self._L.gnnfp_loop_forward_iter(self._h, int(t), sp, C.byref(op), C.byref(self._step_io), self._ws_ptr(),
+                                                self.workspace_bytes, _stream()))
+
+    def forward_end(self):
+        sp, op = self._step_params
+        B.check(self._L.gnnfp_loop_forward_end(self._h, sp, C.byref(op), C.byref(self._step_io), self._ws_ptr(),
+                                               self.workspace_bytes, _stream()))
+        nodes, arc_labels, state0, state, out, k = self._step_keep
+        return k, state, out
+
+    def ws_views(self):
+        """torch views into the workspace: int32 flags[max_iteration+1] and the state slots [slot_count, N, D]."""
+        fo, so, st, sc = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int32()
+        B.check(self._L.gnnfp_loop_ws_offsets(self._h, C.byref(fo), C.byref(so), C.byref(st), C.byref(sc)))
+        base = (self.workspace.data_ptr() + 255) // 256 * 256 - self.workspace.data_ptr()
+        ws = self.workspace[base:]
+        n_flags = int(self.cfg.max_iteration) + 1
+        flags = ws[fo.value: fo.value + 4 * n_flags].view(torch.int32)
+        n, D = self.graph.n_nodes, self.D
+        slots = []
+        for i in range(sc.value):
+            o = so.value + 4 * st.value * i
+            slots.append(ws[o: o + 4 * n * D].view(torch.float32).view(n, D))
+        return flags, slots
 
     def backward(self, d_out=None, d_out_nodes=None, d_state=None, average_st_grads=False,
                  state_tensors=None, out_tensors=None, grad_state=None, grad_out=None):

@@ -160,6 +160,10 @@ typedef struct gnnfp_loop_cfg {
   int32_t nodes_width;      /* columns of `nodes`                                               */
   int32_t arc_label_width;  /* AL = columns of arcs[:, 2:]                                      */
   int32_t want_input_grads; /* bit0 d_nodes, bit1 d_arc_labels, bit2 d_state0 (LGNN chaining)   */
+  int32_t n_active_rows;    /* 0 = all nodes.  >0: net_state runs on rows [0, n_active_rows) only; the
+                               remaining rows are halo copies of remote nodes that the multi-GPU driver
+                               refreshes between iterations (edge-cut partition, homogeneous, no BN,
+                               inference).                                                          */
 } gnnfp_loop_cfg;
 
 int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const gnnfp_loop_cfg* cfg,
@@ -186,6 +190,23 @@ typedef struct gnnfp_loop_io {
 int gnnfp_loop_forward(gnnfp_loop* L, const gnnfp_net_params* state_params /* [max(1,n_types)] */,
                        const gnnfp_net_params* out_params, const gnnfp_loop_io* io,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stepping form of gnnfp_loop_forward (same arguments): begin = prologue + first condition, iter = iteration t
+ * (1-based, gated on the device flag of iteration t-1; writes flag t), end = converged state, net_output,
+ * pooling.  gnnfp_loop_forward == begin; iter(1..max_iteration); end.  Between iter(t) and iter(t+1) a
+ * partitioned driver (a) refreshes the halo rows of state slot t and (b) max-reduces flag t over the ranks;
+ * gnnfp_loop_ws_offsets tells where those live inside the caller's workspace: int32 flags[max_iteration+1]
+ * at byte offset flags_off; state slot of iteration t (t >= 1) at slots_off + slot_index * slot_stride_floats * 4
+ * with slot_index = t-1 (training) or t&1 (inference). */
+int gnnfp_loop_forward_begin(gnnfp_loop* L, const gnnfp_net_params* state_params, const gnnfp_net_params* out_params,
+                             const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream);
+int gnnfp_loop_forward_iter(gnnfp_loop* L, int32_t t, const gnnfp_net_params* state_params,
+                            const gnnfp_net_params* out_params, const gnnfp_loop_io* io, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int gnnfp_loop_forward_end(gnnfp_loop* L, const gnnfp_net_params* state_params, const gnnfp_net_params* out_params,
+                           const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream);
+int gnnfp_loop_ws_offsets(const gnnfp_loop* L, size_t* flags_off, size_t* slots_off, size_t* slot_stride_floats,
+                          int32_t* slot_count);
 
 typedef struct gnnfp_loop_grads {
   const float* d_out;        /* [out_rows, T] dL/d out (may be NULL = zeros)                    */
