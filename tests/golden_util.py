@@ -1,0 +1,45 @@
+"""Load tests/golden/loop_golden.npz (written by tests/golden/make_golden_loop.py from the reference's own code)."""
+import os
+
+import numpy as np
+
+from oracle import structures as S
+
+_G = os.path.join(os.path.dirname(__file__), "golden", "loop_golden.npz")
+CASES = ["graph_S0_bn", "node_S5", "arc_S4_bn", "composite_S6", "lgnn3_S0_bn"]
+KIND = {"graph_S0_bn": "graph", "node_S5": "node", "arc_S4_bn": "arc", "composite_S6": "graph", "lgnn3_S0_bn": "graph"}
+
+
+def _unflatten(store, prefix):
+    if prefix in store:
+        return store[prefix]
+    if f"{prefix}/__len__" in store:
+        return [_unflatten(store, f"{prefix}/{i}") for i in range(int(store[f"{prefix}/__len__"]))]
+    keys = sorted({k[len(prefix) + 1:].split("/")[0] for k in store.files if k.startswith(prefix + "/")})
+    return {k: _unflatten(store, f"{prefix}/{k}") for k in keys}
+
+
+def load(case):
+    store = np.load(_G, allow_pickle=False)
+    d = _unflatten(store, case)
+    gd = d["graph"]
+    tm = gd["type_mask"]
+    g = S.make_graph(gd["nodes"], gd["arcs"], gd["targets"], focus=str(gd["focus"]), set_mask=gd["set_mask"],
+                     output_mask=gd["output_mask"], aggregation_mode=str(gd["mode"]),
+                     node2graph=gd["node2graph"] if int(gd["n_graphs"]) else None,
+                     nodegraph_values=gd["nodegraph_values"] if int(gd["n_graphs"]) else None,
+                     n_graphs=int(gd["n_graphs"]) if int(gd["n_graphs"]) else None,
+                     type_mask=tm if tm.size else None, dim_node_label=gd["dim_node_label"] if tm.size else None)
+
+    def net(nd):
+        out = {"bn": None, "layers": []}
+        if "bn" in nd and isinstance(nd["bn"], dict) and "gamma" in nd["bn"]:
+            b = nd["bn"]
+            out["bn"] = {"gamma": b["gamma"], "beta": b["beta"], "moving_mean": b["moving_mean"], "moving_var": b["moving_var"],
+                         "eps": float(b["eps"]), "momentum": float(b["momentum"])}
+        for l in nd["layers"]:
+            out["layers"].append({"W": l["W"], "b": l["b"], "act": str(l["act"])})
+        return out
+    layers = [{"state": [net(s) for s in L["state"]], "out": net(L["out"])} for L in d["nets"]]
+    cfg = {k: (float(v) if k == "thr" else int(v)) for k, v in d["cfg"].items()}
+    return g, layers, cfg, d["ref"]
