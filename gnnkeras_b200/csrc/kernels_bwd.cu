@@ -186,8 +186,11 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
     if (use_bulk && nr == tc.R) {
       mbar_wait(bar, bar_phase);
       bar_phase ^= 1u;
+      PHASE_MARK(11);
       const float* rp = bulk_relayout(a.src, tc.bulk_src, tc.R, raw, smem + y.oAct[0], y.XSa[0]);
+      PHASE_MARK(12);
       bulk_relayout(a.gsrc, tc.bulk_g, tc.R, rp, dzA, XSdA);
+      PHASE_MARK(13);
       stage_tile(a.src, row0, nr, tc.R, smem + y.oAct[0], y.XSa[0], sc, true, tc.bulk_src);
       stage_tile(a.gsrc, row0, nr, tc.R, dzA, XSdA, sc, true, tc.bulk_g);
     } else {
@@ -363,34 +366,8 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
     }
     // ---- cur = dy (gradient w.r.t. the BN output / the raw input) ---------------------------------
     PHASE_MARK(7);
-    if (y.bn) {   // P_c = sum dy, Qraw_c = sum dy * x  (all threads: column x row group)
-      const float* a0 = smem + y.oAct[0];
-      const int pin = ceil_to(net.in_dim, 4), ind = net.in_dim, XS0 = y.XSa[0];
-      if (T >= ind) {
-        const int ngr = T / ind, c = tid % ind, gg = tid / ind;
-        if (gg < ngr) {
-          float p = 0.f, q = 0.f;
-          for (int r = gg; r < nr; r += ngr) {
-            const float dy = cur[r * XSc + c];
-            p += dy;
-            q = fmaf(dy, a0[r * XS0 + c], q);
-          }
-          atomicAdd(accBN + c, p);
-          atomicAdd(accBN + pin + c, q);
-        }
-      } else {
-        for (int c = tid; c < ind; c += T) {
-          float p = 0.f, q = 0.f;
-          for (int r = 0; r < nr; ++r) {
-            const float dy = cur[r * XSc + c];
-            p += dy;
-            q = fmaf(dy, a0[r * XS0 + c], q);
-          }
-          accBN[c] += p;
-          accBN[pin + c] += q;
-        }
-      }
-    }
+    // (BN batch sums sum dy and sum dy*x need no pass over the tile: dy = dz W^T is linear, so they follow from
+    //  db and the raw dW accumulator at flush time: sum_r dy[r][c] = sum_j W[c][j] db[j],  sum_r dy x = sum_j W[c][j] acc[c][j])
     PHASE_MARK(8);
     const bool bulk_out = tc.bulk_out != 0u && nr == tc.R;
     if (bulk_out) {
@@ -419,8 +396,10 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         }
         ob += tc.R * w;
       }
+      PHASE_MARK(14);
       fence_proxy_async();
       __syncthreads();
+      PHASE_MARK(15);
       if (tid == 0) {
         const float* ob2 = smem + y.oOutRaw;
         for (int p = 0; p < a.src.n_pieces; ++p) {
@@ -516,13 +495,50 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
       off += H;
     }
     if (y.bn && a.bn_partial) {
-      const int pin = ceil_to(net.in_dim, 4);
       const int tot = a.bn_in_total > 0 ? a.bn_in_total : net.in_dim;
       float* bp = a.bn_partial + (size_t)blockIdx.x * 2 * tot + a.bn_c_off;
-      for (int c = tid; c < net.in_dim; c += T) {
-        const float P = accBN[c], Qraw = accBN[pin + c];
-        bp[c] = P;
-        bp[tot + c] = fmaf(bnA[c], Qraw, bnB[c] * P);
+      const int in0 = y.inw[0], H0 = y.inw[1];
+      const float* ab0 = smem + y.oAccb[0];
+      const float* WT0 = smem + y.oWT[0];
+      const int inpad0 = ceil_to(in0, 16);
+      if (REGACC) {
+        // racc lives in registers of the owning threads: stage sum_j W[c][j]*acc[c][j] through accBN (zeroed at start)
+        const int h4 = (H0 + 3) / 4, U = ((in0 + 7) / 8) * h4;
+        int q = 0;
+        for (int u = tid; u < U && q < 2; u += T, ++q) {
+          const int cu = u / h4, ju = u - cu * h4;
+          const int c0 = cu * 8, j0 = ju * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float sQ = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if (c0 + i < in0 && j0 + jj < H0) sQ = fmaf(WT0[(j0 + jj) * inpad0 + c0 + i], (q == 0 ? racc[0][i][jj] : racc[1][i][jj]), sQ);
+            if (c0 + i < in0) atomicAdd(accBN + c0 + i, sQ);
+          }
+        }
+        __syncthreads();
+        for (int c = tid; c < in0; c += T) {
+          float P = 0.f;
+          for (int j = 0; j < H0; ++j) P = fmaf(WT0[j * inpad0 + c], ab0[j], P);
+          const float Qraw = accBN[c];
+          bp[c] = P;
+          bp[tot + c] = fmaf(bnA[c], Qraw, bnB[c] * P);
+        }
+      } else {
+        const float* aw0 = smem + y.oAccW[0];
+        for (int c = tid; c < in0; c += T) {
+          float P = 0.f, Qraw = 0.f;
+          for (int j = 0; j < H0; ++j) {
+            const float wv = WT0[j * inpad0 + c];
+            float av = 0.f;
+            for (int g = 0; g < y.groups[0]; ++g) av += aw0[g * in0 * H0 + c * H0 + j];
+            P = fmaf(wv, ab0[j], P);
+            Qraw = fmaf(wv, av, Qraw);
+          }
+          bp[c] = P;
+          bp[tot + c] = fmaf(bnA[c], Qraw, bnB[c] * P);
+        }
       }
     }
   }
