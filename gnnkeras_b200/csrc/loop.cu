@@ -8,6 +8,7 @@
 // Backward = the BPTT that tf.GradientTape performs in train_step (GNN.py:284-295), hand written:
 //            see loop_bwd.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "loop.h"
 #include "tile.cuh"
@@ -355,6 +356,11 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   for (int t = 0; t < L->nt; ++t) L->nparam_s[t] = net_param_count(L->snet[t]);
   L->nparam_o = net_param_count(L->onet);
   { long long cpr = g->N > 0 ? (2ll * g->A + g->N - 1) / g->N : 4; L->cap_per_row = cpr < 4 ? 4 : (cpr > 16 ? 16 : (int)cpr); }
+  for (int t = 0; t < L->nt; ++t) {
+    const gnnfp_net_desc& d = L->snet[t];
+    L->gemm_ok[t] = d.n_layers == 1 && d.acts[0] != GNNFP_ACT_SOFTMAX && d.widths[0] <= 80 && gemm_rows_supported(ceil_to(d.in_dim, 8) + 8 * 3, d.widths[0]) &&
+                    getenv("GNNFP_NO_GEMM") == nullptr;
+  }
   L->grid_cap = gnnfp_num_sms() * 4;   // backward tile kernels run at most 4 CTAs per SM (tile_cfg_bwd)
 
   // ---- workspace layout ---------------------------------------------------------------------
@@ -375,7 +381,21 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   L->slot_count = cfg->training ? MI : (MI > 0 ? 2 : 0);
   w.slots = off; off = align_up(off + (size_t)L->slot_count * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float));
   w.out_nodes = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
-  w.agg = off; off = align_up(off + (cfg->training ? (size_t)MI : 0) * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float) + 4);
+  w.agg = off; off = align_up(off + (cfg->training ? (size_t)MI : (size_t)(MI > 0 ? 1 : 0)) * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float) + 4);
+  {
+    size_t wf = 0, wt = 0, bc = 0;
+    for (int t = 0; t < L->nt; ++t) {
+      const int in = L->snet[t].in_dim, H = L->snet[t].widths[0];
+      const size_t kp = (size_t)gemm_rows_kpad(ceil_to(in, 8) + 8 * GNNFP_MAXP);
+      const size_t f = kp * gemm_rows_ldw(H) + gemm_rows_ldw(H);
+      const size_t tb = (size_t)ceil_to(H, 8) * ((size_t)ceil_to(in, 16) + 16 * GNNFP_MAXP);
+      wf = f > wf ? f : wf; wt = tb > wt ? tb : wt; bc = (size_t)3 * in > bc ? (size_t)3 * in : bc;
+    }
+    w.wfold_stride = (wf + 63) / 64 * 64; w.wtb_stride = (wt + 63) / 64 * 64; w.bncoef_stride = (bc + 63) / 64 * 64;
+    w.wfold = off; off = align_up(off + L->nt * w.wfold_stride * sizeof(float));
+    w.wtb = off; off = align_up(off + L->nt * w.wtb_stride * sizeof(float));
+    w.bncoef = off; off = align_up(off + L->nt * w.bncoef_stride * sizeof(float));
+  }
   if (cfg->training) {
     const size_t ND = (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float);
     w.dSfin = off; off = align_up(off + ND);
@@ -513,23 +533,56 @@ static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp
   (void)MI; (void)D; (void)N; (void)training; (void)wgt; (void)io; (void)op; (void)sp;
   {
     const int* gate = c.flags() + (t - 1);
-    if (L->bn_train_state) {
-      for (int ty = 0; ty < L->nt; ++ty) {   // Adj^T.state of this iteration: saved + batch statistics
-        AggArgs aa;
-        memset(&aa, 0, sizeof(aa));
-        TileSrc rows;
-        memset(&rows, 0, sizeof(rows));
-        set_rows(L, ty, rows);
-        aa.n_rows = rows.n_rows; aa.rowlist = rows.rowlist; aa.D = D;
-        aa.S = c.S(t - 1); aa.ld = c.ldS(t - 1);
-        aa.rowptr = g->dst_rowptr; aa.idx = g->dst_src; aa.wgt = wgt;
-        aa.out = c.AGG(t);
-        aa.st_sum = c.stA(ty, t - 1); aa.st_sq = aa.st_sum + D;
-        aa.gate = gate;
-        if ((rc = launch_agg_stats(aa, s))) return rc;
-      }
+    for (int ty = 0; ty < L->nt; ++ty) {     // Adj^T.state of this iteration (+ BN batch statistics); saved in training
+      if (!L->bn_train_state && !L->gemm_ok[ty]) continue;
+      AggArgs aa;
+      memset(&aa, 0, sizeof(aa));
+      TileSrc rows;
+      memset(&rows, 0, sizeof(rows));
+      set_rows(L, ty, rows);
+      aa.n_rows = rows.n_rows; aa.rowlist = rows.rowlist; aa.D = D;
+      aa.S = c.S(t - 1); aa.ld = c.ldS(t - 1);
+      aa.rowptr = g->dst_rowptr; aa.idx = g->dst_src; aa.wgt = wgt;
+      aa.out = c.AGG(t);
+      if (L->bn_train_state) { aa.st_sum = c.stA(ty, t - 1); aa.st_sq = aa.st_sum + D; }
+      aa.gate = gate;
+      if ((rc = launch_agg_stats(aa, s))) return rc;
     }
     for (int ty = 0; ty < L->nt; ++ty) {
+      if (!L->gemm_ok[ty]) continue;
+      // ---- pipelined GEMM path: fold BN into the padded weights, then one GEMM with the iteration's epilogue ----
+      TileSrc ts;
+      build_state_src(c, ty, t, ts, 1);
+      FoldArgs fo;
+      memset(&fo, 0, sizeof(fo));
+      fo.src = ts;
+      fill_netdev(L->snet[ty], sp[ty], training, ts.n_rows, fo.net);
+      GemmRowsArgs ga;
+      memset(&ga, 0, sizeof(ga));
+      int k8 = 0;
+      for (int p = 0; p < ts.n_pieces; ++p) {
+        fo.k8[p] = k8;
+        gemm_piece_set(ga.p[p], ts.p[p].ptr, ts.p[p].ld, ts.p[p].width, k8);
+        k8 += ceil_to(ts.p[p].width, 2);
+      }
+      const int H = L->snet[ty].widths[0];
+      float* wf = (float*)(c.ws + L->ws.wfold) + (size_t)ty * L->ws.wfold_stride;
+      fo.Kpad = gemm_rows_kpad(k8); fo.ldw = gemm_rows_ldw(H); fo.Wp = wf; fo.biasp = wf + (size_t)fo.Kpad * fo.ldw;
+      fo.update_moving = training; fo.gate = gate;
+      if ((rc = launch_fold_w(fo, s))) return rc;
+      ga.n_rows = ts.n_rows; ga.rowlist = ts.rowlist; ga.n_pieces = ts.n_pieces; ga.Kpad = fo.Kpad;
+      ga.Wp = fo.Wp; ga.ldw = fo.ldw; ga.N = H; ga.bias = fo.biasp; ga.act = L->snet[ty].acts[0];
+      ga.out = (float*)c.S(t); ga.ld_out = D; ga.fwd = 1;
+      ga.vec2 = D % 2 == 0 && c.ldS(t - 1) % 2 == 0 && ((uintptr_t)c.S(t) & 7) == 0 && ((uintptr_t)c.S(t - 1) & 7) == 0;
+      if (t < MI) {
+        ga.prev = c.S(t - 1); ga.ld_prev = c.ldS(t - 1); ga.thr = L->cfg.state_threshold; ga.flag_next = c.flags() + t;
+        if (L->bn_train_state) { ga.ost_sum = c.stS(ty, t); ga.ost_sq = ga.ost_sum + D; }
+      }
+      ga.gate = gate;
+      if ((rc = launch_gemm_rows(ga, s, PC_FWD_ITER))) return rc;
+    }
+    for (int ty = 0; ty < L->nt; ++ty) {
+      if (L->gemm_ok[ty]) continue;
       FwdArgs fa;
       memset(&fa, 0, sizeof(fa));
       build_state_src(c, ty, t, fa.src, L->bn_train_state ? 1 : 0);

@@ -1,6 +1,7 @@
 // loop.h - the opaque loop plan of gnnfp.h and its workspace layout
 #pragma once
 #include "graph.h"
+#include "gemm.h"
 
 struct WsLayout {
   size_t ctrl = 0, ctrl_bytes = 0;          // int flags[max_iter+1], k, pad | double stats ... (zeroed each forward)
@@ -13,6 +14,8 @@ struct WsLayout {
   // backward
   size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0, dz = 0;
   size_t part_state = 0, part_out = 0, bn_part = 0, bn_const = 0, bn_grad = 0;
+  size_t wfold = 0, wtb = 0, bncoef = 0;    // GEMM path: folded weights per type, W^T blocks, per-iteration BN coefficients
+  size_t wfold_stride = 0, wtb_stride = 0, bncoef_stride = 0;   // floats per type
   size_t bn_const_t = 0, bn_static = 0;     // per-iteration BN constants, running static-column sums
   size_t bwd_zero = 0, bwd_zero_bytes = 0;   // region zeroed at the start of every backward
   size_t total = 0;
@@ -35,6 +38,7 @@ struct gnnfp_loop {
   int slot_count = 0;
   int bn_train_state = 0, bn_train_out = 0;
   int nparam_s[GNNFP_MAX_TYPES]{}, nparam_o = 0;
+  int gemm_ok[GNNFP_MAX_TYPES]{};   // single Dense layer nets run the pipelined GEMM kernels (gemm.cu)
   int cap_per_row = 4;   // CSR scratch capacity per tile row (from A/N)
   int grid_cap = 0;      // upper bound of any backward tile kernel grid (partials are sized by it)
   WsLayout ws;
@@ -54,7 +58,7 @@ struct Ctx {
     if (t == 0) return L->S > 0 ? io->state0 : io->nodes;
     return slots() + (L->cfg.training ? (size_t)(t - 1) : (size_t)(t & 1)) * slot_stride();
   }
-  float* AGG(int t) const { return (float*)(ws + L->ws.agg) + (size_t)(t - 1) * slot_stride(); }   // t = 1..max_iter
+  float* AGG(int t) const { return (float*)(ws + L->ws.agg) + (L->cfg.training ? (size_t)(t - 1) : (size_t)0) * slot_stride(); }   // t = 1..max_iter (one slot in inference)
   int ldS(int t) const { return t == 0 ? (L->S > 0 ? L->S : io->ld_nodes) : L->D; }
   int stXw() const {
     if (!L->composite) return L->LsM;
