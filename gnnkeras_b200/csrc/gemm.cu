@@ -288,91 +288,82 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// dW = X^T dz (+ db) for the rows of this CTA.  Thread (ty, tx) owns dW rows c = ty + 16*i (i < TC) and columns
-// j = tx + 16*m (m < TJ); 8-row chunks of X (all pieces, padded K layout) and dz stream through the cp.async ring.
-template <int TC, int TJ>
+// dW = X^T dz (+ db) over this CTA's rows.  32-row stages of X (all pieces side by side at their even k8 offsets) and dz
+// stream through the cp.async ring; every thread reads the SAME row of the stage at a time (pure broadcasts).  Thread
+// (ty, tx) owns the K quads 64*q + 4*ty .. +3 (q < NQ) and the dz columns gr_col<TJ>(m, tx): 4*NQ x TJ accumulators.
+#define DW_ROWS 32
+template <int NQ, int TJ>
 __global__ void __launch_bounds__(256, 2) gemm_dw_kernel(const __grid_constant__ GemmDwArgs a) {
   if (a.gate && *a.gate == 0) return;
-  constexpr int BC = 16 * TC, BJ = 16 * TJ;
+  constexpr int BK = 64 * NQ, BJ = 16 * TJ, TC = 4 * NQ;
   extern __shared__ __align__(16) float smem[];
-  float* Xs = smem;                                   // [STAGES][8][BC]
-  float* Zs = smem + GEMM_STAGES * 8 * BC;            // [STAGES][8][BJ]
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float* Xs = smem;                                   // [STAGES][DW_ROWS][BK]
+  float* Zs = smem + GEMM_STAGES * DW_ROWS * BK;      // [STAGES][DW_ROWS][BJ]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   const int n = a.n_rows;
-  const int n_chunks_all = (n + 7) / 8;
+  const int n_chunks_all = (n + DW_ROWS - 1) / DW_ROWS;
   const int per_cta = (n_chunks_all + gridDim.x - 1) / gridDim.x;
   const int c0 = blockIdx.x * per_cta;
   const int c1 = min(n_chunks_all, c0 + per_cta);
   const int total = max(0, c1 - c0);
+  const int xpairs = a.Kp >> 1, zpairs = (a.H + 1) >> 1;
+  const bool zal8 = ((reinterpret_cast<uintptr_t>(a.dz) & 7) == 0) && (a.ld_dz % 2 == 0);
 
+  // warp w copies rows w, w+8, w+16, w+24 of the stage; its lanes cover the column pairs
   auto issue = [&](int it) {
     if (it < total) {
       const int st = it % GEMM_STAGES;
-      float* Xd = Xs + st * 8 * BC;
-      float* Zd = Zs + st * 8 * BJ;
-      const int row0 = (c0 + it) * 8;
-      for (int p = 0; p < a.n_pieces; ++p) {
-        const GemmPiece& pc = a.p[p];
-        const int wpad = ceil_to(pc.width, 8);
-        const bool al8 = ((reinterpret_cast<uintptr_t>(pc.ptr) & 7) == 0) && (pc.ld % 2 == 0);
-        if (al8) {
-          const int hw = wpad / 2;
-          for (int e = tid; e < 8 * hw; e += 256) {
-            const int r = e / hw, q = e - r * hw;
-            const int grow = row0 + r;
-            int bytes = 0;
-            const float* src = pc.ptr;
-            if (grow < n) {
-              const int gr = a.rowlist ? a.rowlist[grow] : grow;
-              bytes = max(0, min(8, (pc.width - 2 * q) * 4));
-              if (bytes) src = pc.ptr + (size_t)gr * pc.ld + 2 * q;
-            }
-            cp_async8(Xd + r * BC + pc.k8 + 2 * q, src, bytes);
-          }
+      float* Xd = Xs + st * DW_ROWS * BK;
+      float* Zd = Zs + st * DW_ROWS * BJ;
+      const int row0 = (c0 + it) * DW_ROWS + warp;
+      const bool fullrows = a.rowlist == nullptr && (c0 + it + 1) * DW_ROWS <= n;
+      for (int pp = lane; pp < xpairs; pp += 32) {
+        const int kcol = 2 * pp;
+        int p = 0;
+        while (p + 1 < a.n_pieces && kcol >= a.p[p + 1].k8) ++p;
+        const float* pptr = a.p[p].ptr;
+        const int pld = a.p[p].ld;
+        const int kk = kcol - a.p[p].k8;
+        const int nv = a.p[p].width - kk;
+        const bool al8 = a.p[p].al8 != 0;
+        float* dst = Xd + warp * BK + kcol;
+        if (nv <= 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async8(dst + i * 8 * BK, pptr, 0);
+        } else if (al8 && fullrows) {
+          const float* src = pptr + (size_t)row0 * pld + kk;
+          const int bytes = nv > 1 ? 8 : 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cp_async8(dst + i * 8 * BK, src, bytes); src += (size_t)8 * pld; }
         } else {
-          for (int e = tid; e < 8 * wpad; e += 256) {
-            const int r = e / wpad, q = e - r * wpad;
-            const int grow = row0 + r;
-            int bytes = 0;
-            const float* src = pc.ptr;
-            if (grow < n && q < pc.width) {
-              const int gr = a.rowlist ? a.rowlist[grow] : grow;
-              bytes = 4;
-              src = pc.ptr + (size_t)gr * pc.ld + q;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int grow = row0 + 8 * i;
+            const bool valid = grow < n;
+            const float* src = pptr;
+            if (valid) src = pptr + (size_t)(a.rowlist ? a.rowlist[grow] : grow) * pld + kk;
+            if (al8) cp_async8(dst + i * 8 * BK, src, valid ? (nv > 1 ? 8 : 4) : 0);
+            else {
+              cp_async4(dst + i * 8 * BK, src, valid ? 4 : 0);
+              cp_async4(dst + i * 8 * BK + 1, (valid && nv > 1) ? src + 1 : pptr, (valid && nv > 1) ? 4 : 0);
             }
-            cp_async4(Xd + r * BC + pc.k8 + q, src, bytes);
           }
         }
       }
-      {
-        const bool al8 = ((reinterpret_cast<uintptr_t>(a.dz) & 7) == 0) && (a.ld_dz % 2 == 0);
-        const int hpad = ceil_to(a.H, 2);
-        if (al8) {
-          const int hw = hpad / 2;
-          for (int e = tid; e < 8 * hw; e += 256) {
-            const int r = e / hw, q = e - r * hw;
-            const int grow = row0 + r;
-            int bytes = 0;
-            const float* src = a.dz;
-            if (grow < n) {
-              const int gr = a.rowlist ? a.rowlist[grow] : grow;
-              bytes = max(0, min(8, (a.H - 2 * q) * 4));
-              if (bytes) src = a.dz + (size_t)gr * a.ld_dz + 2 * q;
-            }
-            cp_async8(Zd + r * BJ + 2 * q, src, bytes);
-          }
-        } else {
-          for (int e = tid; e < 8 * a.H; e += 256) {
-            const int r = e / a.H, q = e - r * a.H;
-            const int grow = row0 + r;
-            int bytes = 0;
-            const float* src = a.dz;
-            if (grow < n) {
-              const int gr = a.rowlist ? a.rowlist[grow] : grow;
-              bytes = 4;
-              src = a.dz + (size_t)gr * a.ld_dz + q;
-            }
-            cp_async4(Zd + r * BJ + q, src, bytes);
+      for (int pp = lane; pp < zpairs; pp += 32) {
+        const int j0 = 2 * pp;
+        const int nv = a.H - j0;
+        float* dst = Zd + warp * BJ + j0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int grow = row0 + 8 * i;
+          const bool valid = grow < n;
+          const float* src = a.dz;
+          if (valid) src = a.dz + (size_t)(a.rowlist ? a.rowlist[grow] : grow) * a.ld_dz + j0;
+          if (zal8) cp_async8(dst + i * 8 * BJ, src, valid ? (nv > 1 ? 8 : 4) : 0);
+          else {
+            cp_async4(dst + i * 8 * BJ, src, valid ? 4 : 0);
+            cp_async4(dst + i * 8 * BJ + 1, (valid && nv > 1) ? src + 1 : a.dz, (valid && nv > 1) ? 4 : 0);
           }
         }
       }
@@ -381,7 +372,7 @@ __global__ void __launch_bounds__(256, 2) gemm_dw_kernel(const __grid_constant__
   };
 
   // zero the shared ring once: columns outside the pieces (K padding, H padding) are never written by cp.async
-  for (int e = tid; e < GEMM_STAGES * 8 * (BC + BJ); e += 256) smem[e] = 0.f;
+  for (int e = tid; e < GEMM_STAGES * DW_ROWS * (BK + BJ); e += 256) smem[e] = 0.f;
   __syncthreads();
 
   float acc[TC][TJ];
@@ -399,15 +390,25 @@ __global__ void __launch_bounds__(256, 2) gemm_dw_kernel(const __grid_constant__
     __syncthreads();
     issue(it + GEMM_STAGES - 1);
     const int st = it % GEMM_STAGES;
-    const float* Xd = Xs + st * 8 * BC + ty;
-    const float* Zd = Zs + st * 8 * BJ + tx;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    const float* Xd = Xs + st * DW_ROWS * BK + 4 * ty;
+    const float* Zd = Zs + st * DW_ROWS * BJ;
+#pragma unroll 4
+    for (int r = 0; r < DW_ROWS; ++r) {
       float xv[TC], zv[TJ];
 #pragma unroll
-      for (int i = 0; i < TC; ++i) xv[i] = Xd[k * BC + 16 * i];
+      for (int q = 0; q < NQ; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(Xd + r * BK + 64 * q);
+        xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
+      }
+      if (TJ >= 4) {
+        const float4 t = *reinterpret_cast<const float4*>(Zd + r * BJ + 4 * tx);
+        zv[0] = t.x; zv[1] = t.y; zv[2] = t.z; zv[3] = t.w;
 #pragma unroll
-      for (int m = 0; m < TJ; ++m) zv[m] = Zd[k * BJ + 16 * m];
+        for (int m = 4; m < TJ; ++m) zv[m] = Zd[r * BJ + 64 + 16 * (m - 4) + tx];
+      } else {
+#pragma unroll
+        for (int m = 0; m < TJ; ++m) zv[m] = Zd[r * BJ + tx + 16 * m];
+      }
 #pragma unroll
       for (int i = 0; i < TC; ++i)
 #pragma unroll
@@ -421,22 +422,20 @@ __global__ void __launch_bounds__(256, 2) gemm_dw_kernel(const __grid_constant__
   cp_async_wait<0>();
   __syncthreads();
   // ---- flush: this CTA's partial slot (private, accumulated across launches with +=) -------------------------
-  // padded K index kp -> real input column: pieces are laid out at k8 offsets
   float* part = a.partial + (size_t)blockIdx.x * a.n_params;
   float* sdb = smem;                     // [BJ] db of this CTA (for the BN correction of every row of dW)
-  float* sQ = smem + BJ;                 // [BC] sum_j W[c][j]*acc[c][j]
-  for (int e = tid; e < BJ + BC; e += 256) smem[e] = 0.f;
+  float* sQ = smem + BJ;                 // [BK] sum_j W[c][j]*acc[c][j]
+  for (int e = tid; e < BJ + BK; e += 256) smem[e] = 0.f;
   __syncthreads();
   if (ty == 0) {
 #pragma unroll
-    for (int m = 0; m < TJ; ++m) sdb[tx + 16 * m] = dbacc[m];
+    for (int m = 0; m < TJ; ++m) sdb[gr_col<TJ>(m, tx)] = dbacc[m];
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < TC; ++i) {
-    const int kp = ty + 16 * i;
-    // real column index of padded index kp
-    int creal = -1, coff = 0;
+    const int kp = 64 * (i >> 2) + 4 * ty + (i & 3);
+    int creal = -1, coff = 0;            // padded K index -> real input column (pieces sit at their k8 offsets)
     for (int p = 0; p < a.n_pieces; ++p) {
       if (kp >= a.p[p].k8 && kp < a.p[p].k8 + a.p[p].width) creal = coff + (kp - a.p[p].k8);
       coff += a.p[p].width;
@@ -444,7 +443,7 @@ __global__ void __launch_bounds__(256, 2) gemm_dw_kernel(const __grid_constant__
     float q = 0.f;
 #pragma unroll
     for (int m = 0; m < TJ; ++m) {
-      const int j = tx + 16 * m;
+      const int j = gr_col<TJ>(m, tx);
       if (j < a.H && creal >= 0) {
         float v = acc[i][m];
         if (a.bn_partial) q = fmaf(a.W[(size_t)creal * a.H + j], v, q);
@@ -461,7 +460,7 @@ __global__ void __launch_bounds__(256, 2) gemm_dw_kernel(const __grid_constant__
   if (ty == 0) {
 #pragma unroll
     for (int m = 0; m < TJ; ++m) {
-      const int j = tx + 16 * m;
+      const int j = gr_col<TJ>(m, tx);
       if (j < a.H) part[a.bias_off + j] += dbacc[m];
     }
   }
@@ -536,34 +535,35 @@ void gemm_piece_set(GemmPiece& g, const float* ptr, int ld, int width, int k8) {
   g.al8 = ((reinterpret_cast<uintptr_t>(ptr) & 7) == 0 && ld % 2 == 0) ? 1 : 0;
 }
 
-template <int TC, int TJ>
+template <int NQ, int TJ>
 static int launch_dw_t(const GemmDwArgs& a, cudaStream_t s, int prof_cat, int* grid_out) {
-  constexpr int BC = 16 * TC, BJ = 16 * TJ;
-  const size_t smem = (size_t)GEMM_STAGES * 8 * (BC + BJ) * sizeof(float);
+  constexpr int BK = 64 * NQ, BJ = 16 * TJ;
+  const size_t smem = (size_t)GEMM_STAGES * DW_ROWS * (BK + BJ) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<TC, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_kernel<NQ, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const int n_chunks = (a.n_rows + 7) / 8;
-  const int grid = grid_for((n_chunks + 31) / 32, 2);     // at least 32 row chunks (256 rows) per CTA
+  const int grid = gemm_dw_grid(a.n_rows);
   if (grid_out) *grid_out = grid;
   ProfScope ps(prof_cat, s);
-  gemm_dw_kernel<TC, TJ><<<grid, 256, smem, s>>>(a);
+  gemm_dw_kernel<NQ, TJ><<<grid, 256, smem, s>>>(a);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;
 }
 
 int gemm_dw_supported(int Kp, int H) { return Kp <= 192 && H <= 80; }
-int gemm_dw_grid(int n_rows) { return grid_for((((n_rows + 7) / 8) + 31) / 32, 2); }
+int gemm_dw_grid(int n_rows) { return grid_for((((n_rows + DW_ROWS - 1) / DW_ROWS) + 7) / 8, 2); }   // >= 256 rows per CTA
 
 int launch_gemm_dw(const GemmDwArgs& a, cudaStream_t s, int prof_cat, int* grid_out) {
   if (a.n_rows <= 0) { if (grid_out) *grid_out = 0; return GNNFP_OK; }
-  const int tc = (a.Kp + 15) / 16, tj = (a.H + 15) / 16;
-#define DW_CASE(C, J) if (tc <= C && tj <= J) return launch_dw_t<C, J>(a, s, prof_cat, grid_out)
-  DW_CASE(2, 1); DW_CASE(3, 1); DW_CASE(4, 2); DW_CASE(5, 2); DW_CASE(6, 3); DW_CASE(7, 3); DW_CASE(8, 4); DW_CASE(9, 4); DW_CASE(10, 5);
-  DW_CASE(11, 5); DW_CASE(12, 5);
+  if (a.Kp % 2 != 0 || !gemm_dw_supported(a.Kp, a.H)) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_dw: K=%d, H=%d outside the supported tile shapes", a.Kp, a.H);
+  const int nq = (a.Kp + 63) / 64, tj = (a.H + 15) / 16;
+#define DW_CASE(Q, J) if (nq == Q && tj == J) return launch_dw_t<Q, J>(a, s, prof_cat, grid_out)
+  DW_CASE(1, 1); DW_CASE(1, 2); DW_CASE(1, 3); DW_CASE(1, 4); DW_CASE(1, 5);
+  DW_CASE(2, 1); DW_CASE(2, 2); DW_CASE(2, 3); DW_CASE(2, 4); DW_CASE(2, 5);
+  DW_CASE(3, 1); DW_CASE(3, 2); DW_CASE(3, 3); DW_CASE(3, 4); DW_CASE(3, 5);
 #undef DW_CASE
   GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_dw: K=%d, H=%d outside the supported tile shapes", a.Kp, a.H);
 }

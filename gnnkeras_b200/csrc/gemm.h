@@ -35,7 +35,7 @@ struct GemmDwArgs {
   const int* rowlist;
   int n_pieces;
   GemmPiece p[GEMM_MAXP];
-  int Kp;                    // padded K (multiple of 8, <= 16*TC)
+  int Kp;                    // padded K (even; pieces at even offsets k8)
   const float* dz; int ld_dz; int H;
   float* partial;            // [grid][n_params]: dW at (real k index)*H + j, db at bias_off + j
   int n_params; int bias_off;

@@ -13,6 +13,7 @@
 
 #include "loop.h"
 #include "tile.cuh"
+#include "gemm.h"
 
 // G0 and the loop-invariant aggregates' gradients -> d_state0 / d_nodes
 struct InGradArgs {
@@ -265,6 +266,32 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     }
     nsplit[ty] = ns;
   }
+  // GEMM path (gemm.cu) for homogeneous single-layer nets whose pieces are plain matrices of <= 80 columns: dW by
+  // gemm_dw, dX per destination block by gemm_rows over the transposed weight block (built once per call here).
+  bool gemm_bwd[GNNFP_MAX_TYPES];
+  for (int ty = 0; ty < L->nt; ++ty) {
+    gemm_bwd[ty] = false;
+    if (!dzpath[ty] || !L->gemm_ok[ty] || L->composite || getenv("GNNFP_NO_GEMM_BWD")) continue;
+    TileSrc probe;
+    build_state_src(c, ty, 1, probe, 1);
+    const int H0 = L->snet[ty].widths[0];
+    bool ok = true;
+    int k2 = 0;
+    for (int p = 0; p < probe.n_pieces; ++p) {
+      const Piece& pc = probe.p[p];
+      if (pc.kind != PK_DIRECT || pc.map || pc.rowscale || pc.compact || pc.gate || pc.width > 80) ok = false;
+      k2 += ceil_to(pc.width, 2);
+    }
+    if (!ok || probe.n_pieces > GEMM_MAXP || !gemm_dw_supported(k2, H0) || !gemm_rows_supported(ceil_to(H0, 8), 80)) continue;
+    gemm_bwd[ty] = true;
+    float* wt = (float*)(c.ws + L->ws.wtb) + (size_t)ty * L->ws.wtb_stride;
+    const int KH = gemm_rows_kpad(H0);
+    for (int p = 0; p < probe.n_pieces; ++p) {
+      const int ldw = gemm_rows_ldw(probe.p[p].width);
+      if ((rc = launch_transpose_block(sp[ty].W[0], H0, probe.p[p].col0, probe.p[p].width, KH, ldw, wt, s))) return rc;
+      wt += (size_t)KH * ldw;
+    }
+  }
   for (int t = MI; t >= 1; --t) {
     const int* gate = c.flags() + (t - 1);
     const int wb = t & 1, rb = (t + 1) & 1;
@@ -302,7 +329,53 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
         if (L->snet[ty].has_bn)
           GNNFP_CHECK_CUDA(cudaMemsetAsync(bn_part, 0, (size_t)L->grid_cap * 2 * L->snet[ty].in_dim * sizeof(float), s));
         const int H0 = L->snet[ty].widths[0];
-        for (int si = 0; si < nsplit[ty]; ++si) {
+        int grid_dw = 0;
+        if (gemm_bwd[ty]) {
+          const int in = L->snet[ty].in_dim;
+          float* coef = (float*)(c.ws + L->ws.bncoef) + (size_t)ty * L->ws.bncoef_stride;
+          const bool bn = L->snet[ty].has_bn != 0;
+          if (bn) {
+            BnCoefArgs bc;
+            memset(&bc, 0, sizeof(bc));
+            bc.src = full; bc.net = ndfull; bc.coef = coef; bc.gate = gate;
+            if ((rc = launch_bn_coef(bc, s))) return rc;
+          }
+          GemmDwArgs dw;
+          memset(&dw, 0, sizeof(dw));
+          dw.n_rows = full.n_rows; dw.rowlist = full.rowlist; dw.n_pieces = full.n_pieces;
+          int k2 = 0;
+          for (int p = 0; p < full.n_pieces; ++p) {
+            gemm_piece_set(dw.p[p], full.p[p].ptr, full.p[p].ld, full.p[p].width, k2);
+            k2 += ceil_to(full.p[p].width, 2);
+          }
+          dw.Kp = k2; dw.dz = dzbuf; dw.ld_dz = D; dw.H = H0;
+          dw.partial = part_state + ps_off[ty]; dw.n_params = L->nparam_s[ty]; dw.bias_off = in * H0;
+          dw.W = ndfull.W[0];
+          if (bn) { dw.bnA = coef; dw.bnB = coef + in; dw.gamma = ndfull.gamma; dw.beta = ndfull.beta; dw.bn_partial = bn_part; }
+          dw.gate = gate;
+          if ((rc = launch_gemm_dw(dw, s, PC_BWD_ITER, &grid_dw))) return rc;
+          grid_state[ty] = grid_dw > grid_state[ty] ? grid_dw : grid_state[ty];
+          const float* wt = (const float*)(c.ws + L->ws.wtb) + (size_t)ty * L->ws.wtb_stride;
+          const int KH = gemm_rows_kpad(H0);
+          for (int p = 0; p < full.n_pieces; ++p) {
+            const Piece& pc = full.p[p];
+            const int ldw = gemm_rows_ldw(pc.width);
+            if (pc.gptr) {
+              GemmRowsArgs ga;
+              memset(&ga, 0, sizeof(ga));
+              ga.n_rows = full.n_rows; ga.rowlist = full.rowlist; ga.n_pieces = 1;
+              gemm_piece_set(ga.p[0], dzbuf, D, H0, 0);
+              ga.fwd = 0; ga.Kpad = KH; ga.Wp = wt; ga.ldw = ldw; ga.N = pc.width;
+              ga.colscale = bn ? coef + 2 * in + pc.col0 : nullptr;
+              ga.out = pc.gptr; ga.ld_out = pc.gld; ga.out_add = pc.gmode == GM_ADD;
+              ga.vec2 = pc.gld % 2 == 0 && ((uintptr_t)pc.gptr & 7) == 0;
+              ga.gate = gate;
+              if ((rc = launch_gemm_rows(ga, s, PC_BWD_ITER))) return rc;
+            }
+            wt += (size_t)KH * ldw;
+          }
+        }
+        for (int si = 0; si < (gemm_bwd[ty] ? 0 : nsplit[ty]); ++si) {
           const Split& sp_ = splits[ty][si];
           BwdArgs ba;
           memset(&ba, 0, sizeof(ba));
@@ -345,7 +418,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
           if ((rc = launch_tile_bwd(ba, s))) return rc;
         }
         // BN tail over the whole net (all splits wrote their columns of bn_partial)
-        last_ba.src = full; last_ba.net = ndfull; last_ba.tc.grid = L->grid_cap; last_ba.tc.cap_per_row = L->cap_per_row;
+        last_ba.src = full; last_ba.net = ndfull; last_ba.tc.grid = gemm_bwd[ty] ? grid_dw : L->grid_cap; last_ba.tc.cap_per_row = L->cap_per_row;
         last_ba.bn_partial = bn_part; last_ba.gate = gate;
       } else {
         BwdArgs ba;
