@@ -304,7 +304,10 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
         else if (pc.tag == TAG_STATE) { pc.gptr = dOwn[wb]; pc.gld = D; pc.gmode = GM_STORE; }
         else if (want) {
           if (pc.tag == TAG_NODES) { if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = GM_ADD; } }   // composite nodes[:, :d_t]
-          else if (pc.tag == TAG_STATIC) { pc.gptr = dXs + (pc.ptr - c.Xs()); pc.gld = L->LsM; pc.gmode = GM_ADD; }  // static block columns
+          else if (pc.tag == TAG_STATIC) {   // static block columns; a block of arc-label aggregates only matters for d_arc_labels
+            const bool arcs_only = !L->composite && NLp == 0;
+            if (!arcs_only || (want & 2)) { pc.gptr = dXs + (pc.ptr - c.Xs()); pc.gld = L->LsM; pc.gmode = GM_ADD; }
+          }
         }
       }
       NetDev ndfull;
