@@ -65,14 +65,14 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
   const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
   const int my_tiles = max(0, tile1 - tile0);
   const int NS = (a.Kpad + GR_BK - 1) / GR_BK;        // stages per tile (the last one may be partial)
-  const int total = my_tiles * NS;
 
   // ---- producer: stage `it` = (tile, 32-column group); this thread copies column pair pq of rows ty + 16*i -------
   const int pq = tid & 15;
-  auto issue = [&](int it) {
-    if (it < total) {
-      const int tq = it / NS, sg = it - tq * NS;
-      float* dst = As + (it % GR_STAGES) * BM * GR_AS + ty * GR_AS + 2 * pq;
+  int i_tq = 0, i_sg = 0, i_st = 0;                  // next stage to issue: tile, column group, ring slot
+  auto issue = [&]() {
+    if (i_tq < my_tiles) {
+      const int tq = i_tq, sg = i_sg;
+      float* dst = As + i_st * BM * GR_AS + ty * GR_AS + 2 * pq;
       const int kcol = sg * GR_BK + 2 * pq;           // padded K index of the pair
       if (kcol < a.Kpad) {
         int p = 0;
@@ -111,11 +111,13 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
           }
         }
       }
+      if (++i_sg == NS) { i_sg = 0; ++i_tq; }
+      if (++i_st == GR_STAGES) i_st = 0;
     }
     cp_async_commit();
   };
 
-  for (int s = 0; s < GR_STAGES - 1; ++s) issue(s);
+  for (int s = 0; s < GR_STAGES - 1; ++s) issue();
   {  // resident weights + bias (plain loads; overlapped with the first stages in flight)
     const float4* w4 = reinterpret_cast<const float4*>(a.Wp);
     float4* s4 = reinterpret_cast<float4*>(Ws);
@@ -131,12 +133,14 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
     for (int m = 0; m < TN; ++m) acc[i][m] = 0.f;
   int notconv = 0;
 
-  for (int it = 0; it < total; ++it) {
+  int c_st = 0;
+  for (int tq = 0; tq < my_tiles; ++tq)
+  for (int sg = 0; sg < NS; ++sg) {
     cp_async_wait<GR_STAGES - 2>();
     __syncthreads();
-    issue(it + GR_STAGES - 1);
-    const int tq = it / NS, sg = it - tq * NS;
-    const float* Ad = As + (it % GR_STAGES) * BM * GR_AS + ty * GR_AS;
+    issue();
+    const float* Ad = As + c_st * BM * GR_AS + ty * GR_AS;
+    if (++c_st == GR_STAGES) c_st = 0;
     const float* Wd = Ws + sg * GR_BK * BN;
     const int nkq = min(GR_BK, a.Kpad - sg * GR_BK) >> 2;      // even (Kpad is a multiple of 8)
 #pragma unroll 2

@@ -254,37 +254,62 @@ __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ 
   double su[VEC], sq[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { su[v] = 0.0; sq[v] = 0.0; }
-  if (qx < nq) {
-    for (int r = blockIdx.x * rpb + ry; r < a.n_rows; r += gridDim.x * rpb) {
-      const int gr = a.rowlist ? a.rowlist[r] : r;
-      const int a0 = a.rowptr[gr], a1 = a.rowptr[gr + 1];
-      float acc[VEC];
+  if (qx < nq && ry < rpb) {
+    // two rows per trip: their rowptr -> idx -> state-row load chains overlap (the kernel is latency bound otherwise)
+    const int stride = gridDim.x * rpb;
+    for (int r = blockIdx.x * rpb + ry; r < a.n_rows; r += 2 * stride) {
+      const int r2 = r + stride;
+      const bool has2 = r2 < a.n_rows;
+      const int gr0 = a.rowlist ? a.rowlist[r] : r;
+      const int gr1 = has2 ? (a.rowlist ? a.rowlist[r2] : r2) : gr0;
+      const int b0 = a.rowptr[gr0], e0 = a.rowptr[gr0 + 1];
+      const int b1 = has2 ? a.rowptr[gr1] : 0, e1 = has2 ? a.rowptr[gr1 + 1] : 0;
+      float acc0[VEC], acc1[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-      for (int p = a0; p < a1; p += 4) {
-        float t[4][VEC], wv[4];
+      for (int v = 0; v < VEC; ++v) { acc0[v] = 0.f; acc1[v] = 0.f; }
+      const int n0 = e0 - b0, n1 = e1 - b1;
+      const int nmax = n0 > n1 ? n0 : n1;
+      for (int q = 0; q < nmax; q += 2) {
+        float t0[2][VEC], t1[2][VEC], w0[2], w1[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool ok = p + u < a1;
-          const int pi = ok ? p + u : p;
-          wv[u] = ok ? (a.wgt ? a.wgt[pi] : 1.0f) : 0.0f;
-          load_vec<VEC>(a.S + (size_t)a.idx[pi] * a.ld + qx * VEC, t[u]);
+        for (int u = 0; u < 2; ++u) {
+          const bool ok0 = q + u < n0, ok1 = q + u < n1;
+          const int p0 = ok0 ? b0 + q + u : 0, p1 = ok1 ? b1 + q + u : 0;
+          w0[u] = ok0 ? (a.wgt ? a.wgt[p0] : 1.0f) : 0.0f;
+          w1[u] = ok1 ? (a.wgt ? a.wgt[p1] : 1.0f) : 0.0f;
+          const int i0 = ok0 ? a.idx[p0] : gr0, i1 = ok1 ? a.idx[p1] : gr1;
+          load_vec<VEC>(a.S + (size_t)i0 * a.ld + qx * VEC, t0[u]);
+          load_vec<VEC>(a.S + (size_t)i1 * a.ld + qx * VEC, t1[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (p + u < a1) {
+        for (int u = 0; u < 2; ++u) {
+          if (q + u < n0) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], t[u][v], acc[v]);
+            for (int v = 0; v < VEC; ++v) acc0[v] = fmaf(w0[u], t0[u][v], acc0[v]);
           }
+          if (q + u < n1) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc1[v] = fmaf(w1[u], t1[u][v], acc1[v]);
+          }
+        }
       }
       if (a.out) {
-        float* o = a.out + (size_t)gr * a.D + qx * VEC;
-        if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
-        else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1 % VEC]);
-        else o[0] = acc[0];
+        float* o = a.out + (size_t)gr0 * a.D + qx * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc0[0], acc0[1 % VEC], acc0[2 % VEC], acc0[3 % VEC]);
+        else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(acc0[0], acc0[1 % VEC]);
+        else o[0] = acc0[0];
+        if (has2) {
+          float* o2 = a.out + (size_t)gr1 * a.D + qx * VEC;
+          if (VEC == 4) *reinterpret_cast<float4*>(o2) = make_float4(acc1[0], acc1[1 % VEC], acc1[2 % VEC], acc1[3 % VEC]);
+          else if (VEC == 2) *reinterpret_cast<float2*>(o2) = make_float2(acc1[0], acc1[1 % VEC]);
+          else o2[0] = acc1[0];
+        }
       }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) { su[v] += (double)acc[v]; sq[v] += (double)acc[v] * (double)acc[v]; }
+      for (int v = 0; v < VEC; ++v) {
+        su[v] += (double)acc0[v]; sq[v] += (double)acc0[v] * (double)acc0[v];
+        if (has2) { su[v] += (double)acc1[v]; sq[v] += (double)acc1[v] * (double)acc1[v]; }
+      }
     }
   }
   if (a.st_sum) {
@@ -311,8 +336,7 @@ int launch_agg_stats(const AggArgs& a, cudaStream_t s) {
   else if (a.D % 2 == 0 && a.ld % 2 == 0 && al(a.S, 8) && al(a.out, 8)) vec = 2;
   const int nq = a.D / vec;
   if (nq > 256) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "state width %d too large for the aggregation kernel", a.D);
-  int QX = 1;
-  while (QX < nq) QX *= 2;
+  const int QX = nq;                                  // threads per row (rows may straddle warps)
   const int rpb = 256 / QX;
   long long blocks = ((long long)a.n_rows + rpb - 1) / rpb;
   const long long cap = (long long)gnnfp_num_sms() * 8;
