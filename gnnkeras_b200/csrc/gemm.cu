@@ -193,10 +193,34 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
         const int grow = row0 + 16 * i;
         const bool valid = grow < n;
         float sd = 0.f, sp = 0.f;
+        float v[TN];
+        if (FWD) {
+#pragma unroll
+          for (int m = 0; m < TN; ++m) {
+            const float z = acc[i][m] + cadd[m];
+            v[m] = selu ? selu_fwd(z) : act_fwd(a.act, z);
+          }
+          if (a.act == GNNFP_ACT_SOFTMAX) {   // Keras softmax over the row: its columns live in the 16 lanes sharing ty
+            float mx = -INFINITY;
+#pragma unroll
+            for (int m = 0; m < TN; ++m) if (cval[m]) mx = fmaxf(mx, v[m]);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float se = 0.f;
+#pragma unroll
+            for (int m = 0; m < TN; ++m) { v[m] = cval[m] ? expf(v[m] - mx) : 0.f; se += v[m]; }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+#pragma unroll
+            for (int m = 0; m < TN; ++m) v[m] = v[m] / se;
+          }
+#pragma unroll
+          for (int m = 0; m < TN; ++m) if (!cval[m]) v[m] = 0.f;
+        }
         if (valid) {
           const int gr = a.rowlist ? a.rowlist[grow] : grow;
-          float* orow = a.out + (size_t)gr * a.ld_out;
-          float v[TN], pv[TN];
+          float* orow = a.out + (size_t)(a.out_compact ? grow : gr) * a.ld_out;
+          float pv[TN];
           if (FWD) {
             if (a.prev) {
               const float* prow = a.prev + (size_t)gr * a.ld_prev;
@@ -210,12 +234,6 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
 #pragma unroll
                 for (int m = 0; m < TN; ++m) pv[m] = cval[m] ? prow[col[m]] : 0.f;
               }
-            }
-#pragma unroll
-            for (int m = 0; m < TN; ++m) {
-              const float z = acc[i][m] + cadd[m];
-              v[m] = selu ? selu_fwd(z) : act_fwd(a.act, z);
-              if (!cval[m]) v[m] = 0.f;
             }
             if (a.prev) {
 #pragma unroll

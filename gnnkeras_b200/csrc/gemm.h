@@ -24,6 +24,7 @@ struct GemmRowsArgs {
   const float* colscale;     // [N] or NULL: epilogue multiply (backward: gamma*rstd)
   int act;
   float* out; int ld_out; int out_add;   // out[gr*ld_out + j] (= or +=)
+  int out_compact;           // output row = position in the row set instead of the global row id
   const float* prev; int ld_prev; float thr; int* flag_next;   // convergence epilogue (forward) or NULL
   double* ost_sum; double* ost_sq;                            // output column statistics or NULL
   const int* gate;

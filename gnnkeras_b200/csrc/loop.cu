@@ -361,6 +361,11 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     L->gemm_ok[t] = d.n_layers == 1 && d.acts[0] != GNNFP_ACT_SOFTMAX && d.widths[0] <= 80 && gemm_rows_supported(ceil_to(d.in_dim, 8) + 8 * 3, d.widths[0]) &&
                     getenv("GNNFP_NO_GEMM") == nullptr;
   }
+  {
+    const gnnfp_net_desc& d = L->onet;
+    L->out_gemm_ok = cfg->kind != GNNFP_KIND_ARC && d.n_layers == 1 && d.widths[0] <= (d.acts[0] == GNNFP_ACT_SOFTMAX ? 16 : 80) &&
+                     gemm_rows_supported(ceil_to(d.in_dim, 8) + 8 * 3, d.widths[0]) && getenv("GNNFP_NO_GEMM") == nullptr;
+  }
   L->grid_cap = gnnfp_num_sms() * 4;   // backward tile kernels run at most 4 CTAs per SM (tile_cfg_bwd)
 
   // ---- workspace layout ---------------------------------------------------------------------
@@ -384,17 +389,18 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   w.agg = off; off = align_up(off + (cfg->training ? (size_t)MI : (size_t)(MI > 0 ? 1 : 0)) * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float) + 4);
   {
     size_t wf = 0, wt = 0, bc = 0;
-    for (int t = 0; t < L->nt; ++t) {
-      const int in = L->snet[t].in_dim, H = L->snet[t].widths[0];
+    for (int t = 0; t <= L->nt; ++t) {                 // slot nt: net_output
+      const gnnfp_net_desc& dd = t < L->nt ? L->snet[t] : L->onet;
+      const int in = dd.in_dim, H = dd.widths[0];
       const size_t kp = (size_t)gemm_rows_kpad(ceil_to(in, 8) + 8 * GNNFP_MAXP);
       const size_t f = kp * gemm_rows_ldw(H) + gemm_rows_ldw(H);
       const size_t tb = (size_t)ceil_to(H, 8) * ((size_t)ceil_to(in, 16) + 16 * GNNFP_MAXP);
       wf = f > wf ? f : wf; wt = tb > wt ? tb : wt; bc = (size_t)3 * in > bc ? (size_t)3 * in : bc;
     }
     w.wfold_stride = (wf + 63) / 64 * 64; w.wtb_stride = (wt + 63) / 64 * 64; w.bncoef_stride = (bc + 63) / 64 * 64;
-    w.wfold = off; off = align_up(off + L->nt * w.wfold_stride * sizeof(float));
-    w.wtb = off; off = align_up(off + L->nt * w.wtb_stride * sizeof(float));
-    w.bncoef = off; off = align_up(off + L->nt * w.bncoef_stride * sizeof(float));
+    w.wfold = off; off = align_up(off + (L->nt + 1) * w.wfold_stride * sizeof(float));
+    w.wtb = off; off = align_up(off + (L->nt + 1) * w.wtb_stride * sizeof(float));
+    w.bncoef = off; off = align_up(off + (L->nt + 1) * w.bncoef_stride * sizeof(float));
   }
   if (cfg->training) {
     const size_t ND = (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float);
@@ -643,14 +649,39 @@ static int fwd_end(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_par
       if ((rc = launch_tile_pass(pa, s))) return rc;
     }
     fill_netdev(L->onet, *op, training, fa.src.n_rows, fa.net);
-    fa.tc.cap_per_row = L->cap_per_row;
-    if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;
-    fa.prev_col0 = -1;
     float* on = L->pool ? (float*)(c.ws + L->ws.out_nodes) : io->out;
-    fa.out = on; fa.ld_out = L->T; fa.out_compact = 1;
-    fa.update_moving = training;
-    fa.prof_cat = PC_FWD_OUT;
-    if ((rc = launch_tile_fwd(fa, s))) return rc;
+    if (L->out_gemm_ok) {
+      // single Dense layer over plain matrices: BN folded into padded weights, one pipelined GEMM (softmax in the epilogue)
+      FoldArgs fo;
+      memset(&fo, 0, sizeof(fo));
+      fo.src = fa.src; fo.net = fa.net;
+      GemmRowsArgs ga;
+      memset(&ga, 0, sizeof(ga));
+      int k2 = 0;
+      for (int p = 0; p < fa.src.n_pieces; ++p) {
+        fo.k8[p] = k2;
+        gemm_piece_set(ga.p[p], fa.src.p[p].ptr, fa.src.p[p].ld, fa.src.p[p].width, k2);
+        k2 += ceil_to(fa.src.p[p].width, 2);
+      }
+      const int H = L->onet.widths[0];
+      float* wf = (float*)(c.ws + L->ws.wfold) + (size_t)L->nt * L->ws.wfold_stride;
+      fo.Kpad = gemm_rows_kpad(k2); fo.ldw = gemm_rows_ldw(H); fo.Wp = wf; fo.biasp = wf + (size_t)fo.Kpad * fo.ldw;
+      fo.update_moving = training;
+      if ((rc = launch_fold_w(fo, s))) return rc;
+      ga.n_rows = fa.src.n_rows; ga.rowlist = fa.src.rowlist; ga.n_pieces = fa.src.n_pieces; ga.Kpad = fo.Kpad;
+      ga.Wp = fo.Wp; ga.ldw = fo.ldw; ga.N = H; ga.bias = fo.biasp; ga.act = L->onet.acts[0];
+      ga.out = on; ga.ld_out = L->T; ga.out_compact = 1; ga.fwd = 1;
+      ga.vec2 = L->T % 2 == 0 && ((uintptr_t)on & 7) == 0;
+      if ((rc = launch_gemm_rows(ga, s, PC_FWD_OUT))) return rc;
+    } else {
+      fa.tc.cap_per_row = L->cap_per_row;
+      if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;
+      fa.prev_col0 = -1;
+      fa.out = on; fa.ld_out = L->T; fa.out_compact = 1;
+      fa.update_moving = training;
+      fa.prof_cat = PC_FWD_OUT;
+      if ((rc = launch_tile_fwd(fa, s))) return rc;
+    }
     if (L->pool) {
       const int tot = g->G * L->T;
       k_pool<<<(tot + 255) / 256, 256, 0, s>>>(on, g->graph_ptr, g->ng_val, g->G, L->T, io->out);

@@ -38,6 +38,7 @@ struct gnnfp_loop {
   int slot_count = 0;
   int bn_train_state = 0, bn_train_out = 0;
   int nparam_s[GNNFP_MAX_TYPES]{}, nparam_o = 0;
+  int out_gemm_ok = 0;              // net_output runs on the GEMM kernels (single Dense layer, node / graph focus)
   int gemm_ok[GNNFP_MAX_TYPES]{};   // single Dense layer nets run the pipelined GEMM kernels (gemm.cu)
   int cap_per_row = 4;   // CSR scratch capacity per tile row (from A/N)
   int grid_cap = 0;      // upper bound of any backward tile kernel grid (partials are sized by it)

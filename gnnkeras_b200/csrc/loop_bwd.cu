@@ -483,7 +483,20 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     const size_t tot = (size_t)N * (D > L->NLw ? D : L->NLw);
     int blocks = (int)((tot + 255) / 256);
     if (blocks > 4736) blocks = 4736;
-    if (ia.d_nodes || ia.d_state0) {
+    if (!L->composite && L->S == 0 && MI > 0 && ia.d_nodes && L->NLw == D) {
+      // state0 = nodes (GNN.py:259): d_nodes = G_0 = dOwn_1 + Adj . dAgg_1 - the same streaming kernel as the iterations'
+      // dz with a linear activation (d_nodes was zeroed above and has no other contribution in this configuration)
+      DzArgs da;
+      memset(&da, 0, sizeof(da));
+      da.n_rows = N; da.D = D; da.act = GNNFP_ACT_LINEAR;
+      da.s_t = c.S(0); da.ld_s = c.ldS(0);
+      da.dSfin = dSfin; da.dOwn = dOwn[1]; da.dAgg = dAgg[1];
+      da.rowptr = g->src_rowptr; da.idx = g->src_dst; da.wgt = src_w;
+      da.last_flag = c.flags();
+      da.dz = gr->d_nodes;
+      if (ia.cn) { da.cn = ia.cn; da.agg_next = c.AGG(1); da.in_dim = ia.in_dim; da.own_col0 = 0; da.agg_col0 = D; }
+      if ((rc = launch_dz(da, s))) return rc;
+    } else if (ia.d_nodes || ia.d_state0) {
       k_input_grads_nodes<<<blocks, 256, 0, s>>>(ia);
       GNNFP_COUNT_LAUNCH();
     }
