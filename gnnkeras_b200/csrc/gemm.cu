@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
 
   // ---- producer: stage `it` = (tile, 32-column group); this thread copies column pair pq of rows ty + 16*i -------
   const int pq = tid & 15;
+  const int* arl = a.a_compact ? nullptr : a.rowlist;  // row list of the input pieces
   int i_tq = 0, i_sg = 0, i_st = 0;                  // next stage to issue: tile, column group, ring slot
   auto issue = [&]() {
     if (i_tq < my_tiles) {
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
         if (nv <= 0) {
 #pragma unroll
           for (int i = 0; i < TM; ++i) cp_async8(dst + i * 16 * GR_AS, pptr, 0);
-        } else if (al8 && a.rowlist == nullptr && (tile0 + tq + 1) * BM <= n) {
+        } else if (al8 && arl == nullptr && (tile0 + tq + 1) * BM <= n) {
           const float* src = pptr + (size_t)row0 * pld + kk;
           const size_t step = (size_t)16 * pld;
           const int bytes = nv > 1 ? 8 : 4;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
             const bool valid = grow < n;
             const float* src = pptr;
             if (valid) {
-              const int gr = a.rowlist ? a.rowlist[grow] : grow;
+              const int gr = arl ? arl[grow] : grow;
               src = pptr + (size_t)gr * pld + kk;
             }
             if (al8) {
@@ -248,6 +249,16 @@ __global__ void __launch_bounds__(256, 2) gemm_rows_kernel(const __grid_constant
           } else {
 #pragma unroll
             for (int m = 0; m < TN; ++m) v[m] = acc[i][m] * cadd[m];
+            if (a.corr) {
+              const float* xr = a.corr_x + (size_t)gr * a.corr_ld;
+              const float* k = a.corr + a.corr_col0;
+#pragma unroll
+              for (int m = 0; m < TN; ++m)
+                if (cval[m]) {
+                  const int j = col[m];
+                  v[m] -= k[j] + fmaf(xr[j], k[2 * a.corr_in + j], k[3 * a.corr_in + j]) * k[a.corr_in + j];
+                }
+            }
             if (a.out_add) {
               if (quad) {
                 const float2 p0 = *reinterpret_cast<const float2*>(orow + 4 * tx);
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(256, 2) gemm_dw_kernel(const __grid_constant__
           const int grow = row0 + 8 * i;
           const bool valid = grow < n;
           const float* src = a.dz;
-          if (valid) src = a.dz + (size_t)(a.rowlist ? a.rowlist[grow] : grow) * a.ld_dz + j0;
+          if (valid) src = a.dz + (size_t)((a.rowlist && !a.dz_compact) ? a.rowlist[grow] : grow) * a.ld_dz + j0;
           if (zal8) cp_async8(dst + i * 8 * BJ, src, valid ? (nv > 1 ? 8 : 4) : 0);
           else {
             cp_async4(dst + i * 8 * BJ, src, valid ? 4 : 0);

@@ -25,6 +25,10 @@ struct GemmRowsArgs {
   int act;
   float* out; int ld_out; int out_add;   // out[gr*ld_out + j] (= or +=)
   int out_compact;           // output row = position in the row set instead of the global row id
+  int a_compact;             // input (piece) rows are addressed by position in the row set (a compact dz matrix)
+  // backward epilogue, BN-training correction folded in: out -= c0 + (x*A + B)*c1 with corr = [c0|c1|A|B] x corr_in,
+  // column corr_col0 + j, x = corr_x[gr*corr_ld + j]
+  const float* corr; int corr_in; int corr_col0; const float* corr_x; int corr_ld;
   const float* prev; int ld_prev; float thr; int* flag_next;   // convergence epilogue (forward) or NULL
   double* ost_sum; double* ost_sq;                            // output column statistics or NULL
   const int* gate;
@@ -37,7 +41,7 @@ struct GemmDwArgs {
   int n_pieces;
   GemmPiece p[GEMM_MAXP];
   int Kp;                    // padded K (even; pieces at even offsets k8)
-  const float* dz; int ld_dz; int H;
+  const float* dz; int ld_dz; int H; int dz_compact;   // dz_compact: dz rows by position in the row set
   float* partial;            // [grid][n_params]: dW at (real k index)*H + j, db at bias_off + j
   int n_params; int bias_off;
   // BN: per-CTA sums  P_c = sum_j W[c][j] db[j],  Q_c = rstd*(sum_j W[c][j] acc[c][j]) - mean*rstd*P_c

@@ -99,6 +99,51 @@ static __global__ void k_input_grads_arcs(int A, int AL, int LsM, int col0, cons
   }
 }
 
+// dz of net_output's single Dense layer, compact [M, T]:  g = un-pooled d_out (+ d_out_nodes),  dz = act'(y) g
+// (softmax: dz_j = y_j (g_j - sum_k g_k y_k), as TF's SoftmaxGrad)
+struct OutDzArgs {
+  int M, T, act;
+  const int* rowlist;
+  const float* saved;          // [M, T] outputs of the forward (compact)
+  const float* d_out;          // pooled: row node2graph[gr] scaled by ng_val[gr]; else compact [M, T]
+  const int* map; const float* rowscale;
+  const float* d_out_nodes;    // compact [M, T] or NULL
+  float* dz;
+};
+static __global__ void k_out_dz(const __grid_constant__ OutDzArgs a) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.M; r += gridDim.x * blockDim.x) {
+    const int gr = a.rowlist ? a.rowlist[r] : r;
+    const float* y = a.saved + (size_t)r * a.T;
+    const float* g1 = nullptr;
+    float sc = 1.0f;
+    if (a.d_out) {
+      g1 = a.d_out + (size_t)(a.map ? a.map[gr] : r) * a.T;
+      if (a.rowscale) sc = a.rowscale[gr];
+    }
+    const float* g2 = a.d_out_nodes ? a.d_out_nodes + (size_t)r * a.T : nullptr;
+    float* dz = a.dz + (size_t)r * a.T;
+    if (a.act == GNNFP_ACT_SOFTMAX) {
+      float dot = 0.f;
+      for (int j = 0; j < a.T; ++j) {
+        float g = g1 ? g1[j] * sc : 0.f;
+        if (g2) g += g2[j];
+        dot = fmaf(g, y[j], dot);
+      }
+      for (int j = 0; j < a.T; ++j) {
+        float g = g1 ? g1[j] * sc : 0.f;
+        if (g2) g += g2[j];
+        dz[j] = y[j] * (g - dot);
+      }
+    } else {
+      for (int j = 0; j < a.T; ++j) {
+        float g = g1 ? g1[j] * sc : 0.f;
+        if (g2) g += g2[j];
+        dz[j] = act_bwd(a.act, y[j], g);
+      }
+    }
+  }
+}
+
 extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
                                    const gnnfp_loop_io* io, const gnnfp_loop_grads* gr, gnnfp_net_params* dsp,
                                    gnnfp_net_params* dop, void* workspace, size_t workspace_bytes, void* stream) {
@@ -182,6 +227,79 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
       else if (pc.tag == TAG_NODES) { if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = arc ? GM_ATOMIC : GM_ADD; } }
       else if (pc.tag == TAG_ARC_LABELS) { if ((want & 2) && L->AL > 0) { pc.gptr = gr->d_arc_labels; pc.gld = L->AL; pc.gmode = GM_ADD; } }
     }
+    bool og = L->out_gemm_ok && !arc && getenv("GNNFP_NO_GEMM_BWD") == nullptr && ba.src.n_pieces <= GEMM_MAXP;
+    int ok2 = 0;
+    for (int p = 0; p < ba.src.n_pieces; ++p) {
+      const Piece& pc = ba.src.p[p];
+      if (pc.kind != PK_DIRECT || pc.map || pc.rowscale || pc.compact || pc.gate || pc.width > 80) og = false;
+      ok2 += ceil_to(pc.width, 2);
+    }
+    og = og && gemm_dw_supported(ok2, L->T) && gemm_rows_supported(ceil_to(L->T, 8), 80);
+    if (og) {
+      // GEMM path: dz (compact) -> dW/db + BN sums -> BN constants -> dX per input block with the BN-training
+      // correction folded into the epilogue (no separate fix-up pass over dSfin)
+      const int in = L->onet.in_dim, H = L->T;
+      const bool bn = L->onet.has_bn != 0;
+      float* dzo = (float*)(c.ws + L->ws.dOutN);
+      OutDzArgs oa;
+      memset(&oa, 0, sizeof(oa));
+      oa.M = L->M; oa.T = H; oa.act = L->onet.acts[0]; oa.rowlist = ba.src.rowlist;
+      oa.saved = L->pool ? (const float*)(c.ws + L->ws.out_nodes) : io->out;
+      oa.d_out = gr->d_out;
+      if (gr->d_out && L->pool) { oa.map = g->node2graph; oa.rowscale = g->ng_val; }
+      oa.d_out_nodes = gr->d_out_nodes;
+      oa.dz = dzo;
+      {
+        int blocks = (L->M + 255) / 256;
+        if (blocks > 2368) blocks = 2368;
+        if (blocks < 1) blocks = 1;
+        k_out_dz<<<blocks, 256, 0, s>>>(oa);
+        GNNFP_COUNT_LAUNCH();
+      }
+      float* coef = (float*)(c.ws + L->ws.bncoef) + (size_t)L->nt * L->ws.bncoef_stride;
+      if (bn) {
+        BnCoefArgs bc;
+        memset(&bc, 0, sizeof(bc));
+        bc.src = ba.src; bc.net = ond; bc.coef = coef;
+        if ((rc = launch_bn_coef(bc, s))) return rc;
+      }
+      GemmDwArgs dw;
+      memset(&dw, 0, sizeof(dw));
+      dw.n_rows = ba.src.n_rows; dw.rowlist = ba.src.rowlist; dw.n_pieces = ba.src.n_pieces;
+      int k2 = 0;
+      for (int p = 0; p < ba.src.n_pieces; ++p) {
+        gemm_piece_set(dw.p[p], ba.src.p[p].ptr, ba.src.p[p].ld, ba.src.p[p].width, k2);
+        k2 += ceil_to(ba.src.p[p].width, 2);
+      }
+      dw.Kp = k2; dw.dz = dzo; dw.ld_dz = H; dw.H = H; dw.dz_compact = 1;
+      dw.partial = part_out; dw.n_params = L->nparam_o; dw.bias_off = in * H;
+      dw.W = ond.W[0];
+      if (bn) { dw.bnA = coef; dw.bnB = coef + in; dw.gamma = ond.gamma; dw.beta = ond.beta; dw.bn_partial = bn_part; }
+      if ((rc = launch_gemm_dw(dw, s, PC_BWD_OUT, &grid_out))) return rc;
+      if (bn) {
+        ba.net = ond; ba.bn_partial = bn_part; ba.tc.grid = grid_out;
+        if ((rc = launch_bn_tail(ba, bn_grad + bg_off[L->nt], bn_const, s, 1, nullptr))) return rc;
+      }
+      float* wt = (float*)(c.ws + L->ws.wtb) + (size_t)L->nt * L->ws.wtb_stride;
+      const int KH = gemm_rows_kpad(H);
+      for (int p = 0; p < ba.src.n_pieces; ++p) {
+        const Piece& pc = ba.src.p[p];
+        if (!pc.gptr) continue;
+        const int ldw = gemm_rows_ldw(pc.width);
+        if ((rc = launch_transpose_block(ond.W[0], H, pc.col0, pc.width, KH, ldw, wt, s))) return rc;
+        GemmRowsArgs ga;
+        memset(&ga, 0, sizeof(ga));
+        ga.n_rows = ba.src.n_rows; ga.rowlist = ba.src.rowlist; ga.n_pieces = 1; ga.a_compact = 1;
+        gemm_piece_set(ga.p[0], dzo, H, H, 0);
+        ga.fwd = 0; ga.Kpad = KH; ga.Wp = wt; ga.ldw = ldw; ga.N = pc.width;
+        ga.colscale = bn ? coef + 2 * in + pc.col0 : nullptr;
+        if (bn) { ga.corr = bn_const; ga.corr_in = in; ga.corr_col0 = pc.col0; ga.corr_x = pc.ptr; ga.corr_ld = pc.ld; }
+        ga.out = pc.gptr; ga.ld_out = pc.gld; ga.out_add = pc.gmode == GM_ADD;
+        ga.vec2 = pc.gld % 2 == 0 && ((uintptr_t)pc.gptr & 7) == 0;
+        if ((rc = launch_gemm_rows(ga, s, PC_BWD_OUT))) return rc;
+        wt += (size_t)KH * ldw;
+      }
+    } else {
     ba.gsrc.n_rows = ba.src.n_rows; ba.gsrc.rowlist = ba.src.rowlist; ba.gsrc.in_dim = L->T;
     if (gr->d_out) {
       Piece p = mk_direct(gr->d_out, L->T, L->T, 0);
@@ -206,6 +324,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     ba.prof_cat = PC_BWD_OUT;
     if ((rc = launch_tile_bwd(ba, s))) return rc;
     if (L->onet.has_bn && (rc = launch_bn_tail(ba, bn_grad + bg_off[L->nt], bn_const, s))) return rc;
+    }
   }
 
   // ---- 2. iterations, newest first ---------------------------------------------------------------
