@@ -557,25 +557,25 @@ struct BnReduceArgs {
   float* static_acc;  // optional [2*in_dim]: running sums of c0, c1 over the iterations (static columns)
   const int* gate;
 };
-// one block per 32 columns: thread (cx, gy) sums partial rows gy, gy+8, ... of column cx (4 loads in flight),
-// shared-memory reduction over gy in fixed order (deterministic).
+// one block per 8 columns: thread (cx, gy) sums partial rows gy, gy+32, ... of column cx (up to 4 loads in flight),
+// shared-memory reduction over the 32 row groups in fixed order (deterministic).
+#define BNR_COLS 8
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ BnReduceArgs a) {
   if (a.gate && *a.gate == 0) return;
   extern __shared__ float sm[];
-  __shared__ double redp[8][32], redq[8][32];
+  __shared__ double redp[32][BNR_COLS], redq[32][BNR_COLS];
   const int in = a.net.in_dim;
   float* A = sm;
   float* Bc = sm + in;
-  bn_coefficients(a.src, a.net, 0, A, Bc, nullptr, nullptr);
-  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  const int cx = threadIdx.x & (BNR_COLS - 1), gy = threadIdx.x / BNR_COLS;
+  const int c = blockIdx.x * BNR_COLS + cx;
   double p = 0.0, q = 0.0;
-  if (c < in) {
-    for (int b0 = gy; b0 < a.grid; b0 += 32) {
+  if (c < in) {                                        // issue the partial loads before the (fp64) coefficient math
+    for (int b0 = gy; b0 < a.grid; b0 += 128) {
       float pv[4], qv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int b = b0 + 8 * u;
+        const int b = b0 + 32 * u;
         pv[u] = b < a.grid ? a.bn_partial[(size_t)b * 2 * in + c] : 0.f;
         qv[u] = b < a.grid ? a.bn_partial[(size_t)b * 2 * in + in + c] : 0.f;
       }
@@ -585,10 +585,11 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ 
   }
   redp[gy][cx] = p;
   redq[gy][cx] = q;
+  bn_coefficients(a.src, a.net, 0, A, Bc, nullptr, nullptr);
   __syncthreads();
   if (gy == 0 && c < in) {
     p = 0.0; q = 0.0;
-    for (int g2 = 0; g2 < 8; ++g2) { p += redp[g2][cx]; q += redq[g2][cx]; }
+    for (int g2 = 0; g2 < 32; ++g2) { p += redp[g2][cx]; q += redq[g2][cx]; }
     a.bn_grad[c] += (float)q;
     a.bn_grad[in + c] += (float)p;
     const float ac = a.net.gamma[c] * A[c];
@@ -877,7 +878,7 @@ int launch_bn_tail(const BwdArgs& a, float* bn_grad, float* bn_const, cudaStream
   memset(&ra, 0, sizeof(ra));
   ra.src = a.src; ra.net = a.net; ra.bn_partial = a.bn_partial; ra.grid = a.tc.grid;
   ra.bn_grad = bn_grad; ra.bn_const = bn_const; ra.gate = a.gate; ra.static_acc = static_acc;
-  bn_reduce_kernel<<<(a.net.in_dim + 31) / 32, 256, 2 * a.net.in_dim * sizeof(float), s>>>(ra);
+  bn_reduce_kernel<<<(a.net.in_dim + BNR_COLS - 1) / BNR_COLS, 256, 2 * a.net.in_dim * sizeof(float), s>>>(ra);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   if (a.net.bn_mode != 1 || no_fix) return GNNFP_OK;

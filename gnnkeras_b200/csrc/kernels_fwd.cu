@@ -338,9 +338,19 @@ int launch_agg_stats(const AggArgs& a, cudaStream_t s) {
   if (nq > 256) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "state width %d too large for the aggregation kernel", a.D);
   const int QX = nq;                                  // threads per row (rows may straddle warps)
   const int rpb = 256 / QX;
-  long long blocks = ((long long)a.n_rows + rpb - 1) / rpb;
-  const long long cap = (long long)gnnfp_num_sms() * 8;
+  long long blocks = ((long long)a.n_rows + 2 * rpb - 1) / (2 * rpb);
+  static int occ[3] = {0, 0, 0};                      // resident blocks per SM of the three instantiations: one full wave
+  const int oi = vec == 4 ? 2 : (vec == 2 ? 1 : 0);
+  if (!occ[oi]) {
+    int o = 0;
+    if (vec == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<4>, 256, 0);
+    else if (vec == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<2>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<1>, 256, 0);
+    occ[oi] = o > 0 ? o : 4;
+  }
+  const long long cap = (long long)gnnfp_num_sms() * occ[oi];
   if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
   ProfScope ps(PC_PASS, s);
   if (vec == 4) agg_stats_kernel<4><<<(int)blocks, 256, 0, s>>>(a, QX);
   else if (vec == 2) agg_stats_kernel<2><<<(int)blocks, 256, 0, s>>>(a, QX);
