@@ -58,6 +58,9 @@ enum { PK_DIRECT = 0, PK_GATHER = 1 };
 enum { GM_NONE = 0, GM_STORE = 1, GM_ADD = 2, GM_ATOMIC = 3 };
 enum { TAG_NONE = 0, TAG_STATE = 1, TAG_NODES = 2, TAG_AGG_STATE = 3, TAG_STATIC = 4, TAG_ARC_LABELS = 5 };
 
+// flat index / width with magic = ceil(2^32 / width); width 1 makes the 32-bit magic wrap to 0 -> identity
+__device__ __forceinline__ int div_magic(unsigned e, unsigned magic) { return magic ? (int)__umulhi(e, magic) : (int)e; }
+
 struct Piece {
   const float* ptr;        // source matrix (row-major)
   int ld;                  // its leading dimension

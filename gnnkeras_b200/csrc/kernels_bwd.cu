@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
             const int e = e0 + u * T;
             o[u] = -1; yv[u] = 0.f; gv[u] = 0.f;
             if (e < tc.R * HL) {
-              const int r = (int)__umulhi((unsigned)e, magicHL);
+              const int r = div_magic((unsigned)e, magicHL);
               const int j = e - r * HL;
               o[u] = r * XSdA + j;
               yv[u] = aL[r * XS + j];
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         const unsigned magic = (unsigned)((0x100000000ull + (unsigned)in_l - 1) / (unsigned)in_l);
 #pragma unroll 4
         for (int e = tid; e < tc.R * in_l; e += T) {
-          const int r = (int)__umulhi((unsigned)e, magic);
+          const int r = div_magic((unsigned)e, magic);
           const int c = e - r * in_l;
           oth[r * XSo + c] = act_bwd(actp, al[r * XSl + c], oth[r * XSo + c]);
         }
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
         float4* o4 = reinterpret_cast<float4*>(ob);
 #pragma unroll 2
         for (int i = tid; i < n4; i += T) {
-          int r = (int)__umulhi((unsigned)(4 * i), pc.magic);
+          int r = div_magic((unsigned)(4 * i), pc.magic);
           int c = 4 * i - r * w;
           float vv[4];
 #pragma unroll
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           const int e = e0 + u * T;
           d[u] = nullptr; v[u] = 0.f; old[u] = 0.f;
           if (e < nr * w) {
-            const int r = (int)__umulhi((unsigned)e, pc.magic);
+            const int r = div_magic((unsigned)e, pc.magic);
             const int c = e - r * w;
             v[u] = cur[r * XSc + pc.col0 + c];
             if (y.bn) v[u] *= bnS[pc.col0 + c];
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(256) tile_bnfix_kernel(const __grid_constant__
           dp[u] = nullptr;
           corr[u] = 0.f; old[u] = 0.f;
           if (e < nr * w) {
-            const int r = (int)__umulhi((unsigned)e, pc.magic);
+            const int r = div_magic((unsigned)e, pc.magic);
             const int c = e - r * w;
             const int cc = pc.col0 + c;
             corr[u] = c0[cc] + fmaf(X[r * tc.XS0 + cc], bnA[cc], bnB[cc]) * c1[cc];

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
     if (a.agg_out) {
       const unsigned magicA = (unsigned)((0x100000000ull + (unsigned)a.agg_w - 1) / (unsigned)a.agg_w);
       for (int e = tid; e < nr * a.agg_w; e += T) {
-        const int r = (int)__umulhi((unsigned)e, magicA);
+        const int r = div_magic((unsigned)e, magicA);
         const int j = e - r * a.agg_w;
         const int orow = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
         a.agg_out[(size_t)orow * a.agg_w + j] = buf0[r * tc.XS0 + a.agg_col0 + j];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(512) tile_fwd_kernel(const __grid_constant__ F
     // ---- epilogue: `cur` holds the output tile [R][XSc], first H columns ------------------------
 #pragma unroll 4
     for (int e = tid; e < nr * H; e += T) {
-      const int r = (int)__umulhi((unsigned)e, magicH);
+      const int r = div_magic((unsigned)e, magicH);
       const int j = e - r * H;
       const int orow = a.out_compact ? (row0 + r) : (a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r);
       a.out[(size_t)orow * a.ld_out + j] = cur[r * XSc + j];
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
     __syncthreads();
     if (a.out) {
       for (int e = tid; e < nr * W; e += T) {
-        const int r = (int)__umulhi((unsigned)e, magicW);
+        const int r = div_magic((unsigned)e, magicW);
         const int j = e - r * W;
         const int orow = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
         a.out[(size_t)orow * a.ld_out + j] = X[r * tc.XS0 + j];

@@ -442,7 +442,7 @@ int check_io(const gnnfp_loop* L, const gnnfp_loop_io* io, void* workspace, size
   if (!workspace || workspace_bytes < L->ws.total) GNNFP_FAIL(GNNFP_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, L->ws.total);
   if (((uintptr_t)workspace & 255) != 0) GNNFP_FAIL(GNNFP_E_INVALID, "workspace must be 256-byte aligned");
   if (!io->nodes || io->ld_nodes < L->NLw) GNNFP_FAIL(GNNFP_E_INVALID, "loop: nodes missing or ld_nodes < nodes_width");
-  if (L->AL > 0 && (!io->arc_labels || io->ld_arcs < L->AL)) GNNFP_FAIL(GNNFP_E_INVALID, "loop: arc_labels missing or ld_arcs < AL");
+  if (L->AL > 0 && L->A > 0 && (!io->arc_labels || io->ld_arcs < L->AL)) GNNFP_FAIL(GNNFP_E_INVALID, "loop: arc_labels missing or ld_arcs < AL");
   if (L->S > 0 && !io->state0) GNNFP_FAIL(GNNFP_E_INVALID, "loop: state0 must be passed explicitly when state_vect_dim > 0 (GNN.py:257 draws it unseeded)");
   if (!io->state_out || !io->out) GNNFP_FAIL(GNNFP_E_INVALID, "loop: state_out / out missing");
   return GNNFP_OK;

@@ -207,7 +207,7 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
             const int i = i0 + u * T;
             if (i < n4) {
               const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-              int r = (int)__umulhi((unsigned)(4 * i), pc.magic);
+              int r = div_magic((unsigned)(4 * i), pc.magic);
               int c = 4 * i - r * w;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -231,7 +231,7 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
             v[u] = 0.f;
             off[u] = -1;
             if (e < total) {
-              const int r = (int)__umulhi((unsigned)e, pc.magic);
+              const int r = div_magic((unsigned)e, pc.magic);
               const int c = e - r * w;
               off[u] = r * XS + c0 + c;
               if (on && r < nr) {
@@ -283,7 +283,7 @@ __device__ __forceinline__ void stage_tile(const TileSrc& ts, int row0, int nr, 
         else gather_items<1, 4>(pc, sc, abase, nr, R, X, XS, pc.wgt != nullptr);
       } else {
         for (int e = tid; e < total; e += T) {
-          const int r = (int)__umulhi((unsigned)e, pc.magic);
+          const int r = div_magic((unsigned)e, pc.magic);
           const int c = e - r * w;
           float v = 0.0f;
           if (on && r < nr) {
@@ -360,7 +360,7 @@ __device__ __forceinline__ const float* bulk_relayout(const TileSrc& ts, unsigne
       for (int i = tid; i < n4; i += T) {
         const float4 v = r4[i];
         const float vv[4] = {v.x, v.y, v.z, v.w};
-        int r = (int)__umulhi((unsigned)(4 * i), pc.magic);
+        int r = div_magic((unsigned)(4 * i), pc.magic);
         int c = 4 * i - r * w;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
