@@ -33,7 +33,7 @@ extern long long g_gnnfp_launches;
 
 // optional per-category kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
 enum { PC_OTHER = 0, PC_FWD_ITER = 1, PC_BWD_ITER = 2, PC_PASS = 3, PC_FWD_OUT = 4, PC_BWD_OUT = 5, PC_BNFIX = 6,
-       PC_COUNT = 8 };
+       PC_DZ = 7, PC_BWD_DX = 8, PC_AGG = 9, PC_COUNT = 10 };
 // optional per-phase cycle counters inside the tile kernels (debug; thread 0 of every CTA, clock64)
 #ifdef GNNFP_PHASE_TIMING
 #define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd((unsigned long long*)&g_phase_cycles[i], (unsigned long long)(_t - _pt)); _pt = _t; } } while (0)

@@ -790,7 +790,7 @@ int launch_dz(const DzArgs& a, cudaStream_t s) {
   long long blocks = (items + 255) / 256;
   const long long cap = (long long)gnnfp_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  ProfScope ps(PC_OTHER, s);
+  ProfScope ps(PC_DZ, s);
   if (vec == 4) dz_kernel<4><<<(int)blocks, 256, 0, s>>>(a);
   else if (vec == 2) dz_kernel<2><<<(int)blocks, 256, 0, s>>>(a);
   else dz_kernel<1><<<(int)blocks, 256, 0, s>>>(a);

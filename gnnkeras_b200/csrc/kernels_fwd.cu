@@ -351,7 +351,7 @@ int launch_agg_stats(const AggArgs& a, cudaStream_t s) {
   const long long cap = (long long)gnnfp_num_sms() * occ[oi];
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  ProfScope ps(PC_PASS, s);
+  ProfScope ps(PC_AGG, s);
   if (vec == 4) agg_stats_kernel<4><<<(int)blocks, 256, 0, s>>>(a, QX);
   else if (vec == 2) agg_stats_kernel<2><<<(int)blocks, 256, 0, s>>>(a, QX);
   else agg_stats_kernel<1><<<(int)blocks, 256, 0, s>>>(a, QX);

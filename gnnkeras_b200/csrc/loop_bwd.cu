@@ -492,7 +492,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
               ga.out = pc.gptr; ga.ld_out = pc.gld; ga.out_add = pc.gmode == GM_ADD;
               ga.vec2 = pc.gld % 2 == 0 && ((uintptr_t)pc.gptr & 7) == 0;
               ga.gate = gate;
-              if ((rc = launch_gemm_rows(ga, s, PC_BWD_ITER))) return rc;
+              if ((rc = launch_gemm_rows(ga, s, PC_BWD_DX))) return rc;
             }
             wt += (size_t)KH * ldw;
           }

@@ -254,7 +254,8 @@ long long gnnfp_launch_count(int reset);
 /* Optional per-category kernel timing (CUDA events recorded on the launch stream around every tile
  * kernel; off by default).  Categories: 0 other, 1 state-net forward iteration, 2 state-net backward
  * iteration, 3 tile pass (aggregates / BN statistics), 4 net_output forward, 5 net_output backward,
- * 6 BN backward fix-up.  collect() synchronises, sums milliseconds and launch counts per category and
+ * 6 BN backward fix-up, 7 dz (activation derivative x gathered gradient), 8 state-net backward dX GEMMs (category 2 is
+ * then the dW GEMM alone), 9 Adj^T.state aggregation (+ BN statistics).  collect() synchronises, sums milliseconds and launch counts per category and
  * clears the records. */
 int gnnfp_profile_enable(int on);
 int gnnfp_profile_collect(double* ms_by_cat, long long* count_by_cat, int ncat);
