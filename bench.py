@@ -362,8 +362,15 @@ def main():
         # whole fixed-point iteration against SURVEY 8(d)'s per-node-update figure B = B_f + B_b
         it_ms = msc[1] + msc[2] + msc[7] + msc[8] + msc[9]
         it_bytes = sum(algorithmic_bytes(D, AL, deg, True) + algorithmic_bytes(D, AL, deg, False) for D in WIDTHS) * iters
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        if os.path.exists(tpath):                          # dram__bytes_read+write per launch, one ncu capture of this workload
+            tj = json.load(open(tpath))
+            if dom in tj:
+                traffic, traffic_src = tj[dom]["avg_dram_bytes_per_launch"], "profiles/r1_gemm_traffic.json (" + tj["source"] + ")"
         roof = {"bound": "hbm", "kernel": dom,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "avg_launch_ms": dom_ms / max(1, dom_n),
                 "algorithmic_bytes_per_launch": dom_bytes / max(1, dom_n),
                 "fp32_tflops_achieved": tfl, "fp32_tflops_nominal_peak": fp32_peak, "fp32_frac": tfl / fp32_peak,
