@@ -74,6 +74,7 @@ SYMBOLS = ["gnnfp_last_error", "gnnfp_abi_version", "gnnfp_graph_build", "gnnfp_
            "gnnfp_graph_export", "gnnfp_loop_create", "gnnfp_loop_free", "gnnfp_loop_workspace_bytes",
            "gnnfp_loop_out_rows", "gnnfp_loop_state_dim", "gnnfp_loop_forward", "gnnfp_loop_forward_begin", "gnnfp_loop_forward_iter",
            "gnnfp_loop_forward_end", "gnnfp_loop_ws_offsets", "gnnfp_loop_backward",
+           "gnnfp_loop_backward_step", "gnnfp_loop_bwd_offsets",
            "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step",
            "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect"]
 
@@ -112,6 +113,10 @@ def lib():
     L.gnnfp_loop_backward.argtypes = [_vp, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(LoopIO),
                                       C.POINTER(LoopGrads), C.POINTER(NetParams), C.POINTER(NetParams), _vp,
                                       C.c_size_t, _vp]
+    L.gnnfp_loop_backward_step.argtypes = [_vp, C.c_int32, C.c_int32, C.POINTER(NetParams), C.POINTER(NetParams),
+                                           C.POINTER(LoopIO), C.POINTER(LoopGrads), C.POINTER(NetParams),
+                                           C.POINTER(NetParams), _vp, C.c_size_t, _vp]
+    L.gnnfp_loop_bwd_offsets.argtypes = [_vp, C.POINTER(C.c_size_t)]
     L.gnnfp_update_graph_forward.argtypes = [_vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32,
                                              C.c_int32, _vp, _vp]
     L.gnnfp_update_graph_backward.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32,

@@ -751,7 +751,13 @@ __global__ void __launch_bounds__(256) dz_kernel(const __grid_constant__ DzArgs 
           k0a[v] = cn[ac]; k1a[v] = cn[in + ac]; Aa[v] = cn[2 * in + ac]; Ba[v] = cn[3 * in + ac];
         }
       }
-      const int a0 = a.rowptr[gr], a1 = a.rowptr[gr + 1];
+      if (a.pre) {
+        float pv[VEC];
+        load_vec<VEC>(a.pre + o, pv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) g[v] += pv[v];
+      }
+      const int a0 = a.pre ? 0 : a.rowptr[gr], a1 = a.pre ? 0 : a.rowptr[gr + 1];
       for (int p = a0; p < a1; p += 4) {
         float t[4][VEC], xg[4][VEC], wv[4];
 #pragma unroll

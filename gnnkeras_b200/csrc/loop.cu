@@ -350,7 +350,9 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   L->bn_train_out = cfg->training && L->onet.has_bn;
   if (L->Nact < L->N) {
     if (L->composite) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) loops are homogeneous only");
-    if (cfg->training) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) loops are forward/inference only in this version");
+    if (cfg->training && L->onet.has_bn) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) training does not support BatchNormalization in net_output (global batch statistics)");
+    if (cfg->training && cfg->want_input_grads) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) training does not produce input gradients");
+    if (cfg->training && L->snet[0].n_layers != 1) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) training supports single-Dense-layer net_state only");
     if (L->snet[0].has_bn) PLAN_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) loops do not support BatchNormalization in net_state (global batch statistics)");
   }
   for (int t = 0; t < L->nt; ++t) L->nparam_s[t] = net_param_count(L->snet[t]);
@@ -408,6 +410,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     w.dOwn = off; off = align_up(off + 2 * ND);
     w.dAgg = off; off = align_up(off + 2 * ND);
     w.dz = off; off = align_up(off + ND);
+    if (L->Nact < L->N) { w.pgather = off; off = align_up(off + ND); }
     w.dOutN = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
     size_t ps = 0, bg = 2 * (size_t)L->onet.in_dim;
     int din_max = L->onet.in_dim;

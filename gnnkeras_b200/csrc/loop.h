@@ -12,7 +12,7 @@ struct WsLayout {
   size_t agg = 0;                           // float [max_iter][N, D]: Adj^T.state of every iteration (training)
   size_t out_nodes = 0;                     // float [M, T]
   // backward
-  size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0, dz = 0;
+  size_t dSfin = 0, dOwn = 0, dAgg = 0, dXs = 0, dOutN = 0, dz = 0, pgather = 0;
   size_t part_state = 0, part_out = 0, bn_part = 0, bn_const = 0, bn_grad = 0;
   size_t wfold = 0, wtb = 0, bncoef = 0;    // GEMM path: folded weights per type, W^T blocks, per-iteration BN coefficients
   size_t wfold_stride = 0, wtb_stride = 0, bncoef_stride = 0;   // floats per type
@@ -38,6 +38,8 @@ struct gnnfp_loop {
   int slot_count = 0;
   int bn_train_state = 0, bn_train_out = 0;
   int nparam_s[GNNFP_MAX_TYPES]{}, nparam_o = 0;
+  int bwd_grid_state[GNNFP_MAX_TYPES]{};   // backward: widest partial-slot grids used since the last begin phase
+  int bwd_grid_out = 0;
   int out_gemm_ok = 0;              // net_output runs on the GEMM kernels (single Dense layer, node / graph focus)
   int gemm_ok[GNNFP_MAX_TYPES]{};   // single Dense layer nets run the pipelined GEMM kernels (gemm.cu)
   int cap_per_row = 4;   // CSR scratch capacity per tile row (from A/N)

@@ -144,9 +144,13 @@ static __global__ void k_out_dz(const __grid_constant__ OutDzArgs a) {
   }
 }
 
-extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
-                                   const gnnfp_loop_io* io, const gnnfp_loop_grads* gr, gnnfp_net_params* dsp,
-                                   gnnfp_net_params* dop, void* workspace, size_t workspace_bytes, void* stream) {
+// phases of the backward (the monolithic entry point runs BEGIN | ITERS | END; the stepping entry point runs one at a
+// time so that a multi-GPU driver can reduce the halo rows of Adj . dAgg between iterations)
+enum { PH_BEGIN = 1, PH_ITERS = 2, PH_END = 4, PH_GATHER = 8 };
+
+static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                         const gnnfp_loop_io* io, const gnnfp_loop_grads* gr, gnnfp_net_params* dsp,
+                         gnnfp_net_params* dop, void* workspace, size_t workspace_bytes, void* stream, int phases, int t_only) {
   int rc;
   if ((rc = check_io(L, io, workspace, workspace_bytes))) return rc;
   if (!sp || !op || !gr || !dsp || !dop) GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward: null argument");
@@ -191,11 +195,15 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
   auto cn_t = [&](int t) { return (float*)(c.ws + L->ws.bn_const_t) + (size_t)t * 4 * din_max_; };
   const float* src_w = g->mode == GNNFP_AGG_SUM ? nullptr : g->src_w;
 
-  GNNFP_CHECK_CUDA(cudaMemsetAsync(c.ws + L->ws.bwd_zero, 0, L->ws.bwd_zero_bytes, s));
-  if (gr->d_state) GNNFP_CHECK_CUDA(cudaMemcpyAsync(dSfin, gr->d_state, ND * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  else GNNFP_CHECK_CUDA(cudaMemsetAsync(dSfin, 0, ND * sizeof(float), s));
-  if ((want & 1)) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_nodes, 0, (size_t)N * L->NLw * sizeof(float), s));
-  if ((want & 2) && L->AL > 0) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_arc_labels, 0, (size_t)L->A * L->AL * sizeof(float), s));
+  if (phases & PH_BEGIN) {
+    GNNFP_CHECK_CUDA(cudaMemsetAsync(c.ws + L->ws.bwd_zero, 0, L->ws.bwd_zero_bytes, s));
+    if (gr->d_state) GNNFP_CHECK_CUDA(cudaMemcpyAsync(dSfin, gr->d_state, ND * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    else GNNFP_CHECK_CUDA(cudaMemsetAsync(dSfin, 0, ND * sizeof(float), s));
+    if ((want & 1)) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_nodes, 0, (size_t)N * L->NLw * sizeof(float), s));
+    if ((want & 2) && L->AL > 0) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_arc_labels, 0, (size_t)L->A * L->AL * sizeof(float), s));
+    for (int t = 0; t < GNNFP_MAX_TYPES; ++t) L->bwd_grid_state[t] = 0;
+    L->bwd_grid_out = 0;
+  }
 
   // bn_grad layout: [state net 0 | state net 1 | ... | out net]
   size_t bg_off[GNNFP_MAX_TYPES + 1];
@@ -209,14 +217,14 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     size_t o = 0;
     for (int t = 0; t < L->nt; ++t) { ps_off[t] = o; o += (size_t)L->grid_cap * L->nparam_s[t]; }
   }
-  int grid_state[GNNFP_MAX_TYPES] = {0};
-  int grid_out = 0;
+  int* grid_state = L->bwd_grid_state;       // widest grids used so far: the partial slots the final reduction must read
+  int& grid_out = L->bwd_grid_out;
   const int NLp = (!L->composite && L->S > 0) ? L->NLw : 0;
 
   // ---- 1. net_output backward -----------------------------------------------------------------
   NetDev ond;
   fill_netdev(L->onet, *op, 1, L->M, ond);
-  if (gr->d_out || gr->d_out_nodes) {
+  if ((phases & PH_BEGIN) && (gr->d_out || gr->d_out_nodes)) {
     BwdArgs ba;
     memset(&ba, 0, sizeof(ba));
     build_out_src(c, ba.src);
@@ -405,13 +413,27 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     gemm_bwd[ty] = true;
     float* wt = (float*)(c.ws + L->ws.wtb) + (size_t)ty * L->ws.wtb_stride;
     const int KH = gemm_rows_kpad(H0);
-    for (int p = 0; p < probe.n_pieces; ++p) {
+    for (int p = 0; p < probe.n_pieces && (phases & PH_BEGIN); ++p) {
       const int ldw = gemm_rows_ldw(probe.p[p].width);
       if ((rc = launch_transpose_block(sp[ty].W[0], H0, probe.p[p].col0, probe.p[p].width, KH, ldw, wt, s))) return rc;
       wt += (size_t)KH * ldw;
     }
   }
-  for (int t = MI; t >= 1; --t) {
+  float* pgather = L->Nact < L->N ? (float*)(c.ws + L->ws.pgather) : nullptr;
+  if ((phases & PH_GATHER) && pgather && t_only >= 1 && t_only < MI) {
+    // partitioned graph: this rank's share of Adj . dAgg_{t+1} for ALL local rows (owned + halo); the driver then sums
+    // the halo rows into their owners' rows before iteration t consumes the buffer
+    AggArgs aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.n_rows = N; aa.rowlist = nullptr; aa.D = D;
+    aa.S = dAgg[(t_only + 1) & 1]; aa.ld = D;
+    aa.rowptr = g->src_rowptr; aa.idx = g->src_dst; aa.wgt = src_w;
+    aa.out = pgather;
+    aa.gate = c.flags() + t_only;               // only if iteration t+1 ran
+    if ((rc = launch_agg_stats(aa, s))) return rc;
+  }
+  for (int t = MI; t >= 1 && (phases & PH_ITERS); --t) {
+    if (t_only > 0 && t != t_only) continue;
     const int* gate = c.flags() + (t - 1);
     const int wb = t & 1, rb = (t + 1) & 1;
     for (int ty = 0; ty < L->nt; ++ty) {
@@ -442,6 +464,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
         da.rowptr = g->src_rowptr; da.idx = g->src_dst; da.wgt = src_w;
         da.last_flag = t < MI ? c.flags() + t : nullptr; da.always_last = t == MI;
         da.dz = dzbuf; da.gate = gate;
+        if (pgather && t < MI) da.pre = pgather;
         const bool inline_bn = L->snet[ty].has_bn && !L->composite;
         if (inline_bn && t < MI) {
           da.cn = cn_t(t + 1); da.agg_next = c.AGG(t + 1); da.in_dim = L->snet[ty].in_dim;
@@ -543,6 +566,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
         last_ba.src = full; last_ba.net = ndfull; last_ba.tc.grid = gemm_bwd[ty] ? grid_dw : L->grid_cap; last_ba.tc.cap_per_row = L->cap_per_row;
         last_ba.bn_partial = bn_part; last_ba.gate = gate;
       } else {
+        if (pgather) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "partitioned (n_active_rows) backward supports single-Dense-layer net_state only");
         BwdArgs ba;
         memset(&ba, 0, sizeof(ba));
         ba.src = full;
@@ -581,6 +605,7 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
     }
   }
 
+  if (!(phases & PH_END)) { GNNFP_CHECK_CUDA(cudaGetLastError()); return GNNFP_OK; }
   // ---- 3. input gradients --------------------------------------------------------------------------
   if (want) {
     InGradArgs ia;
@@ -639,5 +664,32 @@ extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, co
   }
   if ((rc = launch_reduce_params(ond, part_out, grid_out, L->nparam_o, bn_grad + bg_off[L->nt], *dop, c.flags(), MI, 0, s))) return rc;
   GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
+extern "C" int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_net_params* op,
+                                   const gnnfp_loop_io* io, const gnnfp_loop_grads* gr, gnnfp_net_params* dsp,
+                                   gnnfp_net_params* dop, void* workspace, size_t workspace_bytes, void* stream) {
+  if (L && L->Nact < L->N) GNNFP_FAIL(GNNFP_E_INVALID, "partitioned (n_active_rows) plans use gnnfp_loop_backward_step (halo gradients must be reduced between iterations)");
+  return backward_impl(L, sp, op, io, gr, dsp, dop, workspace, workspace_bytes, stream, PH_BEGIN | PH_ITERS | PH_END, 0);
+}
+
+// stepping backward: phase 1 = begin (zeroing + net_output backward), 2 = iteration t, 4 = end (input gradients +
+// parameter reduction), 8 = gather Adj . dAgg_{t+1} into the exposed buffer (partitioned graphs, before iteration t < max_iteration)
+extern "C" int gnnfp_loop_backward_step(gnnfp_loop* L, int32_t phase, int32_t t, const gnnfp_net_params* sp,
+                                        const gnnfp_net_params* op, const gnnfp_loop_io* io, const gnnfp_loop_grads* gr,
+                                        gnnfp_net_params* dsp, gnnfp_net_params* dop, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  if (phase != PH_BEGIN && phase != PH_ITERS && phase != PH_END && phase != PH_GATHER)
+    GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward_step: phase %d (1 begin, 2 iteration, 4 end, 8 gather)", phase);
+  if ((phase == PH_ITERS || phase == PH_GATHER) && (!L || t < 1 || t > L->cfg.max_iteration))
+    GNNFP_FAIL(GNNFP_E_INVALID, "loop_backward_step: t=%d outside 1..max_iteration", t);
+  return backward_impl(L, sp, op, io, gr, dsp, dop, workspace, workspace_bytes, stream, phase, t);
+}
+
+extern "C" int gnnfp_loop_bwd_offsets(const gnnfp_loop* L, size_t* gather_off) {
+  if (!L) GNNFP_FAIL(GNNFP_E_INVALID, "loop_bwd_offsets: null plan");
+  if (!(L->Nact < L->N) || !L->cfg.training) GNNFP_FAIL(GNNFP_E_INVALID, "loop_bwd_offsets: the gather buffer exists in partitioned training plans only");
+  if (gather_off) *gather_off = L->ws.pgather;
   return GNNFP_OK;
 }

@@ -192,7 +192,7 @@ class PartitionedLoop:
 
     def __init__(self, plan: HaloPlan, nodes, arcs, net_state, net_output, state_vect_dim, max_iteration,
                  state_threshold, aggregation_mode="sum", set_mask=None, output_mask=None, device="cuda",
-                 exchange=None, reduce_flag=None, group=None):
+                 exchange=None, reduce_flag=None, group=None, training=False, reduce_halo=None):
         from .op import DeviceGraph, LoopPlan
         if aggregation_mode not in ("sum", "average"):
             raise ValueError("partitioned loop supports aggregation modes 'sum' and 'average' "
@@ -213,7 +213,10 @@ class PartitionedLoop:
         self.graph = DeviceGraph(t(plan.local_src, np.int32), t(plan.local_dst, np.int32), n_loc, aggregation_mode,
                                  set_mask=t(sm, np.uint8), output_mask=t(om, np.uint8))
         self.loop = LoopPlan(self.graph, [net_state], net_output, "node", state_vect_dim, max_iteration, state_threshold,
-                             False, self.nodes.shape[1], self.arc_labels.shape[1], n_active_rows=plan.n_own)
+                             bool(training), self.nodes.shape[1], self.arc_labels.shape[1], n_active_rows=plan.n_own)
+        self.training = bool(training)
+        self.reduce_halo = reduce_halo if reduce_halo is not None else (
+            lambda d_halo, d_own: reduce_halo_grads(plan, d_halo, d_own, group))
         self.S, self.max_iteration = int(state_vect_dim), int(max_iteration)
         self.send_idx = torch.as_tensor(np.concatenate(plan.send_rows) if plan.world > 0 else np.zeros(0, np.int64)).to(dev)
         self.exchange = exchange if exchange is not None else (lambda own: exchange_halo(plan, own, group))
@@ -237,12 +240,15 @@ class PartitionedLoop:
     def iterate(self, t):
         self.loop.forward_iter(t)
 
+    def _slot(self, t):
+        return self.slots[t - 1] if self.training else self.slots[t & 1]   # gnnfp.h: slot index of state t
+
     def own_rows(self, t):
-        return self.slots[t & 1][: self.plan.n_own]
+        return self._slot(t)[: self.plan.n_own]
 
     def set_halo(self, t, rows):
         if self.plan.n_halo:
-            self.slots[t & 1][self.plan.n_own:] = rows
+            self._slot(t)[self.plan.n_own:] = rows
 
     def finish_iteration(self, t):
         if t < self.max_iteration:          # the state of iteration max_iteration is final: nobody gathers it
@@ -259,3 +265,42 @@ class PartitionedLoop:
             self.iterate(t)
             self.finish_iteration(t)
         return self.end()
+
+    # ---- backward (training plans): BPTT with the reverse halo exchange between iterations ----------------------
+    # G_t[i] = dOwn_{t+1}[i] + sum_{arcs i->j} w_ij dAgg_{t+1}[j]: the arcs i->j live on the rank that owns j, so each
+    # rank gathers its share for all its local rows (owned + halo), the halo rows travel back to their owners and are
+    # summed there (reduce_halo_grads) before the owners run iteration t.
+    def backward_begin(self, d_out=None, d_state=None, average_st_grads=False):
+        ds = None
+        if d_state is not None:                       # [n_own, D] -> local rows (halo rows carry no direct gradient)
+            ds = torch.zeros((self.plan.n_own + self.plan.n_halo, d_state.shape[1]), dtype=torch.float32, device=d_state.device)
+            ds[: self.plan.n_own] = d_state
+        self.loop.backward_begin(d_out, ds, average_st_grads)
+        self.gbuf = self.loop.gather_view()
+
+    def backward_gather(self, t):
+        self.loop.backward_gather(t)
+
+    def backward_reduce(self, t):
+        n = self.plan.n_own
+        self.reduce_halo(self.gbuf[n:], self.gbuf[:n])
+
+    def backward_iter(self, t):
+        self.loop.backward_iter(t)
+
+    def backward_end(self):
+        """(state-net grads, output-net grads) of this rank's rows: sum them over the ranks (all_reduce SUM)."""
+        return self.loop.backward_end()
+
+    def backward(self, d_out=None, d_state=None, average_st_grads=False):
+        self.backward_begin(d_out, d_state, average_st_grads)
+        for t in range(self.max_iteration, 0, -1):
+            if t < self.max_iteration:
+                self.backward_gather(t)
+                self.backward_reduce(t)
+            self.backward_iter(t)
+        gs, go = self.backward_end()
+        if self.plan.world > 1 and dist.is_initialized():
+            for tns in gs[0] + go:
+                dist.all_reduce(tns, op=dist.ReduceOp.SUM, group=self.group)
+        return gs, go

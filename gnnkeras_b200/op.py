@@ -298,6 +298,7 @@ class LoopPlan:
         k = torch.zeros((), dtype=torch.int32, device=dev)
         self._step_io = self._io(nodes, arc_labels, ld_arcs, state0, state, out, None, k)
         self._step_keep = (nodes, arc_labels, state0, state, out, k)
+        self._step_ld_arcs = ld_arcs
         self._step_params = self._param_arrays()
         sp, op = self._step_params
         B.check(self._L.gnnfp_loop_forward_begin(self._h, sp, C.byref(op), C.byref(self._step_io), self._ws_ptr(),
@@ -313,6 +314,7 @@ class LoopPlan:
         B.check(self._L.gnnfp_loop_forward_end(self._h, sp, C.byref(op), C.byref(self._step_io), self._ws_ptr(),
                                                self.workspace_bytes, _stream()))
         nodes, arc_labels, state0, state, out, k = self._step_keep
+        self._last = (nodes, arc_labels, self._step_ld_arcs, state0, state, out, None, k)
         return k, state, out
 
     def ws_views(self):
@@ -359,6 +361,53 @@ class LoopPlan:
         B.check(self._L.gnnfp_loop_backward(self._h, sp, C.byref(op), C.byref(io), C.byref(gr), dsp, C.byref(dop),
                                             self._ws_ptr(), self.workspace_bytes, _stream()))
         return gs, go, d_nodes, d_arcs, d_state0
+
+    # ---- stepping backward (partitioned graphs): begin / gather(t) / iter(t) / end -------------------------------
+    PH_BEGIN, PH_ITER, PH_END, PH_GATHER = 1, 2, 4, 8
+
+    def _bstep(self, phase, t=0):
+        b = self._bwd_step
+        B.check(self._L.gnnfp_loop_backward_step(self._h, int(phase), int(t), b["sp"], C.byref(b["op"]), C.byref(b["io"]),
+                                                 C.byref(b["gr"]), b["dsp"], C.byref(b["dop"]), self._ws_ptr(),
+                                                 self.workspace_bytes, _stream()))
+
+    def backward_begin(self, d_out=None, d_state=None, average_st_grads=False):
+        nodes, arc_labels, ld_arcs, state0, state, out, out_nodes, k = self._last
+        io = self._io(nodes, arc_labels, ld_arcs, state0, state, out, out_nodes, k)
+        sp, op = self._param_arrays()
+        gs = [[torch.empty_like(t) for t in n.trainable()] for n in self.nets_state]
+        go = [torch.empty_like(t) for t in self.net_output.trainable()]
+        dsp = (B.NetParams * len(self.nets_state))(*[n.params(gs[i]) for i, n in enumerate(self.nets_state)])
+        dop = self.net_output.params(go)
+        gr = B.LoopGrads()
+        keep = []
+        for nm, t in (("d_out", d_out), ("d_state", d_state)):
+            if t is not None:
+                t = t.contiguous().float()
+                keep.append(t)
+                setattr(gr, nm, _ptr(t))
+        gr.average_st_grads = int(bool(average_st_grads))
+        self._bwd_step = dict(io=io, sp=sp, op=op, gs=gs, go=go, dsp=dsp, dop=dop, gr=gr, keep=keep)
+        self._bstep(self.PH_BEGIN)
+
+    def backward_gather(self, t):
+        self._bstep(self.PH_GATHER, t)
+
+    def backward_iter(self, t):
+        self._bstep(self.PH_ITER, t)
+
+    def backward_end(self):
+        self._bstep(self.PH_END)
+        b = self._bwd_step
+        return b["gs"], b["go"]
+
+    def gather_view(self):
+        """torch view [n_nodes, D] of the Adj . dAgg buffer the gather phase fills (partitioned training plans)."""
+        off = C.c_size_t()
+        B.check(self._L.gnnfp_loop_bwd_offsets(self._h, C.byref(off)))
+        base = (self.workspace.data_ptr() + 255) // 256 * 256 - self.workspace.data_ptr()
+        n, D = self.graph.n_nodes, self.D
+        return self.workspace[base:][off.value: off.value + 4 * n * D].view(torch.float32).view(n, D)
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -226,6 +226,21 @@ int gnnfp_loop_backward(gnnfp_loop* L, const gnnfp_net_params* state_params,
                         gnnfp_net_params* d_out_params, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* Stepping form of gnnfp_loop_backward (same arguments) for partitioned graphs (plans created with n_active_rows <
+ * n_nodes; replaces the single tf.GradientTape call of GNN.py:284-295 on each rank):
+ *   phase 1 = begin  (zeroing, net_output backward),
+ *   phase 8 = gather (t < max_iteration): this rank's share of Adj . dAgg_{t+1} for ALL local rows (owned + halo) into the
+ *             [n_nodes, D] buffer at byte offset gnnfp_loop_bwd_offsets().gather_off of the workspace; the driver then sends
+ *             the halo rows to their owners, which ADD them to their rows (the reverse of the forward halo exchange),
+ *   phase 2 = iteration t (newest first: t = max_iteration .. 1) on the owned rows, consuming that buffer,
+ *   phase 4 = end    (deterministic reduction of the parameter gradients of this rank; the caller sums them over ranks).
+ * gnnfp_loop_backward == phase 1; phase 2 for t = max_iteration .. 1; phase 4 on unpartitioned plans. */
+int gnnfp_loop_backward_step(gnnfp_loop* L, int32_t phase, int32_t t, const gnnfp_net_params* state_params,
+                             const gnnfp_net_params* out_params, const gnnfp_loop_io* io, const gnnfp_loop_grads* grads,
+                             gnnfp_net_params* d_state_params, gnnfp_net_params* d_out_params, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int gnnfp_loop_bwd_offsets(const gnnfp_loop* L, size_t* gather_off);
+
 /* ------------------------------------------------------------------------------------------
  * LGNN.update_graph (LGNN.py:175-214): nodes' = [state? | scatter(out_nodes by mask)? | nodes0],
  * arc focus: arc_labels' = [scatter(out)? | arc_labels0].  Forward writes the new matrix;

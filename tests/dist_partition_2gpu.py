@@ -65,6 +65,35 @@ def main():
               f"state rel err {err:.2e}  {ms.item():.3f} ms/forward  "
               f"{b.n_nodes * kk / (ms.item() * 1e-3) / 1e9:.3f} G node-updates/s  halo rows(rank0)={halo}")
         assert kk == int(k1.item()) and err < 1e-5
+    # ---- training: forward + BPTT with the reverse halo reduction (NCCL all-to-all-v) and the gradient all-reduce ------
+    MI = 5
+    plt = D.PartitionedLoop(plan, b.nodes, b.arcs, Net.from_dict(ns, dev), Net.from_dict(no, dev), Dd, MI, 0.0, "average",
+                            device=dev, training=True)
+    kt, st_t, out_t = plt.forward(st0)
+    r_out_full = np.random.default_rng(5).standard_normal((b.n_nodes, 4)).astype(np.float32)
+    r_out = torch.as_tensor(r_out_full[plan.lo:plan.hi]).to(dev)        # all nodes are output nodes here
+    for _ in range(2):
+        gs, go = plt.backward(r_out)
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    for _ in range(3):
+        kt, st_t, out_t = plt.forward(st0)
+        gs, go = plt.backward(r_out)
+    e1.record(); torch.cuda.synchronize()
+    ms_t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        full_t = LoopPlan(g, [Net.from_dict(ns, dev)], Net.from_dict(no, dev), "node", Dd, MI, 0.0, True, 16, 4)
+        k2, s2, o2 = full_t.forward(t(b.nodes, np.float32), arcs[:, 2:], t(s0, np.float32), ld_arcs=arcs.stride(0))
+        gs1, go1, *_ = full_t.backward(torch.as_tensor(r_out_full).to(dev), None, None, False)
+        torch.cuda.synchronize()
+        worst = 0.0
+        for a_, b_ in zip(gs[0] + go, gs1[0] + go1):
+            worst = max(worst, float((a_ - b_).abs().max() / b_.abs().max().clamp_min(1e-30)))
+        print(f"partitioned training: world={world} k={int(kt.item())} fwd+bwd {ms_t.item():.3f} ms/step  "
+              f"{2 * b.n_nodes * MI / (ms_t.item() * 1e-3) / 1e9:.3f} G node-updates/s (fwd+bwd)  "
+              f"max rel grad err vs single GPU {worst:.2e}")
+        assert worst < 2e-5
     dist.destroy_process_group()
 
 
