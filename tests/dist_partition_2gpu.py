@@ -91,7 +91,7 @@ def main():
         for a_, b_ in zip(gs[0] + go, gs1[0] + go1):
             worst = max(worst, float((a_ - b_).abs().max() / b_.abs().max().clamp_min(1e-30)))
         print(f"partitioned training: world={world} k={int(kt.item())} fwd+bwd {ms_t.item():.3f} ms/step  "
-              f"{2 * b.n_nodes * MI / (ms_t.item() * 1e-3) / 1e9:.3f} G node-updates/s (fwd+bwd)  "
+              f"{b.n_nodes * MI / (ms_t.item() * 1e-3) / 1e9:.3f} G node-updates/s (fwd+bwd)  "
               f"max rel grad err vs single GPU {worst:.2e}")
         assert worst < 2e-5
     dist.destroy_process_group()
