@@ -724,7 +724,7 @@ __global__ void reduce_params_kernel(const __grid_constant__ ReduceArgs a) {
 // dz = act'(s_t) * G_t as a streaming kernel (single-layer state nets): the gather over the source-grouped
 // CSR runs with thousands of independent threads instead of inside the persistent GEMM kernel.
 template <int VEC>
-__global__ void __launch_bounds__(256) dz_kernel(const __grid_constant__ DzArgs a) {
+__global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzArgs a) {
   if (a.gate && *a.gate == 0) return;
   const bool last = a.always_last || a.last_flag == nullptr || *a.last_flag == 0;
   const int nq = a.D / VEC;
@@ -794,7 +794,16 @@ int launch_dz(const DzArgs& a, cudaStream_t s) {
   else if (a.D % 2 == 0 && a.ld_s % 2 == 0 && al(a.s_t, 8) && al(a.dSfin, 8) && al(a.dOwn, 8) && al(a.dAgg, 8) && al(a.dz, 8)) vec = 2;
   const long long items = (long long)a.n_rows * (a.D / vec);
   long long blocks = (items + 255) / 256;
-  const long long cap = (long long)gnnfp_num_sms() * 16;
+  static int occ[3] = {0, 0, 0};                      // resident blocks per SM: the grid is a whole number of waves
+  const int oi = vec == 4 ? 2 : (vec == 2 ? 1 : 0);
+  if (!occ[oi]) {
+    int o = 0;
+    if (vec == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<4>, 256, 0);
+    else if (vec == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<2>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<1>, 256, 0);
+    occ[oi] = o > 0 ? o : 4;
+  }
+  const long long cap = (long long)gnnfp_num_sms() * occ[oi] * 3;
   if (blocks > cap) blocks = cap;
   ProfScope ps(PC_DZ, s);
   if (vec == 4) dz_kernel<4><<<(int)blocks, 256, 0, s>>>(a);

@@ -103,9 +103,13 @@ def test_random_sweep_forward_backward(cfg):
     torch.cuda.synchronize()
     _, gs64, go64, *_ = oracle_grads(g, ns, no, S_, max_it, thr, s0, kind, r_out, None, torch.float64)
     _, gs32, go32, *_ = oracle_grads(g, ns, no, S_, max_it, thr, s0, kind, r_out, None, torch.float32)
+    # arc focus scatters d(net_output input) back to the nodes with float atomics (order-dependent rounding): badly
+    # conditioned sums (e.g. a bias gradient that cancels to ~1e-2 of its terms) then move run to run by a few times the
+    # fp32 oracle's own distance to fp64, so the conditioning factor is wider there (measured spread 3..12 x).
+    factor = 32 if kind == "arc" else 8
     for a, b64, b32 in zip(gs[0] + go, gs64[0] + go64, gs32[0] + go32):
         e, e32 = relerr(a.cpu().numpy(), b64), relerr(b32, b64)
-        assert e <= max(2e-5, 8 * e32), (e, e32, tuple(a.shape))
+        assert e <= max(2e-5, factor * e32), (e, e32, tuple(a.shape))
 
 
 @pytest.mark.parametrize("case", ["no_arcs", "single_node_graphs", "all_isolated_but_one"])
