@@ -181,3 +181,62 @@ def test_full_size_properties():
     gsub = ograph_from_batch(sub, "g", "average")
     _, _, _, (k4, state4, out4) = run_cuda(gsub, ns, no, 0, 5, 0.0, True, None, "graph")
     assert torch.equal(state4, state1[:nn]) and torch.equal(out4, out1[:ng])
+
+
+def composite_cases():
+    rng = np.random.default_rng(77)
+    cases = []
+    for i in range(9):
+        cases.append(dict(seed=300 + i, n_types=1 + i % 3, kind=["graph", "node", "arc"][(i // 3) % 3],
+                          mode=["composite_average", "average", "sum"][i % 3], S=int(rng.choice([0, 4])),
+                          bn=bool(i % 2), n_graphs=int(rng.integers(5, 30)), max_it=int(rng.integers(1, 5))))
+    return cases
+
+
+@pytest.mark.parametrize("cfg", composite_cases(),
+                         ids=lambda c: f"{c['seed']}-{c['n_types']}types-{c['kind']}-{c['mode']}-S{c['S']}-bn{int(c['bn'])}")
+def test_random_sweep_composite(cfg):
+    """CompositeGNN (CompositeGNN.py:215-272): 1..3 node types as a one-hot cover, per-type label widths, per-type
+    net_state, composite_average / average / sum - forward and parameter gradients vs the fp64 oracle."""
+    from oracle import loop_numpy as LN2
+    rng = np.random.default_rng(cfg["seed"])
+    NL, AL, T, nt, kind, S_ = 6, 2, 3, cfg["n_types"], cfg["kind"], cfg["S"]
+    b = random_batch(rng, cfg["n_graphs"], NL, AL, T)
+    if kind == "arc" and b.n_arcs == 0:
+        pytest.skip("no arcs drawn")
+    ty = rng.integers(0, nt, b.n_nodes)
+    ty[:nt] = np.arange(nt)[: len(ty[:nt])]                      # every type present
+    b.type_mask = np.eye(nt, dtype=bool)[ty]
+    if kind == "arc":
+        b.set_mask = np.ones(b.n_arcs, bool)
+        b.output_mask = rng.random(b.n_arcs) < 0.8
+        if not b.output_mask.any():
+            b.output_mask[:] = True
+        b.targets = np.eye(T, dtype=np.float32)[rng.integers(0, T, b.n_arcs)]
+    elif kind == "node":
+        b.output_mask = rng.random(b.n_nodes) < 0.7
+        if not b.output_mask.any():
+            b.output_mask[:] = True
+    dnl = [NL] * nt if S_ == 0 else [int(x) for x in rng.integers(2, NL + 1, nt)]
+    g = ograph_from_batch(b, {"graph": "g", "node": "n", "arc": "a"}[kind], cfg["mode"], dim_node_label=dnl)
+    ns, no = nets_for(rng, NL, AL, T, S_, kind, cfg["bn"], "tanh", (), n_types=nt, dnl=dnl)
+    s0 = (0.1 * rng.standard_normal((g.n_nodes, S_))).astype(np.float32) if S_ else None
+    mi = cfg["max_it"]
+    k64, s64, o64 = LN2.loop_composite(g, [copy_net(n) for n in ns], copy_net(no), S_, mi, 0.01, True, s0, np.float64, kind)
+    k32, s32, o32 = LN2.loop_composite(g, [copy_net(n) for n in ns], copy_net(no), S_, mi, 0.01, True, s0, np.float32, kind)
+    if k32 != k64:
+        pytest.skip("threshold tie between the fp32 and fp64 oracles")
+    plan, nets, onet, (k, state, out) = run_cuda(g, ns, no, S_, mi, 0.01, True, s0, kind)
+    assert int(k.item()) == k64
+    assert tol_vs64(relerr(state.cpu().numpy(), s64), relerr(s32, s64))
+    assert tol_vs64(relerr(out.cpu().numpy(), o64), relerr(o32, o64))
+    r_out = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    gs, go, *_ = plan.backward(torch.as_tensor(r_out).to(DEV), None, None, False)
+    torch.cuda.synchronize()
+    _, gs64, go64, *_ = oracle_grads(g, ns, no, S_, mi, 0.01, s0, kind, r_out, None, torch.float64, composite=True)
+    _, gs32, go32, *_ = oracle_grads(g, ns, no, S_, mi, 0.01, s0, kind, r_out, None, torch.float32, composite=True)
+    flat = lambda gsl, gol: [a for n in gsl for a in n] + list(gol)
+    factor = 32 if kind == "arc" else 8
+    for a, b64, b32 in zip(flat(gs, go), flat(gs64, go64), flat(gs32, go32)):
+        a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+        assert relerr(a, b64) <= max(2e-5, factor * relerr(b32, b64)), (relerr(a, b64), relerr(b32, b64), a.shape)
