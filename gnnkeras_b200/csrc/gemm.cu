@@ -10,6 +10,8 @@
 // keep the output tile in registers (TM x TN per thread, 256 threads = 16 x 16 thread grid) and run as persistent
 // CTAs over consecutive tiles, so global latency is hidden behind the FMAs instead of being exposed per phase.
 // All operands are plain row-major matrices: the sparse aggregation is materialised by agg_stats_kernel first.
+#include <stdlib.h>
+
 #include "tile.cuh"
 
 #include "gemm.h"
@@ -547,6 +549,8 @@ static int launch_rows_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
 // N output columns -> (TM, TN): wider outputs take fewer rows per thread to bound registers
 int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   if (a.n_rows <= 0) return GNNFP_OK;
+  static const int tc_min_n = [] { const char* e = getenv("GNNFP_TC"); return e ? atoi(e) : 0; }();   // 0 = off; else min N
+  if (tc_min_n > 0 && a.N >= tc_min_n && gemm_rows_tc_supported(a)) return launch_gemm_rows_tc(a, s, prof_cat);
   const int tn = (a.N + 15) / 16;
   const bool fwd = a.fwd != 0;
   switch (tn) {

@@ -65,6 +65,8 @@ struct BnCoefArgs { TileSrc src; NetDev net; float* coef; const int* gate; };
 int launch_fold_w(const FoldArgs& a, cudaStream_t s);
 int launch_bn_coef(const BnCoefArgs& a, cudaStream_t s);
 int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s, int prof_cat);
+int gemm_rows_tc_supported(const GemmRowsArgs& a);                      // gemm_tc.cu: tcgen05 (3xTF32) version of the same GEMM
+int launch_gemm_rows_tc(const GemmRowsArgs& a, cudaStream_t s, int prof_cat);
 int gemm_rows_ldw(int N);
 int gemm_rows_kpad(int k8);
 int gemm_rows_supported(int k8, int N);
