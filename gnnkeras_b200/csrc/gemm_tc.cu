@@ -96,11 +96,34 @@ __device__ __forceinline__ float tc_selu(float z) {
   return z < 0.0f ? (SELU_SCALE_F * SELU_ALPHA_F) * (e - 1.0f) : SELU_SCALE_F * z;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// column sums of a [32 lanes (rows)] x [32 values per lane (columns)] block: after the 5 exchange rounds lane l holds the
+// total of column l (31 shuffles instead of 32 x 5)
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+
+#define TC_THREADS 288                                  // warps 0-3 converters, 4-7 epilogue, 8 MMA issuer
+
 template <int BN, bool FWD>
-__global__ void __launch_bounds__(256, 1) gemm_rows_tc_kernel(const __grid_constant__ GemmRowsArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __grid_constant__ GemmRowsArgs a) {
   if (a.gate && *a.gate == 0) return;
-  constexpr int CH = BN / 2;                           // accumulator columns per epilogue warp (two warps share a lane quarter)
-  constexpr int OLD = BN + 1;                          // leading dimension of the output staging tile
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; offset arithmetic (not an integer round trip) keeps the pointers in the
   // shared address space for the compiler (LDS/STS instead of generic LD/ST)
@@ -111,82 +134,28 @@ __global__ void __launch_bounds__(256, 1) gemm_rows_tc_kernel(const __grid_const
   uint8_t* Wlo = Whi + (size_t)NKB * wtile;
   uint8_t* Aop = Wlo + (size_t)NKB * wtile;            // [2 buffers][hi, lo][TC_TILE_BYTES]
   float* raw = reinterpret_cast<float*>(Aop + 4 * TC_TILE_BYTES);     // [TC_RAW_STAGES][TC_BM][TC_RAW_LD]
-  float* ost = reinterpret_cast<float*>(Aop);          // output staging [TC_BM][OLD] aliases the operand buffers
-  __shared__ __align__(8) uint64_t bar_ops[2];
-  __shared__ __align__(8) uint64_t bar_tile;
+  __shared__ __align__(8) uint64_t ops_full[2], ops_empty[2], tm_full[2], tm_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[BN];
-  __shared__ double colacc[2][BN];
+  __shared__ double colacc[4][2][BN];                  // per epilogue warp: column sums / sums of squares
+  __shared__ float estage[4][32][17];                  // per epilogue warp: [32 rows x 16 columns] transpose staging
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & 15, ty = tid >> 4;
   const int n = a.n_rows;
   const int n_tiles = (n + TC_BM - 1) / TC_BM;
   const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int tile0 = blockIdx.x * tiles_per_cta;
   const int my_tiles = max(0, min(n_tiles, tile0 + tiles_per_cta) - tile0);
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256));
 
-  if (warp == 0) { tmem_alloc(&tmem_base_s, 128); tmem_relinquish(); }      // whole warp, converged (.sync.aligned)
-  if (tid == 32) { mbar_init(&bar_ops[0], 1); mbar_init(&bar_ops[1], 1); mbar_init(&bar_tile, 1); }
-
-  // ---- producer: raw stage (tile, K block) via 8-byte cp.async; thread copies column pair pq of rows ty + 16*i ------
-  const int pq = tx;
-  int i_tq = 0, i_kb = 0, i_st = 0;
-  auto issue = [&]() {
-    if (i_tq < my_tiles) {
-      if (i_kb == 0 && i_tq + 1 < my_tiles) {
-        // L2 prefetch of the NEXT tile's rows (all pieces): the cp.async of the coming stages then pay L2, not DRAM, latency
-        const int prow = (tile0 + i_tq + 1) * TC_BM + (tid >> 1);
-        if (prow < n) {
-          for (int p = 0; p < a.n_pieces; ++p) {
-            const char* b0 = reinterpret_cast<const char*>(a.p[p].ptr + (size_t)prow * a.p[p].ld);
-            const char* l0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127);
-            const char* l1 = b0 + (size_t)a.p[p].width * 4;
-            for (const char* l = l0 + 128 * (tid & 1); l < l1; l += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
-          }
-        }
-      }
-      float* dst = raw + i_st * TC_BM * TC_RAW_LD + ty * TC_RAW_LD + 2 * pq;
-      const int kcol = i_kb * TC_BK + 2 * pq;
-      int p = 0;
-      while (p + 1 < a.n_pieces && kcol >= a.p[p + 1].k8) ++p;
-      const float* pptr = a.p[p].ptr;
-      const int pld = a.p[p].ld;
-      const int kk = kcol - a.p[p].k8;
-      const int nv = kcol < a.Kpad ? a.p[p].width - kk : 0;
-      const bool al8 = a.p[p].al8 != 0;
-      const int row0 = (tile0 + i_tq) * TC_BM + ty;
-      if (nv <= 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tc_cp_async8(dst + i * 16 * TC_RAW_LD, pptr, 0);
-      } else if (al8 && (tile0 + i_tq + 1) * TC_BM <= n) {
-        const float* src = pptr + (size_t)row0 * pld + kk;
-        const size_t step = (size_t)16 * pld;
-        const int bytes = nv > 1 ? 8 : 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { tc_cp_async8(dst + i * 16 * TC_RAW_LD, src, bytes); src += step; }
-      } else {
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const int grow = row0 + 16 * i;
-          const bool valid = grow < n;
-          const float* src = valid ? pptr + (size_t)grow * pld + kk : pptr;
-          if (al8) {
-            tc_cp_async8(dst + i * 16 * TC_RAW_LD, src, valid ? (nv > 1 ? 8 : 4) : 0);
-          } else {
-            tc_cp_async4(dst + i * 16 * TC_RAW_LD, src, valid ? 4 : 0);
-            tc_cp_async4(dst + i * 16 * TC_RAW_LD + 1, (valid && nv > 1) ? src + 1 : pptr, (valid && nv > 1) ? 4 : 0);
-          }
-        }
-      }
-      if (++i_kb == NKB) { i_kb = 0; ++i_tq; }
-      if (++i_st == TC_RAW_STAGES) i_st = 0;
-    }
-    tc_cp_commit();
-  };
-  for (int i = 0; i < TC_RAW_STAGES - 1; ++i) issue();
-
-  // ---- resident weights: split into TF32 hi / lo, K-major swizzled tiles per K block ------------------------------------
-  for (int e = tid; e < NKB * TC_BK * BN; e += 256) {
+  if (warp == 0) { tmem_alloc(&tmem_base_s, TMEM_COLS); tmem_relinquish(); }      // whole warp, converged (.sync.aligned)
+  if (tid == 32) {
+    mbar_init(&ops_full[0], 128); mbar_init(&ops_full[1], 128);
+    mbar_init(&ops_empty[0], 1); mbar_init(&ops_empty[1], 1);
+    mbar_init(&tm_full[0], 1); mbar_init(&tm_full[1], 1);
+    mbar_init(&tm_empty[0], 128); mbar_init(&tm_empty[1], 128);
+  }
+  // ---- resident weights: split into TF32 hi / lo, K-major swizzled tiles per K block (all threads) ------------------
+  for (int e = tid; e < NKB * TC_BK * BN; e += TC_THREADS) {
     const int k = e / BN, nn = e - k * BN;
     const float w = k < a.Kpad ? a.Wp[(size_t)k * a.ldw + nn] : 0.f;
     const uint32_t hi = tc_tf32(w);
@@ -195,39 +164,92 @@ __global__ void __launch_bounds__(256, 1) gemm_rows_tc_kernel(const __grid_const
     *reinterpret_cast<uint32_t*>(Whi + off) = hi;
     *reinterpret_cast<uint32_t*>(Wlo + off) = lo;
   }
-  for (int j = tid; j < BN; j += 256) sbias[j] = (FWD && a.bias && j < a.N) ? a.bias[j] : 0.f;
-  for (int j = tid; j < 2 * BN; j += 256) (&colacc[0][0])[j] = 0.0;
+  for (int j = tid; j < BN; j += TC_THREADS) sbias[j] = (FWD && a.bias && j < a.N) ? a.bias[j] : 0.f;
+  for (int j = tid; j < 8 * BN; j += TC_THREADS) (&colacc[0][0][0])[j] = 0.0;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
-  // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = BN, M = 128
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-  const uint32_t whi_addr = smem_u32(Whi), wlo_addr = smem_u32(Wlo), aop_addr = smem_u32(Aop);
-
   int notconv = 0;
-  int c_st = 0;                                        // raw ring slot of the current stage
-  uint32_t use0 = 0, use1 = 0;                         // how often each operand buffer has been handed to the tensor core
-  int sidx = 0;                                        // running stage index (operand buffer = sidx & 1)
-  for (int tq = 0; tq < my_tiles; ++tq) {
-    for (int kb = 0; kb < NKB; ++kb, ++sidx) {
-      issue();                                         // prefetch: TC_RAW_STAGES - 1 stages ahead
-      tc_cp_wait<TC_RAW_STAGES - 1>();
-      __syncthreads();                                 // (A) raw stage landed for every thread; previous epilogue done
+
+  if (warp < 4) {
+    // =================== converter warps: cp.async ring -> TF32 hi / lo operand tiles ==================================
+    // thread copies the 8-byte column pair pq of rows ty + 8*i (i < 16) of a stage
+    const int pq = tid & 15, ty = tid >> 4;
+    int i_tq = 0, i_kb = 0, i_st = 0;
+    auto issue = [&]() {
+      if (i_tq < my_tiles) {
+        if (i_kb == 0 && i_tq + 1 < my_tiles) {
+          // L2 prefetch of the NEXT tile's rows (all pieces): the coming stages then pay L2, not DRAM, latency
+          const int prow = (tile0 + i_tq + 1) * TC_BM + tid;
+          if (prow < n) {
+            for (int p = 0; p < a.n_pieces; ++p) {
+              const char* b0 = reinterpret_cast<const char*>(a.p[p].ptr + (size_t)prow * a.p[p].ld);
+              const char* l0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127);
+              const char* l1 = b0 + (size_t)a.p[p].width * 4;
+              for (const char* l = l0; l < l1; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
+            }
+          }
+        }
+        float* dst = raw + i_st * TC_BM * TC_RAW_LD + ty * TC_RAW_LD + 2 * pq;
+        const int kcol = i_kb * TC_BK + 2 * pq;
+        int p = 0;
+        while (p + 1 < a.n_pieces && kcol >= a.p[p + 1].k8) ++p;
+        const float* pptr = a.p[p].ptr;
+        const int pld = a.p[p].ld;
+        const int kk = kcol - a.p[p].k8;
+        const int nv = kcol < a.Kpad ? a.p[p].width - kk : 0;
+        const bool al8 = a.p[p].al8 != 0;
+        const int row0 = (tile0 + i_tq) * TC_BM + ty;
+        if (nv <= 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tc_cp_async8(dst + i * 8 * TC_RAW_LD, pptr, 0);
+        } else if (al8 && (tile0 + i_tq + 1) * TC_BM <= n) {
+          const float* src = pptr + (size_t)row0 * pld + kk;
+          const size_t step = (size_t)8 * pld;
+          const int bytes = nv > 1 ? 8 : 4;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { tc_cp_async8(dst + i * 8 * TC_RAW_LD, src, bytes); src += step; }
+        } else {
+#pragma unroll 2
+          for (int i = 0; i < 16; ++i) {
+            const int grow = row0 + 8 * i;
+            const bool valid = grow < n;
+            const float* src = valid ? pptr + (size_t)grow * pld + kk : pptr;
+            if (al8) {
+              tc_cp_async8(dst + i * 8 * TC_RAW_LD, src, valid ? (nv > 1 ? 8 : 4) : 0);
+            } else {
+              tc_cp_async4(dst + i * 8 * TC_RAW_LD, src, valid ? 4 : 0);
+              tc_cp_async4(dst + i * 8 * TC_RAW_LD + 1, (valid && nv > 1) ? src + 1 : pptr, (valid && nv > 1) ? 4 : 0);
+            }
+          }
+        }
+        if (++i_kb == NKB) { i_kb = 0; ++i_tq; }
+        if (++i_st == TC_RAW_STAGES) i_st = 0;
+      }
+      tc_cp_commit();
+    };
+    for (int i = 0; i < TC_RAW_STAGES - 1; ++i) issue();
+    int c_st = 0;
+    const int total = my_tiles * NKB;
+    for (int sidx = 0; sidx < total; ++sidx) {
+      tc_cp_wait<TC_RAW_STAGES - 2>();
+      named_bar_sync(1, 128);                          // stage sidx has landed for all converter threads, and every thread
+                                                       // has finished reading the slot of stage sidx-1 ...
+      issue();                                         // ... which the prefetch (TC_RAW_STAGES - 1 stages ahead) refills
       const int ob = sidx & 1;
-      const uint32_t uses = ob ? use1 : use0;
-      if (uses > 0) {                                  // MMAs of the previous use of this operand buffer must have completed
-        mbar_wait_bounded(&bar_ops[ob], (uses - 1) & 1);
+      const uint32_t use = (uint32_t)(sidx >> 1);      // how often this operand buffer has been filled before
+      if (use > 0) {                                   // the MMAs that read its previous contents must have completed
+        mbar_wait_bounded(&ops_empty[ob], (use - 1) & 1);
         tc_fence_after();
       }
-      // ---- split raw fp32 -> TF32 hi / lo operand tiles (swizzled) ---------------------------------------------------
       const float* rs = raw + c_st * TC_BM * TC_RAW_LD;
       uint8_t* ahi = Aop + (size_t)ob * 2 * TC_TILE_BYTES;
       uint8_t* alo = ahi + TC_TILE_BYTES;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int it = tid + 256 * j;
+      for (int j = 0; j < 8; ++j) {
+        const int it = tid + 128 * j;
         const int row = it >> 3, ch = it & 7;
         const float4 v = *reinterpret_cast<const float4*>(rs + row * TC_RAW_LD + 4 * ch);
         uint4 h, l;
@@ -241,144 +263,164 @@ __global__ void __launch_bounds__(256, 1) gemm_rows_tc_kernel(const __grid_const
       }
       if (++c_st == TC_RAW_STAGES) c_st = 0;
       fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      __syncthreads();                                 // (B)
-      if (tid == 0) {
-        tc_fence_after();
-        const uint64_t dah = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES);
-        const uint64_t dal = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
-        const uint64_t dbh = tc_desc_sw128(whi_addr + kb * wtile);
-        const uint64_t dbl = tc_desc_sw128(wlo_addr + kb * wtile);
-#pragma unroll
-        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {       // 8 fp32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
-          const uint64_t adv = (uint64_t)(2 * k8);
-          tc_mma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (kb | k8) ? 1u : 0u);
-          tc_mma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-          tc_mma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
-        }
-        tc_commit(&bar_ops[ob]);
-        if (kb == NKB - 1) tc_commit(&bar_tile);
-      }
-      if (ob) ++use1; else ++use0;
+      mbar_arrive(&ops_full[ob]);
     }
-    // ---- epilogue of this tile ---------------------------------------------------------------------------------------
-    mbar_wait_bounded(&bar_tile, (uint32_t)tq & 1u);
-    tc_fence_after();
-    {
-      const int q = warp & 3, h = warp >> 2;
-      const int row = 32 * q + lane;
-      const int grow = (tile0 + tq) * TC_BM + row;
-      const bool valid = grow < n;
-      float acc[CH];
-      const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * CH);
+    tc_cp_wait<0>();
+  } else if (warp == 8) {
+    // =================== MMA issuer: one thread drives the tensor core ====================================================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t whi_addr = smem_u32(Whi), wlo_addr = smem_u32(Wlo), aop_addr = smem_u32(Aop);
+      int sidx = 0;
+      for (int tq = 0; tq < my_tiles; ++tq) {
+        const int tb = tq & 1;
+        if (tq >= 2) {                                 // the epilogue of the tile that used this accumulator must have drained it
+          mbar_wait_bounded(&tm_empty[tb], (uint32_t)((tq >> 1) - 1) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t dcol = tmem_d + (uint32_t)(tb * BN);
+        for (int kb = 0; kb < NKB; ++kb, ++sidx) {
+          const int ob = sidx & 1;
+          mbar_wait_bounded(&ops_full[ob], (uint32_t)(sidx >> 1) & 1u);
+          tc_fence_after();
+          const uint64_t dah = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES);
+          const uint64_t dal = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
+          const uint64_t dbh = tc_desc_sw128(whi_addr + kb * wtile);
+          const uint64_t dbl = tc_desc_sw128(wlo_addr + kb * wtile);
 #pragma unroll
-      for (int c8 = 0; c8 < CH / 8; ++c8) tmem_ld8(taddr + 8 * c8, acc + 8 * c8);
-      tmem_ld_wait();
-      const bool selu = a.act == GNNFP_ACT_SELU;
+          for (int k8 = 0; k8 < TC_BK / 8; ++k8) {     // 8 fp32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
+            const uint64_t adv = (uint64_t)(2 * k8);
+            tc_mma_tf32(dcol, dal + adv, dbh + adv, idesc, (kb | k8) ? 1u : 0u);
+            tc_mma_tf32(dcol, dah + adv, dbl + adv, idesc, 1u);
+            tc_mma_tf32(dcol, dah + adv, dbh + adv, idesc, 1u);
+          }
+          tc_commit(&ops_empty[ob]);                   // operand buffer free once these MMAs have completed
+          if (kb == NKB - 1) tc_commit(&tm_full[tb]);  // accumulator tile complete
+        }
+      }
+    }
+  } else {
+    // =================== epilogue warps: TMEM -> registers (thread = row) -> warp-private staging -> global =================
+    // The accumulator arrives one row per thread; global traffic goes through a [32 x 16] staging block per warp so that
+    // every load / store instruction covers two 64-byte row segments (lanes 0-15 one row, lanes 16-31 the next).
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    float* stg = &estage[q][0][0];
+    const int hr = lane >> 4, hc = lane & 15;          // staging <-> global mapping: row 2*rr + hr, column hc
+    const bool selu = a.act == GNNFP_ACT_SELU;
+    const float* kc = (!FWD && a.corr) ? a.corr + a.corr_col0 : nullptr;
+    const float* auxsrc = FWD ? a.prev : (kc ? a.corr_x : nullptr);
+    const int auxld = FWD ? a.ld_prev : a.corr_ld;
+    for (int tq = 0; tq < my_tiles; ++tq) {
+      const int tb = tq & 1;
+      const int wrow0 = (tile0 + tq) * TC_BM + 32 * q; // first global row of this warp's 32 rows
+      const bool valid = wrow0 + lane < n;
+      mbar_wait_bounded(&tm_full[tb], (uint32_t)(tq >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(tb * BN);
+      float sd = 0.f, sp = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {            // 16 accumulator columns per trip
+        float acc[16], aux[16], old[FWD ? 1 : 16];
+        tmem_ld8(taddr + c0, acc);
+        tmem_ld8(taddr + c0 + 8, acc + 8);
+        const bool cok = c0 + hc < a.N;
+        if (auxsrc) {                                  // old values (FWD) / BN-correction inputs (backward), coalesced
+          float t[16];
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        const int col = h * CH + j;
-        float v = 0.f;
-        if (col < a.N && valid) {
-          if (FWD) {
-            const float z = acc[j] + sbias[col];
-            v = selu ? tc_selu(z) : act_fwd(a.act, z);
+          for (int rr = 0; rr < 16; ++rr) {
+            const int gr = wrow0 + 2 * rr + hr;
+            t[rr] = (cok && gr < n) ? auxsrc[(size_t)gr * auxld + c0 + hc] : 0.f;
+          }
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) stg[(2 * rr + hr) * 17 + hc] = t[rr];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) aux[j] = stg[lane * 17 + j];
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) aux[j] = 0.f;
+        }
+        if (!FWD) {
+          if (a.out_add) {                             // destination contents (accumulating blocks)
+            float t[16];
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const int gr = wrow0 + 2 * rr + hr;
+              t[rr] = (cok && gr < n) ? a.out[(size_t)gr * a.ld_out + c0 + hc] : 0.f;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) stg[(2 * rr + hr) * 17 + hc] = t[rr];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] = stg[lane * 17 + j];
+            __syncwarp();
           } else {
-            v = a.colscale ? acc[j] * a.colscale[col] : acc[j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] = 0.f;
           }
         }
-        ost[row * OLD + col] = v;
-      }
-    }
-    tc_fence_before();
-    __syncthreads();                                   // accumulator drained (next tile may overwrite it), staging complete
-    // ---- coalesced pass over the staged tile: one row per warp, 4 rows in flight; stores, convergence test (FWD),
-    // ---- BN-training correction / accumulation into the destination (backward) ---------------------------------------
-    constexpr int NC = (BN + 31) / 32;                 // column trips of a lane
-    for (int r0 = warp * 16; r0 < warp * 16 + 16; r0 += 4) {
-      float v[4][NC], aux[4][NC];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + u;
-        const int grow = (tile0 + tq) * TC_BM + r;
-        const bool rv = grow < n;
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc) {
-          const int c = lane + 32 * cc;
-          const bool ok = rv && c < a.N;
-          v[u][cc] = ok ? ost[r * OLD + c] : 0.f;
-          aux[u][cc] = 0.f;
-          if (ok) {
-            if (FWD) { if (a.prev) aux[u][cc] = a.prev[(size_t)grow * a.ld_prev + c]; }
-            else {
-              if (a.corr) aux[u][cc] = a.corr_x[(size_t)grow * a.corr_ld + c];
-            }
-          }
+        tmem_ld_wait();
+        if (c0 + 16 >= BN) {                           // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tm_empty[tb]);
         }
-      }
+        float st[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + u;
-        const int grow = (tile0 + tq) * TC_BM + r;
-        const bool rv = grow < n;
-        float sd = 0.f, sp = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc) {
-          const int c = lane + 32 * cc;
-          if (rv && c < a.N) {
-            float* o = a.out + (size_t)grow * a.ld_out + c;
-            float x = v[u][cc];
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          float v = 0.f;
+          if (valid && col < a.N) {
             if (FWD) {
-              const float dd = x - aux[u][cc];
-              sd = fmaf(dd, dd, sd);
-              sp = fmaf(aux[u][cc], aux[u][cc], sp);
-            } else {
-              if (a.corr) {
-                const float* k = a.corr + a.corr_col0;
-                x -= k[c] + fmaf(aux[u][cc], k[2 * a.corr_in + c], k[3 * a.corr_in + c]) * k[a.corr_in + c];
+              const float z = acc[j] + sbias[col];
+              v = selu ? tc_selu(z) : act_fwd(a.act, z);
+              if (a.prev) {
+                const float dd = v - aux[j];
+                sd = fmaf(dd, dd, sd);
+                sp = fmaf(aux[j], aux[j], sp);
               }
-              if (a.out_add) x += *o;
+            } else {
+              v = a.colscale ? acc[j] * a.colscale[col] : acc[j];
+              if (kc) v -= kc[col] + fmaf(aux[j], kc[2 * a.corr_in + col], kc[3 * a.corr_in + col]) * kc[a.corr_in + col];
+              v += old[j];
             }
-            *o = x;
           }
+          st[j] = v;
+          stg[lane * 17 + j] = v;
         }
-        if (FWD && a.prev) {
+        __syncwarp();
 #pragma unroll
-          for (int of = 16; of > 0; of >>= 1) {
-            sd += __shfl_xor_sync(0xffffffffu, sd, of);
-            sp += __shfl_xor_sync(0xffffffffu, sp, of);
-          }
-          if (rv && sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
+        for (int rr = 0; rr < 16; ++rr) {              // coalesced stores: two 64-byte row segments per instruction
+          const int gr = wrow0 + 2 * rr + hr;
+          if (cok && gr < n) a.out[(size_t)gr * a.ld_out + c0 + hc] = stg[(2 * rr + hr) * 17 + hc];
+        }
+        __syncwarp();
+        if (FWD && a.ost_sum) {                        // column statistics of these 16 columns over the warp's 32 rows
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { x[j] = st[j]; x[16 + j] = st[j] * st[j]; }
+          const float tot = warp_colsum32(x, lane);    // lane l < 16: sum of column c0+l; lane l >= 16: sum of squares of c0+l-16
+          const int col = c0 + (lane & 15);
+          if (col < a.N) colacc[q][lane >> 4][col] += (double)tot;
         }
       }
-    }
-    if (FWD && a.ost_sum && tid < a.N) {               // column statistics of the tile (rows past n hold zeros)
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < TC_BM; ++r) {
-        const float x = ost[r * OLD + tid];
-        s1 += x;
-        s2 = fmaf(x, x, s2);
-      }
-      colacc[0][tid] += (double)s1;
-      colacc[1][tid] += (double)s2;
+      if (FWD && a.prev && valid && sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
     }
   }
-  tc_cp_wait<0>();
   if (FWD && a.flag_next) {
     const int any = __syncthreads_or(notconv);
     if (tid == 0 && any) atomicOr(a.flag_next, 1);
   }
-  __syncthreads();
-  if (FWD && a.ost_sum) {
-    for (int j = tid; j < a.N; j += 256) {
-      atomicAdd(a.ost_sum + j, colacc[0][j]);
-      atomicAdd(a.ost_sq + j, colacc[1][j]);
-    }
-  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, 128);
+  if (FWD && a.ost_sum) {
+    for (int j = tid; j < a.N; j += TC_THREADS) {
+      atomicAdd(a.ost_sum + j, colacc[0][0][j] + colacc[1][0][j] + colacc[2][0][j] + colacc[3][0][j]);
+      atomicAdd(a.ost_sq + j, colacc[0][1][j] + colacc[1][1][j] + colacc[2][1][j] + colacc[3][1][j]);
+    }
+  }
+  if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -395,7 +437,7 @@ static int launch_tc_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   const int nsm = gnnfp_num_sms();
   const int grid = n_tiles < nsm ? n_tiles : nsm;
   ProfScope ps(prof_cat, s);
-  gemm_rows_tc_kernel<BN, FWD><<<grid, 256, smem, s>>>(a);
+  gemm_rows_tc_kernel<BN, FWD><<<grid, TC_THREADS, smem, s>>>(a);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;
