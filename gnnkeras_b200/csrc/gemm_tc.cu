@@ -21,8 +21,7 @@
 
 #define TC_BM 128
 #define TC_BK 32
-#define TC_RAW_LD 32                 // floats per raw row (a quarter warp reads one 128-byte row: conflict free)
-#define TC_RAW_STAGES 3
+#define TC_STAGES 3                  // operand ring: [hi (raw fp32, filled by cp.async) | lo] x 16 KB per stage
 #define TC_TILE_BYTES (TC_BM * 128)  // one A operand tile: 128 rows x 128 B
 
 __device__ __forceinline__ void tc_cp_async8(void* dst, const void* src, int src_bytes) {
@@ -91,6 +90,14 @@ __device__ __forceinline__ uint32_t tc_tf32(float x) {
   return r;
 }
 
+// TF32 split without a conversion of the high part: the tensor core reads the top 19 bits of an fp32 operand (the low 13
+// mantissa bits are ignored), so a itself serves as a_hi = trunc(a); a_lo = a - trunc(a) is exact in fp32 and is rounded to
+// 11 significant bits by adding half a TF32 ulp before the hardware truncation
+__device__ __forceinline__ uint32_t tc_lo(uint32_t abits) {
+  const float lo = __uint_as_float(abits) - __uint_as_float(abits & 0xFFFFE000u);
+  return __float_as_uint(lo) + 0x1000u;
+}
+
 __device__ __forceinline__ float tc_selu(float z) {
   const float e = expf(fminf(z, 0.0f));
   return z < 0.0f ? (SELU_SCALE_F * SELU_ALPHA_F) * (e - 1.0f) : SELU_SCALE_F * z;
@@ -119,7 +126,8 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
   return x[0];
 }
 
-#define TC_THREADS 288                                  // warps 0-3 converters, 4-7 epilogue, 8 MMA issuer
+#define TC_THREADS 416                                  // warps 0-3 converters, 4-11 epilogue, 12 MMA issuer
+#define TC_EPI_WARPS 8
 
 template <int BN, bool FWD>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __grid_constant__ GemmRowsArgs a) {
@@ -132,13 +140,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
   const int wtile = BN * 128;                          // bytes of one [BN x 32] weight tile
   uint8_t* Whi = base;
   uint8_t* Wlo = Whi + (size_t)NKB * wtile;
-  uint8_t* Aop = Wlo + (size_t)NKB * wtile;            // [2 buffers][hi, lo][TC_TILE_BYTES]
-  float* raw = reinterpret_cast<float*>(Aop + 4 * TC_TILE_BYTES);     // [TC_RAW_STAGES][TC_BM][TC_RAW_LD]
-  __shared__ __align__(8) uint64_t ops_full[2], ops_empty[2], tm_full[2], tm_empty[2];
+  uint8_t* Aop = Wlo + (size_t)NKB * wtile;            // [TC_STAGES][hi, lo][TC_TILE_BYTES]
+  __shared__ __align__(8) uint64_t ops_full[TC_STAGES], ops_empty[TC_STAGES], tm_full[2], tm_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[BN];
-  __shared__ double colacc[4][2][BN];                  // per epilogue warp: column sums / sums of squares
-  __shared__ float estage[4][32][17];                  // per epilogue warp: [32 rows x 16 columns] transpose staging
+  __shared__ double colacc[TC_EPI_WARPS][2][BN];       // per epilogue warp: column sums / sums of squares
+  __shared__ float estage[TC_EPI_WARPS][32][17];       // per epilogue warp: [32 rows x 16 columns] transpose staging
+  __shared__ float rowpart[2][TC_BM];                  // convergence sums of the second warp of each lane quarter
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n_rows;
   const int n_tiles = (n + TC_BM - 1) / TC_BM;
@@ -149,23 +157,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
 
   if (warp == 0) { tmem_alloc(&tmem_base_s, TMEM_COLS); tmem_relinquish(); }      // whole warp, converged (.sync.aligned)
   if (tid == 32) {
-    mbar_init(&ops_full[0], 128); mbar_init(&ops_full[1], 128);
-    mbar_init(&ops_empty[0], 1); mbar_init(&ops_empty[1], 1);
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&ops_full[i], 128); mbar_init(&ops_empty[i], 1); }
     mbar_init(&tm_full[0], 1); mbar_init(&tm_full[1], 1);
-    mbar_init(&tm_empty[0], 128); mbar_init(&tm_empty[1], 128);
+    mbar_init(&tm_empty[0], 32 * TC_EPI_WARPS); mbar_init(&tm_empty[1], 32 * TC_EPI_WARPS);
   }
   // ---- resident weights: split into TF32 hi / lo, K-major swizzled tiles per K block (all threads) ------------------
   for (int e = tid; e < NKB * TC_BK * BN; e += TC_THREADS) {
     const int k = e / BN, nn = e - k * BN;
     const float w = k < a.Kpad ? a.Wp[(size_t)k * a.ldw + nn] : 0.f;
-    const uint32_t hi = tc_tf32(w);
-    const uint32_t lo = tc_tf32(w - __uint_as_float(hi));
     const int off = (k >> 5) * wtile + tc_sw128_off(nn, k & 31);
-    *reinterpret_cast<uint32_t*>(Whi + off) = hi;
-    *reinterpret_cast<uint32_t*>(Wlo + off) = lo;
+    *reinterpret_cast<uint32_t*>(Whi + off) = __float_as_uint(w);
+    *reinterpret_cast<uint32_t*>(Wlo + off) = tc_lo(__float_as_uint(w));
   }
   for (int j = tid; j < BN; j += TC_THREADS) sbias[j] = (FWD && a.bias && j < a.N) ? a.bias[j] : 0.f;
-  for (int j = tid; j < 8 * BN; j += TC_THREADS) (&colacc[0][0][0])[j] = 0.0;
+  for (int j = tid; j < TC_EPI_WARPS * 2 * BN; j += TC_THREADS) (&colacc[0][0][0])[j] = 0.0;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -174,12 +179,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
   int notconv = 0;
 
   if (warp < 4) {
-    // =================== converter warps: cp.async ring -> TF32 hi / lo operand tiles ==================================
+    // =================== converter warps: cp.async straight into the swizzled hi tile, then the lo tile ================
     // thread copies the 8-byte column pair pq of rows ty + 8*i (i < 16) of a stage
     const int pq = tid & 15, ty = tid >> 4;
-    int i_tq = 0, i_kb = 0, i_st = 0;
+    const int total = my_tiles * NKB;
+    int i_tq = 0, i_kb = 0, i_idx = 0;
     auto issue = [&]() {
-      if (i_tq < my_tiles) {
+      if (i_idx < total) {
         if (i_kb == 0 && i_tq + 1 < my_tiles) {
           // L2 prefetch of the NEXT tile's rows (all pieces): the coming stages then pay L2, not DRAM, latency
           const int prow = (tile0 + i_tq + 1) * TC_BM + tid;
@@ -192,7 +198,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
             }
           }
         }
-        float* dst = raw + i_st * TC_BM * TC_RAW_LD + ty * TC_RAW_LD + 2 * pq;
+        const int slot = i_idx % TC_STAGES;
+        const uint32_t use = (uint32_t)(i_idx / TC_STAGES);
+        if (use > 0) {                                 // the MMAs that read this slot's previous contents must have completed
+          mbar_wait_bounded(&ops_empty[slot], (use - 1) & 1);
+          tc_fence_after();
+        }
+        uint8_t* hi = Aop + (size_t)slot * 2 * TC_TILE_BYTES;
+        // swizzled destination of (row ty + 8*i, pair pq): row & 7 == ty for every i
+        uint8_t* dst = hi + ty * 128 + ((((pq >> 1) ^ ty) & 7) << 4) + ((pq & 1) << 3);
         const int kcol = i_kb * TC_BK + 2 * pq;
         int p = 0;
         while (p + 1 < a.n_pieces && kcol >= a.p[p + 1].k8) ++p;
@@ -204,13 +218,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
         const int row0 = (tile0 + i_tq) * TC_BM + ty;
         if (nv <= 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) tc_cp_async8(dst + i * 8 * TC_RAW_LD, pptr, 0);
+          for (int i = 0; i < 16; ++i) tc_cp_async8(dst + i * 1024, pptr, 0);
         } else if (al8 && (tile0 + i_tq + 1) * TC_BM <= n) {
           const float* src = pptr + (size_t)row0 * pld + kk;
           const size_t step = (size_t)8 * pld;
           const int bytes = nv > 1 ? 8 : 4;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { tc_cp_async8(dst + i * 8 * TC_RAW_LD, src, bytes); src += step; }
+          for (int i = 0; i < 16; ++i) { tc_cp_async8(dst + i * 1024, src, bytes); src += step; }
         } else {
 #pragma unroll 2
           for (int i = 0; i < 16; ++i) {
@@ -218,55 +232,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
             const bool valid = grow < n;
             const float* src = valid ? pptr + (size_t)grow * pld + kk : pptr;
             if (al8) {
-              tc_cp_async8(dst + i * 8 * TC_RAW_LD, src, valid ? (nv > 1 ? 8 : 4) : 0);
+              tc_cp_async8(dst + i * 1024, src, valid ? (nv > 1 ? 8 : 4) : 0);
             } else {
-              tc_cp_async4(dst + i * 8 * TC_RAW_LD, src, valid ? 4 : 0);
-              tc_cp_async4(dst + i * 8 * TC_RAW_LD + 1, (valid && nv > 1) ? src + 1 : pptr, (valid && nv > 1) ? 4 : 0);
+              tc_cp_async4(dst + i * 1024, src, valid ? 4 : 0);
+              tc_cp_async4(dst + i * 1024 + 4, (valid && nv > 1) ? src + 1 : pptr, (valid && nv > 1) ? 4 : 0);
             }
           }
         }
         if (++i_kb == NKB) { i_kb = 0; ++i_tq; }
-        if (++i_st == TC_RAW_STAGES) i_st = 0;
+        ++i_idx;
       }
       tc_cp_commit();
     };
-    for (int i = 0; i < TC_RAW_STAGES - 1; ++i) issue();
-    int c_st = 0;
-    const int total = my_tiles * NKB;
+    for (int i = 0; i < TC_STAGES - 1; ++i) issue();
     for (int sidx = 0; sidx < total; ++sidx) {
-      tc_cp_wait<TC_RAW_STAGES - 2>();
-      named_bar_sync(1, 128);                          // stage sidx has landed for all converter threads, and every thread
-                                                       // has finished reading the slot of stage sidx-1 ...
-      issue();                                         // ... which the prefetch (TC_RAW_STAGES - 1 stages ahead) refills
-      const int ob = sidx & 1;
-      const uint32_t use = (uint32_t)(sidx >> 1);      // how often this operand buffer has been filled before
-      if (use > 0) {                                   // the MMAs that read its previous contents must have completed
-        mbar_wait_bounded(&ops_empty[ob], (use - 1) & 1);
-        tc_fence_after();
-      }
-      const float* rs = raw + c_st * TC_BM * TC_RAW_LD;
-      uint8_t* ahi = Aop + (size_t)ob * 2 * TC_TILE_BYTES;
+      tc_cp_wait<TC_STAGES - 2>();
+      named_bar_sync(1, 128);                          // stage sidx has landed for all converter threads
+      const int slot = sidx % TC_STAGES;
+      uint8_t* ahi = Aop + (size_t)slot * 2 * TC_TILE_BYTES;
       uint8_t* alo = ahi + TC_TILE_BYTES;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int it = tid + 128 * j;
-        const int row = it >> 3, ch = it & 7;
-        const float4 v = *reinterpret_cast<const float4*>(rs + row * TC_RAW_LD + 4 * ch);
-        uint4 h, l;
-        h.x = tc_tf32(v.x); l.x = tc_tf32(v.x - __uint_as_float(h.x));
-        h.y = tc_tf32(v.y); l.y = tc_tf32(v.y - __uint_as_float(h.y));
-        h.z = tc_tf32(v.z); l.z = tc_tf32(v.z - __uint_as_float(h.z));
-        h.w = tc_tf32(v.w); l.w = tc_tf32(v.w - __uint_as_float(h.w));
-        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(ahi + off) = h;
+      for (int j = 0; j < 8; ++j) {                    // lo tile: same swizzled positions, 16 bytes per item
+        const int off = (tid + 128 * j) << 4;
+        const uint4 v = *reinterpret_cast<const uint4*>(ahi + off);
+        uint4 l;
+        l.x = tc_lo(v.x); l.y = tc_lo(v.y); l.z = tc_lo(v.z); l.w = tc_lo(v.w);
         *reinterpret_cast<uint4*>(alo + off) = l;
       }
-      if (++c_st == TC_RAW_STAGES) c_st = 0;
-      fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&ops_full[ob]);
+      fence_proxy_async();                             // cp.async / st.shared writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&ops_full[slot]);
+      issue();                                         // refill the slot of stage sidx-1 once its MMAs have completed
     }
     tc_cp_wait<0>();
-  } else if (warp == 8) {
+  } else if (warp == 4 + TC_EPI_WARPS) {
     // =================== MMA issuer: one thread drives the tensor core ====================================================
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = BN, M = 128
@@ -281,8 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
         }
         const uint32_t dcol = tmem_d + (uint32_t)(tb * BN);
         for (int kb = 0; kb < NKB; ++kb, ++sidx) {
-          const int ob = sidx & 1;
-          mbar_wait_bounded(&ops_full[ob], (uint32_t)(sidx >> 1) & 1u);
+          const int ob = sidx % TC_STAGES;
+          mbar_wait_bounded(&ops_full[ob], (uint32_t)(sidx / TC_STAGES) & 1u);
           tc_fence_after();
           const uint64_t dah = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES);
           const uint64_t dal = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
@@ -305,7 +303,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
     // The accumulator arrives one row per thread; global traffic goes through a [32 x 16] staging block per warp so that
     // every load / store instruction covers two 64-byte row segments (lanes 0-15 one row, lanes 16-31 the next).
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    float* stg = &estage[q][0][0];
+    const int ew = warp - 4;                           // epilogue warp index; warps ew and ew+4 share a lane quarter and
+    const int chalf = ew >> 2;                         // take alternate 16-column chunks
+    float* stg = &estage[ew][0][0];
     const int hr = lane >> 4, hc = lane & 15;          // staging <-> global mapping: row 2*rr + hr, column hc
     const bool selu = a.act == GNNFP_ACT_SELU;
     const float* kc = (!FWD && a.corr) ? a.corr + a.corr_col0 : nullptr;
@@ -319,8 +319,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(tb * BN);
       float sd = 0.f, sp = 0.f;
+      bool handed_back = false;
+#ifdef TC_DEBUG_SKIP_EPI
+      { float acc[8]; tmem_ld8(taddr, acc); tmem_ld_wait(); tc_fence_before(); mbar_arrive(&tm_empty[tb]); if (acc[0] == 123.456f) notconv = 1; continue; }
+#endif
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {            // 16 accumulator columns per trip
+      for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (TC_EPI_WARPS / 4)) {      // 16 accumulator columns per trip
         float acc[16], aux[16], old[FWD ? 1 : 16];
         tmem_ld8(taddr + c0, acc);
         tmem_ld8(taddr + c0 + 8, acc + 8);
@@ -362,9 +366,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           }
         }
         tmem_ld_wait();
-        if (c0 + 16 >= BN) {                           // last read of this accumulator: hand it back to the MMA warp
+        if (c0 + 16 * (TC_EPI_WARPS / 4) >= BN) {      // this thread's last read of the accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tm_empty[tb]);
+          handed_back = true;
         }
         float st[16];
 #pragma unroll
@@ -402,10 +407,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           for (int j = 0; j < 16; ++j) { x[j] = st[j]; x[16 + j] = st[j] * st[j]; }
           const float tot = warp_colsum32(x, lane);    // lane l < 16: sum of column c0+l; lane l >= 16: sum of squares of c0+l-16
           const int col = c0 + (lane & 15);
-          if (col < a.N) colacc[q][lane >> 4][col] += (double)tot;
+          if (col < a.N) colacc[ew][lane >> 4][col] += (double)tot;
         }
       }
-      if (FWD && a.prev && valid && sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
+      if (!handed_back) { tc_fence_before(); mbar_arrive(&tm_empty[tb]); }     // narrow tiles: this warp had no chunk
+      if (FWD && a.prev) {                             // the row's sums are split over the two warps of its lane quarter
+        if (chalf == 1) { rowpart[0][32 * q + lane] = sd; rowpart[1][32 * q + lane] = sp; }
+        named_bar_sync(2, 32 * TC_EPI_WARPS);
+        if (chalf == 0) {
+          sd += rowpart[0][32 * q + lane];
+          sp += rowpart[1][32 * q + lane];
+          if (valid && sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
+        }
+        named_bar_sync(2, 32 * TC_EPI_WARPS);          // rowpart may be overwritten by the next tile
+      }
     }
   }
   if (FWD && a.flag_next) {
@@ -416,8 +431,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
   __syncthreads();
   if (FWD && a.ost_sum) {
     for (int j = tid; j < a.N; j += TC_THREADS) {
-      atomicAdd(a.ost_sum + j, colacc[0][0][j] + colacc[1][0][j] + colacc[2][0][j] + colacc[3][0][j]);
-      atomicAdd(a.ost_sq + j, colacc[0][1][j] + colacc[1][1][j] + colacc[2][1][j] + colacc[3][1][j]);
+      double s1 = 0.0, s2 = 0.0;
+      for (int w = 0; w < TC_EPI_WARPS; ++w) { s1 += colacc[w][0][j]; s2 += colacc[w][1][j]; }
+      atomicAdd(a.ost_sum + j, s1);
+      atomicAdd(a.ost_sq + j, s2);
     }
   }
   if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
@@ -427,7 +444,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
 template <int BN, bool FWD>
 static int launch_tc_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   const int NKB = (a.Kpad + TC_BK - 1) / TC_BK;
-  const size_t smem = (size_t)2 * NKB * BN * 128 + 4 * TC_TILE_BYTES + (size_t)TC_RAW_STAGES * TC_BM * TC_RAW_LD * sizeof(float) + 1024;
+  const size_t smem = (size_t)2 * NKB * BN * 128 + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 1024;
   static size_t attr = 0;
   if (smem > attr) {
     GNNFP_CHECK_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -450,7 +467,7 @@ int gemm_rows_tc_supported(const GemmRowsArgs& a) {
   if (a.ldw != 16 * ((a.N + 15) / 16)) return 0;
   const int NKB = (a.Kpad + TC_BK - 1) / TC_BK;
   const int BN = a.ldw;
-  const size_t smem = (size_t)2 * NKB * BN * 128 + 4 * TC_TILE_BYTES + (size_t)TC_RAW_STAGES * TC_BM * TC_RAW_LD * sizeof(float) + 1024;
+  const size_t smem = (size_t)2 * NKB * BN * 128 + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 1024;
   return smem <= 220 * 1024;
 }
 
