@@ -549,7 +549,9 @@ static int launch_rows_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
 // N output columns -> (TM, TN): wider outputs take fewer rows per thread to bound registers
 int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   if (a.n_rows <= 0) return GNNFP_OK;
-  static const int tc_min_n = [] { const char* e = getenv("GNNFP_TC"); return e ? atoi(e) : 0; }();   // 0 = off; else min N
+  // tensor-core (tcgen05, 3xTF32) version for every eligible shape; GNNFP_TC=0 selects the FP32-pipe kernels below,
+  // GNNFP_TC=<n> restricts the tensor-core path to N >= n output columns
+  static const int tc_min_n = [] { const char* e = getenv("GNNFP_TC"); return e ? atoi(e) : 1; }();
   if (tc_min_n > 0 && a.N >= tc_min_n && gemm_rows_tc_supported(a)) return launch_gemm_rows_tc(a, s, prof_cat);
   const int tn = (a.N + 15) / 16;
   const bool fwd = a.fwd != 0;

@@ -34,15 +34,19 @@ __device__ __forceinline__ void tc_cp_commit() { asm volatile("cp.async.commit_g
 template <int N>
 __device__ __forceinline__ void tc_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// bounded mbarrier wait: a protocol error traps (the launch fails) instead of hanging the device
+// bounded mbarrier wait: try_wait suspends the thread in hardware for a bounded time slice (no busy polling that would
+// steal issue slots from the working warps); a protocol error traps (the launch fails) instead of hanging the device
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  for (int spin = 0; spin < (1 << 26); ++spin) {
+  long long t0 = 0;
+  for (;;) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ll) __trap();        // ~2 s at 2 GHz: far beyond any legitimate wait inside one launch
   }
-  __trap();
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -318,51 +322,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
       mbar_wait_bounded(&tm_full[tb], (uint32_t)(tq >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(tb * BN);
-      float sd = 0.f, sp = 0.f;
+      float sdp[16], spp[16];                          // convergence partial sums of rows 2*rr + hr over this lane's columns
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) { sdp[rr] = 0.f; spp[rr] = 0.f; }
       bool handed_back = false;
 #ifdef TC_DEBUG_SKIP_EPI
       { float acc[8]; tmem_ld8(taddr, acc); tmem_ld_wait(); tc_fence_before(); mbar_arrive(&tm_empty[tb]); if (acc[0] == 123.456f) notconv = 1; continue; }
 #endif
 #pragma unroll 1
       for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (TC_EPI_WARPS / 4)) {      // 16 accumulator columns per trip
-        float acc[16], aux[16], old[FWD ? 1 : 16];
+        float acc[16];
         tmem_ld8(taddr + c0, acc);
         tmem_ld8(taddr + c0 + 8, acc + 8);
+        // coalesced side inputs of this chunk, issued before the accumulator is consumed: lane (hr, hc) owns rows
+        // 2*rr + hr, column c0 + hc (two 64-byte row segments per instruction)
         const bool cok = c0 + hc < a.N;
-        if (auxsrc) {                                  // old values (FWD) / BN-correction inputs (backward), coalesced
-          float t[16];
+        const int nvr = cok ? n - wrow0 - hr : 0;      // rows 2*rr + hr with 2*rr < nvr are inside the matrix
+        float t[16], o[FWD ? 1 : 16];
+        if (auxsrc) {
+          const float* ap = auxsrc + (size_t)(wrow0 + hr) * auxld + c0 + hc;
 #pragma unroll
-          for (int rr = 0; rr < 16; ++rr) {
-            const int gr = wrow0 + 2 * rr + hr;
-            t[rr] = (cok && gr < n) ? auxsrc[(size_t)gr * auxld + c0 + hc] : 0.f;
-          }
-#pragma unroll
-          for (int rr = 0; rr < 16; ++rr) stg[(2 * rr + hr) * 17 + hc] = t[rr];
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) aux[j] = stg[lane * 17 + j];
-          __syncwarp();
+          for (int rr = 0; rr < 16; ++rr) { t[rr] = 2 * rr < nvr ? *ap : 0.f; ap += 2 * auxld; }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) aux[j] = 0.f;
+          for (int rr = 0; rr < 16; ++rr) t[rr] = 0.f;
         }
         if (!FWD) {
-          if (a.out_add) {                             // destination contents (accumulating blocks)
-            float t[16];
+          if (a.out_add) {
+            const float* op = a.out + (size_t)(wrow0 + hr) * a.ld_out + c0 + hc;
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-              const int gr = wrow0 + 2 * rr + hr;
-              t[rr] = (cok && gr < n) ? a.out[(size_t)gr * a.ld_out + c0 + hc] : 0.f;
-            }
-#pragma unroll
-            for (int rr = 0; rr < 16; ++rr) stg[(2 * rr + hr) * 17 + hc] = t[rr];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) old[j] = stg[lane * 17 + j];
-            __syncwarp();
+            for (int rr = 0; rr < 16; ++rr) { o[rr] = 2 * rr < nvr ? *op : 0.f; op += 2 * a.ld_out; }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) old[j] = 0.f;
+            for (int rr = 0; rr < 16; ++rr) o[rr] = 0.f;
           }
         }
         tmem_ld_wait();
@@ -371,53 +363,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           mbar_arrive(&tm_empty[tb]);
           handed_back = true;
         }
-        float st[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 16; ++j) {                 // thread = row: bias + activation (forward) / column scale (backward)
           const int col = c0 + j;
           float v = 0.f;
           if (valid && col < a.N) {
             if (FWD) {
               const float z = acc[j] + sbias[col];
               v = selu ? tc_selu(z) : act_fwd(a.act, z);
-              if (a.prev) {
-                const float dd = v - aux[j];
-                sd = fmaf(dd, dd, sd);
-                sp = fmaf(aux[j], aux[j], sp);
-              }
             } else {
               v = a.colscale ? acc[j] * a.colscale[col] : acc[j];
-              if (kc) v -= kc[col] + fmaf(aux[j], kc[2 * a.corr_in + col], kc[3 * a.corr_in + col]) * kc[a.corr_in + col];
-              v += old[j];
             }
           }
-          st[j] = v;
           stg[lane * 17 + j] = v;
         }
         __syncwarp();
+        float s1 = 0.f, s2 = 0.f;
+        float k0 = 0.f, k1 = 0.f, kA = 0.f, kB = 0.f;
+        if (!FWD && kc && cok) { k0 = kc[c0 + hc]; k1 = kc[a.corr_in + c0 + hc]; kA = kc[2 * a.corr_in + c0 + hc]; kB = kc[3 * a.corr_in + c0 + hc]; }
+        float* outp = a.out + (size_t)(wrow0 + hr) * a.ld_out + c0 + hc;
 #pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {              // coalesced stores: two 64-byte row segments per instruction
-          const int gr = wrow0 + 2 * rr + hr;
-          if (cok && gr < n) a.out[(size_t)gr * a.ld_out + c0 + hc] = stg[(2 * rr + hr) * 17 + hc];
+        for (int rr = 0; rr < 16; ++rr, outp += 2 * a.ld_out) {   // coalesced: stores, convergence sums, statistics, corrections
+          float x = stg[(2 * rr + hr) * 17 + hc];
+          if (2 * rr < nvr) {
+            if (FWD) {
+              const float dd = x - t[rr];
+              sdp[rr] = fmaf(dd, dd, sdp[rr]);
+              spp[rr] = fmaf(t[rr], t[rr], spp[rr]);
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            } else {
+              if (kc) x -= k0 + fmaf(t[rr], kA, kB) * k1;
+              x += o[rr];
+            }
+            *outp = x;
+          }
         }
         __syncwarp();
-        if (FWD && a.ost_sum) {                        // column statistics of these 16 columns over the warp's 32 rows
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { x[j] = st[j]; x[16 + j] = st[j] * st[j]; }
-          const float tot = warp_colsum32(x, lane);    // lane l < 16: sum of column c0+l; lane l >= 16: sum of squares of c0+l-16
-          const int col = c0 + (lane & 15);
-          if (col < a.N) colacc[ew][lane >> 4][col] += (double)tot;
+        if (FWD && a.ost_sum) {                        // column statistics: fold the two row halves, lanes 0-15 own a column
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (hr == 0 && cok) { colacc[ew][0][c0 + hc] += (double)s1; colacc[ew][1][c0 + hc] += (double)s2; }
         }
       }
+      float sd = 0.f, sp = 0.f;                        // row sums: reduce over the 16 column lanes; lane rr of each half keeps row 2*rr + hr
+      if (FWD && a.prev) {
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          float x = sdp[rr], y = spp[rr];
+#pragma unroll
+          for (int of = 8; of > 0; of >>= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, of);
+            y += __shfl_xor_sync(0xffffffffu, y, of);
+          }
+          if (hc == rr) { sd = x; sp = y; }
+        }
+      }
+      const int myrow = 2 * hc + hr;                   // the row (within the warp's 32) whose sums this lane holds
+      const bool myvalid = wrow0 + myrow < n;
       if (!handed_back) { tc_fence_before(); mbar_arrive(&tm_empty[tb]); }     // narrow tiles: this warp had no chunk
       if (FWD && a.prev) {                             // the row's sums are split over the two warps of its lane quarter
-        if (chalf == 1) { rowpart[0][32 * q + lane] = sd; rowpart[1][32 * q + lane] = sp; }
+        if (chalf == 1) { rowpart[0][32 * q + myrow] = sd; rowpart[1][32 * q + myrow] = sp; }
         named_bar_sync(2, 32 * TC_EPI_WARPS);
         if (chalf == 0) {
-          sd += rowpart[0][32 * q + lane];
-          sp += rowpart[1][32 * q + lane];
-          if (valid && sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
+          sd += rowpart[0][32 * q + myrow];
+          sp += rowpart[1][32 * q + myrow];
+          if (myvalid && sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
         }
         named_bar_sync(2, 32 * TC_EPI_WARPS);          // rowpart may be overwritten by the next tile
       }
