@@ -353,8 +353,8 @@ def main():
         cnt = (C.c_longlong * NC)()
         Lib.gnnfp_profile_collect(msc, cnt, NC)
         Lib.gnnfp_profile_enable(0)
-        names = ["other", "state_fwd_iter(gemm_rows fwd)", "state_bwd_dW(gemm_dw)", "tile_pass(prologue, BN statistics)",
-                 "out_fwd", "out_bwd", "bn_fix", "state_bwd_dz(dz_kernel)", "state_bwd_dX(gemm_rows bwd)",
+        names = ["other", "state_fwd_iter(gemm_rows_tc fwd)", "state_bwd_dW(gemm_dw)", "tile_pass(prologue, BN statistics)",
+                 "out_fwd", "out_bwd", "bn_fix", "state_bwd_dz(dz_kernel)", "state_bwd_dX(gemm_rows_tc bwd)",
                  "aggregate(agg_stats)"]
         shares = {names[i]: {"ms": msc[i], "launches": int(cnt[i])} for i in range(len(names))}
         nsteps_p = min(args.steps, 6)
@@ -363,15 +363,15 @@ def main():
         kmean = float(np.mean([int(k.item()) for kk, _ in ks for k in kk]))
         iters = Nn * kmean * nsteps_p                     # node-updates per layer in the profiled steps
         # per-kernel algorithmic traffic (fp32 words that must move once, SURVEY 8(d) convention: raw inputs, no re-reads)
-        #   gemm_rows fwd : read s (D) + Adj^T s (D) + invariant columns (AL), write s' (D)
+        #   gemm_rows_tc fwd : read s (D) + Adj^T s (D) + invariant columns (AL), write s' (D)
         #   gemm_dw       : read the same inputs (2D + AL) + dz (D); dW/db stay on chip
         #   gemm_rows dX  : two launches per iteration, each reads dz (D) and writes one D-wide block
         cand = {
-            "gemm_rows_kernel<fwd>": (msc[1], int(cnt[1]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
+            "gemm_rows_tc_kernel<fwd>": (msc[1], int(cnt[1]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
                                       sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
             "gemm_dw_kernel": (msc[2], int(cnt[2]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
                                sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
-            "gemm_rows_kernel<bwd dX>": (msc[8], int(cnt[8]), sum(4 * (4 * D) for D in WIDTHS) * iters,
+            "gemm_rows_tc_kernel<bwd dX>": (msc[8], int(cnt[8]), sum(4 * (4 * D) for D in WIDTHS) * iters,
                                          sum(2 * (2 * D) * D for D in WIDTHS) * iters),
         }
         dom = max(cand, key=lambda k_: cand[k_][0])
@@ -403,7 +403,7 @@ def main():
                            "frac is the HBM fraction the contract asks for",
                 "fixed_point_iteration": {"ms": it_ms, "algorithmic_GBps": it_bytes / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0,
                                           "frac_of_hbm_peak": (it_bytes / (it_ms * 1e-3) / 1e9) / peak if it_ms > 0 else 0.0,
-                                          "kernels": "gemm_rows fwd + agg_stats + dz + gemm_dw + gemm_rows dX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
+                                          "kernels": "gemm_rows_tc fwd (tcgen05 3xTF32) + agg_stats + dz + gemm_dw + gemm_rows_tc dX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
                 "kernel_time_by_category_ms": shares,
                 "note": "achieved = algorithmic bytes of the kernel's launches / their CUDA-event durations "
                         "(events recorded by the library on the launch stream, separate profiled pass of the same steps)"}
