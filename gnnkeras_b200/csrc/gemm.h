@@ -71,6 +71,8 @@ int gemm_rows_ldw(int N);
 int gemm_rows_kpad(int k8);
 int gemm_rows_supported(int k8, int N);
 int launch_gemm_dw(const GemmDwArgs& a, cudaStream_t s, int prof_cat, int* grid_out);
+int gemm_dw_tc_supported(const GemmDwArgs& a);                          // gemm_tc.cu: tcgen05 (3xTF32) version
+int launch_gemm_dw_tc(const GemmDwArgs& a, cudaStream_t s, int prof_cat, int* grid_out);
 int gemm_dw_supported(int Kp, int H);
 int gemm_dw_grid(int n_rows);
 int launch_transpose_block(const float* W, int H, int col0, int width, int Kpad, int ldw, float* out, cudaStream_t s);

@@ -495,3 +495,270 @@ int launch_gemm_rows_tc(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
     default: GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_rows_tc: %d output columns", a.ldw);
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// dW = X^T dz on the tensor cores.  The reduction runs over the rows, so both operands are needed "transposed":
+//     D[j, c] (+)= sum_r dz[r, j] * X[r, c]        A = dz^T [128 (H valid) x 32 rows],  B = X^T [NT x 32 rows], K-major
+// with NT = 16*ceil((Kp + 1)/16) <= 256 output columns: the Kp input columns, one column of ones (so that D[j, Kp] = db_j
+// comes out of the same MMAs) and zero padding.  Per persistent CTA (one per SM, 160 threads):
+//   * 4 converter warps: 8-byte cp.async of 32 rows of all pieces and of dz into a raw stage (row-major, leading dimension
+//     = 2 mod 4 floats so that the 8-byte column reads below are conflict free), then the transposing split: lane r reads
+//     raw[r][c..c+1] and writes 4-byte hi / lo words into row c of the swizzled K-major operand tile (one full 128-byte
+//     operand row per warp store: conflict free);
+//   * 1 MMA warp: 12 tcgen05.mma (M = 128, N = NT, K = 8, 3xTF32) per stage, accumulating over ALL rows of the CTA in TMEM;
+//   * no per-tile epilogue: after the last stage the accumulator is staged through shared memory once and flushed with
+//     the same BN algebra as gemm_dw_kernel (per-CTA partial slot, P_c / Q_c sums).
+#define DW_TC_THREADS 160
+#define DW_TC_ROWS 32
+
+__global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __grid_constant__ GemmDwArgs a, int NT, int RAWLD) {
+  if (a.gate && *a.gate == 0) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int btile = NT * 128;                          // bytes of one X^T operand tile
+  const int slot_bytes = 2 * TC_TILE_BYTES + 2 * btile;       // [A_hi | A_lo | B_hi | B_lo]
+  uint8_t* ops = base;                                 // [2 slots]
+  float* raw = reinterpret_cast<float*>(ops + 2 * (size_t)slot_bytes);      // [2][DW_TC_ROWS][RAWLD]
+  __shared__ __align__(8) uint64_t ops_full[2], ops_empty[2], done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n_rows;
+  const int n_chunks_all = (n + DW_TC_ROWS - 1) / DW_TC_ROWS;
+  const int per_cta = (n_chunks_all + gridDim.x - 1) / gridDim.x;
+  const int c0 = blockIdx.x * per_cta;
+  const int total = max(0, min(n_chunks_all, c0 + per_cta) - c0);
+  const int Kp = a.Kp, H = a.H;
+  const int npairs = (Kp + H + 1) >> 1;                // column pairs of a raw row: [X pieces (Kp) | dz (H)]
+
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
+  if (tid == 32) {
+    mbar_init(&ops_full[0], 128); mbar_init(&ops_full[1], 128);
+    mbar_init(&ops_empty[0], 1); mbar_init(&ops_empty[1], 1);
+    mbar_init(&done_bar, 1);
+  }
+  // zero the operand slots once (padding rows of both operands are never written afterwards), then the row of ones
+  for (int e = tid; e < 2 * slot_bytes / 16; e += DW_TC_THREADS) reinterpret_cast<uint4*>(ops)[e] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (tid < 64) {
+    const int sl = tid >> 5, r = tid & 31;
+    *reinterpret_cast<float*>(ops + (size_t)sl * slot_bytes + 2 * TC_TILE_BYTES + tc_sw128_off(Kp, r)) = 1.0f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp < 4) {
+    // ---- per-thread description of the (up to 4) column pairs this lane copies: pair lane + 32*q of every row -------
+    const float* pbase[4];
+    int pld[4], pbytes[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kcol = 2 * (lane + 32 * q);
+      pbase[q] = a.dz; pld[q] = 0; pbytes[q] = -1;     // -1: pair outside the row
+      if (kcol < Kp) {
+        int p = 0;
+        while (p + 1 < a.n_pieces && kcol >= a.p[p + 1].k8) ++p;
+        const int kk = kcol - a.p[p].k8, nv = a.p[p].width - kk;
+        pbase[q] = a.p[p].ptr + (nv > 0 ? kk : 0); pld[q] = a.p[p].ld;
+        pbytes[q] = nv <= 0 ? 0 : (nv > 1 ? 8 : 4);
+      } else if (kcol < Kp + H) {
+        const int j0 = kcol - Kp, nv = H - j0;
+        pbase[q] = a.dz + j0; pld[q] = a.ld_dz; pbytes[q] = nv > 1 ? 8 : 4;
+      } else if (kcol < 2 * npairs) {
+        pbytes[q] = 0;
+      }
+    }
+    auto issue = [&](int it) {
+      if (it < total) {
+        float* dst = raw + (it & 1) * DW_TC_ROWS * RAWLD;
+        const int row0 = (c0 + it) * DW_TC_ROWS;
+        if (it + 2 < total) {                          // L2 prefetch two stages ahead: one line per lane and row segment
+          const int prow = (c0 + it + 2) * DW_TC_ROWS + lane;
+          if (prow < n && warp < a.n_pieces) {
+            const char* b0 = reinterpret_cast<const char*>(a.p[warp].ptr + (size_t)prow * a.p[warp].ld);
+            const char* l1 = b0 + (size_t)a.p[warp].width * 4;
+            for (const char* l = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127); l < l1; l += 128)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
+          }
+          if (prow < n && warp == 3) {
+            const char* b0 = reinterpret_cast<const char*>(a.dz + (size_t)prow * a.ld_dz);
+            const char* l1 = b0 + (size_t)H * 4;
+            for (const char* l = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127); l < l1; l += 128)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (pbytes[q] < 0) continue;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {                // warp w copies rows w, w+4, ... of the stage
+            const int r = warp + 4 * i;
+            const int grow = row0 + r;
+            const bool ok = grow < n && pbytes[q] > 0;
+            tc_cp_async8(dst + r * RAWLD + 2 * (lane + 32 * q), ok ? pbase[q] + (size_t)grow * pld[q] : a.dz, ok ? pbytes[q] : 0);
+          }
+        }
+      }
+      tc_cp_commit();
+    };
+    issue(0);
+    for (int it = 0; it < total; ++it) {
+      tc_cp_wait<0>();
+      named_bar_sync(1, 128);                          // stage `it` landed; everyone is done reading the other raw slot
+      issue(it + 1);
+      const int slot = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      if (use > 0) { mbar_wait_bounded(&ops_empty[slot], (use - 1) & 1); tc_fence_after(); }
+      uint8_t* Ahi = ops + (size_t)slot * slot_bytes;
+      uint8_t* Alo = Ahi + TC_TILE_BYTES;
+      uint8_t* Bhi = Alo + TC_TILE_BYTES;
+      uint8_t* Blo = Bhi + btile;
+      const float* rs = raw + slot * DW_TC_ROWS * RAWLD;
+      const int koff = ((lane >> 2) << 4) + ((lane & 3) << 2);          // unswizzled byte offset of row (lane) inside an operand row
+      for (int pp = warp; pp < npairs; pp += 4) {      // transposing split: lane = row of the stage, pair pp = two columns
+        const float2 v = *reinterpret_cast<const float2*>(rs + lane * RAWLD + 2 * pp);
+        const uint32_t b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cidx = 2 * pp + e;
+          const uint32_t bits = e ? b1 : b0;
+          uint8_t* hi; uint8_t* lo; int orow;
+          if (cidx < Kp) { hi = Bhi; lo = Blo; orow = cidx; }
+          else { hi = Ahi; lo = Alo; orow = cidx - Kp; }
+          if (cidx < Kp + H) {
+            const int off = (orow >> 3) * 1024 + (orow & 7) * 128 + (koff ^ ((orow & 7) << 4));
+            *reinterpret_cast<uint32_t*>(hi + off) = bits;
+            *reinterpret_cast<uint32_t*>(lo + off) = tc_lo(bits);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&ops_full[slot]);
+    }
+    tc_cp_wait<0>();
+  } else if (lane == 0) {
+    // ---- MMA issuer -------------------------------------------------------------------------------------------------------
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t ops_addr = smem_u32(ops);
+    for (int it = 0; it < total; ++it) {
+      const int slot = it & 1;
+      mbar_wait_bounded(&ops_full[slot], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t sa = ops_addr + slot * slot_bytes;
+      const uint64_t dah = tc_desc_sw128(sa), dal = tc_desc_sw128(sa + TC_TILE_BYTES);
+      const uint64_t dbh = tc_desc_sw128(sa + 2 * TC_TILE_BYTES), dbl = tc_desc_sw128(sa + 2 * TC_TILE_BYTES + btile);
+#pragma unroll
+      for (int k8 = 0; k8 < DW_TC_ROWS / 8; ++k8) {
+        const uint64_t adv = (uint64_t)(2 * k8);
+        tc_mma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (it | k8) ? 1u : 0u);
+        tc_mma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+        tc_mma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+      }
+      tc_commit(&ops_empty[slot]);
+    }
+    tc_commit(&done_bar);
+  }
+  // ---- flush: accumulator -> shared memory (sD[c][j]) -> BN algebra -> this CTA's partial slot -------------------------
+  constexpr int HS = 129;                              // leading dimension of sD (rows of D = 128 TMEM lanes)
+  float* sD = reinterpret_cast<float*>(ops);           // [NT][HS] <= 2 operand slots
+  if (warp < 4) {
+    if (total > 0) {
+      mbar_wait_bounded(&done_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * warp) << 16);
+      for (int cc = 0; cc < NT; cc += 8) {
+        float v[8];
+        tmem_ld8(taddr + cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sD[(cc + i) * HS + 32 * warp + lane] = v[i];
+      }
+    } else {
+      for (int cc = 0; cc < NT; ++cc) sD[cc * HS + tid] = 0.f;
+    }
+    tc_fence_before();
+    named_bar_sync(1, 128);
+    float* part = a.partial + (size_t)blockIdx.x * a.n_params;
+    const float* sdb = sD + Kp * HS;                   // db_j = D[j][Kp] (the column of ones)
+    int K = 0;
+    for (int p = 0; p < a.n_pieces; ++p) K += a.p[p].width;
+    for (int e = tid; e < K * H; e += 128) {
+      const int c = e / H, j = e - c * H;
+      int kp = 0, coff = 0;
+      for (int p = 0; p < a.n_pieces; ++p) {
+        if (c >= coff && c < coff + a.p[p].width) kp = a.p[p].k8 + (c - coff);
+        coff += a.p[p].width;
+      }
+      float v = sD[kp * HS + j];
+      if (a.bnA) v = a.gamma[c] * fmaf(a.bnA[c], v, a.bnB[c] * sdb[j]) + a.beta[c] * sdb[j];
+      part[(size_t)c * H + j] += v;
+    }
+    for (int j = tid; j < H; j += 128) part[a.bias_off + j] += sdb[j];
+    if (a.bn_partial) {
+      float* bp = a.bn_partial + (size_t)blockIdx.x * 2 * K;
+      for (int c = tid; c < K; c += 128) {
+        int kp = 0, coff = 0;
+        for (int p = 0; p < a.n_pieces; ++p) {
+          if (c >= coff && c < coff + a.p[p].width) kp = a.p[p].k8 + (c - coff);
+          coff += a.p[p].width;
+        }
+        float P = 0.f, Q = 0.f;
+        for (int j = 0; j < H; ++j) {
+          const float w = a.W[(size_t)c * H + j];
+          P = fmaf(w, sdb[j], P);
+          Q = fmaf(w, sD[kp * HS + j], Q);
+        }
+        bp[c] = P;
+        bp[K + c] = fmaf(a.bnA[c], Q, a.bnB[c] * P);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
+static void dw_tc_geometry(const GemmDwArgs& a, int* NT, int* RAWLD, size_t* smem) {
+  *NT = 16 * ((a.Kp + 1 + 15) / 16);
+  int ld = a.Kp + a.H + (a.H & 1);
+  while (ld % 4 != 2) ++ld;                            // = 2 mod 4 floats: 8-byte column reads of 32 rows are conflict free
+  *RAWLD = ld;
+  const size_t slot = 2 * (size_t)TC_TILE_BYTES + 2 * (size_t)(*NT) * 128;
+  const size_t sd = (size_t)(*NT) * 129 * sizeof(float);
+  const size_t opsz = 2 * slot > sd ? 2 * slot : sd;
+  *smem = opsz + 2 * (size_t)DW_TC_ROWS * ld * sizeof(float) + 1024;
+}
+
+int gemm_dw_tc_supported(const GemmDwArgs& a) {
+  if (a.rowlist != nullptr || a.dz_compact || a.Kp % 2 != 0 || a.H > 128 || a.Kp + 1 > 256 || a.n_pieces > 3) return 0;
+  if (a.Kp + a.H > 256) return 0;                      // 4 column pairs per lane cover at most 256 raw columns
+  if (((uintptr_t)a.dz & 7) != 0 || a.ld_dz % 2 != 0) return 0;
+  for (int p = 0; p < a.n_pieces; ++p) if (!a.p[p].al8) return 0;
+  int NT, RAWLD; size_t smem;
+  dw_tc_geometry(a, &NT, &RAWLD, &smem);
+  return smem <= 224 * 1024;
+}
+
+int launch_gemm_dw_tc(const GemmDwArgs& a, cudaStream_t s, int prof_cat, int* grid_out) {
+  if (a.n_rows <= 0) { if (grid_out) *grid_out = 0; return GNNFP_OK; }
+  int NT, RAWLD; size_t smem;
+  dw_tc_geometry(a, &NT, &RAWLD, &smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(gemm_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int n_chunks = (a.n_rows + DW_TC_ROWS - 1) / DW_TC_ROWS;
+  const int nsm = gnnfp_num_sms();
+  int grid = (n_chunks + 7) / 8;                       // >= 256 rows per CTA
+  if (grid > nsm) grid = nsm;
+  if (grid < 1) grid = 1;
+  if (grid_out) *grid_out = grid;
+  ProfScope ps(prof_cat, s);
+  gemm_dw_tc_kernel<<<grid, DW_TC_THREADS, smem, s>>>(a, NT, RAWLD);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
