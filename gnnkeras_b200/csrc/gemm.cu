@@ -597,7 +597,8 @@ int gemm_dw_grid(int n_rows) { return grid_for((((n_rows + DW_ROWS - 1) / DW_ROW
 
 int launch_gemm_dw(const GemmDwArgs& a, cudaStream_t s, int prof_cat, int* grid_out) {
   if (a.n_rows <= 0) { if (grid_out) *grid_out = 0; return GNNFP_OK; }
-  static const int tc_dw = [] { const char* e = getenv("GNNFP_TC_DW"); return e ? atoi(e) : 0; }();
+  // tensor-core (tcgen05, 3xTF32) version for every eligible shape; GNNFP_TC_DW=0 selects the FP32-pipe kernel below
+  static const int tc_dw = [] { const char* e = getenv("GNNFP_TC_DW"); return e ? atoi(e) : 1; }();
   if (tc_dw > 0 && gemm_dw_tc_supported(a)) return launch_gemm_dw_tc(a, s, prof_cat, grid_out);
   if (a.Kp % 2 != 0 || !gemm_dw_supported(a.Kp, a.H)) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_dw: K=%d, H=%d outside the supported tile shapes", a.Kp, a.H);
   const int nq = (a.Kp + 63) / 64, tj = (a.H + 15) / 16;

@@ -508,7 +508,9 @@ int launch_gemm_rows_tc(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
 //   * 1 MMA warp: 12 tcgen05.mma (M = 128, N = NT, K = 8, 3xTF32) per stage, accumulating over ALL rows of the CTA in TMEM;
 //   * no per-tile epilogue: after the last stage the accumulator is staged through shared memory once and flushed with
 //     the same BN algebra as gemm_dw_kernel (per-CTA partial slot, P_c / Q_c sums).
-#define DW_TC_THREADS 160
+#define DW_TC_CONV_WARPS 8
+#define DW_TC_CONV_THREADS (32 * DW_TC_CONV_WARPS)
+#define DW_TC_THREADS (DW_TC_CONV_THREADS + 32)
 #define DW_TC_ROWS 32
 
 __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __grid_constant__ GemmDwArgs a, int NT, int RAWLD) {
@@ -521,6 +523,8 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
   float* raw = reinterpret_cast<float*>(ops + 2 * (size_t)slot_bytes);      // [2][DW_TC_ROWS][RAWLD]
   __shared__ __align__(8) uint64_t ops_full[2], ops_empty[2], done_bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_gam[256], s_bet[256], s_bA[256], s_bB[256];
+  __shared__ int s_kp[256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n_rows;
   const int n_chunks_all = (n + DW_TC_ROWS - 1) / DW_TC_ROWS;
@@ -528,13 +532,25 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
   const int c0 = blockIdx.x * per_cta;
   const int total = max(0, min(n_chunks_all, c0 + per_cta) - c0);
   const int Kp = a.Kp, H = a.H;
-  const int npairs = (Kp + H + 1) >> 1;                // column pairs of a raw row: [X pieces (Kp) | dz (H)]
+  const int xpairs = Kp >> 1, zpairs = (H + 1) >> 1, npairs = xpairs + zpairs;   // raw row: [X pieces (Kp) | dz (H)]
+  int K = 0;
+  for (int p = 0; p < a.n_pieces; ++p) K += a.p[p].width;
 
   if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
   if (tid == 32) {
-    mbar_init(&ops_full[0], 128); mbar_init(&ops_full[1], 128);
+    mbar_init(&ops_full[0], DW_TC_CONV_THREADS); mbar_init(&ops_full[1], DW_TC_CONV_THREADS);
     mbar_init(&ops_empty[0], 1); mbar_init(&ops_empty[1], 1);
     mbar_init(&done_bar, 1);
+  }
+  for (int c = tid; c < K; c += DW_TC_THREADS) {       // per-column constants of the flush
+    int kp = 0, coff = 0;
+    for (int p = 0; p < a.n_pieces; ++p) {
+      if (c >= coff && c < coff + a.p[p].width) kp = a.p[p].k8 + (c - coff);
+      coff += a.p[p].width;
+    }
+    s_kp[c] = kp;
+    s_gam[c] = a.bnA ? a.gamma[c] : 1.f; s_bet[c] = a.bnA ? a.beta[c] : 0.f;
+    s_bA[c] = a.bnA ? a.bnA[c] : 1.f; s_bB[c] = a.bnA ? a.bnB[c] : 0.f;
   }
   // zero the operand slots once (padding rows of both operands are never written afterwards), then the row of ones
   for (int e = tid; e < 2 * slot_bytes / 16; e += DW_TC_THREADS) reinterpret_cast<uint4*>(ops)[e] = make_uint4(0u, 0u, 0u, 0u);
@@ -549,20 +565,23 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
-  if (warp < 4) {
+  if (warp < DW_TC_CONV_WARPS) {
     // ---- per-thread description of the (up to 4) column pairs this lane copies: pair lane + 32*q of every row -------
     const float* pbase[4];
     int pld[4], pbytes[4];
+    bool pal8[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int kcol = 2 * (lane + 32 * q);
       pbase[q] = a.dz; pld[q] = 0; pbytes[q] = -1;     // -1: pair outside the row
+      pal8[q] = true;
       if (kcol < Kp) {
         int p = 0;
         while (p + 1 < a.n_pieces && kcol >= a.p[p + 1].k8) ++p;
         const int kk = kcol - a.p[p].k8, nv = a.p[p].width - kk;
         pbase[q] = a.p[p].ptr + (nv > 0 ? kk : 0); pld[q] = a.p[p].ld;
         pbytes[q] = nv <= 0 ? 0 : (nv > 1 ? 8 : 4);
+        pal8[q] = a.p[p].al8 != 0;
       } else if (kcol < Kp + H) {
         const int j0 = kcol - Kp, nv = H - j0;
         pbase[q] = a.dz + j0; pld[q] = a.ld_dz; pbytes[q] = nv > 1 ? 8 : 4;
@@ -582,7 +601,7 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
             for (const char* l = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127); l < l1; l += 128)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
           }
-          if (prow < n && warp == 3) {
+          if (prow < n && warp == DW_TC_CONV_WARPS - 1) {
             const char* b0 = reinterpret_cast<const char*>(a.dz + (size_t)prow * a.ld_dz);
             const char* l1 = b0 + (size_t)H * 4;
             for (const char* l = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127); l < l1; l += 128)
@@ -593,45 +612,57 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
         for (int q = 0; q < 4; ++q) {
           if (pbytes[q] < 0) continue;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {                // warp w copies rows w, w+4, ... of the stage
-            const int r = warp + 4 * i;
+          for (int i = 0; i < DW_TC_ROWS / DW_TC_CONV_WARPS; ++i) {       // warp w copies rows w, w+8, ... of the stage
+            const int r = warp + DW_TC_CONV_WARPS * i;
             const int grow = row0 + r;
             const bool ok = grow < n && pbytes[q] > 0;
-            tc_cp_async8(dst + r * RAWLD + 2 * (lane + 32 * q), ok ? pbase[q] + (size_t)grow * pld[q] : a.dz, ok ? pbytes[q] : 0);
+            float* d = dst + r * RAWLD + 2 * (lane + 32 * q);
+            const float* src = ok ? pbase[q] + (size_t)grow * pld[q] : a.dz;
+            if (pal8[q]) tc_cp_async8(d, src, ok ? pbytes[q] : 0);
+            else {                                     // piece whose rows are not 8-byte aligned: two 4-byte copies
+              tc_cp_async4(d, src, ok ? 4 : 0);
+              tc_cp_async4(d + 1, (ok && pbytes[q] == 8) ? src + 1 : a.dz, (ok && pbytes[q] == 8) ? 4 : 0);
+            }
           }
         }
       }
       tc_cp_commit();
     };
     issue(0);
+    const int koff = ((lane >> 2) << 4) + ((lane & 3) << 2);            // unswizzled byte offset of stage row `lane` inside an operand row
     for (int it = 0; it < total; ++it) {
       tc_cp_wait<0>();
-      named_bar_sync(1, 128);                          // stage `it` landed; everyone is done reading the other raw slot
+      named_bar_sync(1, DW_TC_CONV_THREADS);           // stage `it` landed; everyone is done reading the other raw slot
       issue(it + 1);
       const int slot = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       if (use > 0) { mbar_wait_bounded(&ops_empty[slot], (use - 1) & 1); tc_fence_after(); }
       uint8_t* Ahi = ops + (size_t)slot * slot_bytes;
-      uint8_t* Alo = Ahi + TC_TILE_BYTES;
-      uint8_t* Bhi = Alo + TC_TILE_BYTES;
-      uint8_t* Blo = Bhi + btile;
-      const float* rs = raw + slot * DW_TC_ROWS * RAWLD;
-      const int koff = ((lane >> 2) << 4) + ((lane & 3) << 2);          // unswizzled byte offset of row (lane) inside an operand row
-      for (int pp = warp; pp < npairs; pp += 4) {      // transposing split: lane = row of the stage, pair pp = two columns
-        const float2 v = *reinterpret_cast<const float2*>(rs + lane * RAWLD + 2 * pp);
-        const uint32_t b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int cidx = 2 * pp + e;
-          const uint32_t bits = e ? b1 : b0;
-          uint8_t* hi; uint8_t* lo; int orow;
-          if (cidx < Kp) { hi = Bhi; lo = Blo; orow = cidx; }
-          else { hi = Ahi; lo = Alo; orow = cidx - Kp; }
-          if (cidx < Kp + H) {
-            const int off = (orow >> 3) * 1024 + (orow & 7) * 128 + (koff ^ ((orow & 7) << 4));
-            *reinterpret_cast<uint32_t*>(hi + off) = bits;
-            *reinterpret_cast<uint32_t*>(lo + off) = tc_lo(bits);
-          }
+      uint8_t* Bhi = Ahi + 2 * TC_TILE_BYTES;
+      const float* rs = raw + slot * DW_TC_ROWS * RAWLD + lane * RAWLD;
+      // transposing split: lane = row of the stage; one warp store writes a whole 128-byte operand row (conflict free)
+#pragma unroll 2
+      for (int pp = warp; pp < xpairs; pp += DW_TC_CONV_WARPS) {         // X columns 2pp, 2pp+1 -> rows of B = X^T
+        const float2 v = *reinterpret_cast<const float2*>(rs + 2 * pp);
+        const int orow = 2 * pp;                       // even: orow and orow + 1 share an 8-row group
+        uint8_t* h0 = Bhi + (orow >> 3) * 1024 + (orow & 7) * 128 + (koff ^ ((orow & 7) << 4));
+        uint8_t* h1 = Bhi + (orow >> 3) * 1024 + ((orow & 7) + 1) * 128 + (koff ^ (((orow & 7) + 1) << 4));
+        *reinterpret_cast<uint32_t*>(h0) = __float_as_uint(v.x);
+        *reinterpret_cast<uint32_t*>(h0 + btile) = tc_lo(__float_as_uint(v.x));
+        *reinterpret_cast<uint32_t*>(h1) = __float_as_uint(v.y);
+        *reinterpret_cast<uint32_t*>(h1 + btile) = tc_lo(__float_as_uint(v.y));
+      }
+#pragma unroll 2
+      for (int pp = warp; pp < zpairs; pp += DW_TC_CONV_WARPS) {         // dz columns 2pp, 2pp+1 -> rows of A = dz^T
+        const float2 v = *reinterpret_cast<const float2*>(rs + Kp + 2 * pp);
+        const int orow = 2 * pp;
+        uint8_t* h0 = Ahi + (orow >> 3) * 1024 + (orow & 7) * 128 + (koff ^ ((orow & 7) << 4));
+        uint8_t* h1 = Ahi + (orow >> 3) * 1024 + ((orow & 7) + 1) * 128 + (koff ^ (((orow & 7) + 1) << 4));
+        *reinterpret_cast<uint32_t*>(h0) = __float_as_uint(v.x);
+        *reinterpret_cast<uint32_t*>(h0 + TC_TILE_BYTES) = tc_lo(__float_as_uint(v.x));
+        if (orow + 1 < H) {
+          *reinterpret_cast<uint32_t*>(h1) = __float_as_uint(v.y);
+          *reinterpret_cast<uint32_t*>(h1 + TC_TILE_BYTES) = tc_lo(__float_as_uint(v.y));
         }
       }
       fence_proxy_async();
@@ -663,55 +694,60 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
   // ---- flush: accumulator -> shared memory (sD[c][j]) -> BN algebra -> this CTA's partial slot -------------------------
   constexpr int HS = 129;                              // leading dimension of sD (rows of D = 128 TMEM lanes)
   float* sD = reinterpret_cast<float*>(ops);           // [NT][HS] <= 2 operand slots
-  if (warp < 4) {
+  if (warp < DW_TC_CONV_WARPS) {
     if (total > 0) {
       mbar_wait_bounded(&done_bar, 0);
       tc_fence_after();
-      const uint32_t taddr = tmem_d + ((uint32_t)(32 * warp) << 16);
-      for (int cc = 0; cc < NT; cc += 8) {
+      const int q = warp & 3;                          // TMEM lane quarter; the two warps of a quarter take alternate column groups
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16);
+      for (int cc = 8 * (warp >> 2); cc < NT; cc += 16) {
         float v[8];
         tmem_ld8(taddr + cc, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sD[(cc + i) * HS + 32 * warp + lane] = v[i];
+        for (int i = 0; i < 8; ++i) sD[(cc + i) * HS + 32 * q + lane] = v[i];
       }
     } else {
-      for (int cc = 0; cc < NT; ++cc) sD[cc * HS + tid] = 0.f;
+      for (int e = tid; e < NT * 128; e += DW_TC_CONV_THREADS) sD[(e >> 7) * HS + (e & 127)] = 0.f;
     }
     tc_fence_before();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, DW_TC_CONV_THREADS);
     float* part = a.partial + (size_t)blockIdx.x * a.n_params;
     const float* sdb = sD + Kp * HS;                   // db_j = D[j][Kp] (the column of ones)
-    int K = 0;
-    for (int p = 0; p < a.n_pieces; ++p) K += a.p[p].width;
-    for (int e = tid; e < K * H; e += 128) {
-      const int c = e / H, j = e - c * H;
-      int kp = 0, coff = 0;
-      for (int p = 0; p < a.n_pieces; ++p) {
-        if (c >= coff && c < coff + a.p[p].width) kp = a.p[p].k8 + (c - coff);
-        coff += a.p[p].width;
+    const int KH = K * H;
+    for (int e0 = tid; e0 < KH; e0 += 4 * DW_TC_CONV_THREADS) {          // 4 read-modify-writes in flight per thread
+      float old[4], v[4];
+      int idx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * DW_TC_CONV_THREADS;
+        idx[u] = e < KH ? e : -1;
+        old[u] = 0.f; v[u] = 0.f;
+        if (e < KH) {
+          const int c = e / H, j = e - c * H;
+          old[u] = part[e];
+          const float x = sD[s_kp[c] * HS + j];
+          v[u] = a.bnA ? s_gam[c] * fmaf(s_bA[c], x, s_bB[c] * sdb[j]) + s_bet[c] * sdb[j] : x;
+        }
       }
-      float v = sD[kp * HS + j];
-      if (a.bnA) v = a.gamma[c] * fmaf(a.bnA[c], v, a.bnB[c] * sdb[j]) + a.beta[c] * sdb[j];
-      part[(size_t)c * H + j] += v;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (idx[u] >= 0) part[idx[u]] = old[u] + v[u];
     }
-    for (int j = tid; j < H; j += 128) part[a.bias_off + j] += sdb[j];
+    for (int j = tid; j < H; j += DW_TC_CONV_THREADS) part[a.bias_off + j] += sdb[j];
     if (a.bn_partial) {
       float* bp = a.bn_partial + (size_t)blockIdx.x * 2 * K;
-      for (int c = tid; c < K; c += 128) {
-        int kp = 0, coff = 0;
-        for (int p = 0; p < a.n_pieces; ++p) {
-          if (c >= coff && c < coff + a.p[p].width) kp = a.p[p].k8 + (c - coff);
-          coff += a.p[p].width;
-        }
+      for (int c = tid; c < K; c += DW_TC_CONV_THREADS) {
+        const float* wr = a.W + (size_t)c * H;
+        const float* dr = sD + s_kp[c] * HS;
         float P = 0.f, Q = 0.f;
+#pragma unroll 4
         for (int j = 0; j < H; ++j) {
-          const float w = a.W[(size_t)c * H + j];
+          const float w = wr[j];
           P = fmaf(w, sdb[j], P);
-          Q = fmaf(w, sD[kp * HS + j], Q);
+          Q = fmaf(w, dr[j], Q);
         }
         bp[c] = P;
-        bp[K + c] = fmaf(a.bnA[c], Q, a.bnB[c] * P);
+        bp[K + c] = fmaf(s_bA[c], Q, s_bB[c] * P);
       }
     }
   }
@@ -735,10 +771,9 @@ int gemm_dw_tc_supported(const GemmDwArgs& a) {
   if (a.rowlist != nullptr || a.dz_compact || a.Kp % 2 != 0 || a.H > 128 || a.Kp + 1 > 256 || a.n_pieces > 3) return 0;
   if (a.Kp + a.H > 256) return 0;                      // 4 column pairs per lane cover at most 256 raw columns
   if (((uintptr_t)a.dz & 7) != 0 || a.ld_dz % 2 != 0) return 0;
-  for (int p = 0; p < a.n_pieces; ++p) if (!a.p[p].al8) return 0;
   int NT, RAWLD; size_t smem;
   dw_tc_geometry(a, &NT, &RAWLD, &smem);
-  return smem <= 224 * 1024;
+  return smem <= 220 * 1024;
 }
 
 int launch_gemm_dw_tc(const GemmDwArgs& a, cudaStream_t s, int prof_cat, int* grid_out) {
