@@ -353,7 +353,7 @@ def main():
         cnt = (C.c_longlong * NC)()
         Lib.gnnfp_profile_collect(msc, cnt, NC)
         Lib.gnnfp_profile_enable(0)
-        names = ["other", "state_fwd_iter(gemm_rows_tc fwd)", "state_bwd_dW(gemm_dw)", "tile_pass(prologue, BN statistics)",
+        names = ["other", "state_fwd_iter(gemm_rows_tc fwd)", "state_bwd_dW(gemm_dw_tc)", "tile_pass(prologue, BN statistics)",
                  "out_fwd", "out_bwd", "bn_fix", "state_bwd_dz(dz_kernel)", "state_bwd_dX(gemm_rows_tc bwd)",
                  "aggregate(agg_stats)"]
         shares = {names[i]: {"ms": msc[i], "launches": int(cnt[i])} for i in range(len(names))}
@@ -364,12 +364,12 @@ def main():
         iters = Nn * kmean * nsteps_p                     # node-updates per layer in the profiled steps
         # per-kernel algorithmic traffic (fp32 words that must move once, SURVEY 8(d) convention: raw inputs, no re-reads)
         #   gemm_rows_tc fwd : read s (D) + Adj^T s (D) + invariant columns (AL), write s' (D)
-        #   gemm_dw       : read the same inputs (2D + AL) + dz (D); dW/db stay on chip
+        #   gemm_dw_tc    : read the same inputs (2D + AL) + dz (D); dW/db stay on chip
         #   gemm_rows dX  : two launches per iteration, each reads dz (D) and writes one D-wide block
         cand = {
             "gemm_rows_tc_kernel<fwd>": (msc[1], int(cnt[1]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
                                       sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
-            "gemm_dw_kernel": (msc[2], int(cnt[2]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
+            "gemm_dw_tc_kernel": (msc[2], int(cnt[2]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
                                sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
             "gemm_rows_tc_kernel<bwd dX>": (msc[8], int(cnt[8]), sum(4 * (4 * D) for D in WIDTHS) * iters,
                                          sum(2 * (2 * D) * D for D in WIDTHS) * iters),
@@ -383,7 +383,8 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # nominal FFMA peak at the boost clock
-        tfl = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        tfl = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0      # useful (fp32-equivalent) flops
+        tf32_peak = 1100.0                                  # dense TF32 tensor peak (B200_PROFILING.md); each product = 3 MMAs
         # whole fixed-point iteration against SURVEY 8(d)'s per-node-update figure B = B_f + B_b
         it_ms = msc[1] + msc[2] + msc[7] + msc[8] + msc[9]
         it_bytes = sum(algorithmic_bytes(D, AL, deg, True) + algorithmic_bytes(D, AL, deg, False) for D in WIDTHS) * iters
@@ -398,12 +399,15 @@ def main():
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "avg_launch_ms": dom_ms / max(1, dom_n),
                 "algorithmic_bytes_per_launch": dom_bytes / max(1, dom_n),
-                "fp32_tflops_achieved": tfl, "fp32_tflops_nominal_peak": fp32_peak, "fp32_frac": tfl / fp32_peak,
-                "binding": "FP32 FMA pipe (33 flop/B on this workload, ridge 11.5 flop/B): fp32_frac is the binding fraction, "
-                           "frac is the HBM fraction the contract asks for",
+                "useful_tflops_achieved": tfl, "tf32_mma_tflops_issued": 3 * tfl, "tf32_tensor_peak_tflops": tf32_peak,
+                "tensor_frac": 3 * tfl / tf32_peak, "fp32_pipe_nominal_peak_tflops": fp32_peak,
+                "binding": "the GEMM kernels run on tcgen05 (3xTF32: 3 MMAs per product); with the math on the tensor pipe the "
+                           "33 flop/B workload is HBM-bound by the roofline (ridge ~57 flop/B at 1.1 PF/3), so frac is against the "
+                           "measured HBM peak; what limits the kernels today is operand conversion / epilogue instruction issue "
+                           "and L2 latency at one CTA per SM (DESIGN.md 6)",
                 "fixed_point_iteration": {"ms": it_ms, "algorithmic_GBps": it_bytes / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0,
                                           "frac_of_hbm_peak": (it_bytes / (it_ms * 1e-3) / 1e9) / peak if it_ms > 0 else 0.0,
-                                          "kernels": "gemm_rows_tc fwd (tcgen05 3xTF32) + agg_stats + dz + gemm_dw + gemm_rows_tc dX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
+                                          "kernels": "gemm_rows_tc fwd (tcgen05 3xTF32) + agg_stats + dz + gemm_dw_tc + gemm_rows_tc dX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
                 "kernel_time_by_category_ms": shares,
                 "note": "achieved = algorithmic bytes of the kernel's launches / their CUDA-event durations "
                         "(events recorded by the library on the launch stream, separate profiled pass of the same steps)"}
