@@ -85,3 +85,32 @@ def test_cuda_lgnn_matches_reference_code_goldens():
     for a, b64, b32 in zip(mine, r64["grads"], r32["grads"]):
         ok, info = _ok(a.cpu().numpy(), b64, b32)
         assert ok, (tuple(a.shape), info)
+
+
+@pytest.mark.parametrize("mode", ["sum", "average", "normalized"])
+def test_device_structures_match_reference_on_mutag(mode):
+    """The device structure builder (gnnfp_graph_build) against the sparse matrices the REFERENCE's own
+    graph_class.py produced for a merged batch of real MUTAG graphs (tests/golden/mutag_structures.npz):
+    ArcNode / Adjacency values bit-exact (graph_class.py:82-126), NodeGraph values bit-exact (:128-138), and the
+    destination-grouped CSR consistent with the Adjacency pattern."""
+    import os
+    from gnnkeras_b200 import _lib as B
+    from gnnkeras_b200.op import DeviceGraph
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mutag_structures.npz"), allow_pickle=True)
+    arcs = gold[f"merge_{mode}_arcs"]
+    n_nodes = gold[f"merge_{mode}_nodes"].shape[0]
+    src, dst = arcs[:, 0].astype(np.int32), arcs[:, 1].astype(np.int32)
+    n2g = gold[f"merge_{mode}_NodeGraph_col"].astype(np.int32)
+    n_graphs = int(gold[f"merge_{mode}_NodeGraph_shape"][1])
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    ones = t(np.ones(n_nodes, np.uint8))
+    dg = DeviceGraph(t(src), t(dst), n_nodes, mode, t(n2g), n_graphs, None, ones, ones, None, mask_len=n_nodes)
+    # reference: Adjacency[src_a, dst_a] = ArcNode[a, dst_a] = v_a, COO in arc order after tf.sparse.reorder
+    assert np.array_equal(gold[f"merge_{mode}_Adjacency_row"], src) and np.array_equal(gold[f"merge_{mode}_Adjacency_col"], dst)
+    assert np.array_equal(dg.export(B.X_ARC_VALUE).view(np.uint32), gold[f"merge_{mode}_ArcNode_data"].view(np.uint32))
+    assert np.array_equal(dg.export(B.X_ARC_VALUE).view(np.uint32), gold[f"merge_{mode}_Adjacency_data"].view(np.uint32))
+    assert np.array_equal(dg.export(B.X_NODEGRAPH_VALUE).view(np.uint32), gold[f"merge_{mode}_NodeGraph_data"].view(np.uint32))
+    rp, col, aid = dg.export(B.X_DST_ROWPTR), dg.export(B.X_DST_SRC), dg.export(B.X_DST_ARC)
+    assert np.array_equal(np.diff(rp), np.bincount(dst, minlength=n_nodes))
+    assert np.array_equal(col, src[aid]) and np.array_equal(np.repeat(np.arange(n_nodes), np.diff(rp)), dst[aid])
+    assert all(np.all(np.diff(aid[rp[i]:rp[i + 1]]) > 0) for i in range(n_nodes))     # arc order inside a row = TF's summation order
