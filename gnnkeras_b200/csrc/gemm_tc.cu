@@ -45,7 +45,8 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (ok) return;
     const long long now = clock64();
     if (t0 == 0) t0 = now;
-    else if (now - t0 > 4000000000ll) __trap();        // ~2 s at 2 GHz: far beyond any legitimate wait inside one launch
+    else if (now - t0 > 120000000000ll) __trap();      // ~60 s at 2 GHz: a protocol error must not hang the device for ever,
+                                                       // yet time-slicing with other contexts must not trip it
   }
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
