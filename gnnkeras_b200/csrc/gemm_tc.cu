@@ -609,6 +609,31 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
               asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
           }
         }
+        if (row0 + DW_TC_ROWS <= n) {                  // full stage: no row predicates, strength-reduced addresses
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (pbytes[q] < 0) continue;
+            float* d = dst + warp * RAWLD + 2 * (lane + 32 * q);
+            if (pbytes[q] == 0) {
+#pragma unroll
+              for (int i = 0; i < DW_TC_ROWS / DW_TC_CONV_WARPS; ++i) tc_cp_async8(d + i * DW_TC_CONV_WARPS * RAWLD, a.dz, 0);
+            } else {
+              const float* src = pbase[q] + (size_t)(row0 + warp) * pld[q];
+              const size_t step = (size_t)DW_TC_CONV_WARPS * pld[q];
+              if (pal8[q]) {
+#pragma unroll
+                for (int i = 0; i < DW_TC_ROWS / DW_TC_CONV_WARPS; ++i) { tc_cp_async8(d + i * DW_TC_CONV_WARPS * RAWLD, src, pbytes[q]); src += step; }
+              } else {
+#pragma unroll
+                for (int i = 0; i < DW_TC_ROWS / DW_TC_CONV_WARPS; ++i) {
+                  tc_cp_async4(d + i * DW_TC_CONV_WARPS * RAWLD, src, 4);
+                  tc_cp_async4(d + i * DW_TC_CONV_WARPS * RAWLD + 1, pbytes[q] == 8 ? src + 1 : a.dz, pbytes[q] == 8 ? 4 : 0);
+                  src += step;
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (pbytes[q] < 0) continue;
@@ -626,6 +651,7 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
             }
           }
         }
+        }
       }
       tc_cp_commit();
     };
@@ -642,28 +668,37 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
       uint8_t* Bhi = Ahi + 2 * TC_TILE_BYTES;
       const float* rs = raw + slot * DW_TC_ROWS * RAWLD + lane * RAWLD;
       // transposing split: lane = row of the stage; one warp store writes a whole 128-byte operand row (conflict free)
-#pragma unroll 2
-      for (int pp = warp; pp < xpairs; pp += DW_TC_CONV_WARPS) {         // X columns 2pp, 2pp+1 -> rows of B = X^T
-        const float2 v = *reinterpret_cast<const float2*>(rs + 2 * pp);
-        const int orow = 2 * pp;                       // even: orow and orow + 1 share an 8-row group
-        uint8_t* h0 = Bhi + (orow >> 3) * 1024 + (orow & 7) * 128 + (koff ^ ((orow & 7) << 4));
-        uint8_t* h1 = Bhi + (orow >> 3) * 1024 + ((orow & 7) + 1) * 128 + (koff ^ (((orow & 7) + 1) << 4));
-        *reinterpret_cast<uint32_t*>(h0) = __float_as_uint(v.x);
-        *reinterpret_cast<uint32_t*>(h0 + btile) = tc_lo(__float_as_uint(v.x));
-        *reinterpret_cast<uint32_t*>(h1) = __float_as_uint(v.y);
-        *reinterpret_cast<uint32_t*>(h1 + btile) = tc_lo(__float_as_uint(v.y));
-      }
-#pragma unroll 2
-      for (int pp = warp; pp < zpairs; pp += DW_TC_CONV_WARPS) {         // dz columns 2pp, 2pp+1 -> rows of A = dz^T
-        const float2 v = *reinterpret_cast<const float2*>(rs + Kp + 2 * pp);
-        const int orow = 2 * pp;
-        uint8_t* h0 = Ahi + (orow >> 3) * 1024 + (orow & 7) * 128 + (koff ^ ((orow & 7) << 4));
-        uint8_t* h1 = Ahi + (orow >> 3) * 1024 + ((orow & 7) + 1) * 128 + (koff ^ (((orow & 7) + 1) << 4));
-        *reinterpret_cast<uint32_t*>(h0) = __float_as_uint(v.x);
-        *reinterpret_cast<uint32_t*>(h0 + TC_TILE_BYTES) = tc_lo(__float_as_uint(v.x));
-        if (orow + 1 < H) {
+      // pair pp = warp + 8k -> operand rows 2*warp + 16k (+1): the row's position inside its 8-row group is fixed per warp,
+      // only the group advances (2 groups = 2048 bytes per k)
+      {
+        const int ro = (2 * warp) & 7;
+        const int off0 = ((2 * warp) >> 3) * 1024 + ro * 128 + (koff ^ (ro << 4));
+        const int off1 = ((2 * warp) >> 3) * 1024 + (ro + 1) * 128 + (koff ^ ((ro + 1) << 4));
+        uint8_t* h0 = Bhi + off0;
+        uint8_t* h1 = Bhi + off1;
+        const float* rp = rs + 2 * warp;
+#pragma unroll 4
+        for (int pp = warp; pp < xpairs; pp += DW_TC_CONV_WARPS) {       // X columns 2pp, 2pp+1 -> rows of B = X^T
+          const float2 v = *reinterpret_cast<const float2*>(rp);
+          *reinterpret_cast<uint32_t*>(h0) = __float_as_uint(v.x);
+          *reinterpret_cast<uint32_t*>(h0 + btile) = tc_lo(__float_as_uint(v.x));
           *reinterpret_cast<uint32_t*>(h1) = __float_as_uint(v.y);
-          *reinterpret_cast<uint32_t*>(h1 + TC_TILE_BYTES) = tc_lo(__float_as_uint(v.y));
+          *reinterpret_cast<uint32_t*>(h1 + btile) = tc_lo(__float_as_uint(v.y));
+          h0 += 2048; h1 += 2048; rp += 2 * DW_TC_CONV_WARPS;
+        }
+        uint8_t* g0 = Ahi + off0;
+        uint8_t* g1 = Ahi + off1;
+        rp = rs + Kp + 2 * warp;
+#pragma unroll 2
+        for (int pp = warp; pp < zpairs; pp += DW_TC_CONV_WARPS) {       // dz columns 2pp, 2pp+1 -> rows of A = dz^T
+          const float2 v = *reinterpret_cast<const float2*>(rp);
+          *reinterpret_cast<uint32_t*>(g0) = __float_as_uint(v.x);
+          *reinterpret_cast<uint32_t*>(g0 + TC_TILE_BYTES) = tc_lo(__float_as_uint(v.x));
+          if (2 * pp + 1 < H) {
+            *reinterpret_cast<uint32_t*>(g1) = __float_as_uint(v.y);
+            *reinterpret_cast<uint32_t*>(g1 + TC_TILE_BYTES) = tc_lo(__float_as_uint(v.y));
+          }
+          g0 += 2048; g1 += 2048; rp += 2 * DW_TC_CONV_WARPS;
         }
       }
       fence_proxy_async();
