@@ -36,17 +36,20 @@ __device__ __forceinline__ void tc_cp_wait() { asm volatile("cp.async.wait_group
 
 // bounded mbarrier wait: try_wait suspends the thread in hardware for a bounded time slice (no busy polling that would
 // steal issue slots from the working warps); a protocol error traps (the launch fails) instead of hanging the device
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  long long t0 = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (ok) return;
-    const long long now = clock64();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 120000000000ll) __trap();      // ~60 s at 2 GHz: a protocol error must not hang the device for ever,
-                                                       // yet time-slicing with other contexts must not trip it
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  for (int spin = 0;; ++spin) {
+    __nanosleep(40);                                   // a waiting role must not eat the issue slots of the working warps
+    if (mbar_try(bar, parity)) return;
+    if ((spin & 1023) == 1023 && clock64() - t0 > 120000000000ll) __trap();   // ~60 s at 2 GHz: a protocol error must not hang
+                                                       // the device for ever, yet time-slicing with other contexts must not trip it
   }
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
