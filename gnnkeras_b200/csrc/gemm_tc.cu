@@ -15,6 +15,8 @@
 //     stores, the per-row convergence test and the next BN's column statistics.
 // Operands cannot come by TMA here: the state matrices have leading dimension D (e.g. 78 floats = 312 B), not a multiple
 // of 16 bytes, so the tile is gathered with 8-byte cp.async and laid out by the split pass.
+#include <type_traits>
+
 #include "tile.cuh"
 
 #include "gemm.h"
@@ -333,20 +335,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
 #ifdef TC_DEBUG_SKIP_EPI
       { float acc[8]; tmem_ld8(taddr, acc); tmem_ld_wait(); tc_fence_before(); mbar_arrive(&tm_empty[tb]); if (acc[0] == 123.456f) notconv = 1; continue; }
 #endif
-#pragma unroll 1
-      for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (TC_EPI_WARPS / 4)) {      // 16 accumulator columns per trip
+      // one 16-column chunk; FULL = all 32 rows of the warp and all 16 columns are inside the matrix (warp uniform), which
+      // removes every per-element predicate from the common case
+      auto chunk = [&](int c0, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         float acc[16];
         tmem_ld8(taddr + c0, acc);
         tmem_ld8(taddr + c0 + 8, acc + 8);
         // coalesced side inputs of this chunk, issued before the accumulator is consumed: lane (hr, hc) owns rows
         // 2*rr + hr, column c0 + hc (two 64-byte row segments per instruction)
-        const bool cok = c0 + hc < a.N;
-        const int nvr = cok ? n - wrow0 - hr : 0;      // rows 2*rr + hr with 2*rr < nvr are inside the matrix
+        const bool cok = FULL || c0 + hc < a.N;
+        const int nvr = FULL ? 32 : (cok ? n - wrow0 - hr : 0);      // rows 2*rr + hr with 2*rr < nvr are inside the matrix
         float t[16], o[FWD ? 1 : 16];
         if (auxsrc) {
           const float* ap = auxsrc + (size_t)(wrow0 + hr) * auxld + c0 + hc;
 #pragma unroll
-          for (int rr = 0; rr < 16; ++rr) { t[rr] = 2 * rr < nvr ? *ap : 0.f; ap += 2 * auxld; }
+          for (int rr = 0; rr < 16; ++rr) { t[rr] = (FULL || 2 * rr < nvr) ? *ap : 0.f; ap += 2 * auxld; }
         } else {
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) t[rr] = 0.f;
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           if (a.out_add) {
             const float* op = a.out + (size_t)(wrow0 + hr) * a.ld_out + c0 + hc;
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) { o[rr] = 2 * rr < nvr ? *op : 0.f; op += 2 * a.ld_out; }
+            for (int rr = 0; rr < 16; ++rr) { o[rr] = (FULL || 2 * rr < nvr) ? *op : 0.f; op += 2 * a.ld_out; }
           } else {
 #pragma unroll
             for (int rr = 0; rr < 16; ++rr) o[rr] = 0.f;
@@ -367,20 +371,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           mbar_arrive(&tm_empty[tb]);
           handed_back = true;
         }
+        // thread = row: bias + activation (forward) / column scale (backward)
+        float v[16];
+        if (FWD) {
+          if (selu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {                 // thread = row: bias + activation (forward) / column scale (backward)
-          const int col = c0 + j;
-          float v = 0.f;
-          if (valid && col < a.N) {
-            if (FWD) {
-              const float z = acc[j] + sbias[col];
-              v = selu ? tc_selu(z) : act_fwd(a.act, z);
-            } else {
-              v = a.colscale ? acc[j] * a.colscale[col] : acc[j];
-            }
+            for (int j = 0; j < 16; ++j) v[j] = tc_selu(acc[j] + sbias[c0 + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act_fwd(a.act, acc[j] + sbias[c0 + j]);
           }
-          stg[lane * 17 + j] = v;
+        } else if (a.colscale) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = acc[j] * ((FULL || c0 + j < a.N) ? a.colscale[c0 + j] : 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = acc[j];
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = (FULL || (valid && c0 + j < a.N)) ? v[j] : 0.f;
         __syncwarp();
         float s1 = 0.f, s2 = 0.f;
         float k0 = 0.f, k1 = 0.f, kA = 0.f, kB = 0.f;
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
 #pragma unroll
         for (int rr = 0; rr < 16; ++rr, outp += 2 * a.ld_out) {   // coalesced: stores, convergence sums, statistics, corrections
           float x = stg[(2 * rr + hr) * 17 + hc];
-          if (2 * rr < nvr) {
+          if (FULL || 2 * rr < nvr) {
             if (FWD) {
               const float dd = x - t[rr];
               sdp[rr] = fmaf(dd, dd, sdp[rr]);
@@ -409,6 +418,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
           if (hr == 0 && cok) { colacc[ew][0][c0 + hc] += (double)s1; colacc[ew][1][c0 + hc] += (double)s2; }
         }
+      };
+      const bool rows_full = wrow0 + 32 <= n;
+#pragma unroll 1
+      for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (TC_EPI_WARPS / 4)) {      // 16 accumulator columns per trip
+        if (rows_full && c0 + 16 <= a.N) chunk(c0, std::true_type{});
+        else chunk(c0, std::false_type{});
       }
       float sd = 0.f, sp = 0.f;                        // row sums: reduce over the 16 column lanes; lane rr of each half keeps row 2*rr + hr
       if (FWD && a.prev) {
