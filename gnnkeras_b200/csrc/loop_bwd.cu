@@ -465,7 +465,9 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
         da.last_flag = t < MI ? c.flags() + t : nullptr; da.always_last = t == MI;
         da.dz = dzbuf; da.gate = gate;
         if (pgather && t < MI) da.pre = pgather;
-        const bool inline_bn = L->snet[ty].has_bn && !L->composite;
+        // BN-training correction of iteration t+1's raw gradients: applied here where they are consumed - unless the GEMM
+        // path already folded it into the dX epilogue of iteration t+1 (then dOwn / dAgg are final)
+        const bool inline_bn = L->snet[ty].has_bn && !L->composite && !gemm_bwd[ty];
         if (inline_bn && t < MI) {
           da.cn = cn_t(t + 1); da.agg_next = c.AGG(t + 1); da.in_dim = L->snet[ty].in_dim;
           da.own_col0 = 0; da.agg_col0 = D + NLp;
@@ -500,6 +502,13 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
           dw.gate = gate;
           if ((rc = launch_gemm_dw(dw, s, PC_BWD_ITER, &grid_dw))) return rc;
           grid_state[ty] = grid_dw > grid_state[ty] ? grid_dw : grid_state[ty];
+          if (bn) {   // batch sums are complete after dW: constants c0 | c1 | rstd | -mean*rstd of this iteration, BEFORE dX, so that
+                      // the dX epilogue can apply dx = a dy - (c0 + x~ c1) while it writes (no correction pass, no gathers later)
+            BwdArgs tb;
+            memset(&tb, 0, sizeof(tb));
+            tb.src = full; tb.net = ndfull; tb.tc.grid = grid_dw; tb.bn_partial = bn_part; tb.gate = gate;
+            if ((rc = launch_bn_tail(tb, bn_grad + bg_off[ty], cn_t(t), s, 1, nullptr))) return rc;
+          }
           const float* wt = (const float*)(c.ws + L->ws.wtb) + (size_t)ty * L->ws.wtb_stride;
           const int KH = gemm_rows_kpad(H0);
           for (int p = 0; p < full.n_pieces; ++p) {
@@ -512,6 +521,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
               gemm_piece_set(ga.p[0], dzbuf, D, H0, 0);
               ga.fwd = 0; ga.Kpad = KH; ga.Wp = wt; ga.ldw = ldw; ga.N = pc.width;
               ga.colscale = bn ? coef + 2 * in + pc.col0 : nullptr;
+              if (bn) { ga.corr = cn_t(t); ga.corr_in = in; ga.corr_col0 = pc.col0; ga.corr_x = pc.ptr; ga.corr_ld = pc.ld; }
               ga.out = pc.gptr; ga.ld_out = pc.gld; ga.out_add = pc.gmode == GM_ADD;
               ga.vec2 = pc.gld % 2 == 0 && ((uintptr_t)pc.gptr & 7) == 0;
               ga.gate = gate;
@@ -596,7 +606,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
         if ((rc = launch_tile_bwd(ba, s))) return rc;
         last_ba = ba;
       }
-      if (L->snet[ty].has_bn) {
+      if (L->snet[ty].has_bn && !gemm_bwd[ty]) {
         const bool inline_bn = dzpath[ty] && !L->composite;
         if (inline_bn) rc = launch_bn_tail(last_ba, bn_grad + bg_off[ty], cn_t(t), s, 1, want ? bn_static : nullptr);
         else rc = launch_bn_tail(last_ba, bn_grad + bg_off[ty], bn_const, s);
@@ -620,7 +630,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     ia.d_nodes = (want & 1) ? gr->d_nodes : nullptr;
     ia.d_state0 = ((want & 4) && L->S > 0) ? gr->d_state0 : nullptr;
     ia.want = want;
-    if (!L->composite && dzpath[0] && L->snet[0].has_bn) {
+    if (!L->composite && dzpath[0] && L->snet[0].has_bn && !gemm_bwd[0]) {
       ia.cn = cn_t(1); ia.csum = bn_static; ia.in_dim = L->snet[0].in_dim;
       ia.s0 = c.S(0); ia.ld0 = c.ldS(0); ia.agg1 = MI > 0 ? c.AGG(1) : nullptr; ia.Xs = c.Xs();
     }
