@@ -212,12 +212,13 @@ struct AggArgs {            // AGG = Adj^T . S (dst-CSR gather) as a streaming k
   const int* rowlist;
   int D;
   const float* S; int ld;
-  const int* rowptr; const int* idx; const float* wgt;
+  const int* rowptr; const int* idx; const float* wgt;   // rowptr NULL = direct rows (entry of row r is S[r])
   float* out;              // [N, D] by global row id (may be NULL)
+  int ld_out;              // leading dimension of out (0 = D)
   double* st_sum; double* st_sq;   // [D] each (may be NULL)
   const int* gate;
 };
-int launch_agg_stats(const AggArgs& a, cudaStream_t s);
+int launch_agg_stats(const AggArgs& a, cudaStream_t s, int prof_cat = 0);
 
 // launchers (kernels.cu)
 int launch_tile_fwd(const FwdArgs& a, cudaStream_t s);

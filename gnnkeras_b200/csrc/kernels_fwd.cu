@@ -255,60 +255,76 @@ __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ 
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { su[v] = 0.0; sq[v] = 0.0; }
   if (qx < nq && ry < rpb) {
-    // two rows per trip: their rowptr -> idx -> state-row load chains overlap (the kernel is latency bound otherwise)
+    // NR rows per trip: their rowptr -> idx -> state-row load chains overlap (the kernel is latency bound otherwise);
+    // arc order inside a row is kept (sequential fmaf), absent arcs are predicated off
+    constexpr int NR = 4;
+    const int ldo = a.ld_out ? a.ld_out : a.D;
     const int stride = gridDim.x * rpb;
-    for (int r = blockIdx.x * rpb + ry; r < a.n_rows; r += 2 * stride) {
-      const int r2 = r + stride;
-      const bool has2 = r2 < a.n_rows;
-      const int gr0 = a.rowlist ? a.rowlist[r] : r;
-      const int gr1 = has2 ? (a.rowlist ? a.rowlist[r2] : r2) : gr0;
-      const int b0 = a.rowptr[gr0], e0 = a.rowptr[gr0 + 1];
-      const int b1 = has2 ? a.rowptr[gr1] : 0, e1 = has2 ? a.rowptr[gr1 + 1] : 0;
-      float acc0[VEC], acc1[VEC];
+    for (int r = blockIdx.x * rpb + ry; r < a.n_rows; r += NR * stride) {
+      int gr[NR], b[NR], n[NR];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) { acc0[v] = 0.f; acc1[v] = 0.f; }
-      const int n0 = e0 - b0, n1 = e1 - b1;
-      const int nmax = n0 > n1 ? n0 : n1;
+      for (int j = 0; j < NR; ++j) {
+        const int rj = r + j * stride;
+        gr[j] = rj < a.n_rows ? (a.rowlist ? a.rowlist[rj] : rj) : -1;
+      }
+      int nmax = 0;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        if (a.rowptr) {
+          b[j] = gr[j] >= 0 ? a.rowptr[gr[j]] : 0;
+          n[j] = gr[j] >= 0 ? a.rowptr[gr[j] + 1] - b[j] : 0;
+        } else {                                   // direct rows (statistics / copy of S itself): one unit entry per row
+          b[j] = gr[j];
+          n[j] = gr[j] >= 0 ? 1 : 0;
+        }
+        nmax = n[j] > nmax ? n[j] : nmax;
+      }
+      float acc[NR][VEC];
+#pragma unroll
+      for (int j = 0; j < NR; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
       for (int q = 0; q < nmax; q += 2) {
-        float t0[2][VEC], t1[2][VEC], w0[2], w1[2];
+        float tv[NR][2][VEC], w[NR][2];
+        int ix[NR][2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const bool ok0 = q + u < n0, ok1 = q + u < n1;
-          const int p0 = ok0 ? b0 + q + u : 0, p1 = ok1 ? b1 + q + u : 0;
-          w0[u] = ok0 ? (a.wgt ? a.wgt[p0] : 1.0f) : 0.0f;
-          w1[u] = ok1 ? (a.wgt ? a.wgt[p1] : 1.0f) : 0.0f;
-          const int i0 = ok0 ? a.idx[p0] : gr0, i1 = ok1 ? a.idx[p1] : gr1;
-          load_vec<VEC>(a.S + (size_t)i0 * a.ld + qx * VEC, t0[u]);
-          load_vec<VEC>(a.S + (size_t)i1 * a.ld + qx * VEC, t1[u]);
-        }
+        for (int j = 0; j < NR; ++j)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (q + u < n0) {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc0[v] = fmaf(w0[u], t0[u][v], acc0[v]);
+          for (int u = 0; u < 2; ++u) {
+            const bool ok = q + u < n[j];
+            ix[j][u] = ok ? (a.idx ? a.idx[b[j] + q + u] : b[j] + q + u) : -1;
+            w[j][u] = ok ? (a.wgt ? a.wgt[b[j] + q + u] : 1.0f) : 0.0f;
           }
-          if (q + u < n1) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc1[v] = fmaf(w1[u], t1[u][v], acc1[v]);
+        for (int j = 0; j < NR; ++j)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (ix[j][u] >= 0) load_vec<VEC>(a.S + (size_t)ix[j][u] * a.ld + qx * VEC, tv[j][u]);
+            else {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) tv[j][u][v] = 0.f;
+            }
           }
-        }
-      }
-      if (a.out) {
-        float* o = a.out + (size_t)gr0 * a.D + qx * VEC;
-        if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc0[0], acc0[1 % VEC], acc0[2 % VEC], acc0[3 % VEC]);
-        else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(acc0[0], acc0[1 % VEC]);
-        else o[0] = acc0[0];
-        if (has2) {
-          float* o2 = a.out + (size_t)gr1 * a.D + qx * VEC;
-          if (VEC == 4) *reinterpret_cast<float4*>(o2) = make_float4(acc1[0], acc1[1 % VEC], acc1[2 % VEC], acc1[3 % VEC]);
-          else if (VEC == 2) *reinterpret_cast<float2*>(o2) = make_float2(acc1[0], acc1[1 % VEC]);
-          else o2[0] = acc1[0];
-        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j)
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (ix[j][u] >= 0) {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[j][v] = fmaf(w[j][u], tv[j][u][v], acc[j][v]);
+            }
       }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        su[v] += (double)acc0[v]; sq[v] += (double)acc0[v] * (double)acc0[v];
-        if (has2) { su[v] += (double)acc1[v]; sq[v] += (double)acc1[v] * (double)acc1[v]; }
+      for (int j = 0; j < NR; ++j) {
+        if (gr[j] < 0) continue;
+        if (a.out) {
+          float* o = a.out + (size_t)gr[j] * ldo + qx * VEC;
+          if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[j][0], acc[j][1 % VEC], acc[j][2 % VEC], acc[j][3 % VEC]);
+          else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1 % VEC]);
+          else o[0] = acc[j][0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { su[v] += (double)acc[j][v]; sq[v] += (double)acc[j][v] * (double)acc[j][v]; }
       }
     }
   }
@@ -328,17 +344,18 @@ __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ 
   }
 }
 
-int launch_agg_stats(const AggArgs& a, cudaStream_t s) {
+int launch_agg_stats(const AggArgs& a, cudaStream_t s, int prof_cat) {
   if (a.n_rows <= 0) return GNNFP_OK;
   auto al = [&](const void* p, int m) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
   int vec = 1;
-  if (a.D % 4 == 0 && a.ld % 4 == 0 && al(a.S, 16) && al(a.out, 16)) vec = 4;
-  else if (a.D % 2 == 0 && a.ld % 2 == 0 && al(a.S, 8) && al(a.out, 8)) vec = 2;
+  const int ldo = a.ld_out ? a.ld_out : a.D;
+  if (a.D % 4 == 0 && a.ld % 4 == 0 && ldo % 4 == 0 && al(a.S, 16) && al(a.out, 16)) vec = 4;
+  else if (a.D % 2 == 0 && a.ld % 2 == 0 && ldo % 2 == 0 && al(a.S, 8) && al(a.out, 8)) vec = 2;
   const int nq = a.D / vec;
   if (nq > 256) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "state width %d too large for the aggregation kernel", a.D);
   const int QX = nq;                                  // threads per row (rows may straddle warps)
   const int rpb = 256 / QX;
-  long long blocks = ((long long)a.n_rows + 2 * rpb - 1) / (2 * rpb);
+  long long blocks = ((long long)a.n_rows + 4 * rpb - 1) / (4 * rpb);
   static int occ[3] = {0, 0, 0};                      // resident blocks per SM of the three instantiations: one full wave
   const int oi = vec == 4 ? 2 : (vec == 2 ? 1 : 0);
   if (!occ[oi]) {
@@ -351,7 +368,7 @@ int launch_agg_stats(const AggArgs& a, cudaStream_t s) {
   const long long cap = (long long)gnnfp_num_sms() * occ[oi];
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  ProfScope ps(PC_AGG, s);
+  ProfScope ps(prof_cat ? prof_cat : PC_AGG, s);
   if (vec == 4) agg_stats_kernel<4><<<(int)blocks, 256, 0, s>>>(a, QX);
   else if (vec == 2) agg_stats_kernel<2><<<(int)blocks, 256, 0, s>>>(a, QX);
   else agg_stats_kernel<1><<<(int)blocks, 256, 0, s>>>(a, QX);
@@ -459,6 +476,23 @@ int launch_tile_fwd(const FwdArgs& a, cudaStream_t s) {
 
 int launch_tile_pass(const PassArgs& a, cudaStream_t s) {
   if (a.src.n_rows <= 0) return GNNFP_OK;
+  // a single plain piece (one matrix, or one CSR gather of it) needs no tile: the streaming gather kernel
+  // copies / aggregates it and takes the column statistics at several TB/s
+  if (a.src.n_pieces == 1) {
+    const Piece& pc = a.src.p[0];
+    if (pc.col0 == 0 && pc.width == a.src.in_dim && !pc.accumulate && !pc.compact && !pc.map && !pc.rowscale &&
+        !pc.gate && (pc.kind == PK_DIRECT || pc.kind == PK_GATHER) && pc.width <= 256) {
+      AggArgs aa;
+      memset(&aa, 0, sizeof(aa));
+      aa.n_rows = a.src.n_rows; aa.rowlist = a.src.rowlist; aa.D = pc.width;
+      aa.S = pc.ptr; aa.ld = pc.ld;
+      if (pc.kind == PK_GATHER) { aa.rowptr = pc.rowptr; aa.idx = pc.idx; aa.wgt = pc.wgt; }
+      aa.out = a.out; aa.ld_out = a.ld_out;
+      aa.st_sum = a.st_sum; aa.st_sq = a.st_sq;
+      aa.gate = a.gate;
+      return launch_agg_stats(aa, s, PC_PASS);
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     GNNFP_CHECK_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
