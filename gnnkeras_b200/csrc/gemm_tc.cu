@@ -23,7 +23,8 @@
 
 #define TC_BM 128
 #define TC_BK 32
-#define TC_STAGES 3                  // operand ring: [hi (raw fp32, filled by cp.async) | lo] x 16 KB per stage
+#define TC_STAGES 3                  // minimum depth of the operand ring: [hi (raw fp32, filled by cp.async) | lo] x 16 KB per stage
+#define TC_MAX_STAGES 6              // the launcher deepens the ring up to this while shared memory allows (more rows in flight)
 #define TC_TILE_BYTES (TC_BM * 128)  // one A operand tile: 128 rows x 128 B
 
 __device__ __forceinline__ void tc_cp_async8(void* dst, const void* src, int src_bytes) {
@@ -140,7 +141,7 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
 #define TC_EPI_WARPS 8
 
 template <int BN, bool FWD>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __grid_constant__ GemmRowsArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __grid_constant__ GemmRowsArgs a, const int NST) {
   if (a.gate && *a.gate == 0) return;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; offset arithmetic (not an integer round trip) keeps the pointers in the
@@ -150,8 +151,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
   const int wtile = BN * 128;                          // bytes of one [BN x 32] weight tile
   uint8_t* Whi = base;
   uint8_t* Wlo = Whi + (size_t)NKB * wtile;
-  uint8_t* Aop = Wlo + (size_t)NKB * wtile;            // [TC_STAGES][hi, lo][TC_TILE_BYTES]
-  __shared__ __align__(8) uint64_t ops_full[TC_STAGES], ops_empty[TC_STAGES], tm_full[2], tm_empty[2];
+  uint8_t* Aop = Wlo + (size_t)NKB * wtile;            // [NST][hi, lo][TC_TILE_BYTES]
+  __shared__ __align__(8) uint64_t ops_full[TC_MAX_STAGES], ops_empty[TC_MAX_STAGES], tm_full[2], tm_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[BN];
   __shared__ double colacc[TC_EPI_WARPS][2][BN];       // per epilogue warp: column sums / sums of squares
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
 
   if (warp == 0) { tmem_alloc(&tmem_base_s, TMEM_COLS); tmem_relinquish(); }      // whole warp, converged (.sync.aligned)
   if (tid == 32) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&ops_full[i], 128); mbar_init(&ops_empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&ops_full[i], 128); mbar_init(&ops_empty[i], 1); }
     mbar_init(&tm_full[0], 1); mbar_init(&tm_full[1], 1);
     mbar_init(&tm_empty[0], 32 * TC_EPI_WARPS); mbar_init(&tm_empty[1], 32 * TC_EPI_WARPS);
   }
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
     // thread copies the 8-byte column pair pq of rows ty + 8*i (i < 16) of a stage
     const int pq = tid & 15, ty = tid >> 4;
     const int total = my_tiles * NKB;
-    int i_tq = 0, i_kb = 0, i_idx = 0;
+    int i_tq = 0, i_kb = 0, i_idx = 0, i_slot = 0;
+    uint32_t i_use = 0;                                // ring position of the next stage to issue: slot, and how often it was used
     auto issue = [&]() {
       if (i_idx < total) {
         if (i_kb == 0 && i_tq + 1 < my_tiles) {
@@ -208,8 +210,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
             }
           }
         }
-        const int slot = i_idx % TC_STAGES;
-        const uint32_t use = (uint32_t)(i_idx / TC_STAGES);
+        const int slot = i_slot;
+        const uint32_t use = i_use;
+        if (++i_slot == NST) { i_slot = 0; ++i_use; }
         if (use > 0) {                                 // the MMAs that read this slot's previous contents must have completed
           mbar_wait_bounded(&ops_empty[slot], (use - 1) & 1);
           tc_fence_after();
@@ -254,11 +257,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
       }
       tc_cp_commit();
     };
-    for (int i = 0; i < TC_STAGES - 1; ++i) issue();
+    for (int i = 0; i < NST - 1; ++i) issue();
+    int c_slot = 0;
     for (int sidx = 0; sidx < total; ++sidx) {
-      tc_cp_wait<TC_STAGES - 2>();
+      switch (NST) {                                   // all but the NST - 2 newest groups have landed
+        case 3: tc_cp_wait<1>(); break;
+        case 4: tc_cp_wait<2>(); break;
+        case 5: tc_cp_wait<3>(); break;
+        default: tc_cp_wait<4>(); break;
+      }
       named_bar_sync(1, 128);                          // stage sidx has landed for all converter threads
-      const int slot = sidx % TC_STAGES;
+      const int slot = c_slot;
+      if (++c_slot == NST) c_slot = 0;
       uint8_t* ahi = Aop + (size_t)slot * 2 * TC_TILE_BYTES;
       uint8_t* alo = ahi + TC_TILE_BYTES;
 #pragma unroll
@@ -280,7 +290,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t whi_addr = smem_u32(Whi), wlo_addr = smem_u32(Wlo), aop_addr = smem_u32(Aop);
-      int sidx = 0;
+      int ob = 0;
+      uint32_t oph = 0;                                // ring slot of the next stage and its mbarrier phase
       for (int tq = 0; tq < my_tiles; ++tq) {
         const int tb = tq & 1;
         if (tq >= 2) {                                 // the epilogue of the tile that used this accumulator must have drained it
@@ -288,9 +299,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           tc_fence_after();
         }
         const uint32_t dcol = tmem_d + (uint32_t)(tb * BN);
-        for (int kb = 0; kb < NKB; ++kb, ++sidx) {
-          const int ob = sidx % TC_STAGES;
-          mbar_wait_bounded(&ops_full[ob], (uint32_t)(sidx / TC_STAGES) & 1u);
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait_bounded(&ops_full[ob], oph);
           tc_fence_after();
           const uint64_t dah = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES);
           const uint64_t dal = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
@@ -305,6 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           }
           tc_commit(&ops_empty[ob]);                   // operand buffer free once these MMAs have completed
           if (kb == NKB - 1) tc_commit(&tm_full[tb]);  // accumulator tile complete
+          if (++ob == NST) { ob = 0; oph ^= 1u; }
         }
       }
     }
@@ -474,7 +485,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
 template <int BN, bool FWD>
 static int launch_tc_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   const int NKB = (a.Kpad + TC_BK - 1) / TC_BK;
-  const size_t smem = (size_t)2 * NKB * BN * 128 + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 1024;
+  static size_t smem_cap = 0;                          // dynamic shared memory this instantiation may use next to its static arrays
+  if (!smem_cap) {
+    cudaFuncAttributes fa;
+    int dev = 0, optin = 0;
+    GNNFP_CHECK_CUDA(cudaGetDevice(&dev));
+    GNNFP_CHECK_CUDA(cudaFuncGetAttributes(&fa, gemm_rows_tc_kernel<BN, FWD>));
+    GNNFP_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    smem_cap = (size_t)optin - fa.sharedSizeBytes;
+  }
+  // the deepest operand ring that fits: more stages = more rows in flight per SM (one CTA per SM, latency bound otherwise)
+  int nst = TC_STAGES;
+  static const int nst_max = getenv("GNNFP_TC_STAGES") ? atoi(getenv("GNNFP_TC_STAGES")) : TC_MAX_STAGES;
+  while (nst < nst_max && nst < TC_MAX_STAGES &&
+         (size_t)2 * NKB * BN * 128 + (size_t)(nst + 1) * 2 * TC_TILE_BYTES + 1024 <= smem_cap) ++nst;
+  const size_t smem = (size_t)2 * NKB * BN * 128 + (size_t)nst * 2 * TC_TILE_BYTES + 1024;
+  if (smem > smem_cap) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_rows_tc: %zu bytes of shared memory needed, %zu available", smem, smem_cap);
   static size_t attr = 0;
   if (smem > attr) {
     GNNFP_CHECK_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -484,7 +510,7 @@ static int launch_tc_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   const int nsm = gnnfp_num_sms();
   const int grid = n_tiles < nsm ? n_tiles : nsm;
   ProfScope ps(prof_cat, s);
-  gemm_rows_tc_kernel<BN, FWD><<<grid, TC_THREADS, smem, s>>>(a);
+  gemm_rows_tc_kernel<BN, FWD><<<grid, TC_THREADS, smem, s>>>(a, nst);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;

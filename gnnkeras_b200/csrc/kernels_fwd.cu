@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
 // Adj^T . S with thousands of independent threads: thread (qx, ry) owns the VEC-wide column chunk qx of
 // rows ry, ry + rows_per_block * gridDim, ...; per-thread fp64 column partials, one block reduction, one
 // fp64 atomicAdd per column and block.  Arc order inside a row is preserved (sequential fmaf).
-template <int VEC>
+template <int VEC, bool DIRECT, bool WGT>
 __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ AggArgs a, int QX) {
   if (a.gate && *a.gate == 0) return;
   __shared__ double red[256 * 2];
@@ -256,69 +256,86 @@ __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ 
   for (int v = 0; v < VEC; ++v) { su[v] = 0.0; sq[v] = 0.0; }
   if (qx < nq && ry < rpb) {
     // NR rows per trip: their rowptr -> idx -> state-row load chains overlap (the kernel is latency bound otherwise);
-    // arc order inside a row is kept (sequential fmaf), absent arcs are predicated off
-    constexpr int NR = 4;
-    const int ldo = a.ld_out ? a.ld_out : a.D;
+    // arc order inside a row is kept (sequential fmaf), absent arcs are predicated off.  DIRECT (no CSR: the row's
+    // only entry is S[row], weight 1) is the column-statistics / copy pass of a plain matrix.
+    constexpr int NR = DIRECT ? 8 : 4;
+    const int n_rows = a.n_rows;
+    const int* __restrict__ rowlist = a.rowlist;
+    const float* __restrict__ Sq = a.S + qx * VEC;
+    const size_t ld = (size_t)a.ld;
+    float* __restrict__ outq = a.out ? a.out + qx * VEC : nullptr;
+    const size_t ldo = (size_t)(a.ld_out ? a.ld_out : a.D);
     const int stride = gridDim.x * rpb;
-    for (int r = blockIdx.x * rpb + ry; r < a.n_rows; r += NR * stride) {
-      int gr[NR], b[NR], n[NR];
+    for (int r = blockIdx.x * rpb + ry; r < n_rows; r += NR * stride) {
+      int gr[NR];
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int rj = r + j * stride;
-        gr[j] = rj < a.n_rows ? (a.rowlist ? a.rowlist[rj] : rj) : -1;
-      }
-      int nmax = 0;
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        if (a.rowptr) {
-          b[j] = gr[j] >= 0 ? a.rowptr[gr[j]] : 0;
-          n[j] = gr[j] >= 0 ? a.rowptr[gr[j] + 1] - b[j] : 0;
-        } else {                                   // direct rows (statistics / copy of S itself): one unit entry per row
-          b[j] = gr[j];
-          n[j] = gr[j] >= 0 ? 1 : 0;
-        }
-        nmax = n[j] > nmax ? n[j] : nmax;
+        gr[j] = rj < n_rows ? (rowlist ? rowlist[rj] : rj) : -1;
       }
       float acc[NR][VEC];
+      if (DIRECT) {
 #pragma unroll
-      for (int j = 0; j < NR; ++j)
+        for (int j = 0; j < NR; ++j) {
+          if (gr[j] >= 0) load_vec<VEC>(Sq + (size_t)gr[j] * ld, acc[j]);
+          else {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
-      for (int q = 0; q < nmax; q += 2) {
-        float tv[NR][2][VEC], w[NR][2];
-        int ix[NR][2];
-#pragma unroll
-        for (int j = 0; j < NR; ++j)
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const bool ok = q + u < n[j];
-            ix[j][u] = ok ? (a.idx ? a.idx[b[j] + q + u] : b[j] + q + u) : -1;
-            w[j][u] = ok ? (a.wgt ? a.wgt[b[j] + q + u] : 1.0f) : 0.0f;
+            for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
           }
+        }
+      } else {
+        const int* __restrict__ rowptr = a.rowptr;
+        const int* __restrict__ idx = a.idx;
+        const float* __restrict__ wgt = a.wgt;
+        int b[NR], n[NR];
+        int nmax = 0;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          b[j] = gr[j] >= 0 ? rowptr[gr[j]] : 0;
+          n[j] = gr[j] >= 0 ? rowptr[gr[j] + 1] - b[j] : 0;
+          nmax = n[j] > nmax ? n[j] : nmax;
+        }
 #pragma unroll
         for (int j = 0; j < NR; ++j)
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (ix[j][u] >= 0) load_vec<VEC>(a.S + (size_t)ix[j][u] * a.ld + qx * VEC, tv[j][u]);
-            else {
+          for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
+        for (int q = 0; q < nmax; q += 2) {
+          float tv[NR][2][VEC], w[NR][2];
+          int ix[NR][2];
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) tv[j][u][v] = 0.f;
+          for (int j = 0; j < NR; ++j)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const bool ok = q + u < n[j];
+              ix[j][u] = ok ? idx[b[j] + q + u] : -1;
+              if (WGT) w[j][u] = ok ? wgt[b[j] + q + u] : 0.0f;
+              else w[j][u] = 1.0f;
             }
-          }
 #pragma unroll
-        for (int j = 0; j < NR; ++j)
+          for (int j = 0; j < NR; ++j)
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
-            if (ix[j][u] >= 0) {
+            for (int u = 0; u < 2; ++u) {
+              if (ix[j][u] >= 0) load_vec<VEC>(Sq + (size_t)ix[j][u] * ld, tv[j][u]);
+              else {
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) acc[j][v] = fmaf(w[j][u], tv[j][u][v], acc[j][v]);
+                for (int v = 0; v < VEC; ++v) tv[j][u][v] = 0.f;
+              }
             }
+#pragma unroll
+          for (int j = 0; j < NR; ++j)
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (ix[j][u] >= 0) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[j][v] = fmaf(w[j][u], tv[j][u][v], acc[j][v]);
+              }
+        }
       }
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         if (gr[j] < 0) continue;
-        if (a.out) {
-          float* o = a.out + (size_t)gr[j] * ldo + qx * VEC;
+        if (outq) {
+          float* o = outq + (size_t)gr[j] * ldo;
           if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[j][0], acc[j][1 % VEC], acc[j][2 % VEC], acc[j][3 % VEC]);
           else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1 % VEC]);
           else o[0] = acc[j][0];
@@ -344,6 +361,30 @@ __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ 
   }
 }
 
+template <int VEC, bool DIRECT, bool WGT>
+static int launch_agg_t(const AggArgs& a, int QX, int rpb, cudaStream_t s) {
+  constexpr int NR = DIRECT ? 8 : 4;
+  long long blocks = ((long long)a.n_rows + NR * rpb - 1) / (NR * rpb);
+  static int occ = 0;                                  // resident blocks per SM of this instantiation: one full wave
+  if (!occ) {
+    int o = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<VEC, DIRECT, WGT>, 256, 0);
+    occ = o > 0 ? o : 4;
+  }
+  const long long cap = (long long)gnnfp_num_sms() * occ;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  agg_stats_kernel<VEC, DIRECT, WGT><<<(int)blocks, 256, 0, s>>>(a, QX);
+  return 0;
+}
+
+template <int VEC>
+static int launch_agg_v(const AggArgs& a, int QX, int rpb, cudaStream_t s) {
+  if (!a.rowptr) return launch_agg_t<VEC, true, false>(a, QX, rpb, s);
+  if (a.wgt) return launch_agg_t<VEC, false, true>(a, QX, rpb, s);
+  return launch_agg_t<VEC, false, false>(a, QX, rpb, s);
+}
+
 int launch_agg_stats(const AggArgs& a, cudaStream_t s, int prof_cat) {
   if (a.n_rows <= 0) return GNNFP_OK;
   auto al = [&](const void* p, int m) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
@@ -355,23 +396,10 @@ int launch_agg_stats(const AggArgs& a, cudaStream_t s, int prof_cat) {
   if (nq > 256) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "state width %d too large for the aggregation kernel", a.D);
   const int QX = nq;                                  // threads per row (rows may straddle warps)
   const int rpb = 256 / QX;
-  long long blocks = ((long long)a.n_rows + 4 * rpb - 1) / (4 * rpb);
-  static int occ[3] = {0, 0, 0};                      // resident blocks per SM of the three instantiations: one full wave
-  const int oi = vec == 4 ? 2 : (vec == 2 ? 1 : 0);
-  if (!occ[oi]) {
-    int o = 0;
-    if (vec == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<4>, 256, 0);
-    else if (vec == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<2>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<1>, 256, 0);
-    occ[oi] = o > 0 ? o : 4;
-  }
-  const long long cap = (long long)gnnfp_num_sms() * occ[oi];
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
   ProfScope ps(prof_cat ? prof_cat : PC_AGG, s);
-  if (vec == 4) agg_stats_kernel<4><<<(int)blocks, 256, 0, s>>>(a, QX);
-  else if (vec == 2) agg_stats_kernel<2><<<(int)blocks, 256, 0, s>>>(a, QX);
-  else agg_stats_kernel<1><<<(int)blocks, 256, 0, s>>>(a, QX);
+  if (vec == 4) launch_agg_v<4>(a, QX, rpb, s);
+  else if (vec == 2) launch_agg_v<2>(a, QX, rpb, s);
+  else launch_agg_v<1>(a, QX, rpb, s);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;
