@@ -553,6 +553,16 @@ int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   // GNNFP_TC=<n> restricts the tensor-core path to N >= n output columns
   static const int tc_min_n = [] { const char* e = getenv("GNNFP_TC"); return e ? atoi(e) : 1; }();
   if (tc_min_n > 0 && a.N >= tc_min_n && gemm_rows_tc_supported(a)) return launch_gemm_rows_tc(a, s, prof_cat);
+  if (a.nblk == 2) {                                   // two output blocks that do not fit one tensor-core launch: one launch each
+    GemmRowsArgs b0 = a, b1 = a;
+    b0.nblk = 0;
+    b1.nblk = 0;
+    b1.Wp = a.Wp2; b1.colscale = a.colscale2; b1.corr_col0 = a.corr_col02; b1.corr_x = a.corr_x2; b1.corr_ld = a.corr_ld2;
+    b1.out = a.out2; b1.ld_out = a.ld_out2; b1.out_add = a.out_add2;
+    b1.vec2 = a.ld_out2 % 2 == 0 && ((uintptr_t)a.out2 & 7) == 0;
+    const int rc = launch_gemm_rows(b0, s, prof_cat);
+    return rc ? rc : launch_gemm_rows(b1, s, prof_cat);
+  }
   const int tn = (a.N + 15) / 16;
   const bool fwd = a.fwd != 0;
   switch (tn) {

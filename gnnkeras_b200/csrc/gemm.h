@@ -29,6 +29,12 @@ struct GemmRowsArgs {
   // backward epilogue, BN-training correction folded in: out -= c0 + (x*A + B)*c1 with corr = [c0|c1|A|B] x corr_in,
   // column corr_col0 + j, x = corr_x[gr*corr_ld + j]
   const float* corr; int corr_in; int corr_col0; const float* corr_x; int corr_ld;
+  // second output block of the backward epilogue (nblk == 2): the same A operand (dz) against a second weight block of
+  // the same shape, written to its own destination - dOwn and dAgg of one iteration in ONE launch.  launch_gemm_rows
+  // splits it into two launches where the tensor-core kernel cannot take both.
+  int nblk;
+  const float* Wp2; const float* colscale2; int corr_col02; const float* corr_x2; int corr_ld2;
+  float* out2; int ld_out2; int out_add2;
   const float* prev; int ld_prev; float thr; int* flag_next;   // convergence epilogue (forward) or NULL
   double* ost_sum; double* ost_sq;                            // output column statistics or NULL
   const int* gate;

@@ -24,7 +24,8 @@
 #define TC_BM 128
 #define TC_BK 32
 #define TC_STAGES 3                  // minimum depth of the operand ring: [hi (raw fp32, filled by cp.async) | lo] x 16 KB per stage
-#define TC_MAX_STAGES 6              // the launcher deepens the ring up to this while shared memory allows (more rows in flight)
+#define TC_MAX_STAGES 6              // GNNFP_TC_STAGES=<n> deepens the ring while shared memory allows; measured SLOWER on B200 (13.7 vs 13.0
+                                     // ms/step at 6 stages: the converter warps stall issuing the extra cp.async), so the default stays 3
 #define TC_TILE_BYTES (TC_BM * 128)  // one A operand tile: 128 rows x 128 B
 
 __device__ __forceinline__ void tc_cp_async8(void* dst, const void* src, int src_bytes) {
@@ -140,7 +141,7 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
 #define TC_THREADS 416                                  // warps 0-3 converters, 4-11 epilogue, 12 MMA issuer
 #define TC_EPI_WARPS 8
 
-template <int BN, bool FWD>
+template <int BN, bool FWD, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __grid_constant__ GemmRowsArgs a, const int NST) {
   if (a.gate && *a.gate == 0) return;
   extern __shared__ uint8_t smem_raw[];
@@ -149,13 +150,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int NKB = (a.Kpad + TC_BK - 1) / TC_BK;
   const int wtile = BN * 128;                          // bytes of one [BN x 32] weight tile
+  // resident weights: [NB output blocks][hi | lo][NKB][BN x 32]; NB == 2: a second output block computed from the same
+  // A operand (backward dX of two equally wide pieces, e.g. dOwn and dAgg: dz is loaded and split once)
   uint8_t* Whi = base;
   uint8_t* Wlo = Whi + (size_t)NKB * wtile;
-  uint8_t* Aop = Wlo + (size_t)NKB * wtile;            // [NST][hi, lo][TC_TILE_BYTES]
+  uint8_t* Aop = base + (size_t)NB * 2 * NKB * wtile;  // [NST][hi, lo][TC_TILE_BYTES]
   __shared__ __align__(8) uint64_t ops_full[TC_MAX_STAGES], ops_empty[TC_MAX_STAGES], tm_full[2], tm_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[BN];
-  __shared__ double colacc[TC_EPI_WARPS][2][BN];       // per epilogue warp: column sums / sums of squares
+  __shared__ double colacc[FWD ? TC_EPI_WARPS : 1][2][BN];   // per epilogue warp: column sums / sums of squares (forward only)
   __shared__ float estage[TC_EPI_WARPS][32][17];       // per epilogue warp: [32 rows x 16 columns] transpose staging
   __shared__ float rowpart[2][TC_BM];                  // convergence sums of the second warp of each lane quarter
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -164,7 +167,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
   const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int tile0 = blockIdx.x * tiles_per_cta;
   const int my_tiles = max(0, min(n_tiles, tile0 + tiles_per_cta) - tile0);
-  constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256));
+  constexpr uint32_t TMEM_NEED = 2 * NB * BN;          // double-buffered accumulators of every output block
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
 
   if (warp == 0) { tmem_alloc(&tmem_base_s, TMEM_COLS); tmem_relinquish(); }      // whole warp, converged (.sync.aligned)
   if (tid == 32) {
@@ -173,15 +177,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
     mbar_init(&tm_empty[0], 32 * TC_EPI_WARPS); mbar_init(&tm_empty[1], 32 * TC_EPI_WARPS);
   }
   // ---- resident weights: split into TF32 hi / lo, K-major swizzled tiles per K block (all threads) ------------------
-  for (int e = tid; e < NKB * TC_BK * BN; e += TC_THREADS) {
-    const int k = e / BN, nn = e - k * BN;
-    const float w = k < a.Kpad ? a.Wp[(size_t)k * a.ldw + nn] : 0.f;
-    const int off = (k >> 5) * wtile + tc_sw128_off(nn, k & 31);
-    *reinterpret_cast<uint32_t*>(Whi + off) = __float_as_uint(w);
-    *reinterpret_cast<uint32_t*>(Wlo + off) = tc_lo(__float_as_uint(w));
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const float* Wsrc = b == 0 ? a.Wp : a.Wp2;
+    uint8_t* whi = Whi + (size_t)b * 2 * NKB * wtile;
+    uint8_t* wlo = Wlo + (size_t)b * 2 * NKB * wtile;
+    for (int e = tid; e < NKB * TC_BK * BN; e += TC_THREADS) {
+      const int k = e / BN, nn = e - k * BN;
+      const float w = k < a.Kpad ? Wsrc[(size_t)k * a.ldw + nn] : 0.f;
+      const int off = (k >> 5) * wtile + tc_sw128_off(nn, k & 31);
+      *reinterpret_cast<uint32_t*>(whi + off) = __float_as_uint(w);
+      *reinterpret_cast<uint32_t*>(wlo + off) = tc_lo(__float_as_uint(w));
+    }
   }
   for (int j = tid; j < BN; j += TC_THREADS) sbias[j] = (FWD && a.bias && j < a.N) ? a.bias[j] : 0.f;
-  for (int j = tid; j < TC_EPI_WARPS * 2 * BN; j += TC_THREADS) (&colacc[0][0][0])[j] = 0.0;
+  for (int j = tid; j < (FWD ? TC_EPI_WARPS : 1) * 2 * BN; j += TC_THREADS) (&colacc[0][0][0])[j] = 0.0;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -298,20 +308,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           mbar_wait_bounded(&tm_empty[tb], (uint32_t)((tq >> 1) - 1) & 1u);
           tc_fence_after();
         }
-        const uint32_t dcol = tmem_d + (uint32_t)(tb * BN);
+        const uint32_t dcol0 = tmem_d + (uint32_t)(tb * NB * BN);
         for (int kb = 0; kb < NKB; ++kb) {
           mbar_wait_bounded(&ops_full[ob], oph);
           tc_fence_after();
           const uint64_t dah = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES);
           const uint64_t dal = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
-          const uint64_t dbh = tc_desc_sw128(whi_addr + kb * wtile);
-          const uint64_t dbl = tc_desc_sw128(wlo_addr + kb * wtile);
 #pragma unroll
-          for (int k8 = 0; k8 < TC_BK / 8; ++k8) {     // 8 fp32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
-            const uint64_t adv = (uint64_t)(2 * k8);
-            tc_mma_tf32(dcol, dal + adv, dbh + adv, idesc, (kb | k8) ? 1u : 0u);
-            tc_mma_tf32(dcol, dah + adv, dbl + adv, idesc, 1u);
-            tc_mma_tf32(dcol, dah + adv, dbh + adv, idesc, 1u);
+          for (int b = 0; b < NB; ++b) {
+            const uint32_t dcol = dcol0 + (uint32_t)(b * BN);
+            const uint64_t dbh = tc_desc_sw128(whi_addr + (b * 2 * NKB + kb) * wtile);
+            const uint64_t dbl = tc_desc_sw128(wlo_addr + (b * 2 * NKB + kb) * wtile);
+#pragma unroll
+            for (int k8 = 0; k8 < TC_BK / 8; ++k8) {   // 8 fp32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
+              const uint64_t adv = (uint64_t)(2 * k8);
+              tc_mma_tf32(dcol, dal + adv, dbh + adv, idesc, (kb | k8) ? 1u : 0u);
+              tc_mma_tf32(dcol, dah + adv, dbl + adv, idesc, 1u);
+              tc_mma_tf32(dcol, dah + adv, dbh + adv, idesc, 1u);
+            }
           }
           tc_commit(&ops_empty[ob]);                   // operand buffer free once these MMAs have completed
           if (kb == NKB - 1) tc_commit(&tm_full[tb]);  // accumulator tile complete
@@ -329,112 +343,121 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
     float* stg = &estage[ew][0][0];
     const int hr = lane >> 4, hc = lane & 15;          // staging <-> global mapping: row 2*rr + hr, column hc
     const bool selu = a.act == GNNFP_ACT_SELU;
-    const float* kc = (!FWD && a.corr) ? a.corr + a.corr_col0 : nullptr;
-    const float* auxsrc = FWD ? a.prev : (kc ? a.corr_x : nullptr);
-    const int auxld = FWD ? a.ld_prev : a.corr_ld;
     for (int tq = 0; tq < my_tiles; ++tq) {
       const int tb = tq & 1;
       const int wrow0 = (tile0 + tq) * TC_BM + 32 * q; // first global row of this warp's 32 rows
       const bool valid = wrow0 + lane < n;
       mbar_wait_bounded(&tm_full[tb], (uint32_t)(tq >> 1) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(tb * BN);
       float sdp[16], spp[16];                          // convergence partial sums of rows 2*rr + hr over this lane's columns
 #pragma unroll
       for (int rr = 0; rr < 16; ++rr) { sdp[rr] = 0.f; spp[rr] = 0.f; }
       bool handed_back = false;
 #ifdef TC_DEBUG_SKIP_EPI
-      { float acc[8]; tmem_ld8(taddr, acc); tmem_ld_wait(); tc_fence_before(); mbar_arrive(&tm_empty[tb]); if (acc[0] == 123.456f) notconv = 1; continue; }
+      { const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(tb * NB * BN); float acc[8]; tmem_ld8(taddr, acc); tmem_ld_wait(); tc_fence_before(); mbar_arrive(&tm_empty[tb]); if (acc[0] == 123.456f) notconv = 1; continue; }
 #endif
-      // one 16-column chunk; FULL = all 32 rows of the warp and all 16 columns are inside the matrix (warp uniform), which
-      // removes every per-element predicate from the common case
-      auto chunk = [&](int c0, auto full_tag) {
-        constexpr bool FULL = decltype(full_tag)::value;
-        float acc[16];
-        tmem_ld8(taddr + c0, acc);
-        tmem_ld8(taddr + c0 + 8, acc + 8);
-        // coalesced side inputs of this chunk, issued before the accumulator is consumed: lane (hr, hc) owns rows
-        // 2*rr + hr, column c0 + hc (two 64-byte row segments per instruction)
-        const bool cok = FULL || c0 + hc < a.N;
-        const int nvr = FULL ? 32 : (cok ? n - wrow0 - hr : 0);      // rows 2*rr + hr with 2*rr < nvr are inside the matrix
-        float t[16], o[FWD ? 1 : 16];
-        if (auxsrc) {
-          const float* ap = auxsrc + (size_t)(wrow0 + hr) * auxld + c0 + hc;
-#pragma unroll
-          for (int rr = 0; rr < 16; ++rr) { t[rr] = (FULL || 2 * rr < nvr) ? *ap : 0.f; ap += 2 * auxld; }
-        } else {
-#pragma unroll
-          for (int rr = 0; rr < 16; ++rr) t[rr] = 0.f;
-        }
-        if (!FWD) {
-          if (a.out_add) {
-            const float* op = a.out + (size_t)(wrow0 + hr) * a.ld_out + c0 + hc;
-#pragma unroll
-            for (int rr = 0; rr < 16; ++rr) { o[rr] = (FULL || 2 * rr < nvr) ? *op : 0.f; op += 2 * a.ld_out; }
-          } else {
-#pragma unroll
-            for (int rr = 0; rr < 16; ++rr) o[rr] = 0.f;
-          }
-        }
-        tmem_ld_wait();
-        if (c0 + 16 * (TC_EPI_WARPS / 4) >= BN) {      // this thread's last read of the accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tm_empty[tb]);
-          handed_back = true;
-        }
-        // thread = row: bias + activation (forward) / column scale (backward)
-        float v[16];
-        if (FWD) {
-          if (selu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = tc_selu(acc[j] + sbias[c0 + j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = act_fwd(a.act, acc[j] + sbias[c0 + j]);
-          }
-        } else if (a.colscale) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = acc[j] * ((FULL || c0 + j < a.N) ? a.colscale[c0 + j] : 0.f);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = acc[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = (FULL || (valid && c0 + j < a.N)) ? v[j] : 0.f;
-        __syncwarp();
-        float s1 = 0.f, s2 = 0.f;
-        float k0 = 0.f, k1 = 0.f, kA = 0.f, kB = 0.f;
-        if (!FWD && kc && cok) { k0 = kc[c0 + hc]; k1 = kc[a.corr_in + c0 + hc]; kA = kc[2 * a.corr_in + c0 + hc]; kB = kc[3 * a.corr_in + c0 + hc]; }
-        float* outp = a.out + (size_t)(wrow0 + hr) * a.ld_out + c0 + hc;
-#pragma unroll
-        for (int rr = 0; rr < 16; ++rr, outp += 2 * a.ld_out) {   // coalesced: stores, convergence sums, statistics, corrections
-          float x = stg[(2 * rr + hr) * 17 + hc];
-          if (FULL || 2 * rr < nvr) {
-            if (FWD) {
-              const float dd = x - t[rr];
-              sdp[rr] = fmaf(dd, dd, sdp[rr]);
-              spp[rr] = fmaf(t[rr], t[rr], spp[rr]);
-              s1 += x;
-              s2 = fmaf(x, x, s2);
-            } else {
-              if (kc) x -= k0 + fmaf(t[rr], kA, kB) * k1;
-              x += o[rr];
-            }
-            *outp = x;
-          }
-        }
-        __syncwarp();
-        if (FWD && a.ost_sum) {                        // column statistics: fold the two row halves, lanes 0-15 own a column
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          if (hr == 0 && cok) { colacc[ew][0][c0 + hc] += (double)s1; colacc[ew][1][c0 + hc] += (double)s2; }
-        }
-      };
       const bool rows_full = wrow0 + 32 <= n;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {                   // output blocks of this row tile (accumulators tb*NB + b)
+        const bool second = NB == 2 && b == 1;
+        const bool last_blk = b == NB - 1;
+        float* const e_out = second ? a.out2 : a.out;
+        const int e_ldo = second ? a.ld_out2 : a.ld_out;
+        const int e_add = second ? a.out_add2 : a.out_add;
+        const float* const e_cs = second ? a.colscale2 : a.colscale;
+        const float* const kc = (!FWD && a.corr) ? a.corr + (second ? a.corr_col02 : a.corr_col0) : nullptr;
+        const float* const auxsrc = FWD ? a.prev : (kc ? (second ? a.corr_x2 : a.corr_x) : nullptr);
+        const int auxld = FWD ? a.ld_prev : (second ? a.corr_ld2 : a.corr_ld);
+        const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)((tb * NB + b) * BN);
+        // one 16-column chunk; FULL = all 32 rows of the warp and all 16 columns are inside the matrix (warp uniform), which
+        // removes every per-element predicate from the common case
+        auto chunk = [&](int c0, auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
+          float acc[16];
+          tmem_ld8(taddr + c0, acc);
+          tmem_ld8(taddr + c0 + 8, acc + 8);
+          // coalesced side inputs of this chunk, issued before the accumulator is consumed: lane (hr, hc) owns rows
+          // 2*rr + hr, column c0 + hc (two 64-byte row segments per instruction)
+          const bool cok = FULL || c0 + hc < a.N;
+          const int nvr = FULL ? 32 : (cok ? n - wrow0 - hr : 0);      // rows 2*rr + hr with 2*rr < nvr are inside the matrix
+          float t[16], o[FWD ? 1 : 16];
+          if (auxsrc) {
+            const float* ap = auxsrc + (size_t)(wrow0 + hr) * auxld + c0 + hc;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) { t[rr] = (FULL || 2 * rr < nvr) ? *ap : 0.f; ap += 2 * auxld; }
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) t[rr] = 0.f;
+          }
+          if (!FWD) {
+            if (e_add) {
+              const float* op = e_out + (size_t)(wrow0 + hr) * e_ldo + c0 + hc;
+#pragma unroll
+              for (int rr = 0; rr < 16; ++rr) { o[rr] = (FULL || 2 * rr < nvr) ? *op : 0.f; op += 2 * e_ldo; }
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < 16; ++rr) o[rr] = 0.f;
+            }
+          }
+          tmem_ld_wait();
+          if (last_blk && c0 + 16 * (TC_EPI_WARPS / 4) >= BN) {      // this thread's last read of the accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tm_empty[tb]);
+            handed_back = true;
+          }
+          // thread = row: bias + activation (forward) / column scale (backward)
+          float v[16];
+          if (FWD) {
+            if (selu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = tc_selu(acc[j] + sbias[c0 + j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = act_fwd(a.act, acc[j] + sbias[c0 + j]);
+            }
+          } else if (e_cs) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = acc[j] * ((FULL || c0 + j < a.N) ? e_cs[c0 + j] : 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = acc[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = (FULL || (valid && c0 + j < a.N)) ? v[j] : 0.f;
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+          float k0 = 0.f, k1 = 0.f, kA = 0.f, kB = 0.f;
+          if (!FWD && kc && cok) { k0 = kc[c0 + hc]; k1 = kc[a.corr_in + c0 + hc]; kA = kc[2 * a.corr_in + c0 + hc]; kB = kc[3 * a.corr_in + c0 + hc]; }
+          float* outp = e_out + (size_t)(wrow0 + hr) * e_ldo + c0 + hc;
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr, outp += 2 * e_ldo) {   // coalesced: stores, convergence sums, statistics, corrections
+            float x = stg[(2 * rr + hr) * 17 + hc];
+            if (FULL || 2 * rr < nvr) {
+              if (FWD) {
+                const float dd = x - t[rr];
+                sdp[rr] = fmaf(dd, dd, sdp[rr]);
+                spp[rr] = fmaf(t[rr], t[rr], spp[rr]);
+                s1 += x;
+                s2 = fmaf(x, x, s2);
+              } else {
+                if (kc) x -= k0 + fmaf(t[rr], kA, kB) * k1;
+                x += o[rr];
+              }
+              *outp = x;
+            }
+          }
+          __syncwarp();
+          if (FWD && a.ost_sum) {                        // column statistics: fold the two row halves, lanes 0-15 own a column
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+            if (hr == 0 && cok) { colacc[FWD ? ew : 0][0][c0 + hc] += (double)s1; colacc[FWD ? ew : 0][1][c0 + hc] += (double)s2; }
+          }
+        };
 #pragma unroll 1
-      for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (TC_EPI_WARPS / 4)) {      // 16 accumulator columns per trip
-        if (rows_full && c0 + 16 <= a.N) chunk(c0, std::true_type{});
-        else chunk(c0, std::false_type{});
+        for (int c0 = 16 * chalf; c0 < BN; c0 += 16 * (TC_EPI_WARPS / 4)) {      // 16 accumulator columns per trip
+          if (rows_full && c0 + 16 <= a.N) chunk(c0, std::true_type{});
+          else chunk(c0, std::false_type{});
+        }
       }
       float sd = 0.f, sp = 0.f;                        // row sums: reduce over the 16 column lanes; lane rr of each half keeps row 2*rr + hr
       if (FWD && a.prev) {
@@ -482,7 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, bool FWD>
+template <int BN, bool FWD, int NB>
 static int launch_tc_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   const int NKB = (a.Kpad + TC_BK - 1) / TC_BK;
   static size_t smem_cap = 0;                          // dynamic shared memory this instantiation may use next to its static arrays
@@ -490,27 +513,26 @@ static int launch_tc_t(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
     cudaFuncAttributes fa;
     int dev = 0, optin = 0;
     GNNFP_CHECK_CUDA(cudaGetDevice(&dev));
-    GNNFP_CHECK_CUDA(cudaFuncGetAttributes(&fa, gemm_rows_tc_kernel<BN, FWD>));
+    GNNFP_CHECK_CUDA(cudaFuncGetAttributes(&fa, gemm_rows_tc_kernel<BN, FWD, NB>));
     GNNFP_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     smem_cap = (size_t)optin - fa.sharedSizeBytes;
   }
-  // the deepest operand ring that fits: more stages = more rows in flight per SM (one CTA per SM, latency bound otherwise)
   int nst = TC_STAGES;
-  static const int nst_max = getenv("GNNFP_TC_STAGES") ? atoi(getenv("GNNFP_TC_STAGES")) : TC_MAX_STAGES;
+  static const int nst_max = getenv("GNNFP_TC_STAGES") ? atoi(getenv("GNNFP_TC_STAGES")) : TC_STAGES;
   while (nst < nst_max && nst < TC_MAX_STAGES &&
-         (size_t)2 * NKB * BN * 128 + (size_t)(nst + 1) * 2 * TC_TILE_BYTES + 1024 <= smem_cap) ++nst;
-  const size_t smem = (size_t)2 * NKB * BN * 128 + (size_t)nst * 2 * TC_TILE_BYTES + 1024;
+         (size_t)NB * 2 * NKB * BN * 128 + (size_t)(nst + 1) * 2 * TC_TILE_BYTES + 1024 <= smem_cap) ++nst;
+  const size_t smem = (size_t)NB * 2 * NKB * BN * 128 + (size_t)nst * 2 * TC_TILE_BYTES + 1024;
   if (smem > smem_cap) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_rows_tc: %zu bytes of shared memory needed, %zu available", smem, smem_cap);
   static size_t attr = 0;
   if (smem > attr) {
-    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNFP_CHECK_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, FWD, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   const int n_tiles = (a.n_rows + TC_BM - 1) / TC_BM;
   const int nsm = gnnfp_num_sms();
   const int grid = n_tiles < nsm ? n_tiles : nsm;
   ProfScope ps(prof_cat, s);
-  gemm_rows_tc_kernel<BN, FWD><<<grid, TC_THREADS, smem, s>>>(a, nst);
+  gemm_rows_tc_kernel<BN, FWD, NB><<<grid, TC_THREADS, smem, s>>>(a, nst);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;
@@ -523,20 +545,31 @@ int gemm_rows_tc_supported(const GemmRowsArgs& a) {
   if (a.ldw != 16 * ((a.N + 15) / 16)) return 0;
   const int NKB = (a.Kpad + TC_BK - 1) / TC_BK;
   const int BN = a.ldw;
-  const size_t smem = (size_t)2 * NKB * BN * 128 + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 1024;
-  return smem <= 220 * 1024;
+  const int NB = a.nblk == 2 ? 2 : 1;
+  if (NB == 2 && (a.fwd || BN > 64)) return 0;         // two output blocks: backward only; 80 columns do not fit next to the ring
+  const size_t smem = (size_t)NB * 2 * NKB * BN * 128 + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 1024;
+  return smem <= (NB == 2 ? 200 : 220) * 1024;
 }
 
 int launch_gemm_rows_tc(const GemmRowsArgs& a, cudaStream_t s, int prof_cat) {
   if (a.n_rows <= 0) return GNNFP_OK;
   if (!gemm_rows_tc_supported(a)) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_rows_tc: shape N=%d K=%d not supported", a.N, a.Kpad);
   const bool fwd = a.fwd != 0;
+  if (a.nblk == 2) {
+    switch (a.ldw) {
+      case 16: return launch_tc_t<16, false, 2>(a, s, prof_cat);
+      case 32: return launch_tc_t<32, false, 2>(a, s, prof_cat);
+      case 48: return launch_tc_t<48, false, 2>(a, s, prof_cat);
+      case 64: return launch_tc_t<64, false, 2>(a, s, prof_cat);
+      default: GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_rows_tc: two output blocks of %d columns", a.ldw);
+    }
+  }
   switch (a.ldw) {
-    case 16: return fwd ? launch_tc_t<16, true>(a, s, prof_cat) : launch_tc_t<16, false>(a, s, prof_cat);
-    case 32: return fwd ? launch_tc_t<32, true>(a, s, prof_cat) : launch_tc_t<32, false>(a, s, prof_cat);
-    case 48: return fwd ? launch_tc_t<48, true>(a, s, prof_cat) : launch_tc_t<48, false>(a, s, prof_cat);
-    case 64: return fwd ? launch_tc_t<64, true>(a, s, prof_cat) : launch_tc_t<64, false>(a, s, prof_cat);
-    case 80: return fwd ? launch_tc_t<80, true>(a, s, prof_cat) : launch_tc_t<80, false>(a, s, prof_cat);
+    case 16: return fwd ? launch_tc_t<16, true, 1>(a, s, prof_cat) : launch_tc_t<16, false, 1>(a, s, prof_cat);
+    case 32: return fwd ? launch_tc_t<32, true, 1>(a, s, prof_cat) : launch_tc_t<32, false, 1>(a, s, prof_cat);
+    case 48: return fwd ? launch_tc_t<48, true, 1>(a, s, prof_cat) : launch_tc_t<48, false, 1>(a, s, prof_cat);
+    case 64: return fwd ? launch_tc_t<64, true, 1>(a, s, prof_cat) : launch_tc_t<64, false, 1>(a, s, prof_cat);
+    case 80: return fwd ? launch_tc_t<80, true, 1>(a, s, prof_cat) : launch_tc_t<80, false, 1>(a, s, prof_cat);
     default: GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "gemm_rows_tc: %d output columns", a.ldw);
   }
 }

@@ -511,11 +511,15 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
           }
           const float* wt = (const float*)(c.ws + L->ws.wtb) + (size_t)ty * L->ws.wtb_stride;
           const int KH = gemm_rows_kpad(H0);
+          // one dX launch per gradient destination; two destinations of the same width (dOwn_t and dAgg_t) share a
+          // launch: dz is loaded and split once, two accumulators per row tile (gemm.h: nblk == 2)
+          GemmRowsArgs dx[GNNFP_MAXP];
+          int ndx = 0;
           for (int p = 0; p < full.n_pieces; ++p) {
             const Piece& pc = full.p[p];
             const int ldw = gemm_rows_ldw(pc.width);
             if (pc.gptr) {
-              GemmRowsArgs ga;
+              GemmRowsArgs& ga = dx[ndx++];
               memset(&ga, 0, sizeof(ga));
               ga.n_rows = full.n_rows; ga.rowlist = full.rowlist; ga.n_pieces = 1;
               gemm_piece_set(ga.p[0], dzbuf, D, H0, 0);
@@ -525,9 +529,21 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
               ga.out = pc.gptr; ga.ld_out = pc.gld; ga.out_add = pc.gmode == GM_ADD;
               ga.vec2 = pc.gld % 2 == 0 && ((uintptr_t)pc.gptr & 7) == 0;
               ga.gate = gate;
-              if ((rc = launch_gemm_rows(ga, s, PC_BWD_DX))) return rc;
             }
             wt += (size_t)KH * ldw;
+          }
+          static const int no_pair = getenv("GNNFP_NO_DX_PAIR") ? 1 : 0;
+          for (int i = 0; i < ndx; ++i) {
+            if (dx[i].n_rows < 0) continue;              // already merged into an earlier launch
+            for (int j = i + 1; j < ndx && !no_pair && dx[i].nblk == 0; ++j) {
+              if (dx[j].n_rows < 0 || dx[j].N != dx[i].N || dx[j].ldw != dx[i].ldw) continue;
+              dx[i].nblk = 2;
+              dx[i].Wp2 = dx[j].Wp; dx[i].colscale2 = dx[j].colscale;
+              dx[i].corr_col02 = dx[j].corr_col0; dx[i].corr_x2 = dx[j].corr_x; dx[i].corr_ld2 = dx[j].corr_ld;
+              dx[i].out2 = dx[j].out; dx[i].ld_out2 = dx[j].ld_out; dx[i].out_add2 = dx[j].out_add;
+              dx[j].n_rows = -1;
+            }
+            if ((rc = launch_gemm_rows(dx[i], s, PC_BWD_DX))) return rc;
           }
         }
         for (int si = 0; si < (gemm_bwd[ty] ? 0 : nsplit[ty]); ++si) {
