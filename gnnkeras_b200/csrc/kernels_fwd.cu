@@ -13,6 +13,7 @@
 // Persistent grids (a multiple of the SM count), weights staged once per CTA into shared memory,
 // activations kept row-major with an odd stride so that lane==row accesses are conflict-free and
 // weight reads are 128-bit broadcasts.
+#include <stdlib.h>
 #include "tile.cuh"
 
 // shared-memory layout as integer offsets (floats from the start of dynamic shared memory).  Kept in
@@ -244,10 +245,13 @@ __global__ void __launch_bounds__(256) tile_pass_kernel(const __grid_constant__ 
 // Adj^T . S with thousands of independent threads: thread (qx, ry) owns the VEC-wide column chunk qx of
 // rows ry, ry + rows_per_block * gridDim, ...; per-thread fp64 column partials, one block reduction, one
 // fp64 atomicAdd per column and block.  Arc order inside a row is preserved (sequential fmaf).
-template <int VEC, bool DIRECT, bool WGT>
-__global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ AggArgs a, int QX) {
+// BT threads per block: the statistics end in one fp64 atomicAdd per column and BLOCK on the same 2 D addresses, and
+// same-address atomics serialise in L2 (measured ~8 us per launch with 4 x 148 blocks), so the narrow instantiations
+// run ONE 1024-thread block per SM.
+template <int VEC, bool DIRECT, bool WGT, int BT>
+__global__ void __launch_bounds__(BT) agg_stats_kernel(const __grid_constant__ AggArgs a, int QX) {
   if (a.gate && *a.gate == 0) return;
-  __shared__ double red[256 * 2];
+  __shared__ double red[BT * 2];
   const int nq = a.D / VEC;
   const int qx = threadIdx.x % QX, ry = threadIdx.x / QX;
   const int rpb = blockDim.x / QX;
@@ -348,11 +352,11 @@ __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ 
   if (a.st_sum) {
     for (int v = 0; v < VEC; ++v) {
       red[threadIdx.x] = su[v];
-      red[256 + threadIdx.x] = sq[v];
+      red[BT + threadIdx.x] = sq[v];
       __syncthreads();
       if (ry == 0 && qx < nq) {
         double s1 = 0.0, s2 = 0.0;
-        for (int y2 = 0; y2 < rpb; ++y2) { s1 += red[y2 * QX + qx]; s2 += red[256 + y2 * QX + qx]; }
+        for (int y2 = 0; y2 < rpb; ++y2) { s1 += red[y2 * QX + qx]; s2 += red[BT + y2 * QX + qx]; }
         atomicAdd(a.st_sum + qx * VEC + v, s1);
         atomicAdd(a.st_sq + qx * VEC + v, s2);
       }
@@ -362,27 +366,30 @@ __global__ void __launch_bounds__(256) agg_stats_kernel(const __grid_constant__ 
 }
 
 template <int VEC, bool DIRECT, bool WGT>
-static int launch_agg_t(const AggArgs& a, int QX, int rpb, cudaStream_t s) {
+static int launch_agg_t(const AggArgs& a, int QX, cudaStream_t s) {
   constexpr int NR = DIRECT ? 8 : 4;
+  constexpr int BT = VEC == 4 ? 256 : 1024;            // VEC == 4 needs more than 64 registers per thread
+  const int rpb = BT / QX;
   long long blocks = ((long long)a.n_rows + NR * rpb - 1) / (NR * rpb);
   static int occ = 0;                                  // resident blocks per SM of this instantiation: one full wave
   if (!occ) {
     int o = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<VEC, DIRECT, WGT>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, agg_stats_kernel<VEC, DIRECT, WGT, BT>, BT, 0);
     occ = o > 0 ? o : 4;
   }
-  const long long cap = (long long)gnnfp_num_sms() * occ;
+  static const int waves = getenv("GNNFP_AGG_WAVES") ? atoi(getenv("GNNFP_AGG_WAVES")) : 1;
+  const long long cap = (long long)gnnfp_num_sms() * occ * (waves > 0 ? waves : 1);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  agg_stats_kernel<VEC, DIRECT, WGT><<<(int)blocks, 256, 0, s>>>(a, QX);
+  agg_stats_kernel<VEC, DIRECT, WGT, BT><<<(int)blocks, BT, 0, s>>>(a, QX);
   return 0;
 }
 
 template <int VEC>
-static int launch_agg_v(const AggArgs& a, int QX, int rpb, cudaStream_t s) {
-  if (!a.rowptr) return launch_agg_t<VEC, true, false>(a, QX, rpb, s);
-  if (a.wgt) return launch_agg_t<VEC, false, true>(a, QX, rpb, s);
-  return launch_agg_t<VEC, false, false>(a, QX, rpb, s);
+static int launch_agg_v(const AggArgs& a, int QX, cudaStream_t s) {
+  if (!a.rowptr) return launch_agg_t<VEC, true, false>(a, QX, s);
+  if (a.wgt) return launch_agg_t<VEC, false, true>(a, QX, s);
+  return launch_agg_t<VEC, false, false>(a, QX, s);
 }
 
 int launch_agg_stats(const AggArgs& a, cudaStream_t s, int prof_cat) {
@@ -395,11 +402,10 @@ int launch_agg_stats(const AggArgs& a, cudaStream_t s, int prof_cat) {
   const int nq = a.D / vec;
   if (nq > 256) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "state width %d too large for the aggregation kernel", a.D);
   const int QX = nq;                                  // threads per row (rows may straddle warps)
-  const int rpb = 256 / QX;
   ProfScope ps(prof_cat ? prof_cat : PC_AGG, s);
-  if (vec == 4) launch_agg_v<4>(a, QX, rpb, s);
-  else if (vec == 2) launch_agg_v<2>(a, QX, rpb, s);
-  else launch_agg_v<1>(a, QX, rpb, s);
+  if (vec == 4) launch_agg_v<4>(a, QX, s);
+  else if (vec == 2) launch_agg_v<2>(a, QX, s);
+  else launch_agg_v<1>(a, QX, s);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;
