@@ -365,13 +365,14 @@ def main():
         # per-kernel algorithmic traffic (fp32 words that must move once, SURVEY 8(d) convention: raw inputs, no re-reads)
         #   gemm_rows_tc fwd : read s (D) + Adj^T s (D) + invariant columns (AL), write s' (D)
         #   gemm_dw_tc    : read the same inputs (2D + AL) + dz (D); dW/db stay on chip
-        #   gemm_rows dX  : two launches per iteration, each reads dz (D) and writes one D-wide block
+        #   gemm_rows dX  : reads dz (D) once, writes dOwn and dAgg (D each) - one launch for both where the two
+        #                   accumulator blocks fit (D <= 64), else one launch per destination
         cand = {
             "gemm_rows_tc_kernel<fwd>": (msc[1], int(cnt[1]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
                                       sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
             "gemm_dw_tc_kernel": (msc[2], int(cnt[2]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
                                sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
-            "gemm_rows_tc_kernel<bwd dX>": (msc[8], int(cnt[8]), sum(4 * (4 * D) for D in WIDTHS) * iters,
+            "gemm_rows_tc_kernel<bwd dX>": (msc[8], int(cnt[8]), sum(4 * (3 * D) for D in WIDTHS) * iters,
                                          sum(2 * (2 * D) * D for D in WIDTHS) * iters),
         }
         dom = max(cand, key=lambda k_: cand[k_][0])
