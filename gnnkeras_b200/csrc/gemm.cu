@@ -656,16 +656,17 @@ __global__ void __launch_bounds__(256) fold_w_kernel(const __grid_constant__ Fol
     }
     a.Wp[e] = w;
   }
-  if (blockIdx.x == 0)
-    for (int j = tid; j < a.ldw; j += blockDim.x) {
-      float bj = 0.f;
-      if (j < H) {
-        bj = net.b[0][j];
-        if (net.bn_mode)
-          for (int c = 0; c < in; ++c) bj = fmaf(B[c], net.W[0][(size_t)c * H + j], bj);
-      }
-      a.biasp[j] = bj;
-    }
+  // folded bias b_j + sum_c B_c W[c][j]: one warp per output column (lanes split the input columns, fixed-order
+  // shuffle reduction), spread over all blocks - a serial loop over the input columns per thread cost ~8 us per launch
+  const int lane = tid & 31, wpb = blockDim.x >> 5;
+  for (int j = blockIdx.x * wpb + (tid >> 5); j < a.ldw; j += gridDim.x * wpb) {
+    float part = 0.f;
+    if (j < H && net.bn_mode)
+      for (int c = lane; c < in; c += 32) part = fmaf(B[c], net.W[0][(size_t)c * H + j], part);
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
+    if (lane == 0) a.biasp[j] = j < H ? net.b[0][j] + part : 0.f;
+  }
 }
 
 int launch_fold_w(const FoldArgs& a, cudaStream_t s) {
