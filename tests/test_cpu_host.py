@@ -91,3 +91,32 @@ def test_oracle_restatements_agree():
     assert k32 == k64 == kt
     assert np.abs(s32 - s64).max() < 1e-4 and np.abs(st.detach().numpy() - s32).max() < 1e-4
     assert np.abs(o32 - o64).max() < 1e-5 and np.abs(ot.detach().numpy() - o32).max() < 1e-5
+
+
+def test_merge_without_resort_equals_the_reference_constructor_path():
+    """GraphObject.merge skips the np.unique(axis=0) of graph_class.py:47 on the merged arcs (members are sorted and
+    unique, offsets grow): the rows must be exactly what the re-sorting constructor produces - duplicated input rows,
+    multi-arcs with different labels, self loops, isolated nodes and an arc-less member included."""
+    rng = np.random.default_rng(7)
+    for focus in ("n", "g", "a"):
+        glist = []
+        for i in range(12):
+            n = int(rng.integers(1, 9))
+            a = int(rng.integers(0, 14)) if i != 3 else 0
+            arcs = np.concatenate([rng.integers(0, n, (a, 2)), rng.integers(0, 2, (a, 2))], axis=1).astype(np.float32)
+            if a > 2:
+                arcs = np.concatenate([arcs, arcs[:2]], axis=0)       # duplicated rows: dropped by the member's constructor
+            if focus == "a":
+                arcs = np.unique(arcs, axis=0)
+                if len(arcs) == 0:
+                    arcs = np.array([[0, 0, 1, 0]], np.float32)
+            n_t = {"n": n, "g": 1, "a": len(arcs)}[focus]
+            glist.append(GraphObject(nodes=rng.random((n, 3)), arcs=arcs, targets=rng.random((n_t, 2)), focus=focus,
+                                     aggregation_mode="average"))
+        m = GraphObject.merge(glist, focus, "average")
+        ref = GraphObject(nodes=m.nodes, arcs=m.arcs, targets=m.targets, focus=focus, set_mask=m.set_mask,
+                          output_mask=m.output_mask, aggregation_mode="average",
+                          NodeGraph=m.getNodeGraph() if focus == "g" else None)          # re-sorting constructor
+        assert m.arcs.dtype == ref.arcs.dtype and np.array_equal(m.arcs, ref.arcs)
+        assert m.nodes.shape[0] == sum(g.nodes.shape[0] for g in glist)
+        assert m.arcs.shape[0] == sum(g.arcs.shape[0] for g in glist)
