@@ -4,4 +4,4 @@ The arithmetic lives in ``libgnnfp.so`` (hand-written CUDA, C ABI in ``include/g
 the host-side mirror of the reference's interface for that path.  Importing the package does not load
 the library; any compute entry point does, and fails loudly if it is missing (there is no CPU fallback).
 """
-__all__ = ["op", "models", "nets", "graph", "sequencers", "synthetic"]
+__all__ = ["op", "models", "nets", "graph", "sequencers", "batcher", "synthetic"]

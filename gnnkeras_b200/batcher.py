@@ -1,0 +1,185 @@
+"""Device-side batcher: the whole dataset lives on the GPU in flat arrays and a batch is assembled
+there, so an epoch needs neither a host ``merge`` per batch nor a host->device copy of graph data.
+
+The reference rebuilds EVERY batch on the host at construction and at every epoch end
+(``GraphSequencers.py:42-46, 123-127``: ``merge`` = offset the node ids, concatenate, block-diagonal NodeGraph,
+``graph_class.py:385-413``, then ``fromGraphObject``, ``:539-560``).  Here ``GraphStore`` keeps, per member graph,
+its node rows, arc rows (LOCAL node ids, already sorted and unique - ``graph_class.py:47``), targets, masks and
+NodeGraph entries back to back, and ``assemble(ids)`` produces exactly the arrays ``GraphObject.merge([graphs[i] for
+i in ids])`` would hold - bit for bit, checked in ``tests/test_cpu_batcher.py`` - by range gathers:
+
+    rows of member i in the batch = store rows [ptr[i], ptr[i+1]),   arc ids += (nodes of the members before it)
+
+The index arithmetic is a handful of torch calls on tensors of the store's device (plumbing: sizes are known on the
+host, nothing synchronises); the integer structures of the assembled batch (CSR, weights, mask lists) are then built by
+``libgnnfp`` (``DeviceGraph`` -> ``gnnfp_graph_build``), as for every other batch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .graph import CompositeGraphObject, CompositeGraphTensor, GraphObject, GraphTensor
+
+
+def _ptr(lens: np.ndarray) -> np.ndarray:
+    return np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+
+
+class GraphStore:
+    """Flat, device-resident copy of a list of (Composite)GraphObjects sharing focus / label widths."""
+
+    def __init__(self, graphs: Sequence[GraphObject], device="cuda"):
+        graphs = list(graphs)
+        if not graphs:
+            raise ValueError("GraphStore needs at least one graph")
+        g0 = graphs[0]
+        self.focus = g0.focus
+        self.composite = isinstance(g0, CompositeGraphObject)
+        if any(g.focus != self.focus or isinstance(g, CompositeGraphObject) != self.composite for g in graphs):
+            raise ValueError("all graphs of a store must share focus and kind")
+        if len({tuple(g.DIM_NODE_LABEL) for g in graphs}) != 1:        # composite_graph_class.py:153
+            raise AssertionError("DIM_NODE_LABEL not unique among graphs in :param glist:")
+        if any(g.arc_values is not None for g in graphs):
+            raise NotImplementedError("explicit ArcNode values are rebuilt by merge in the reference; not stored")
+        self.dim_node_label = np.array(g0.DIM_NODE_LABEL, ndmin=1, dtype=int)
+        self.device = torch.device(device)
+        self.n = len(graphs)
+        # host-side sizes (batch geometry is known without touching the device)
+        self.n_nodes = np.array([g.nodes.shape[0] for g in graphs], np.int64)
+        self.n_arcs = np.array([g.arcs.shape[0] for g in graphs], np.int64)
+        self.n_tgt = np.array([g.targets.shape[0] for g in graphs], np.int64)
+        self.n_mask = np.array([len(g.set_mask) for g in graphs], np.int64)
+        self.n_sub = np.array([g.n_graphs for g in graphs], np.int64)   # NodeGraph columns of the member (0 = no NodeGraph)
+        self.has_nodegraph = bool(np.all(self.n_sub > 0))              # merge keeps NodeGraph only if every member has one
+        self.masks_true = np.array([bool(np.all(g.set_mask)) and bool(np.all(g.output_mask)) for g in graphs])
+        self.node_ptr, self.arc_ptr = _ptr(self.n_nodes), _ptr(self.n_arcs)
+        self.tgt_ptr, self.mask_ptr = _ptr(self.n_tgt), _ptr(self.n_mask)
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(dt))).to(self.device)
+        cat = lambda xs: np.concatenate(xs, axis=0)
+        self.nodes = up(cat([g.nodes for g in graphs]), np.float32)
+        self.arcs = up(cat([g.arcs for g in graphs]), np.float32)      # columns 0-1: node ids LOCAL to the member
+        self.targets = up(cat([g.targets for g in graphs]), np.float32)
+        self.sample_weight = up(cat([g.sample_weight for g in graphs]), np.float32)
+        self.set_mask = up(cat([g.set_mask for g in graphs]), np.uint8)
+        self.output_mask = up(cat([g.output_mask for g in graphs]), np.uint8)
+        self.node2graph = self.nodegraph_values = None
+        if self.has_nodegraph:
+            self.node2graph = up(cat([g.node2graph for g in graphs]), np.int32)
+            self.nodegraph_values = up(cat([g.nodegraph_values for g in graphs]), np.float32)
+        self.type_mask = up(cat([g.type_mask for g in graphs]), np.uint8) if self.composite else None   # [sum N, n_types]
+        self._dev_ptrs = {k: torch.from_numpy(v).to(self.device) for k, v in
+                          (("node", self.node_ptr), ("arc", self.arc_ptr), ("tgt", self.tgt_ptr), ("mask", self.mask_ptr))}
+
+    def __len__(self):
+        return self.n
+
+    # ---- range gather: rows [ptr[i], ptr[i+1]) of every selected member, back to back ---------------------------------
+    def _ranges(self, which: str, ids_dev: torch.Tensor, lens_host: np.ndarray):
+        """Returns (store row of every batch row, member position of every batch row)."""
+        total = int(lens_host.sum())
+        lens = torch.from_numpy(lens_host).to(self.device)
+        seg = torch.repeat_interleave(torch.arange(len(lens_host), device=self.device), lens, output_size=total)
+        first = torch.cumsum(lens, 0) - lens                       # first batch row of every member
+        pos = torch.arange(total, device=self.device) - first[seg]
+        return self._dev_ptrs[which][ids_dev][seg] + pos, seg
+
+    def assemble(self, ids) -> dict:
+        """The arrays of ``merge([graphs[i] for i in ids])`` as tensors on the store's device."""
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        if ids.size == 0 or ids.min() < 0 or ids.max() >= self.n:
+            raise IndexError("graph ids out of range")
+        ids_dev = torch.from_numpy(ids).to(self.device)
+        nn, na = self.n_nodes[ids], self.n_arcs[ids]
+        row_n, seg_n = self._ranges("node", ids_dev, nn)
+        row_a, seg_a = self._ranges("arc", ids_dev, na)
+        row_t, _ = self._ranges("tgt", ids_dev, self.n_tgt[ids])
+        mask_is_arc = self.focus == "a"
+        row_m = row_a if mask_is_arc else row_n                     # masks run over arcs (focus 'a') or nodes
+        if not np.array_equal(self.n_mask[ids], na if mask_is_arc else nn):
+            row_m, _ = self._ranges("mask", ids_dev, self.n_mask[ids])
+        nn_dev = torch.from_numpy(nn).to(self.device)
+        node_off = torch.cumsum(nn_dev, 0) - nn_dev                 # nodes of the members before this one
+        arcs = self.arcs[row_a]
+        arcs[:, :2] += node_off[seg_a].to(arcs.dtype)[:, None]      # graph_class.py:391-394
+        out = {"nodes": self.nodes[row_n], "arcs": arcs, "targets": self.targets[row_t],
+               "sample_weight": self.sample_weight[row_t], "set_mask": self.set_mask[row_m],
+               "output_mask": self.output_mask[row_m], "node2graph": None, "nodegraph_values": None, "n_graphs": 0,
+               "type_mask": None, "masks_all_true": bool(np.all(self.masks_true[ids])),
+               "n_nodes": int(nn.sum()), "n_arcs": int(na.sum())}
+        if self.has_nodegraph:                                       # block-diagonal NodeGraph (graph_class.py:407)
+            ns = torch.from_numpy(self.n_sub[ids]).to(self.device)
+            sub_off = (torch.cumsum(ns, 0) - ns).to(torch.int32)
+            out["node2graph"] = self.node2graph[row_n] + sub_off[seg_n]
+            out["nodegraph_values"] = self.nodegraph_values[row_n]
+            out["n_graphs"] = int(self.n_sub[ids].sum())
+        if self.composite:
+            out["type_mask"] = self.type_mask[row_n]
+        return out
+
+    def batch(self, ids, aggregation_mode: str) -> GraphTensor:
+        """Assembled batch + its device-built integer structures (needs the CUDA library)."""
+        from .op import DeviceGraph
+        a = self.assemble(ids)
+        ij = a["arcs"][:, :2].to(torch.int32)      # node ids are stored as float32 in arcs (graph_class.py:47)
+        src, dst = ij[:, 0].contiguous(), ij[:, 1].contiguous()
+        sm = om = None
+        if not a["masks_all_true"]:
+            sm, om = a["set_mask"], a["output_mask"]
+        tm = a["type_mask"].t().contiguous() if self.composite else None          # [n_types, N] as it reaches the model
+        graph = DeviceGraph(src, dst, a["n_nodes"], aggregation_mode, a["node2graph"], a["n_graphs"],
+                            a["nodegraph_values"], sm, om, tm, None, mask_len=int(a["set_mask"].numel()))
+        cls = CompositeGraphTensor if self.composite else GraphTensor
+        return cls(a["nodes"], a["arcs"], a["targets"], a["sample_weight"], sm, om, self.dim_node_label, graph,
+                   aggregation_mode, self.focus, tm)
+
+
+class DeviceMultiGraphSequencer:
+    """``MultiGraphSequencer`` (GraphSequencers.py:12-127) over a ``GraphStore``: same constructor arguments, ``len``,
+    ``__getitem__`` tuple layout and ``on_epoch_end`` behaviour, but an epoch end only redraws the permutation
+    (the reference shuffles the graph list and re-merges every batch on the host)."""
+
+    def __init__(self, graphs, focus: str, aggregation_mode: str, batch_size: int = 32, shuffle: bool = True,
+                 device="cuda"):
+        if isinstance(graphs, GraphStore):
+            self.store = graphs
+        else:
+            self.store = GraphStore(graphs if isinstance(graphs, list) else [graphs], device)
+        if self.store.focus != focus:
+            raise ValueError("focus of the graphs and of the sequencer differ")
+        self.focus, self.aggregation_mode = focus, aggregation_mode
+        self.batch_size, self.shuffle = int(batch_size), shuffle
+        self.order = np.arange(len(self.store))
+        self._cache: List[Optional[GraphTensor]] = [None] * len(self)
+
+    def __len__(self):
+        return int(np.ceil(len(self.store) / self.batch_size))
+
+    def batch_ids(self, index: int) -> np.ndarray:
+        return self.order[index * self.batch_size: (index + 1) * self.batch_size]
+
+    def get_batch(self, index):
+        if self._cache[index] is None:
+            self._cache[index] = self.store.batch(self.batch_ids(index), self.aggregation_mode)
+        g = self._cache[index]
+        return g, g.set_mask
+
+    def __getitem__(self, index):
+        g, set_mask = self.get_batch(index)
+        out = [g.nodes, g.arcs, g.DIM_NODE_LABEL, g.set_mask, g.output_mask, g.Adjacency, g.ArcNode, g.NodeGraph]
+        if self.store.composite:                    # GraphSequencers.py:240-244
+            out.insert(3, g.type_mask)
+            out.insert(-3, g.CompositeAdjacencies)
+        if self.focus == 'g' or set_mask is None:
+            targets, sample_weight = g.targets, g.sample_weight
+        else:
+            mask = set_mask.bool()[g.output_mask.bool()]                 # tf.boolean_mask(set_mask, output_mask)
+            targets, sample_weight = g.targets[mask], g.sample_weight[mask]
+        return out, targets, sample_weight
+
+    def on_epoch_end(self):
+        if self.shuffle:
+            np.random.shuffle(self.order)                                # GraphSequencers.py:123-127, without the re-merge
+            self._cache = [None] * len(self)
