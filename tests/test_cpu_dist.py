@@ -54,7 +54,7 @@ def _worker(rank, world, port, ret):
 
 def test_gloo_world2():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # not fork: the test process is multi-threaded (torch)
     ret = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
