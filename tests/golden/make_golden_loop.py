@@ -7,7 +7,7 @@ over the TensorFlow-API shim in ``tests/golden/tfshim`` (PyTorch-CPU underneath;
 here).  Inputs follow the Sequencer tuple layout (GraphSequencers.py:104-120, 232-245).  For every case we store
 inputs, weights, the random initial state the reference drew (GNN.py:257), and the reference's k / state / out and
 the gradients of a fixed scalar loss w.r.t. all trainable variables, in float64 and float32.
-Output: tests/golden/loop_golden.npz
+Output: tests/golden/loop_golden.npz (CPU oracle + CUDA path), tests/golden/loop_golden_extra.npz (CPU oracle)
 """
 import os
 import sys
@@ -101,7 +101,6 @@ def flatten(prefix, obj, out):
 
 def main():
     rng = np.random.default_rng(2024)
-    store = {}
 
     def nets(NL, AL, T, S_, kind, bn, act, n_types=0, dnl=None):
         D = S_ if S_ else NL
@@ -146,6 +145,41 @@ def main():
         nl = 14 + nl + 2
     cases.append(("lgnn3_S0_bn", GNNgraphBased, g, None, None, 0, 3, 0.01, {"lgnn_layers": layers}))
 
+    write_cases(cases, "loop_golden.npz")
+
+    # ---- extra cases (CPU pinning of the oracle only; their own generator so that the file above never changes) --------
+    rng = np.random.default_rng(2025)
+    extra = []
+    # E1. node-focused, S=0, 'normalized' aggregation (1/A of the merged batch, graph_class.py:113-114), BN + selu, both masks
+    b = mutag_shaped_batch(5, seed=11)
+    b.set_mask = rng.random(b.n_nodes) < 0.8
+    b.output_mask = rng.random(b.n_nodes) < 0.6
+    g = ograph_from_batch(b, "n", "normalized")
+    ns, no = nets(14, 3, 2, 0, "node", True, "selu")
+    extra.append(("node_S0_normalized_bn", GNNnodeBased, g, ns, no, 0, 4, 0.01, {}))
+    # E2. graph-focused, S=3, 'sum', hidden layers in both nets (MLP.py:12-78: BN first, then Dense...), no BN
+    b = mutag_shaped_batch(6, seed=12)
+    g = ograph_from_batch(b, "g", "sum")
+    ns = make_net(rng, 2 * 3 + 2 * 14 + 3, [8, 3], ["tanh", "tanh"], False, scale=0.5, dtype=np.float64)
+    no = make_net(rng, 3 + 14, [6, 2], ["tanh", "softmax"], False, dtype=np.float64)
+    extra.append(("graph_S3_sum_hidden", GNNgraphBased, g, ns, no, 3, 5, 0.01, {}))
+    # E3. composite node-focused, 3 node types, 'average', S=4, BN, output mask
+    b = mutag_shaped_batch(5, seed=13, n_types=3)
+    b.output_mask = rng.random(b.n_nodes) < 0.7
+    g = ograph_from_batch(b, "n", "average", dim_node_label=[14, 9, 6])
+    ns, no = nets(14, 3, 2, 4, "node", True, "tanh", n_types=3, dnl=[14, 9, 6])
+    extra.append(("composite3_node_S4_bn", CompositeGNNnodeBased, g, ns, no, 4, 3, 0.01, {"composite": True}))
+    # E4. arc-focused, S=0, 'sum', no BN, all masks true
+    b = mutag_shaped_batch(4, seed=14)
+    b.set_mask = np.ones(b.n_arcs, bool); b.output_mask = np.ones(b.n_arcs, bool)
+    g = ograph_from_batch(b, "a", "sum")
+    ns, no = nets(14, 3, 3, 0, "arc", False, "tanh")
+    extra.append(("arc_S0_sum", GNNarcBased, g, ns, no, 0, 3, 0.01, {}))
+    write_cases(extra, "loop_golden_extra.npz")
+
+
+def write_cases(cases, fname):
+    store = {}
     for name, cls, g, ns, no, S_, mi, thr, kw in cases:
         res = run_case(name, cls, g, ns, no, S_, mi, thr, **kw)
         print(name, "k =", res["float64"]["k"], "out[0] shape", res["float64"]["outs"][0].shape)
@@ -158,8 +192,8 @@ def main():
         netlist = kw.get("lgnn_layers") or [(ns, no)]
         flatten(f"{name}/nets", [dict(state=(s_ if isinstance(s_, list) else [s_]), out=o_) for s_, o_ in netlist], store)
         flatten(f"{name}/cfg", dict(S=S_, max_iteration=mi, thr=thr), store)
-    np.savez_compressed(os.path.join(HERE, "loop_golden.npz"), **store)
-    print("wrote", os.path.join(HERE, "loop_golden.npz"), len(store), "arrays")
+    np.savez_compressed(os.path.join(HERE, fname), **store)
+    print("wrote", os.path.join(HERE, fname), len(store), "arrays")
 
 
 if __name__ == "__main__":

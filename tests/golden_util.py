@@ -6,8 +6,15 @@ import numpy as np
 from oracle import structures as S
 
 _G = os.path.join(os.path.dirname(__file__), "golden", "loop_golden.npz")
+_GX = os.path.join(os.path.dirname(__file__), "golden", "loop_golden_extra.npz")
 CASES = ["graph_S0_bn", "node_S5", "arc_S4_bn", "composite_S6", "lgnn3_S0_bn"]
-KIND = {"graph_S0_bn": "graph", "node_S5": "node", "arc_S4_bn": "arc", "composite_S6": "graph", "lgnn3_S0_bn": "graph"}
+# second file from the same generator: pins the CPU oracle on more of the reference's code paths ('normalized' and
+# 'sum' aggregation, hidden layers, three node types, state_vect_dim 0 with arc focus); the CUDA path is compared with
+# the oracle on such configurations by the property sweeps, the golden GPU test keeps to CASES
+EXTRA_CASES = ["node_S0_normalized_bn", "graph_S3_sum_hidden", "composite3_node_S4_bn", "arc_S0_sum"]
+KIND = {"graph_S0_bn": "graph", "node_S5": "node", "arc_S4_bn": "arc", "composite_S6": "graph", "lgnn3_S0_bn": "graph",
+        "node_S0_normalized_bn": "node", "graph_S3_sum_hidden": "graph", "composite3_node_S4_bn": "node",
+        "arc_S0_sum": "arc"}
 
 
 def _unflatten(store, prefix):
@@ -20,7 +27,7 @@ def _unflatten(store, prefix):
 
 
 def load(case):
-    store = np.load(_G, allow_pickle=False)
+    store = np.load(_GX if case in EXTRA_CASES else _G, allow_pickle=False)
     d = _unflatten(store, case)
     gd = d["graph"]
     tm = gd["type_mask"]

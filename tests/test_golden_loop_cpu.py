@@ -8,14 +8,14 @@ from oracle import loop_numpy as LN
 from oracle import loop_torch as LT
 from oracle.adapt import copy_net
 
-from golden_util import CASES, KIND, load
+from golden_util import CASES, EXTRA_CASES, KIND, load
 
 
 def _rel(a, b):
     return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-30))
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + EXTRA_CASES)
 def test_oracle_forward_matches_reference_code(case):
     g, layers, cfg, ref = load(case)
     r64 = ref["float64"]
@@ -43,7 +43,7 @@ def test_oracle_forward_matches_reference_code(case):
     assert _rel(out, r64["outs"][0]) < 1e-9
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + EXTRA_CASES)
 def test_oracle_gradients_match_reference_code(case):
     g, layers, cfg, ref = load(case)
     r64 = ref["float64"]
