@@ -23,7 +23,7 @@ def make_graphs(focus, n_graphs, seed, composite=False, masked=False):
         sm = om = None
         if masked and focus != "g":
             sm, om = rng.random(n_mask) < 0.7, rng.random(n_mask) < 0.7
-        n_t = 1 if focus == "g" else n_mask
+        n_t = 1 if focus == "g" else (n_mask if om is None else int(om.sum()))   # one target row per output-masked row
         kw = dict(nodes=rng.random((n, 4)), arcs=arcs, targets=rng.random((n_t, 2)), focus=focus, set_mask=sm,
                   output_mask=om, sample_weight=float(rng.integers(1, 4)))
         if composite:
@@ -88,3 +88,57 @@ def test_sequencer_geometry_and_errors():
         seq.store.assemble([10])
     with pytest.raises(ValueError):
         GraphStore(graphs + make_graphs("n", 1, seed=1), device="cpu")
+
+
+class _CheckingDeviceGraph:
+    """Stand-in for op.DeviceGraph on a machine without a GPU: applies the argument checks of the real constructor
+    (dtype, contiguity, lengths - everything except 'lives on the GPU') and records what it was given."""
+
+    def __init__(self, src, dst, n_nodes, aggregation_mode="sum", node2graph=None, n_graphs=0, nodegraph_values=None,
+                 set_mask=None, output_mask=None, type_mask=None, arc_values=None, mask_len=None):
+        def req(t, dtype):
+            assert t.dtype == dtype and t.is_contiguous(), (t.dtype, dtype, t.is_contiguous())
+        req(src, torch.int32), req(dst, torch.int32)
+        assert src.numel() == dst.numel() and (src.numel() == 0 or int(max(src.max(), dst.max())) < n_nodes)
+        if node2graph is not None and n_graphs > 0:
+            req(node2graph, torch.int32)
+            assert node2graph.numel() == n_nodes and int(node2graph.max()) < n_graphs
+            if nodegraph_values is not None:
+                req(nodegraph_values, torch.float32)
+        ml = n_nodes if mask_len is None else int(mask_len)
+        for m in (set_mask, output_mask):
+            if m is not None:
+                req(m, torch.uint8)
+                assert m.numel() == ml
+        self.n_types = 0
+        if type_mask is not None:
+            req(type_mask, torch.uint8)
+            assert type_mask.dim() == 2 and type_mask.shape[1] == n_nodes
+            self.n_types = int(type_mask.shape[0])
+        assert arc_values is None
+        self.src, self.dst, self.n_nodes, self.n_graphs = src, dst, n_nodes, n_graphs
+        self.aggregation_mode, self.mask_len = aggregation_mode, ml
+
+
+@pytest.mark.parametrize("focus,composite,masked", [("g", False, False), ("n", False, True), ("a", False, True),
+                                                    ("g", True, False), ("n", True, True)])
+def test_batch_hands_the_library_well_formed_arguments(monkeypatch, focus, composite, masked):
+    import gnnkeras_b200.op as op
+    monkeypatch.setattr(op, "DeviceGraph", _CheckingDeviceGraph)
+    graphs = make_graphs(focus, 9, seed=21, composite=composite, masked=masked)
+    mode = "composite_average" if composite else "average"
+    seq = DeviceMultiGraphSequencer(GraphStore(graphs, device="cpu"), focus, mode, batch_size=4, shuffle=False)
+    for i in range(len(seq)):
+        out, targets, sw = seq[i]
+        ids = seq.batch_ids(i)
+        ref = (CompositeGraphObject if composite else GraphObject).merge([graphs[j] for j in ids], focus, mode)
+        g = seq.get_batch(i)[0]
+        assert len(out) == (10 if composite else 8)                       # GraphSequencers.py:109-120 / 240-244
+        assert np.array_equal(g.graph.src.numpy(), ref.arcs[:, 0].astype(np.int32))
+        assert np.array_equal(g.graph.dst.numpy(), ref.arcs[:, 1].astype(np.int32))
+        assert g.graph.mask_len == len(ref.set_mask) and g.graph.aggregation_mode == mode
+        if focus == "g" or not masked:
+            assert np.array_equal(targets.numpy(), ref.targets)
+        else:                                                              # tf.boolean_mask(set_mask, output_mask) rows
+            keep = ref.set_mask[ref.output_mask]
+            assert np.array_equal(targets.numpy(), ref.targets[keep]) and sw.shape[0] == int(keep.sum())
