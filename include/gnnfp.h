@@ -162,8 +162,9 @@ typedef struct gnnfp_loop_cfg {
   int32_t want_input_grads; /* bit0 d_nodes, bit1 d_arc_labels, bit2 d_state0 (LGNN chaining)   */
   int32_t n_active_rows;    /* 0 = all nodes.  >0: net_state runs on rows [0, n_active_rows) only; the
                                remaining rows are halo copies of remote nodes that the multi-GPU driver
-                               refreshes between iterations (edge-cut partition, homogeneous, no BN,
-                               inference).                                                          */
+                               refreshes between iterations (edge-cut partition; homogeneous, no BN;
+                               inference, and training with a single-Dense-layer net_state through
+                               gnnfp_loop_backward_step).                                           */
 } gnnfp_loop_cfg;
 
 int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const gnnfp_loop_cfg* cfg,
