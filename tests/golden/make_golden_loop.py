@@ -52,7 +52,7 @@ def sequencer_tuple(g, dtype, composite=False):
     return out
 
 
-def run_case(name, cls, g, ns, no, S_, max_it, thr, composite=False, lgnn_layers=None):
+def run_case(name, cls, g, ns, no, S_, max_it, thr, composite=False, lgnn_layers=None, training=True):
     res = {}
     for fx, dt in (("float64", torch.float64), ("float32", torch.float32)):
         tf.set_floatx(fx)
@@ -61,7 +61,10 @@ def run_case(name, cls, g, ns, no, S_, max_it, thr, composite=False, lgnn_layers
         if lgnn_layers is None:
             tns = [tf.net_from_dict(n, dt) for n in ns] if composite else tf.net_from_dict(ns, dt)
             model = cls(tns, tf.net_from_dict(no, dt), S_, max_it, thr)
-            k, state, out = model(sequencer_tuple(g, dt, composite), training=True)
+            if training:
+                k, state, out = model(sequencer_tuple(g, dt, composite), training=True)
+            else:   # call() returns only `out` in inference (GNN.py:176-177): take (k, state, out) from Loop itself
+                k, state, out = model.Loop(*model.process_inputs(sequencer_tuple(g, dt, composite)), training=False)
             outs = [out]
             wS = [v for n in (tns if composite else [tns]) for v in n.trainable_variables]
             wO = model.net_output.trainable_variables
@@ -175,6 +178,16 @@ def main():
     g = ograph_from_batch(b, "a", "sum")
     ns, no = nets(14, 3, 3, 0, "arc", False, "tanh")
     extra.append(("arc_S0_sum", GNNarcBased, g, ns, no, 0, 3, 0.01, {}))
+    # E5 / E6. inference mode (BatchNormalization on its moving statistics, MLP.py:12-78 + Keras BN semantics)
+    b = mutag_shaped_batch(6, seed=15)
+    g = ograph_from_batch(b, "g", "average")
+    ns, no = nets(14, 3, 2, 0, "graph", True, "selu")
+    extra.append(("graph_S0_bn_infer", GNNgraphBased, g, ns, no, 0, 5, 0.01, {"training": False}))
+    b = mutag_shaped_batch(5, seed=16)
+    b.output_mask = rng.random(b.n_nodes) < 0.6
+    g = ograph_from_batch(b, "n", "average")
+    ns, no = nets(14, 3, 2, 5, "node", True, "tanh")
+    extra.append(("node_S5_bn_infer", GNNnodeBased, g, ns, no, 5, 4, 0.01, {"training": False}))
     write_cases(extra, "loop_golden_extra.npz")
 
 
@@ -191,7 +204,10 @@ def write_cases(cases, fname):
                                       dim_node_label=g.dim_node_label), store)
         netlist = kw.get("lgnn_layers") or [(ns, no)]
         flatten(f"{name}/nets", [dict(state=(s_ if isinstance(s_, list) else [s_]), out=o_) for s_, o_ in netlist], store)
-        flatten(f"{name}/cfg", dict(S=S_, max_iteration=mi, thr=thr), store)
+        cfg = dict(S=S_, max_iteration=mi, thr=thr)
+        if not kw.get("training", True):
+            cfg["training"] = 0
+        flatten(f"{name}/cfg", cfg, store)
     np.savez_compressed(os.path.join(HERE, fname), **store)
     print("wrote", os.path.join(HERE, fname), len(store), "arrays")
 

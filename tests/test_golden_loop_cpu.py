@@ -36,7 +36,8 @@ def test_oracle_forward_matches_reference_code(case):
         k, state, out = LN.loop_composite(g, [copy_net(n) for n in layers[0]["state"]], copy_net(layers[0]["out"]), S_, mi, thr,
                                           True, s0, np.float64, kind)
     else:
-        k, state, out = LN.loop_homogeneous(g, copy_net(layers[0]["state"][0]), copy_net(layers[0]["out"]), S_, mi, thr, True,
+        k, state, out = LN.loop_homogeneous(g, copy_net(layers[0]["state"][0]), copy_net(layers[0]["out"]), S_, mi, thr,
+                                            bool(cfg.get("training", 1)),
                                             s0, np.float64, kind)
     assert float(k) == float(r64["k"][0])
     assert _rel(state, r64["states"][0]) < 1e-9
@@ -67,7 +68,7 @@ def test_oracle_gradients_match_reference_code(case):
             params = [p for n in tns for p in LT.trainable(n)] + LT.trainable(tno)
         else:
             tns, tno = LT.net_to_torch(layers[0]["state"][0], dt), LT.net_to_torch(layers[0]["out"], dt)
-            k, state, out = LT.loop_homogeneous(tg, nodes, arcs, tns, tno, S_, mi, thr, True, s0, kind)
+            k, state, out = LT.loop_homogeneous(tg, nodes, arcs, tns, tno, S_, mi, thr, bool(cfg.get("training", 1)), s0, kind)
             params = LT.trainable(tns) + LT.trainable(tno)
         outs = [out]
     loss = sum((o * torch.tensor(r, dtype=dt)).sum() for o, r in zip(outs, r64["rws"]))
