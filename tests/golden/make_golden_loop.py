@@ -25,6 +25,7 @@ import tensorflow as tf                                   # the shim
 from GNN.Models.GNN import GNNnodeBased, GNNarcBased, GNNgraphBased            # reference, unmodified
 from GNN.Models.CompositeGNN import CompositeGNNnodeBased, CompositeGNNgraphBased
 from GNN.Models.LGNN import LGNN
+from GNN.Models.CompositeLGNN import CompositeLGNN
 from gnnkeras_b200.synthetic import make_net, mutag_shaped_batch
 from oracle.adapt import ograph_from_batch
 
@@ -69,10 +70,16 @@ def run_case(name, cls, g, ns, no, S_, max_it, thr, composite=False, lgnn_layers
             wS = [v for n in (tns if composite else [tns]) for v in n.trainable_variables]
             wO = model.net_output.trainable_variables
         else:
-            gnns = [cls(tf.net_from_dict(s_, dt), tf.net_from_dict(o_, dt), S_, max_it, thr) for s_, o_ in lgnn_layers]
-            model = LGNN(gnns, True, True)
-            k, state, outs = model(sequencer_tuple(g, dt), training=True)
-            wS = [v for gn in gnns for v in gn.net_state.trainable_variables]
+            if composite:      # one net_state per node type and layer (CompositeGNN.py:26-60), CompositeLGNN.py:25-57
+                gnns = [cls([tf.net_from_dict(n, dt) for n in s_], tf.net_from_dict(o_, dt), S_, max_it, thr) for s_, o_ in lgnn_layers]
+                model = CompositeLGNN(gnns, True, True)
+                k, state, outs = model(sequencer_tuple(g, dt, True), training=True)
+                wS = [v for gn in gnns for n in gn.net_state for v in n.trainable_variables]
+            else:
+                gnns = [cls(tf.net_from_dict(s_, dt), tf.net_from_dict(o_, dt), S_, max_it, thr) for s_, o_ in lgnn_layers]
+                model = LGNN(gnns, True, True)
+                k, state, outs = model(sequencer_tuple(g, dt), training=True)
+                wS = [v for gn in gnns for v in gn.net_state.trainable_variables]
             wO = [v for gn in gnns for v in gn.net_output.trainable_variables]
         rng = np.random.default_rng(7)
         loss = 0
@@ -188,6 +195,14 @@ def main():
     g = ograph_from_batch(b, "n", "average")
     ns, no = nets(14, 3, 2, 5, "node", True, "tanh")
     extra.append(("node_S5_bn_infer", GNNnodeBased, g, ns, no, 5, 4, 0.01, {"training": False}))
+    # E7. CompositeLGNN: 2 graph-focused composite layers, 2 node types, S=4, get_state & get_output (labels of layer 1 =
+    #     [state | scattered output | labels], every type's width grows by S + T: LGNN.py:175-214)
+    b = mutag_shaped_batch(5, seed=17, n_types=2)
+    g = ograph_from_batch(b, "g", "composite_average", dim_node_label=[14, 9])
+    layers, add = [], 4 + 2
+    layers.append(nets(14, 3, 2, 4, "graph", True, "tanh", n_types=2, dnl=[14, 9]))
+    layers.append(nets(14 + add, 3, 2, 4, "graph", True, "tanh", n_types=2, dnl=[14 + add, 9 + add]))
+    extra.append(("clgnn2_S4_bn", CompositeGNNgraphBased, g, None, None, 4, 3, 0.01, {"lgnn_layers": layers, "composite": True}))
     write_cases(extra, "loop_golden_extra.npz")
 
 

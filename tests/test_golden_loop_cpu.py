@@ -23,10 +23,12 @@ def test_oracle_forward_matches_reference_code(case):
     kind = KIND[case]
     composite = g.type_mask is not None
     draws = r64["draws"]
-    if case.startswith("lgnn"):
-        specs = [{"net_state": copy_net(L["state"][0]), "net_output": copy_net(L["out"]), "state_vect_dim": S_,
+    if "lgnn" in case:
+        st = (lambda L: [copy_net(n) for n in L["state"]]) if composite else (lambda L: copy_net(L["state"][0]))
+        specs = [{"net_state": st(L), "net_output": copy_net(L["out"]), "state_vect_dim": S_,
                   "max_iteration": mi, "state_threshold": thr, "kind": kind} for L in layers]
-        K, states, outs = LN.loop_lgnn(g, specs, True, True, training=True, dtype=np.float64)
+        K, states, outs = LN.loop_lgnn(g, specs, True, True, training=True, state0s=list(draws) if S_ else None,
+                                       dtype=np.float64, composite=composite)
         assert [float(k) for k in K] == list(r64["k"])
         for a, b in zip(states, r64["states"]): assert _rel(a, b) < 1e-9
         for a, b in zip(outs, r64["outs"]): assert _rel(a, b) < 1e-9
@@ -54,11 +56,14 @@ def test_oracle_gradients_match_reference_code(case):
     dt = torch.float64
     tg = LT.TorchGraph(g, dt)
     nodes, arcs = torch.tensor(g.nodes, dtype=dt), torch.tensor(g.arcs, dtype=dt)
-    if case.startswith("lgnn"):
-        specs = [{"net_state": LT.net_to_torch(L["state"][0], dt), "net_output": LT.net_to_torch(L["out"], dt),
+    if "lgnn" in case:
+        st = (lambda L: [LT.net_to_torch(n, dt) for n in L["state"]]) if composite else (lambda L: LT.net_to_torch(L["state"][0], dt))
+        specs = [{"net_state": st(L), "net_output": LT.net_to_torch(L["out"], dt),
                   "state_vect_dim": S_, "max_iteration": mi, "state_threshold": thr, "kind": kind} for L in layers]
-        K, states, outs = LT.loop_lgnn(tg, nodes, arcs, specs, True, True, True, None)
-        params = [p for s in specs for p in LT.trainable(s["net_state"])] + [p for s in specs for p in LT.trainable(s["net_output"])]
+        s0s = [torch.tensor(d, dtype=dt) for d in r64["draws"]] if S_ else None
+        K, states, outs = LT.loop_lgnn(tg, nodes, arcs, specs, True, True, True, s0s, composite=composite)
+        per_layer = lambda s: [p for n in s["net_state"] for p in LT.trainable(n)] if composite else LT.trainable(s["net_state"])
+        params = [p for s in specs for p in per_layer(s)] + [p for s in specs for p in LT.trainable(s["net_output"])]
     else:
         s0 = torch.tensor(r64["draws"][0], dtype=dt) if S_ else None
         if composite:
