@@ -203,6 +203,17 @@ def main():
     layers.append(nets(14, 3, 2, 4, "graph", True, "tanh", n_types=2, dnl=[14, 9]))
     layers.append(nets(14 + add, 3, 2, 4, "graph", True, "tanh", n_types=2, dnl=[14 + add, 9 + add]))
     extra.append(("clgnn2_S4_bn", CompositeGNNgraphBased, g, None, None, 4, 3, 0.01, {"lgnn_layers": layers, "composite": True}))
+    # E8. LGNN, 2 node-focused layers with masks, S=3: update_graph scatters the masked rows' outputs back to their nodes
+    #     (tf.scatter_nd, LGNN.py:195-210) and every layer draws its own initial state (GNN.py:257)
+    b = mutag_shaped_batch(5, seed=18)
+    b.set_mask = rng.random(b.n_nodes) < 0.8
+    b.output_mask = rng.random(b.n_nodes) < 0.7
+    g = ograph_from_batch(b, "n", "average")
+    layers, nl = [], 14
+    for _ in range(2):
+        layers.append(nets(nl, 3, 2, 3, "node", False, "tanh"))
+        nl = nl + 3 + 2
+    extra.append(("lgnn2_node_S3_masks", GNNnodeBased, g, None, None, 3, 3, 0.01, {"lgnn_layers": layers}))
     write_cases(extra, "loop_golden_extra.npz")
 
 

@@ -12,11 +12,11 @@ CASES = ["graph_S0_bn", "node_S5", "arc_S4_bn", "composite_S6", "lgnn3_S0_bn"]
 # 'sum' aggregation, hidden layers, three node types, state_vect_dim 0 with arc focus); the CUDA path is compared with
 # the oracle on such configurations by the property sweeps, the golden GPU test keeps to CASES
 EXTRA_CASES = ["node_S0_normalized_bn", "graph_S3_sum_hidden", "composite3_node_S4_bn", "arc_S0_sum",
-               "graph_S0_bn_infer", "node_S5_bn_infer", "clgnn2_S4_bn"]
+               "graph_S0_bn_infer", "node_S5_bn_infer", "clgnn2_S4_bn", "lgnn2_node_S3_masks"]
 KIND = {"graph_S0_bn": "graph", "node_S5": "node", "arc_S4_bn": "arc", "composite_S6": "graph", "lgnn3_S0_bn": "graph",
         "node_S0_normalized_bn": "node", "graph_S3_sum_hidden": "graph", "composite3_node_S4_bn": "node",
         "arc_S0_sum": "arc", "graph_S0_bn_infer": "graph", "node_S5_bn_infer": "node",
-        "clgnn2_S4_bn": "graph"}
+        "clgnn2_S4_bn": "graph", "lgnn2_node_S3_masks": "node"}
 
 
 def _unflatten(store, prefix):
