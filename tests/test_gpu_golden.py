@@ -8,7 +8,7 @@ import torch
 from gnnkeras_b200 import models as M
 from gnnkeras_b200.op import Net
 
-from golden_util import CASES, KIND, load
+from golden_util import CASES, EXTRA_CASES, KIND, load
 from test_gpu_models import gt_from_ograph
 from util import DEV, relerr, run_cuda
 
@@ -20,7 +20,8 @@ def _ok(a, b64, b32):
     return e <= max(2e-5, 8 * e32), (e, e32)
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if not c.startswith("lgnn")])
+# UNTESTED draft (round-2 prep): the CPU-only extra goldens (training and inference) through the CUDA path as well
+@pytest.mark.parametrize("case", [c for c in CASES + EXTRA_CASES if "lgnn" not in c])
 def test_cuda_matches_reference_code_goldens(case):
     g, layers, cfg, ref = load(case)
     r64, r32 = ref["float64"], ref["float32"]
@@ -32,10 +33,13 @@ def test_cuda_matches_reference_code_goldens(case):
     ns = [f32(n) for n in layers[0]["state"]] if composite else f32(layers[0]["state"][0])
     no = f32(layers[0]["out"])
     s0 = r64["draws"][0].astype(np.float32) if S_ else None
-    plan, nets, onet, (k, state, out) = run_cuda(g, ns, no, S_, mi, thr, True, s0, kind)
+    training = bool(cfg.get("training", 1))
+    plan, nets, onet, (k, state, out) = run_cuda(g, ns, no, S_, mi, thr, training, s0, kind)
     assert float(k.item()) == float(r64["k"][0])
     ok, info = _ok(state.cpu().numpy(), r64["states"][0], r32["states"][0]); assert ok, info
     ok, info = _ok(out.cpu().numpy(), r64["outs"][0], r32["outs"][0]); assert ok, info
+    if not training:
+        return
     gs, go, *_ = plan.backward(torch.as_tensor(r64["rws"][0].astype(np.float32)).to(DEV), None, None, False)
     torch.cuda.synchronize()
     mine = [t for n in gs for t in n] + list(go)

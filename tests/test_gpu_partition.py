@@ -17,14 +17,14 @@ from util import DEV, relerr, run_cuda
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,mode,thr", [(2, "average", 0.01), (3, "sum", 0.05)])
-def test_partitioned_matches_global(world, mode, thr):
+@pytest.mark.parametrize("world,mode,thr,dim", [(2, "average", 0.01, 8), (3, "sum", 0.05, 8), (2, "average", 0.01, 32)])
+def test_partitioned_matches_global(world, mode, thr, dim):
     rng = np.random.default_rng(5)
     b = random_graph(3000, 24000, seed=7, dim_node_label=6, dim_arc_label=2, dim_target=3, locality=0.7, band=200)
     b.output_mask = rng.random(b.n_nodes) < 0.5
     g = S.make_graph(b.nodes, b.arcs, b.targets, focus="n", set_mask=b.set_mask, output_mask=b.output_mask,
                      aggregation_mode=mode)
-    S_, D_ = 8, 8
+    S_, D_ = dim, dim            # dim 32 = BASELINE configs[4] (state_dim 32)
     scale = 0.4 if mode == "average" else 0.05
     ns = make_net(rng, 2 * D_ + 2 * 6 + 2, [D_], ["tanh"], False, scale)
     no = make_net(rng, D_ + 6, [3], ["softmax"], False)
@@ -73,8 +73,8 @@ def test_partitioned_matches_global(world, mode, thr):
     assert relerr(np.concatenate(states), state.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("world,mode", [(2, "average"), (3, "sum")])
-def test_partitioned_backward_matches_global(world, mode):
+@pytest.mark.parametrize("world,mode,dim", [(2, "average", 8), (3, "sum", 8), (2, "average", 32)])
+def test_partitioned_backward_matches_global(world, mode, dim):
     """BPTT on the partitioned graph (stepping backward C ABI + reverse halo reduction between iterations): the
     parameter gradients summed over the ranks equal the unpartitioned CUDA backward and the fp64 oracle."""
     from test_gpu_backward import oracle_grads
@@ -83,7 +83,7 @@ def test_partitioned_backward_matches_global(world, mode):
     b.output_mask = rng.random(b.n_nodes) < 0.5
     g = S.make_graph(b.nodes, b.arcs, b.targets, focus="n", set_mask=b.set_mask, output_mask=b.output_mask,
                      aggregation_mode=mode)
-    S_, D_, MI, thr = 8, 8, 4, 0.0
+    S_, D_, MI, thr = dim, dim, 4, 0.0
     scale = 0.4 if mode == "average" else 0.05
     ns = make_net(rng, 2 * D_ + 2 * 6 + 2, [D_], ["tanh"], False, scale)
     no = make_net(rng, D_ + 6, [3], ["softmax"], False)
