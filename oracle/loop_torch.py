@@ -131,6 +131,7 @@ class TorchGraph:
         if g.n_graphs > 0:
             self.nodegraph = SparseT(np.arange(N), g.node2graph, g.nodegraph_values, g.n_graphs, N, dtype, fast)
         self.mask = torch.as_tensor(np.logical_and(g.set_mask, g.output_mask))
+        self.trace = None              # tests may set a list: every iteration's new state is appended (detached)
         self.comp_adj = None
         if g.type_mask is not None:
             self.type_mask = torch.as_tensor(g.type_mask.transpose().copy())
@@ -155,6 +156,8 @@ def loop_homogeneous(tg, nodes, arcs, net_state, net_output, state_vect_dim, max
         agg_states = tg.adj.mm(state)
         inp = torch.cat(comps + [agg_states, agg_nodes, agg_arcs], dim=1)
         state_new = mlp_forward(net_state, inp, training)
+        if tg.trace is not None:
+            tg.trace.append(state_new.detach())
         k, state, state_old = k + 1, state_new, state
     sc = torch.cat([state, nodes], dim=1) if state_vect_dim else state
     if kind == "arc":

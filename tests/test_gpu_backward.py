@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 
 
 def oracle_grads(g, ns, no, S_, max_it, thr, s0, kind, r_out, r_state, dtype, average=False, composite=False,
-                 want_inputs=False):
+                 want_inputs=False, trace=None):
     tg = LT.TorchGraph(g, dtype)
+    tg.trace = trace
     tns = [LT.net_to_torch(n, dtype) for n in ns] if composite else LT.net_to_torch(ns, dtype)
     tno = LT.net_to_torch(no, dtype)
     nodes = torch.tensor(g.nodes, dtype=dtype, requires_grad=want_inputs)

@@ -29,9 +29,16 @@ def test_c2_shaped_lgnn5_train_step():
 
 
 @pytest.mark.parametrize("NL,bn,act,kind", [(62, True, "selu", "graph"), (78, True, "selu", "graph"),
+                                            (62, True, "tanh", "graph"), (78, True, "sigmoid", "graph"),
                                             (78, False, "tanh", "node"), (70, True, "tanh", "node")])
 def test_wide_state_forward_backward(NL, bn, act, kind):
-    """One GNN whose state is as wide as C2's last layers (state0 = the node labels, dense random)."""
+    """One GNN whose state is as wide as C2's last layers (state0 = the node labels, dense random).
+
+    selu has a kink at 0 (slope 1.758 -> 1.051): a pre-activation within rounding distance of 0 can land on the other
+    side in any fp32 implementation (the fp32 oracle shows the same sporadic 1e-4 .. 1e-3 gradient deviations from the
+    fp64 oracle, scratch measurement over seeds), and ONE flipped element moves a weight gradient by ~1e-3 of its
+    max-norm at this batch size.  Like threshold ties of the iteration count, such kink ties are counted from the fp64
+    oracle's own states and reported; the flat tolerance applies whenever there is none."""
     b = mutag_shaped_batch(260, seed=31)
     rng = np.random.default_rng(17)
     b.nodes = (0.5 * rng.standard_normal((b.n_nodes, NL))).astype(np.float32)
@@ -52,13 +59,19 @@ def test_wide_state_forward_backward(NL, bn, act, kind):
     r_state = rng.standard_normal((g.n_nodes, NL)).astype(np.float32)
     gs, go, d_nodes, _, _ = plan.backward(torch.as_tensor(r_out).to(DEV), None, torch.as_tensor(r_state).to(DEV), False)
     torch.cuda.synchronize()
-    _, gs64, go64, gi64, _, _ = oracle_grads(g, ns, no, 0, MI, 0.01, None, kind, r_out, r_state, torch.float64, want_inputs=True)
+    trace = []
+    _, gs64, go64, gi64, _, _ = oracle_grads(g, ns, no, 0, MI, 0.01, None, kind, r_out, r_state, torch.float64, want_inputs=True, trace=trace)
     _, gs32, go32, gi32, _, _ = oracle_grads(g, ns, no, 0, MI, 0.01, None, kind, r_out, r_state, torch.float32, want_inputs=True)
+    # kink ties: selu outputs within 1e-5 * slope of 0 in the fp64 run (|z| < ~1e-5: 3xTF32 rounding distance at K = 160)
+    ties = int(sum(int((st.abs() < 1.76e-5).sum()) for st in trace)) if act in ("selu", "relu") else 0
+    if ties:
+        print(f"kink ties (|selu output| < 1.76e-5 in the fp64 oracle): {ties}")
+    allow = 2e-3 * ties
     for a, b64, b32 in zip(gs[0] + go, gs64[0] + go64, gs32[0] + go32):
         e, e32 = relerr(a.cpu().numpy(), b64), relerr(b32, b64)
-        assert e <= max(2e-5, 8 * e32), (e, e32, tuple(a.shape))
+        assert e <= max(2e-5, 8 * e32, allow), (e, e32, ties, tuple(a.shape))
     e, e32 = relerr(d_nodes.cpu().numpy(), gi64[0]), relerr(gi32[0], gi64[0])
-    assert e <= max(2e-5, 8 * e32), (e, e32)
+    assert e <= max(2e-5, 8 * e32, allow), (e, e32, ties)
 
 
 @pytest.mark.parametrize("n_types", [1, 2])
@@ -74,11 +87,13 @@ def test_c3_shaped_clgnn_shared_output_net(n_types):
     _, no = nets_for(rng, 14, AL, T, S_, "graph", True, "selu", (), n_types=n_types, dnl=dnl0)     # Dense(10 -> 2), shared
     specs, dnl, nl = [], list(dnl0), 14
     for _ in range(layers):
-        ns, _ = nets_for(rng, nl, AL, T, S_, "graph", True, "selu", (), n_types=n_types, dnl=dnl, scale=0.6)
+        # update_graph prepends [state | out] to the ORIGINAL labels (LGNN.py:195-210): every layer after the first sees
+        # 14 + S + T columns, while dim_node_label keeps accumulating (LGNN.py:212) and nodes[:, :d] clamps
+        ns, _ = nets_for(rng, nl, AL, T, S_, "graph", True, "selu", (), n_types=n_types, dnl=[min(d, nl) for d in dnl], scale=0.6)
         specs.append({"net_state": ns, "net_output": no, "state_vect_dim": S_, "max_iteration": MI,
                       "state_threshold": 0.01, "kind": "graph"})
         add = S_ + T
-        nl, dnl = nl + add, [d + add for d in dnl]
+        nl, dnl = 14 + add, [d + add for d in dnl]
     s0s = [(0.1 * rng.standard_normal((g.n_nodes, S_))).astype(np.float32) for _ in range(layers)]
 
     def oracle(dtype):
