@@ -198,6 +198,9 @@ struct DzArgs {             // dz[i] = act'(s_t[i]) * G_t[i],  G_t = last ? dSfi
   const int* last_flag;    // G = dSfin iff last_flag == NULL || *last_flag == 0
   int always_last;
   float* dz;               // [N, D] by global row id
+  int ldg;                 // leading dimension of dSfin / dOwn / dAgg / dz / pre (0 = D)
+  int ld_agg;              // leading dimension of agg_next (0 = D)
+  int ld_dz;               // leading dimension of dz (0 = ldg)
   const float* pre;        // optional [N, D]: Adj . dAgg already gathered (partitioned graphs) - replaces the CSR gather
   const int* gate;
   // BN training (homogeneous nets): constants [c0|c1|rstd|-mean*rstd] x in_dim of iteration t+1 and its saved Adj^T.s

@@ -728,11 +728,12 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
   if (a.gate && *a.gate == 0) return;
   const bool last = a.always_last || a.last_flag == nullptr || *a.last_flag == 0;
   const int nq = a.D / VEC;
+  const int ldg = a.ldg ? a.ldg : a.D, lda = a.ld_agg ? a.ld_agg : a.D, ldz = a.ld_dz ? a.ld_dz : ldg;
   const long long items = (long long)a.n_rows * nq;
   for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(it / nq), q = (int)(it - (long long)r * nq);
     const int gr = a.rowlist ? a.rowlist[r] : r;
-    const size_t o = (size_t)gr * a.D + q * VEC;
+    const size_t o = (size_t)gr * ldg + q * VEC;
     float g[VEC], yv[VEC];
     load_vec<VEC>(a.s_t + (size_t)gr * a.ld_s + q * VEC, yv);
     if (last) {
@@ -765,9 +766,9 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
           const bool ok = p + u < a1;
           const int pi = ok ? p + u : p;
           wv[u] = ok ? (a.wgt ? a.wgt[pi] : 1.0f) : 0.0f;
-          const size_t so = (size_t)a.idx[pi] * a.D + q * VEC;
+          const size_t so = (size_t)a.idx[pi] * ldg + q * VEC;
           load_vec<VEC>(a.dAgg + so, t[u]);
-          if (cn) load_vec<VEC>(a.agg_next + so, xg[u]);
+          if (cn) load_vec<VEC>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC, xg[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -782,7 +783,7 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
       }
     }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) a.dz[o + v] = act_bwd(a.act, yv[v], g[v]);
+    for (int v = 0; v < VEC; ++v) a.dz[(size_t)gr * ldz + q * VEC + v] = act_bwd(a.act, yv[v], g[v]);
   }
 }
 
@@ -790,8 +791,12 @@ int launch_dz(const DzArgs& a, cudaStream_t s) {
   if (a.n_rows <= 0) return GNNFP_OK;
   auto al = [&](const void* p, int m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
   int vec = 1;
-  if (a.D % 4 == 0 && a.ld_s % 4 == 0 && al(a.s_t, 16) && al(a.dSfin, 16) && al(a.dOwn, 16) && al(a.dAgg, 16) && al(a.dz, 16)) vec = 4;
-  else if (a.D % 2 == 0 && a.ld_s % 2 == 0 && al(a.s_t, 8) && al(a.dSfin, 8) && al(a.dOwn, 8) && al(a.dAgg, 8) && al(a.dz, 8)) vec = 2;
+  const int ldg = a.ldg ? a.ldg : a.D, lda = a.ld_agg ? a.ld_agg : a.D;
+  const int ldz = a.ld_dz ? a.ld_dz : ldg;
+  const bool g4 = ldg % 4 == 0 && ldz % 4 == 0 && (!a.agg_next || (lda % 4 == 0 && al(a.agg_next, 16))) && (!a.pre || al(a.pre, 16));
+  const bool g2 = ldg % 2 == 0 && ldz % 2 == 0 && (!a.agg_next || (lda % 2 == 0 && al(a.agg_next, 8))) && (!a.pre || al(a.pre, 8));
+  if (g4 && a.D % 4 == 0 && a.ld_s % 4 == 0 && al(a.s_t, 16) && al(a.dSfin, 16) && al(a.dOwn, 16) && al(a.dAgg, 16) && al(a.dz, 16)) vec = 4;
+  else if (g2 && a.D % 2 == 0 && a.ld_s % 2 == 0 && al(a.s_t, 8) && al(a.dSfin, 8) && al(a.dOwn, 8) && al(a.dAgg, 8) && al(a.dz, 8)) vec = 2;
   const long long items = (long long)a.n_rows * (a.D / vec);
   long long blocks = (items + 255) / 256;
   static int occ[3] = {0, 0, 0};                      // resident blocks per SM: the grid is a whole number of waves

@@ -12,6 +12,7 @@
 
 #include "loop.h"
 #include "tile.cuh"
+#include "rows_tma.h"
 
 // ---- error / misc -------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -104,13 +105,14 @@ __device__ __forceinline__ int count_k(const int* flags, int max_iter) {
 }
 
 // state_out = S_k ; k_out = k
+// slot_mode: 0 = slot k-1 (training), 1 = slot k&1 (inference), 2 = slot k (interleaved layout, training)
 static __global__ void k_finalize(const int* flags, int max_iter, const float* s0, int ld0, const float* slots,
-                                  size_t slot_stride, int training, int n, int D, float* state_out, int* k_out) {
+                                  size_t slot_stride, int slot_mode, int ld_slot, int n, int D, float* state_out, int* k_out) {
   const int k = count_k(flags, max_iter);
   const float* src;
   int ld;
   if (k == 0) { src = s0; ld = ld0; }
-  else { src = slots + (training ? (size_t)(k - 1) : (size_t)(k & 1)) * slot_stride; ld = D; }
+  else { src = slots + (slot_mode == 0 ? (size_t)(k - 1) : (slot_mode == 1 ? (size_t)(k & 1) : (size_t)k)) * slot_stride; ld = ld_slot; }
   const size_t total = (size_t)n * D;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t r = e / D;
@@ -128,6 +130,22 @@ static __global__ void k_pool(const float* out_nodes, const int* graph_ptr, cons
   float acc = 0.f;
   for (int i = graph_ptr[gi]; i < graph_ptr[gi + 1]; ++i) acc = fmaf(ng_val[i], out_nodes[(size_t)i * T + j], acc);
   out[e] = acc;
+}
+
+// interleaved layout: slot 0 columns [0, D) = initial state; columns [2D, 2D + LsM) of the first n_slots slots = static block
+static __global__ void k_xlay_init(const float* s0, int ld0, const float* Xs, int ldXs, int LsM, float* slots, size_t stride,
+                                   int n_slots, int ldX, int D, int n) {
+  const int W = D + n_slots * LsM;
+  const size_t total = (size_t)n * W;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / W;
+    const int j = (int)(e - r * W);
+    if (j < D) slots[r * ldX + j] = s0[r * ld0 + j];
+    else {
+      const int q = (j - D) / LsM, x = (j - D) - q * LsM;
+      slots[(size_t)q * stride + r * ldX + 2 * D + x] = Xs[r * ldXs + x];
+    }
+  }
 }
 
 // ---- piece builders -----------------------------------------------------------------------------
@@ -176,16 +194,16 @@ void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts, int agg_direct) {
     if (bn) { p0.st_sum = c.stS(0, t - 1); p0.st_sq = p0.st_sum + D; }
     add_piece(ts, p0);
     if (NLp) {
-      Piece p1 = mk_direct(c.Xs(), L->LsM, NLp, D);
+      Piece p1 = mk_direct(c.Xs(), L->ldXs, NLp, D);
       p1.tag = TAG_STATIC;
       if (bn) { p1.st_sum = c.stX(0); p1.st_sq = c.stX(0) + xw; }
       add_piece(ts, p1);
     }
-    Piece p2 = agg_direct ? mk_direct(c.AGG(t), D, D, D + NLp) : mk_gather(Sp, ld, D, D + NLp, g->dst_rowptr, g->dst_src, wgt, g->A);
+    Piece p2 = agg_direct ? mk_direct(c.AGG(t), c.ldA(), D, D + NLp) : mk_gather(Sp, ld, D, D + NLp, g->dst_rowptr, g->dst_src, wgt, g->A);
     p2.tag = TAG_AGG_STATE;
     if (bn) { p2.st_sum = c.stA(0, t - 1); p2.st_sq = p2.st_sum + D; }
     add_piece(ts, p2);
-    Piece p3 = mk_direct(c.Xs() + NLp, L->LsM, NLp + L->AL, 2 * D + NLp);
+    Piece p3 = mk_direct(c.Xs() + NLp, L->ldXs, NLp + L->AL, 2 * D + NLp);
     p3.tag = TAG_STATIC;
     if (bn) { p3.st_sum = c.stX(0) + NLp; p3.st_sq = c.stX(0) + xw + NLp; }
     add_piece(ts, p3);
@@ -199,11 +217,11 @@ void build_state_src(const Ctx& c, int ty, int t, TileSrc& ts, int agg_direct) {
     p1.tag = TAG_STATE;
     if (bn) { p1.st_sum = c.stS(ty, t - 1); p1.st_sq = p1.st_sum + D; }
     add_piece(ts, p1);
-    Piece p2 = agg_direct ? mk_direct(c.AGG(t), D, D, d + D) : mk_gather(Sp, ld, D, d + D, g->dst_rowptr, g->dst_src, wgt, g->A);
+    Piece p2 = agg_direct ? mk_direct(c.AGG(t), c.ldA(), D, d + D) : mk_gather(Sp, ld, D, d + D, g->dst_rowptr, g->dst_src, wgt, g->A);
     p2.tag = TAG_AGG_STATE;
     if (bn) { p2.st_sum = c.stA(ty, t - 1); p2.st_sq = p2.st_sum + D; }
     add_piece(ts, p2);
-    Piece p3 = mk_direct(c.Xs(), L->LsM, L->sum_dt + L->AL, d + 2 * D);
+    Piece p3 = mk_direct(c.Xs(), L->ldXs, L->sum_dt + L->AL, d + 2 * D);
     p3.tag = TAG_STATIC;
     if (bn) { p3.st_sum = c.stX(ty) + d; p3.st_sq = c.stX(ty) + xw + d; }
     add_piece(ts, p3);
@@ -369,6 +387,26 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
                      gemm_rows_supported(ceil_to(d.in_dim, 8) + 8 * 3, d.widths[0]) && getenv("GNNFP_NO_GEMM") == nullptr;
   }
   L->grid_cap = gnnfp_num_sms() * 4;   // backward tile kernels run at most 4 CTAs per SM (tile_cfg_bwd)
+  // ---- TMA path (rows_tma.cu): homogeneous single-Dense-layer state net on an unpartitioned row set.  Chosen here by
+  // ---- shape, never as a fallback after a failure; GNNFP_NO_RT=1 keeps the cp.async kernels (debug / comparison) ------
+  L->ldG = L->D; L->ldXs = L->LsM; L->ldX = L->D;
+  {
+    static const int no_rt = getenv("GNNFP_NO_RT") ? 1 : 0;
+    if (!no_rt && !L->composite && L->gemm_ok[0] && L->Nact == L->N && cfg->max_iteration > 0 && L->D <= 96 && rows_tma_available()) {
+      const int inl = L->LsM > 0 && L->LsM <= 8;
+      const int w0 = 2 * L->D + (inl ? L->LsM : 0);
+      const int nkc = (w0 + 31) / 32 + (inl ? 0 : (L->LsM + 31) / 32);
+      RowsTmaArgs pf, pd;
+      memset(&pf, 0, sizeof(pf));
+      memset(&pd, 0, sizeof(pd));
+      pf.mode = RT_FWD; pf.n_kc = nkc; pf.n_oc = (L->D + 31) / 32; pf.BN = ceil_to(L->D, 16);
+      pd.mode = RT_DX; pd.n_kc = (L->D + 31) / 32; pd.n_oc = 2 * ((L->D + 31) / 32); pd.BN = 2 * ceil_to(L->D, 16);
+      if (nkc <= RT_MAXKC && rows_tma_finish(pf) == GNNFP_OK && (!cfg->training || rows_tma_finish(pd) == GNNFP_OK)) {
+        L->xlay = 1; L->xs_inline = inl;
+        L->ldX = ceil_to(w0, 4); L->ldG = ceil_to(L->D, 4); L->ldXs = ceil_to(L->LsM, 4);
+      }
+    }
+  }
 
   // ---- workspace layout ---------------------------------------------------------------------
   WsLayout& w = L->ws;
@@ -384,11 +422,13 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   w.stX = off; off = align_up(off + (size_t)L->nt * 2 * (xw > 0 ? xw : 1) * sizeof(double));
   w.stO = off; off = align_up(off + (size_t)2 * L->out_in * sizeof(double));
   w.ctrl_bytes = off - w.ctrl;
-  w.Xs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float));
-  L->slot_count = cfg->training ? MI : (MI > 0 ? 2 : 0);
-  w.slots = off; off = align_up(off + (size_t)L->slot_count * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float));
+  w.Xs = off; off = align_up(off + (size_t)L->N * (L->ldXs > 0 ? L->ldXs : 1) * sizeof(float));
+  const size_t slot_floats = ((size_t)L->N * (L->xlay ? L->ldX : L->D) + 31) / 32 * 32;
+  if (L->xlay) L->slot_count = cfg->training ? MI + 1 : 2;        // X_0 .. X_MI (slot 0 = copy of the initial state)
+  else L->slot_count = cfg->training ? MI : (MI > 0 ? 2 : 0);
+  w.slots = off; off = align_up(off + (size_t)L->slot_count * slot_floats * sizeof(float));
   w.out_nodes = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
-  w.agg = off; off = align_up(off + (cfg->training ? (size_t)MI : (size_t)(MI > 0 ? 1 : 0)) * (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float) + 4);
+  w.agg = off; off = align_up(off + (L->xlay ? (size_t)0 : (cfg->training ? (size_t)MI : (size_t)(MI > 0 ? 1 : 0))) * slot_floats * sizeof(float) + 4);
   {
     size_t wf = 0, wt = 0, bc = 0;
     for (int t = 0; t <= L->nt; ++t) {                 // slot nt: net_output
@@ -405,7 +445,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     w.bncoef = off; off = align_up(off + (L->nt + 1) * w.bncoef_stride * sizeof(float));
   }
   if (cfg->training) {
-    const size_t ND = (((size_t)L->N * L->D + 31) / 32 * 32) * sizeof(float);
+    const size_t ND = (((size_t)L->N * L->ldG + 31) / 32 * 32) * sizeof(float);
     w.dSfin = off; off = align_up(off + ND);
     w.dOwn = off; off = align_up(off + 2 * ND);
     w.dAgg = off; off = align_up(off + 2 * ND);
@@ -423,7 +463,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     w.bn_const = off; off = align_up(off + (size_t)4 * din_max * sizeof(float));
     w.bn_const_t = off; off = align_up(off + (size_t)(MI + 2) * 4 * din_max * sizeof(float));
     w.bwd_zero = off;
-    w.dXs = off; off = align_up(off + (size_t)L->N * (L->LsM > 0 ? L->LsM : 1) * sizeof(float) * (cfg->want_input_grads ? 1 : 0) + 4);
+    w.dXs = off; off = align_up(off + (size_t)L->N * (L->ldXs > 0 ? L->ldXs : 1) * sizeof(float) * (cfg->want_input_grads ? 1 : 0) + 4);
     w.part_state = off; off = align_up(off + (size_t)L->grid_cap * ps * sizeof(float));
     w.part_out = off; off = align_up(off + (size_t)L->grid_cap * L->nparam_o * sizeof(float));
     w.bn_grad = off; off = align_up(off + bg * sizeof(float));
@@ -485,7 +525,7 @@ static int fwd_begin(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_p
       }
       add_piece(pa.src, mk_gather(io->arc_labels, io->ld_arcs, L->AL, col, g->dst_rowptr, g->dst_arc, wgt, g->A));
     }
-    pa.out = c.Xs(); pa.ld_out = L->LsM;
+    pa.out = c.Xs(); pa.ld_out = L->ldXs;
     pa.tc.cap_per_row = L->cap_per_row;
     if ((rc = tile_cfg_pass(L->LsM, N, &pa.tc))) return rc;
     if ((rc = launch_tile_pass(pa, s))) return rc;
@@ -497,7 +537,7 @@ static int fwd_begin(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_p
       set_rows(L, ty, pa.src);
       pa.src.in_dim = L->dt[ty] + L->LsM;
       add_piece(pa.src, mk_direct(io->nodes, io->ld_nodes, L->dt[ty], 0));
-      add_piece(pa.src, mk_direct(c.Xs(), L->LsM, L->LsM, L->dt[ty]));
+      add_piece(pa.src, mk_direct(c.Xs(), L->ldXs, L->LsM, L->dt[ty]));
       // stX(ty) is laid out [d_t | LsM] with stride stXw: the pass writes sums to [0,in_dim) and squares
       // to [stXw, stXw+in_dim)
       pa.st_sum = c.stX(ty); pa.st_sq = c.stX(ty) + c.stXw();
@@ -505,6 +545,14 @@ static int fwd_begin(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_p
       if ((rc = tile_cfg_pass(pa.src.in_dim, pa.src.n_rows, &pa.tc))) return rc;
       if ((rc = launch_tile_pass(pa, s))) return rc;
     }
+  }
+  if (L->xlay) {   // X_0[:, 0:D] = the caller's initial state; inline static columns into every slot
+    const int ns = L->xs_inline ? L->slot_count : 0;
+    const size_t tot = (size_t)N * (D + (size_t)ns * L->LsM);
+    int blocks = (int)((tot + 255) / 256);
+    if (blocks > 2368) blocks = 2368;
+    k_xlay_init<<<blocks, 256, 0, s>>>(c.S0user(), c.ldS0user(), c.Xs(), L->ldXs, L->LsM, c.slots(), c.slot_stride(), ns, L->ldX, D, N);
+    GNNFP_COUNT_LAUNCH();
   }
   // ---- condition before the first iteration ------------------------------------------------------
   {
@@ -527,6 +575,53 @@ static int fwd_begin(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_p
   }
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return rc;
+}
+
+// argument block of the TMA forward iteration t: operand chunks over X_{t-1} = [S_{t-1} | Adj^T S_{t-1} | static?] (+ the
+// static block Xs when it is not inline), output chunks of S_t, the previous state as the side input of the convergence test
+static int rt_build_fwd(const Ctx& c, int t, const gnnfp_net_params* sp, RowsTmaArgs& ra) {
+  gnnfp_loop* L = c.L;
+  const int MI = L->cfg.max_iteration, D = L->D, N = L->N, LsM = L->LsM;
+  const int NLp = L->S > 0 ? L->NLw : 0;
+  int rc;
+  memset(&ra, 0, sizeof(ra));
+  ra.mode = RT_FWD; ra.n_rows = L->Nact; ra.H = D;
+  build_state_src(c, 0, t, ra.src, 1);
+  fill_netdev(L->snet[0], sp[0], L->cfg.training, ra.src.n_rows, ra.net);
+  ra.update_moving = L->cfg.training; ra.act = L->snet[0].acts[0];
+  const int w0 = 2 * D + (L->xs_inline ? LsM : 0);
+  if ((rc = rows_tma_map(&ra.maps[0], c.S(t - 1), N, w0, L->ldX))) return rc;
+  if (!L->xs_inline && LsM > 0 && (rc = rows_tma_map(&ra.maps[1], c.Xs(), N, LsM, L->ldXs))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[2], c.S(t - 1), N, D, L->ldX))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[3], c.S(t), N, D, L->ldX))) return rc;
+  // input column (row of W) of X-slot column m / static column x: the net sees [S | nodes? | Adj^T S | agg_nodes | agg_arcs]
+  auto stat_col = [&](int x) { return x < NLp ? D + x : 2 * D + x; };
+  auto slot_col = [&](int m) { return m < D ? m : (m < 2 * D ? D + NLp + (m - D) : stat_col(m - 2 * D)); };
+  for (int c0 = 0; c0 < w0; c0 += RT_CHUNK) {
+    RtKChunk& k = ra.kc[ra.n_kc++];
+    k.map = 0; k.col0 = c0; k.width = w0 - c0 < RT_CHUNK ? w0 - c0 : RT_CHUNK; k.k8 = (k.width + 7) / 8;
+    for (int j = 0; j < RT_CHUNK; ++j) k.wrow[j] = (short)(j < k.width ? slot_col(c0 + j) : -1);
+  }
+  if (!L->xs_inline)
+    for (int c0 = 0; c0 < LsM; c0 += RT_CHUNK) {
+      RtKChunk& k = ra.kc[ra.n_kc++];
+      k.map = 1; k.col0 = c0; k.width = LsM - c0 < RT_CHUNK ? LsM - c0 : RT_CHUNK; k.k8 = (k.width + 7) / 8;
+      for (int j = 0; j < RT_CHUNK; ++j) k.wrow[j] = (short)(j < k.width ? stat_col(c0 + j) : -1);
+    }
+  for (int c0 = 0; c0 < D; c0 += RT_CHUNK) {
+    RtOChunk& o = ra.oc[ra.n_oc];
+    o.acc_col0 = c0; o.out_map = 3; o.out_col0 = c0;
+    o.aux_map = t < MI ? 2 : -1; o.aux_col0 = c0; o.cidx0 = c0;
+    o.width = D - c0 < RT_CHUNK ? D - c0 : RT_CHUNK; o.st_slot = ra.n_oc;
+    ++ra.n_oc;
+  }
+  ra.BN = ceil_to(D, 16);
+  if (t < MI) {
+    ra.thr = L->cfg.state_threshold; ra.flag_next = c.flags() + t;
+    if (L->bn_train_state) { ra.ost_sum = c.stS(0, t); ra.ost_sq = ra.ost_sum + D; }
+  }
+  ra.gate = c.flags() + (t - 1);
+  return rows_tma_finish(ra);
 }
 
 // iteration t (1-based), gated on the device flag written by iteration t-1 (GNN.py:265)
@@ -552,13 +647,18 @@ static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp
       aa.n_rows = rows.n_rows; aa.rowlist = rows.rowlist; aa.D = D;
       aa.S = c.S(t - 1); aa.ld = c.ldS(t - 1);
       aa.rowptr = g->dst_rowptr; aa.idx = g->dst_src; aa.wgt = wgt;
-      aa.out = c.AGG(t);
+      aa.out = c.AGG(t); aa.ld_out = c.ldA();
       if (L->bn_train_state) { aa.st_sum = c.stA(ty, t - 1); aa.st_sq = aa.st_sum + D; }
       aa.gate = gate;
       if ((rc = launch_agg_stats(aa, s))) return rc;
     }
+    if (L->xlay) {
+      RowsTmaArgs ra;
+      if ((rc = rt_build_fwd(c, t, sp, ra))) return rc;
+      if ((rc = launch_rows_tma(ra, s, PC_FWD_ITER))) return rc;
+    }
     for (int ty = 0; ty < L->nt; ++ty) {
-      if (!L->gemm_ok[ty]) continue;
+      if (!L->gemm_ok[ty] || L->xlay) continue;
       // ---- pipelined GEMM path: fold BN into the padded weights, then one GEMM with the iteration's epilogue ----
       TileSrc ts;
       build_state_src(c, ty, t, ts, 1);
@@ -581,7 +681,7 @@ static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp
       if ((rc = launch_fold_w(fo, s))) return rc;
       ga.n_rows = ts.n_rows; ga.rowlist = ts.rowlist; ga.n_pieces = ts.n_pieces; ga.Kpad = fo.Kpad;
       ga.Wp = fo.Wp; ga.ldw = fo.ldw; ga.N = H; ga.bias = fo.biasp; ga.act = L->snet[ty].acts[0];
-      ga.out = (float*)c.S(t); ga.ld_out = D; ga.fwd = 1;
+      ga.out = (float*)c.S(t); ga.ld_out = c.ldS(t); ga.fwd = 1;
       ga.vec2 = D % 2 == 0 && c.ldS(t - 1) % 2 == 0 && ((uintptr_t)c.S(t) & 7) == 0 && ((uintptr_t)c.S(t - 1) & 7) == 0;
       if (t < MI) {
         ga.prev = c.S(t - 1); ga.ld_prev = c.ldS(t - 1); ga.thr = L->cfg.state_threshold; ga.flag_next = c.flags() + t;
@@ -604,7 +704,7 @@ static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp
       fa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;
       fa.prev_col0 = L->composite ? L->dt[ty] : 0;
-      fa.out = (float*)c.S(t); fa.ld_out = D; fa.out_compact = 0;
+      fa.out = (float*)c.S(t); fa.ld_out = c.ldS(t); fa.out_compact = 0;
       if (L->bn_train_state && t < MI) { fa.ost_sum = c.stS(ty, t); fa.ost_sq = fa.ost_sum + D; }
       if (t < MI) { fa.prev = c.S(t - 1); fa.ld_prev = c.ldS(t - 1); fa.thr = L->cfg.state_threshold; fa.flag_next = c.flags() + t; }
       fa.gate = gate;
@@ -632,8 +732,8 @@ static int fwd_end(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_par
     const size_t total = (size_t)N * D;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 2368) blocks = 2368;
-    k_finalize<<<blocks, 256, 0, s>>>(c.flags(), MI, c.S(0), c.ldS(0), c.slots(), c.slot_stride(), training, N, D,
-                                      io->state_out, io->k_out);
+    k_finalize<<<blocks, 256, 0, s>>>(c.flags(), MI, c.S0user(), c.ldS0user(), c.slots(), c.slot_stride(),
+                                      training ? (L->xlay ? 2 : 0) : 1, L->xlay ? L->ldX : D, N, D, io->state_out, io->k_out);
     GNNFP_COUNT_LAUNCH();
   }
   // ---- net_output (+ pooling) ----------------------------------------------------------------------------
@@ -747,7 +847,7 @@ extern "C" int gnnfp_loop_ws_offsets(const gnnfp_loop* L, size_t* flags_off, siz
   if (!L) GNNFP_FAIL(GNNFP_E_INVALID, "loop_ws_offsets: null plan");
   if (flags_off) *flags_off = L->ws.flags;
   if (slots_off) *slots_off = L->ws.slots;
-  if (slot_stride_floats) *slot_stride_floats = ((size_t)L->N * L->D + 31) / 32 * 32;
+  if (slot_stride_floats) *slot_stride_floats = ((size_t)L->N * (L->xlay ? L->ldX : L->D) + 31) / 32 * 32;
   if (slot_count) *slot_count = L->slot_count;
   return GNNFP_OK;
 }

@@ -42,6 +42,14 @@ struct gnnfp_loop {
   int bwd_grid_out = 0;
   int out_gemm_ok = 0;              // net_output runs on the GEMM kernels (single Dense layer, node / graph focus)
   int gemm_ok[GNNFP_MAX_TYPES]{};   // single Dense layer nets run the pipelined GEMM kernels (gemm.cu)
+  // TMA path (rows_tma.cu): homogeneous single-Dense-layer state nets keep every iteration's state and aggregate
+  // interleaved in ONE row-major slot per iteration,  X_t = [S_t (D) | Adj^T S_t (D) | static columns (inline, optional)],
+  // with 16-byte aligned row pitches so that the tensor-map TMA unit can load / store every matrix of the loop
+  int xlay = 0;          // interleaved layout + rows_tma kernels in use
+  int ldX = 0;           // floats per row of an X slot
+  int ldG = 0;           // leading dimension of dz / dOwn / dAgg / dSfin  (D unless xlay)
+  int ldXs = 0;          // leading dimension of the static block Xs / dXs  (LsM unless xlay)
+  int xs_inline = 0;     // static columns are copied into every X slot (few columns: saves one operand chunk per tile)
   int cap_per_row = 4;   // CSR scratch capacity per tile row (from A/N)
   int grid_cap = 0;      // upper bound of any backward tile kernel grid (partials are sized by it)
   WsLayout ws;
@@ -56,13 +64,21 @@ struct Ctx {
   int* flags() const { return (int*)(ws + L->ws.flags); }
   float* Xs() const { return (float*)(ws + L->ws.Xs); }
   float* slots() const { return (float*)(ws + L->ws.slots); }
-  size_t slot_stride() const { return ((size_t)L->N * L->D + 31) / 32 * 32; }   // 128-byte aligned slots (vector staging)
+  size_t slot_stride() const { return ((size_t)L->N * (L->xlay ? L->ldX : L->D) + 31) / 32 * 32; }   // 128-byte aligned slots
+  const float* S0user() const { return L->S > 0 ? io->state0 : io->nodes; }   // the caller's initial state
+  int ldS0user() const { return L->S > 0 ? L->S : io->ld_nodes; }
+  int xslot(int t) const { return L->cfg.training ? t : (t & 1); }            // xlay: slot of iteration t (0 = the copy of the initial state)
   const float* S(int t) const {   // state after t iterations
-    if (t == 0) return L->S > 0 ? io->state0 : io->nodes;
+    if (L->xlay) return slots() + (size_t)xslot(t) * slot_stride();
+    if (t == 0) return S0user();
     return slots() + (L->cfg.training ? (size_t)(t - 1) : (size_t)(t & 1)) * slot_stride();
   }
-  float* AGG(int t) const { return (float*)(ws + L->ws.agg) + (L->cfg.training ? (size_t)(t - 1) : (size_t)0) * slot_stride(); }   // t = 1..max_iter (one slot in inference)
-  int ldS(int t) const { return t == 0 ? (L->S > 0 ? L->S : io->ld_nodes) : L->D; }
+  float* AGG(int t) const {       // Adj^T S_{t-1}, t = 1..max_iter (one slot in inference)
+    if (L->xlay) return slots() + (size_t)xslot(t - 1) * slot_stride() + L->D;
+    return (float*)(ws + L->ws.agg) + (L->cfg.training ? (size_t)(t - 1) : (size_t)0) * slot_stride();
+  }
+  int ldS(int t) const { return L->xlay ? L->ldX : (t == 0 ? ldS0user() : L->D); }
+  int ldA() const { return L->xlay ? L->ldX : L->D; }
   int stXw() const {
     if (!L->composite) return L->LsM;
     int m = 0;

@@ -14,6 +14,7 @@
 #include "loop.h"
 #include "tile.cuh"
 #include "gemm.h"
+#include "rows_tma.h"
 
 // G0 and the loop-invariant aggregates' gradients -> d_state0 / d_nodes
 struct InGradArgs {
@@ -28,6 +29,7 @@ struct InGradArgs {
   // inline BN-training correction (homogeneous single-layer nets): constants of iteration 1 and static sums
   const float* cn; const float* csum; int in_dim;
   const float* s0; int ld0; const float* agg1; const float* Xs;
+  int ldg, ld_agg1;                   // leading dimensions of dSfin / dOwn1 / dAgg1 and of agg1
 };
 static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a) {
   const int W = a.D > a.NLw ? a.D : a.NLw;
@@ -39,18 +41,18 @@ static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a)
     if (j < a.D) {   // G0 = dL/d state0
       float g0;
       if (ran) {
-        g0 = a.dOwn1[(size_t)i * a.D + j];
+        g0 = a.dOwn1[(size_t)i * a.ldg + j];
         const float* cn = a.cn;
         const int in = a.in_dim, ac = a.D + a.NLp + j;
         if (cn) g0 -= cn[j] + fmaf(a.s0[(size_t)i * a.ld0 + j], cn[2 * in + j], cn[3 * in + j]) * cn[in + j];
         for (int p = a0; p < a1; ++p) {
-          const size_t so = (size_t)a.src_dst[p] * a.D + j;
+          const size_t so = (size_t)a.src_dst[p] * a.ldg + j;
           float tv = a.dAgg1[so];
-          if (cn) tv -= cn[ac] + fmaf(a.agg1[so], cn[2 * in + ac], cn[3 * in + ac]) * cn[in + ac];
+          if (cn) tv -= cn[ac] + fmaf(a.agg1[(size_t)a.src_dst[p] * a.ld_agg1 + j], cn[2 * in + ac], cn[3 * in + ac]) * cn[in + ac];
           g0 = fmaf(a.src_w ? a.src_w[p] : 1.0f, tv, g0);
         }
       } else {
-        g0 = a.dSfin[(size_t)i * a.D + j];
+        g0 = a.dSfin[(size_t)i * a.ldg + j];
       }
       if (a.S > 0) { if (a.d_state0) a.d_state0[(size_t)i * a.S + j] = g0; }
       else if (a.d_nodes) a.d_nodes[(size_t)i * a.NLw + j] += g0;           // state0 = nodes (GNN.py:259)
@@ -59,7 +61,7 @@ static __global__ void k_input_grads_nodes(const __grid_constant__ InGradArgs a)
       float g = 0.f;
       if (!a.composite) {
         if (a.NLp) {   // own-label columns + Adj . d(agg_nodes)
-          const bool fixs = a.cn != nullptr && ran;
+          const bool fixs = a.cn != nullptr && a.csum != nullptr && ran;
           const int in = a.in_dim, ic0 = a.D + j, ic1 = 2 * a.D + a.NLp + j;      // input columns of Xs[:, j] and Xs[:, NLp + j]
           g = a.dXs[(size_t)i * a.LsM + j];
           if (fixs) g -= a.csum[ic0] + fmaf(a.Xs[(size_t)i * a.LsM + j], a.cn[2 * in + ic0], a.cn[3 * in + ic0]) * a.csum[in + ic0];
@@ -86,7 +88,7 @@ static __global__ void k_input_grads_arcs(int A, int AL, int LsM, int col0, cons
                                           const float* dXs, float* d_arcs, const float* cn, const float* csum,
                                           int in_dim, int in_col0, const float* Xs, const int* flags) {
   const size_t total = (size_t)A * AL;
-  const bool fixs = cn != nullptr && flags[0] != 0;
+  const bool fixs = cn != nullptr && csum != nullptr && flags[0] != 0;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int ar = (int)(e / AL), c = (int)(e - (size_t)ar * AL);
     const size_t so = (size_t)dst[ar] * LsM + col0 + c;
@@ -144,6 +146,46 @@ static __global__ void k_out_dz(const __grid_constant__ OutDzArgs a) {
   }
 }
 
+// argument block of the TMA backward dX of iteration t:  [dOwn_t | dAgg_t] = dz_t (W^T . gamma rstd) - BN-training correction,
+// both input blocks in one pass over dz (the side inputs x = S_{t-1} / Adj^T S_{t-1} come from the interleaved slot X_{t-1})
+static int rt_build_dx(const Ctx& c, int t, const gnnfp_net_params* sp, const float* dz, float* dOwn, float* dAgg,
+                       const float* coef, const float* cn, const int* gate, RowsTmaArgs& ra) {
+  gnnfp_loop* L = c.L;
+  const int D = L->D, N = L->N, in = L->snet[0].in_dim, H0 = L->snet[0].widths[0];
+  const int NLp = L->S > 0 ? L->NLw : 0;
+  const bool bn = L->snet[0].has_bn != 0;
+  int rc;
+  memset(&ra, 0, sizeof(ra));
+  ra.mode = RT_DX; ra.n_rows = L->Nact; ra.H = H0;
+  if ((rc = rows_tma_map(&ra.maps[0], dz, N, H0, L->ldG))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[1], c.S(t - 1), N, D, L->ldX))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[2], c.S(t - 1), N, 2 * D, L->ldX))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[3], dOwn, N, D, L->ldG))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[4], dAgg, N, D, L->ldG))) return rc;
+  for (int c0 = 0; c0 < H0; c0 += RT_CHUNK) {
+    RtKChunk& k = ra.kc[ra.n_kc++];
+    k.map = 0; k.col0 = c0; k.width = H0 - c0 < RT_CHUNK ? H0 - c0 : RT_CHUNK; k.k8 = (k.width + 7) / 8;
+    for (int j = 0; j < RT_CHUNK; ++j) k.wrow[j] = (short)(j < k.width ? c0 + j : -1);
+  }
+  const int Dp = ceil_to(D, 16);
+  ra.n_blk = 2;
+  ra.blk_acc0[0] = 0; ra.blk_in0[0] = 0; ra.blk_w[0] = D;
+  ra.blk_acc0[1] = Dp; ra.blk_in0[1] = D + NLp; ra.blk_w[1] = D;
+  for (int b = 0; b < 2; ++b)
+    for (int c0 = 0; c0 < D; c0 += RT_CHUNK) {
+      RtOChunk& o = ra.oc[ra.n_oc++];
+      o.acc_col0 = ra.blk_acc0[b] + c0; o.out_map = 3 + b; o.out_col0 = c0;
+      o.aux_map = (bn && cn) ? 1 + b : -1; o.aux_col0 = b ? D + c0 : c0;
+      o.cidx0 = ra.blk_in0[b] + c0; o.width = D - c0 < RT_CHUNK ? D - c0 : RT_CHUNK;
+    }
+  ra.BN = 2 * Dp;
+  ra.W = sp[0].W[0];
+  ra.colscale = bn ? coef + 2 * in : nullptr;
+  ra.corr = bn ? cn : nullptr; ra.corr_in = in;       // cn == NULL: the consumer (dz_kernel / input-gradient kernels) applies the correction
+  ra.gate = gate;
+  return rows_tma_finish(ra);
+}
+
 // phases of the backward (the monolithic entry point runs BEGIN | ITERS | END; the stepping entry point runs one at a
 // time so that a multi-GPU driver can reduce the halo rows of Adj . dAgg between iterations)
 enum { PH_BEGIN = 1, PH_ITERS = 2, PH_END = 4, PH_GATHER = 8 };
@@ -178,7 +220,8 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
   Ctx c{L, io, (char*)workspace, s};
   const gnnfp_graph* g = L->g;
   const int MI = L->cfg.max_iteration, D = L->D, N = L->N;
-  const size_t ND = (size_t)N * D;
+  const int ldG = L->ldG;
+  const size_t ND = (size_t)N * ldG;
   float* dSfin = (float*)(c.ws + L->ws.dSfin);
   const size_t NDa = (ND + 31) / 32 * 32;
   float* dOwn[2] = {(float*)(c.ws + L->ws.dOwn), (float*)(c.ws + L->ws.dOwn) + NDa};
@@ -197,7 +240,8 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
 
   if (phases & PH_BEGIN) {
     GNNFP_CHECK_CUDA(cudaMemsetAsync(c.ws + L->ws.bwd_zero, 0, L->ws.bwd_zero_bytes, s));
-    if (gr->d_state) GNNFP_CHECK_CUDA(cudaMemcpyAsync(dSfin, gr->d_state, ND * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (gr->d_state) GNNFP_CHECK_CUDA(cudaMemcpy2DAsync(dSfin, (size_t)ldG * sizeof(float), gr->d_state, (size_t)D * sizeof(float),
+                                                        (size_t)D * sizeof(float), (size_t)N, cudaMemcpyDeviceToDevice, s));
     else GNNFP_CHECK_CUDA(cudaMemsetAsync(dSfin, 0, ND * sizeof(float), s));
     if ((want & 1)) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_nodes, 0, (size_t)N * L->NLw * sizeof(float), s));
     if ((want & 2) && L->AL > 0) GNNFP_CHECK_CUDA(cudaMemsetAsync(gr->d_arc_labels, 0, (size_t)L->A * L->AL * sizeof(float), s));
@@ -231,7 +275,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     const bool arc = L->cfg.kind == GNNFP_KIND_ARC;
     for (int p = 0; p < ba.src.n_pieces; ++p) {
       Piece& pc = ba.src.p[p];
-      if (pc.tag == TAG_STATE) { pc.gptr = dSfin; pc.gld = D; pc.gmode = arc ? GM_ATOMIC : GM_ADD; }
+      if (pc.tag == TAG_STATE) { pc.gptr = dSfin; pc.gld = ldG; pc.gmode = arc ? GM_ATOMIC : GM_ADD; }
       else if (pc.tag == TAG_NODES) { if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = arc ? GM_ATOMIC : GM_ADD; } }
       else if (pc.tag == TAG_ARC_LABELS) { if ((want & 2) && L->AL > 0) { pc.gptr = gr->d_arc_labels; pc.gld = L->AL; pc.gmode = GM_ADD; } }
     }
@@ -426,7 +470,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     AggArgs aa;
     memset(&aa, 0, sizeof(aa));
     aa.n_rows = N; aa.rowlist = nullptr; aa.D = D;
-    aa.S = dAgg[(t_only + 1) & 1]; aa.ld = D;
+    aa.S = dAgg[(t_only + 1) & 1]; aa.ld = ldG;
     aa.rowptr = g->src_rowptr; aa.idx = g->src_dst; aa.wgt = src_w;
     aa.out = pgather;
     aa.gate = c.flags() + t_only;               // only if iteration t+1 ran
@@ -441,13 +485,13 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
       build_state_src(c, ty, t, full, 1);
       for (int p = 0; p < full.n_pieces; ++p) {
         Piece& pc = full.p[p];
-        if (pc.tag == TAG_AGG_STATE) { pc.gptr = dAgg[wb]; pc.gld = D; pc.gmode = GM_STORE; }
-        else if (pc.tag == TAG_STATE) { pc.gptr = dOwn[wb]; pc.gld = D; pc.gmode = GM_STORE; }
+        if (pc.tag == TAG_AGG_STATE) { pc.gptr = dAgg[wb]; pc.gld = ldG; pc.gmode = GM_STORE; }
+        else if (pc.tag == TAG_STATE) { pc.gptr = dOwn[wb]; pc.gld = ldG; pc.gmode = GM_STORE; }
         else if (want) {
           if (pc.tag == TAG_NODES) { if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = GM_ADD; } }   // composite nodes[:, :d_t]
           else if (pc.tag == TAG_STATIC) {   // static block columns; a block of arc-label aggregates only matters for d_arc_labels
             const bool arcs_only = !L->composite && NLp == 0;
-            if (!arcs_only || (want & 2)) { pc.gptr = dXs + (pc.ptr - c.Xs()); pc.gld = L->LsM; pc.gmode = GM_ADD; }
+            if (!arcs_only || (want & 2)) { pc.gptr = dXs + (pc.ptr - c.Xs()); pc.gld = L->ldXs; pc.gmode = GM_ADD; }
           }
         }
       }
@@ -459,7 +503,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
         DzArgs da;
         memset(&da, 0, sizeof(da));
         da.n_rows = full.n_rows; da.rowlist = full.rowlist; da.D = D; da.act = L->snet[ty].acts[0];
-        da.s_t = c.S(t); da.ld_s = D;
+        da.s_t = c.S(t); da.ld_s = c.ldS(t); da.ldg = ldG; da.ld_agg = c.ldA();
         da.dSfin = dSfin; da.dOwn = dOwn[rb]; da.dAgg = dAgg[rb];
         da.rowptr = g->src_rowptr; da.idx = g->src_dst; da.wgt = src_w;
         da.last_flag = t < MI ? c.flags() + t : nullptr; da.always_last = t == MI;
@@ -467,7 +511,9 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
         if (pgather && t < MI) da.pre = pgather;
         // BN-training correction of iteration t+1's raw gradients: applied here where they are consumed - unless the GEMM
         // path already folded it into the dX epilogue of iteration t+1 (then dOwn / dAgg are final)
-        const bool inline_bn = L->snet[ty].has_bn && !L->composite && !gemm_bwd[ty];
+        // (TMA path with a state width that is not a multiple of 4: the Adj^T S block of an X slot starts at an unaligned
+        //  column, which a tensor-map box cannot address as the dX epilogue's side input - those plans correct here too)
+        const bool inline_bn = L->snet[ty].has_bn && !L->composite && (!gemm_bwd[ty] || (L->xlay && D % 4 != 0));
         if (inline_bn && t < MI) {
           da.cn = cn_t(t + 1); da.agg_next = c.AGG(t + 1); da.in_dim = L->snet[ty].in_dim;
           da.own_col0 = 0; da.agg_col0 = D + NLp;
@@ -495,7 +541,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
             gemm_piece_set(dw.p[p], full.p[p].ptr, full.p[p].ld, full.p[p].width, k2);
             k2 += ceil_to(full.p[p].width, 2);
           }
-          dw.Kp = k2; dw.dz = dzbuf; dw.ld_dz = D; dw.H = H0;
+          dw.Kp = k2; dw.dz = dzbuf; dw.ld_dz = ldG; dw.H = H0;
           dw.partial = part_state + ps_off[ty]; dw.n_params = L->nparam_s[ty]; dw.bias_off = in * H0;
           dw.W = ndfull.W[0];
           if (bn) { dw.bnA = coef; dw.bnB = coef + in; dw.gamma = ndfull.gamma; dw.beta = ndfull.beta; dw.bn_partial = bn_part; }
@@ -515,14 +561,19 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
           // launch: dz is loaded and split once, two accumulators per row tile (gemm.h: nblk == 2)
           GemmRowsArgs dx[GNNFP_MAXP];
           int ndx = 0;
+          if (L->xlay) {   // dOwn_t and dAgg_t: one TMA-fed launch (rows_tma.cu); other gradient destinations below
+            RowsTmaArgs ra;
+            if ((rc = rt_build_dx(c, t, sp, dzbuf, dOwn[wb], dAgg[wb], coef, D % 4 == 0 ? cn_t(t) : nullptr, gate, ra))) return rc;
+            if ((rc = launch_rows_tma(ra, s, PC_BWD_DX))) return rc;
+          }
           for (int p = 0; p < full.n_pieces; ++p) {
             const Piece& pc = full.p[p];
             const int ldw = gemm_rows_ldw(pc.width);
-            if (pc.gptr) {
+            if (pc.gptr && !(L->xlay && (pc.tag == TAG_STATE || pc.tag == TAG_AGG_STATE))) {
               GemmRowsArgs& ga = dx[ndx++];
               memset(&ga, 0, sizeof(ga));
               ga.n_rows = full.n_rows; ga.rowlist = full.rowlist; ga.n_pieces = 1;
-              gemm_piece_set(ga.p[0], dzbuf, D, H0, 0);
+              gemm_piece_set(ga.p[0], dzbuf, ldG, H0, 0);
               ga.fwd = 0; ga.Kpad = KH; ga.Wp = wt; ga.ldw = ldw; ga.N = pc.width;
               ga.colscale = bn ? coef + 2 * in + pc.col0 : nullptr;
               if (bn) { ga.corr = cn_t(t); ga.corr_in = in; ga.corr_col0 = pc.col0; ga.corr_x = pc.ptr; ga.corr_ld = pc.ld; }
@@ -553,7 +604,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
           ba.src.n_rows = full.n_rows; ba.src.rowlist = full.rowlist; ba.src.in_dim = sp_.width;
           for (int p = sp_.p0; p < sp_.p1; ++p) { Piece pc = full.p[p]; pc.col0 -= sp_.c_off; ba.src.p[ba.src.n_pieces++] = pc; }
           ba.gsrc.n_rows = full.n_rows; ba.gsrc.rowlist = full.rowlist; ba.gsrc.in_dim = D;
-          add_piece(ba.gsrc, mk_direct(dzbuf, D, D, 0));
+          add_piece(ba.gsrc, mk_direct(dzbuf, ldG, D, 0));
           ba.net = ndfull;
           ba.net.in_dim = sp_.width;
           ba.net.W[0] = ndfull.W[0] + (size_t)sp_.c_off * H0;
@@ -598,14 +649,14 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
         ba.src = full;
         ba.gsrc.n_rows = ba.src.n_rows; ba.gsrc.rowlist = ba.src.rowlist; ba.gsrc.in_dim = D;
         {
-          Piece pa = mk_direct(dSfin, D, D, 0);
+          Piece pa = mk_direct(dSfin, ldG, D, 0);
           if (t < MI) { pa.gate = c.flags() + t; pa.gate_pol = 0; }   // enabled iff iteration t+1 did not run
           add_piece(ba.gsrc, pa);
           if (t < MI) {
-            Piece pb = mk_direct(dOwn[rb], D, D, 0);
+            Piece pb = mk_direct(dOwn[rb], ldG, D, 0);
             pb.accumulate = 1; pb.gate = c.flags() + t; pb.gate_pol = 1;
             add_piece(ba.gsrc, pb);
-            Piece pc2 = mk_gather(dAgg[rb], D, D, 0, g->src_rowptr, g->src_dst, src_w, g->A);
+            Piece pc2 = mk_gather(dAgg[rb], ldG, D, 0, g->src_rowptr, g->src_dst, src_w, g->A);
             pc2.accumulate = 1; pc2.gate = c.flags() + t; pc2.gate_pol = 1;
             add_piece(ba.gsrc, pc2);
           }
@@ -614,7 +665,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
         ba.tc.cap_per_row = L->cap_per_row;
         if ((rc = tile_cfg_bwd(ba.net, ba.src.n_rows, D, &ba.tc))) return rc;
         grid_state[ty] = ba.tc.grid > grid_state[ty] ? ba.tc.grid : grid_state[ty];
-        ba.saved_out = c.S(t); ba.ld_saved = D; ba.saved_compact = 0;
+        ba.saved_out = c.S(t); ba.ld_saved = c.ldS(t); ba.saved_compact = 0;
         ba.partial = part_state + ps_off[ty]; ba.n_params = L->nparam_s[ty];
         ba.bn_partial = bn_part;
         ba.gate = gate;
@@ -636,7 +687,8 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
   if (want) {
     InGradArgs ia;
     memset(&ia, 0, sizeof(ia));
-    ia.N = N; ia.D = D; ia.S = L->S; ia.NLp = NLp; ia.NLw = L->NLw; ia.AL = L->AL; ia.LsM = L->LsM;
+    ia.N = N; ia.D = D; ia.S = L->S; ia.NLp = NLp; ia.NLw = L->NLw; ia.AL = L->AL; ia.LsM = L->ldXs;   // LsM: row pitch of Xs / dXs
+    ia.ldg = ldG; ia.ld_agg1 = c.ldA();
     ia.composite = L->composite; ia.nt = L->nt;
     int o = 0;
     for (int t = 0; t < L->nt; ++t) { ia.dt[t] = L->dt[t]; ia.doff[t] = o; o += L->dt[t]; }
@@ -646,8 +698,9 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     ia.d_nodes = (want & 1) ? gr->d_nodes : nullptr;
     ia.d_state0 = ((want & 4) && L->S > 0) ? gr->d_state0 : nullptr;
     ia.want = want;
-    if (!L->composite && dzpath[0] && L->snet[0].has_bn && !gemm_bwd[0]) {
-      ia.cn = cn_t(1); ia.csum = bn_static; ia.in_dim = L->snet[0].in_dim;
+    const bool rt_inline = L->xlay && gemm_bwd[0] && D % 4 != 0;   // own / aggregate corrections left to the consumers (static columns: dX epilogue)
+    if (!L->composite && dzpath[0] && L->snet[0].has_bn && (!gemm_bwd[0] || rt_inline)) {
+      ia.cn = cn_t(1); ia.csum = rt_inline ? nullptr : bn_static; ia.in_dim = L->snet[0].in_dim;
       ia.s0 = c.S(0); ia.ld0 = c.ldS(0); ia.agg1 = MI > 0 ? c.AGG(1) : nullptr; ia.Xs = c.Xs();
     }
     const size_t tot = (size_t)N * (D > L->NLw ? D : L->NLw);
@@ -659,7 +712,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
       DzArgs da;
       memset(&da, 0, sizeof(da));
       da.n_rows = N; da.D = D; da.act = GNNFP_ACT_LINEAR;
-      da.s_t = c.S(0); da.ld_s = c.ldS(0);
+      da.s_t = c.S(0); da.ld_s = c.ldS(0); da.ldg = ldG; da.ld_agg = c.ldA(); da.ld_dz = L->NLw;
       da.dSfin = dSfin; da.dOwn = dOwn[1]; da.dAgg = dAgg[1];
       da.rowptr = g->src_rowptr; da.idx = g->src_dst; da.wgt = src_w;
       da.last_flag = c.flags();
@@ -675,7 +728,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
       const size_t ta = (size_t)L->A * L->AL;
       int b2 = (int)((ta + 255) / 256);
       if (b2 > 4736) b2 = 4736;
-      k_input_grads_arcs<<<b2, 256, 0, s>>>(L->A, L->AL, L->LsM, col0, g->dst, g->arc_val, dXs, gr->d_arc_labels,
+      k_input_grads_arcs<<<b2, 256, 0, s>>>(L->A, L->AL, L->ldXs, col0, g->dst, g->arc_val, dXs, gr->d_arc_labels,
                                             ia.cn, ia.csum, ia.in_dim, 2 * D + col0, c.Xs(), c.flags());
       GNNFP_COUNT_LAUNCH();
     }

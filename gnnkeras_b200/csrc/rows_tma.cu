@@ -1,0 +1,492 @@
+// rows_tma.cu - TMA-fed row GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, FP32
+// accumulators in TMEM).  One kernel, two uses:
+//
+//   RT_FWD  one fixed-point iteration of a single-Dense-layer state net (reference GNN.py:217-236 `convergence` +
+//           the `condition` test of GNN.py:196-214):   S_t = act(BN([S_{t-1} | nodes? | Adj^T S_{t-1} | static]) W + b)
+//           - BatchNormalization is folded into the shared-memory weights by every CTA from the fp64 batch sums the
+//             previous launch left (no separate fold / coefficient launches),
+//           - epilogue: bias + activation, per-row convergence test against the previous state, column statistics of
+//             S_t for the next iteration's BatchNormalization, all from the output stage in shared memory.
+//   RT_DX   backward of the same layer w.r.t. its input blocks:   [dOwn_t | dAgg_t] = dz (W^T . gamma rstd) - BN correction
+//           (both blocks from ONE pass over dz: the MMA N covers both weight blocks).
+//
+// Data path per persistent CTA (one per SM, 15 warps):
+//   warp 12 (one thread)  TMA producer: cp.async.bulk.tensor 2-D boxes of [128 rows x 32 columns] fp32 straight into the
+//                         K-major SWIZZLE_128B operand tile "hi" of a ring stage (ragged rows / columns are zero-filled by
+//                         the TMA unit: no predicates anywhere).  The tensor core reads the top 19 bits of an fp32 word,
+//                         so the raw tile IS a_hi = trunc_tf32(a).
+//   warps 4-7             converters, thread = row: a_lo = rn_tf32(a - a_hi) into the stage's "lo" tile (same swizzled
+//                         position: conflict-free 128-bit accesses), fence.proxy.async, mbarrier arrive.
+//   warp 13 (one thread)  MMA issuer: 3 tcgen05.mma (lo.hi, hi.lo, hi.hi) per 8-wide K step against the resident
+//                         W_hi / W_lo tiles; tcgen05.commit frees the stage / publishes the accumulator (two TMEM buffers).
+//   warps 0-3             epilogue, thread = row: tcgen05.ld 32 columns, activation / correction against the side input that
+//                         the out thread preloaded INTO the output stage by TMA (previous state / BN input x), results
+//                         written back in place (swizzled 128-bit stores).
+//   warps 8-11            column warps (RT_FWD), lane = column: column sums / sums of squares of the finished output stage.
+//   warp 14 (one thread)  out thread: TMA preload of the side input, TMA store of the finished stage (rows / columns outside
+//                         the matrix are clipped by the TMA unit).
+// SASS: UTMALDG / UTMASTG (tensor TMA), UTCHMMA, LDTM, UTCBAR.
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include "rows_tma.h"
+#include "tc.cuh"
+
+#define RT_THREADS 480
+#define RT_W_EPI 0
+#define RT_W_CONV 4
+#define RT_W_COL 8
+#define RT_W_PROD 12
+#define RT_W_MMA 13
+#define RT_W_OUT 14
+#define RT_STAT_SLOTS 4
+
+__device__ __forceinline__ void rt_tma_load(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void rt_tma_store(const CUtensorMap* map, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void rt_tmem_ld32(uint32_t addr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(addr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_constant__ RowsTmaArgs a) {
+  if (a.gate && *a.gate == 0) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int BN = a.BN, NKC = a.n_kc, NOC = a.n_oc, NST = a.n_stages, NOS = a.n_ostages;
+  const int wtile = BN * 128;                          // bytes of one [BN x 32] weight tile
+  uint8_t* Whi = base;                                 // [NKC][BN x 32] hi, then lo
+  uint8_t* Wlo = Whi + (size_t)NKC * wtile;
+  uint8_t* ring = Wlo + (size_t)NKC * wtile;           // [NST][hi | lo]
+  uint8_t* outst = ring + (size_t)NST * 2 * RT_STAGE_BYTES;   // [NOS]
+  __shared__ __align__(8) uint64_t slot_empty[8], hi_full[8], ops_full[8], tm_full[2], tm_empty[2], aux_full[4], out_full[4], col_done[4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int notconv_s;
+  __shared__ __align__(16) float s_c[4][RT_MAXIN];     // FWD: BN a | b | mean | var per input column
+  __shared__ __align__(16) float s_tab[RT_MAXOC][4][32];   // per output chunk: FWD bias;  DX c0 | c1 | A | B
+  __shared__ float s_part[4][128];
+  __shared__ double s_stat[4][RT_STAT_SLOTS][2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n_rows;
+  const int n_tiles = (n + RT_ROWS - 1) / RT_ROWS;
+  const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile0 = blockIdx.x * tiles_per_cta;
+  const int my_tiles = max(0, min(n_tiles, tile0 + tiles_per_cta) - tile0);
+  const bool use_col = MODE == RT_FWD && a.ost_sum != nullptr;
+
+  if (warp == RT_W_MMA) { tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols); tmem_relinquish(); }
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&slot_empty[i], 1); mbar_init(&hi_full[i], 1); mbar_init(&ops_full[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128); }
+    for (int i = 0; i < NOS; ++i) { mbar_init(&aux_full[i], 1); mbar_init(&out_full[i], 128); mbar_init(&col_done[i], 128); }
+    notconv_s = 0;
+  }
+  // ---- per-column constants ------------------------------------------------------------------------------------------
+  if (MODE == RT_FWD) {
+    if (a.net.bn_mode) {
+      const bool upd = a.update_moving && a.net.bn_mode == 1 && blockIdx.x == 0;
+      bn_coefficients(a.src, a.net, 1, s_c[0], s_c[1], upd ? s_c[2] : nullptr, upd ? s_c[3] : nullptr);
+    }
+  } else {
+    for (int e = tid; e < NOC * 32; e += RT_THREADS) {
+      const int o = e >> 5, j = e & 31;
+      const int c = a.oc[o].cidx0 + j;
+      const bool ok = a.corr != nullptr && j < a.oc[o].width;
+      s_tab[o][0][j] = ok ? a.corr[c] : 0.f;
+      s_tab[o][1][j] = ok ? a.corr[a.corr_in + c] : 0.f;
+      s_tab[o][2][j] = ok ? a.corr[2 * a.corr_in + c] : 0.f;
+      s_tab[o][3][j] = ok ? a.corr[3 * a.corr_in + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- resident weights: TF32 hi / lo, K-major SWIZZLE_128B tiles per K chunk -------------------------------------------
+  const int H = a.H;
+  if (MODE == RT_FWD) {
+    const float* Wg = a.net.W[0];
+    const bool bn = a.net.bn_mode != 0;
+    if (bn && a.update_moving && a.net.bn_mode == 1 && blockIdx.x == 0) {   // Keras _assign_moving_average: v -= (v - value) * (1 - momentum)
+      const float decay = (float)(1.0 - (double)a.net.bn_momentum);
+      for (int c = tid; c < a.net.in_dim; c += RT_THREADS) {
+        a.net.mmean[c] -= (a.net.mmean[c] - s_c[2][c]) * decay;
+        a.net.mvar[c] -= (a.net.mvar[c] - s_c[3][c]) * decay;
+      }
+    }
+    for (int e = tid; e < NKC * 32 * BN; e += RT_THREADS) {
+      const int kc = e / (32 * BN), r = e - kc * 32 * BN;
+      const int k = r / BN, nn = r - k * BN;
+      const int c = a.kc[kc].wrow[k];
+      float w = 0.f;
+      if (c >= 0 && nn < H) { w = Wg[(size_t)c * H + nn]; if (bn) w *= s_c[0][c]; }
+      const int off = kc * wtile + tc_sw128_off(nn, k);
+      *reinterpret_cast<uint32_t*>(Whi + off) = __float_as_uint(w);
+      *reinterpret_cast<uint32_t*>(Wlo + off) = tc_lo(__float_as_uint(w));
+    }
+    // folded bias b_j + sum_c B_c W[c][j]: 4 fixed groups of input columns per output column, combined in a fixed order
+    // (the launcher keeps BN <= 112 in this mode: 4 * BN <= RT_THREADS)
+    if (tid < 4 * BN) {
+      const int g = tid / BN, nn = tid - g * BN;
+      float part = 0.f;
+      if (bn && nn < H)
+        for (int c = g; c < a.net.in_dim; c += 4) part = fmaf(s_c[1][c], Wg[(size_t)c * H + nn], part);
+      s_part[g][nn] = part;
+    }
+    __syncthreads();
+    for (int e = tid; e < NOC * 32; e += RT_THREADS) {
+      const int o = e >> 5, j = e & 31;
+      const int nn = a.oc[o].cidx0 + j;
+      float b = 0.f;
+      if (j < a.oc[o].width && nn < H) {
+        b = a.net.b[0][nn];
+        if (bn) b += (s_part[0][nn] + s_part[1][nn]) + (s_part[2][nn] + s_part[3][nn]);
+      }
+      s_tab[o][0][j] = b;
+    }
+  } else {
+    for (int e = tid; e < NKC * 32 * BN; e += RT_THREADS) {
+      const int kc = e / (32 * BN), r = e - kc * 32 * BN;
+      const int nn = r >> 5, k = r & 31;
+      const int j = a.kc[kc].wrow[k];
+      float w = 0.f;
+      if (j >= 0 && j < H) {
+        for (int b = 0; b < a.n_blk; ++b)
+          if (nn >= a.blk_acc0[b] && nn < a.blk_acc0[b] + a.blk_w[b]) {
+            const int c = a.blk_in0[b] + (nn - a.blk_acc0[b]);
+            w = a.W[(size_t)c * H + j];
+            if (a.colscale) w *= a.colscale[c];
+          }
+      }
+      const int off = kc * wtile + tc_sw128_off(nn, k);
+      *reinterpret_cast<uint32_t*>(Whi + off) = __float_as_uint(w);
+      *reinterpret_cast<uint32_t*>(Wlo + off) = tc_lo(__float_as_uint(w));
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == RT_W_PROD) {
+    // =================== TMA producer: operand "hi" tiles ==========================================================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t use = 0;
+      for (int tq = 0; tq < my_tiles; ++tq) {
+        const int row0 = (tile0 + tq) * RT_ROWS;
+        for (int kc = 0; kc < NKC; ++kc) {
+          if (use > 0) mbar_wait_bounded(&slot_empty[slot], (use - 1) & 1);
+          mbar_expect_tx(&hi_full[slot], RT_STAGE_BYTES);
+          rt_tma_load(ring + (size_t)slot * 2 * RT_STAGE_BYTES, &a.maps[a.kc[kc].map], a.kc[kc].col0, row0, &hi_full[slot]);
+          if (++slot == NST) { slot = 0; ++use; }
+        }
+      }
+    }
+  } else if (warp == RT_W_MMA) {
+    // =================== MMA issuer ================================================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(RT_ROWS >> 4) << 24);
+      const uint32_t whi_addr = smem_u32(Whi), wlo_addr = smem_u32(Wlo), ring_addr = smem_u32(ring);
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int tq = 0; tq < my_tiles; ++tq) {
+        const int tb = tq & 1;
+        if (tq >= 2) { mbar_wait_bounded(&tm_empty[tb], (uint32_t)((tq >> 1) - 1) & 1u); tc_fence_after(); }
+        const uint32_t dcol = tmem_d + (uint32_t)(tb * BN);
+        uint32_t acc = 0;
+        for (int kc = 0; kc < NKC; ++kc) {
+          mbar_wait_bounded(&ops_full[slot], ph);
+          tc_fence_after();
+          const uint64_t dah = tc_desc_sw128(ring_addr + slot * 2 * RT_STAGE_BYTES);
+          const uint64_t dal = tc_desc_sw128(ring_addr + slot * 2 * RT_STAGE_BYTES + RT_STAGE_BYTES);
+          const uint64_t dbh = tc_desc_sw128(whi_addr + kc * wtile);
+          const uint64_t dbl = tc_desc_sw128(wlo_addr + kc * wtile);
+          const int k8n = a.kc[kc].k8;
+          for (int k8 = 0; k8 < k8n; ++k8) {           // 8 fp32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
+            const uint64_t adv = (uint64_t)(2 * k8);
+            tc_mma_tf32(dcol, dal + adv, dbh + adv, idesc, acc);
+            acc = 1u;
+            tc_mma_tf32(dcol, dah + adv, dbl + adv, idesc, 1u);
+            tc_mma_tf32(dcol, dah + adv, dbh + adv, idesc, 1u);
+          }
+          tc_commit(&slot_empty[slot]);
+          if (kc == NKC - 1) tc_commit(&tm_full[tb]);
+          if (++slot == NST) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == RT_W_OUT) {
+    // =================== out thread: side-input preload + store of the finished output stages ============================
+    if (lane == 0) {
+      const int total = my_tiles * NOC;
+      for (int g = 0; g < total + NOS - 1; ++g) {
+        if (g < total) {
+          const int s = g % NOS, tq = g / NOC, o = g - tq * NOC;
+          if (a.oc[o].aux_map >= 0) {
+            mbar_expect_tx(&aux_full[s], RT_STAGE_BYTES);
+            rt_tma_load(outst + (size_t)s * RT_STAGE_BYTES, &a.maps[a.oc[o].aux_map], a.oc[o].aux_col0, (tile0 + tq) * RT_ROWS, &aux_full[s]);
+          } else {
+            mbar_arrive(&aux_full[s]);
+          }
+        }
+        const int h = g - (NOS - 1);
+        if (h >= 0) {
+          const int s = h % NOS, tq = h / NOC, o = h - tq * NOC;
+          mbar_wait_bounded(use_col ? &col_done[s] : &out_full[s], (uint32_t)(h / NOS) & 1u);
+          rt_tma_store(&a.maps[a.oc[o].out_map], a.oc[o].out_col0, (tile0 + tq) * RT_ROWS, outst + (size_t)s * RT_STAGE_BYTES);
+          bulk_commit();
+          bulk_wait_read0();                           // the stage may be refilled by the next preload
+        }
+      }
+      bulk_wait0();
+    }
+  } else if (warp >= RT_W_CONV && warp < RT_W_CONV + 4) {
+    // =================== converters: thread = row, lo tile of the landed stage ==============================================
+    const int r = tid - 32 * RT_W_CONV;
+    const int rbase = (r >> 3) * 1024 + (r & 7) * 128, rx = r & 7;
+    int slot = 0;
+    uint32_t ph = 0;
+    for (int tq = 0; tq < my_tiles; ++tq) {
+      for (int kc = 0; kc < NKC; ++kc) {
+        mbar_wait_bounded(&hi_full[slot], ph);
+        uint8_t* hi = ring + (size_t)slot * 2 * RT_STAGE_BYTES + rbase;
+        uint8_t* lo = hi + RT_STAGE_BYTES;
+        const int nl = 2 * a.kc[kc].k8;                // 16-byte chunks that carry data
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          if (l < nl) {
+            const int off = (l ^ rx) << 4;
+            const uint4 v = *reinterpret_cast<const uint4*>(hi + off);
+            uint4 w;
+            w.x = tc_lo(v.x); w.y = tc_lo(v.y); w.z = tc_lo(v.z); w.w = tc_lo(v.w);
+            *reinterpret_cast<uint4*>(lo + off) = w;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&ops_full[slot]);
+        if (++slot == NST) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp < 4) {
+    // =================== epilogue: thread = row ==================================================================================
+    const int r = tid;
+    const int rbase = (r >> 3) * 1024 + (r & 7) * 128, rx = r & 7;
+    const uint32_t lane_addr = (uint32_t)(32 * warp) << 16;
+    const bool selu = a.act == GNNFP_ACT_SELU;
+    const bool conv = MODE == RT_FWD && a.flag_next != nullptr;
+    int os = 0;
+    uint32_t oph = 0;
+    int notconv = 0;
+    for (int tq = 0; tq < my_tiles; ++tq) {
+      const int tb = tq & 1;
+      mbar_wait_bounded(&tm_full[tb], (uint32_t)(tq >> 1) & 1u);
+      tc_fence_after();
+      float sd = 0.f, sp = 0.f;
+      for (int o = 0; o < NOC; ++o) {
+        const int width = a.oc[o].width;
+        const bool has_aux = a.oc[o].aux_map >= 0;
+        float acc[32];
+        rt_tmem_ld32(tmem_d + lane_addr + (uint32_t)(tb * BN + a.oc[o].acc_col0), acc);
+        mbar_wait_bounded(&aux_full[os], oph);         // the stage is free, the side input (if any) has landed
+        tmem_ld_wait();
+        if (o == NOC - 1) { tc_fence_before(); mbar_arrive(&tm_empty[tb]); }
+        uint8_t* st = outst + (size_t)os * RT_STAGE_BYTES + rbase;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          if (4 * l < width) {
+            float4* p4 = reinterpret_cast<float4*>(st + ((l ^ rx) << 4));
+            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_aux) pv = *p4;
+            const float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+            float v[4];
+            if (MODE == RT_FWD) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_tab[o][0][4 * l]);
+              const float ba[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float z = acc[4 * l + jj] + ba[jj];
+                float y = selu ? tc_selu(z) : act_fwd(a.act, z);
+                if (4 * l + jj >= width) y = 0.f;
+                const float d = y - pa[jj];
+                sd = fmaf(d, d, sd);
+                sp = fmaf(pa[jj], pa[jj], sp);
+                v[jj] = y;
+              }
+            } else {
+              const float4 k0 = *reinterpret_cast<const float4*>(&s_tab[o][0][4 * l]);
+              const float4 k1 = *reinterpret_cast<const float4*>(&s_tab[o][1][4 * l]);
+              const float4 kA = *reinterpret_cast<const float4*>(&s_tab[o][2][4 * l]);
+              const float4 kB = *reinterpret_cast<const float4*>(&s_tab[o][3][4 * l]);
+              v[0] = acc[4 * l + 0] - (k0.x + fmaf(pa[0], kA.x, kB.x) * k1.x);
+              v[1] = acc[4 * l + 1] - (k0.y + fmaf(pa[1], kA.y, kB.y) * k1.y);
+              v[2] = acc[4 * l + 2] - (k0.z + fmaf(pa[2], kA.z, kB.z) * k1.z);
+              v[3] = acc[4 * l + 3] - (k0.w + fmaf(pa[3], kA.w, kB.w) * k1.w);
+            }
+            *p4 = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&out_full[os]);
+        if (++os == NOS) { os = 0; oph ^= 1u; }
+      }
+      if (conv && (tile0 + tq) * RT_ROWS + r < n && sqrtf(sd) > a.thr * sqrtf(sp)) notconv = 1;
+    }
+    if (conv && notconv) notconv_s = 1;
+  } else if (warp >= RT_W_COL && warp < RT_W_COL + 4) {
+    // =================== column warps: lane = column, statistics of the finished output stage ================================
+    const int cw = warp - RT_W_COL;
+    double s1[RT_STAT_SLOTS], s2[RT_STAT_SLOTS];
+#pragma unroll
+    for (int q = 0; q < RT_STAT_SLOTS; ++q) { s1[q] = 0.0; s2[q] = 0.0; }
+    if (use_col) {
+      int os = 0;
+      uint32_t oph = 0;
+      const int coff = ((lane >> 2) << 4), cin = (lane & 3) << 2;
+      for (int tq = 0; tq < my_tiles; ++tq) {
+        const int rfirst = (tile0 + tq) * RT_ROWS + 32 * cw;
+        const int nv = min(32, max(0, n - rfirst));
+        for (int o = 0; o < NOC; ++o) {
+          mbar_wait_bounded(&out_full[os], oph);
+          float p1 = 0.f, p2 = 0.f;
+          if (lane < a.oc[o].width) {
+            const uint8_t* st = outst + (size_t)os * RT_STAGE_BYTES + (4 * cw) * 1024;
+#pragma unroll 8
+            for (int rr = 0; rr < nv; ++rr) {
+              const float x = *reinterpret_cast<const float*>(st + (rr >> 3) * 1024 + (rr & 7) * 128 + (coff ^ ((rr & 7) << 4)) + cin);
+              p1 += x;
+              p2 = fmaf(x, x, p2);
+            }
+          }
+          mbar_arrive(&col_done[os]);
+          const int slot = a.oc[o].st_slot;
+#pragma unroll
+          for (int q = 0; q < RT_STAT_SLOTS; ++q)
+            if (q == slot) { s1[q] += (double)p1; s2[q] += (double)p2; }
+          if (++os == NOS) { os = 0; oph ^= 1u; }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RT_STAT_SLOTS; ++q) { s_stat[cw][q][0][lane] = s1[q]; s_stat[cw][q][1][lane] = s2[q]; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (MODE == RT_FWD) {
+    if (a.flag_next && tid == 0 && notconv_s) atomicOr(a.flag_next, 1);
+    if (use_col) {
+      for (int e = tid; e < NOC * 32; e += RT_THREADS) {
+        const int o = e >> 5, j = e & 31;
+        if (j < a.oc[o].width) {
+          const int q = a.oc[o].st_slot, c = a.oc[o].cidx0 + j;
+          atomicAdd(a.ost_sum + c, (s_stat[0][q][0][j] + s_stat[1][q][0][j]) + (s_stat[2][q][0][j] + s_stat[3][q][0][j]));
+          atomicAdd(a.ost_sq + c, (s_stat[0][q][1][j] + s_stat[1][q][1][j]) + (s_stat[2][q][1][j] + s_stat[3][q][1][j]));
+        }
+      }
+    }
+  }
+  if (warp == RT_W_MMA) tmem_dealloc(tmem_d, (uint32_t)a.tmem_cols);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled rt_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+int rows_tma_available() {
+  static const int off = getenv("GNNFP_NO_TMA") ? 1 : 0;
+  return !off && rt_encoder() != nullptr;
+}
+int rows_tma_ok(const float* ptr, int ld) { return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0 && ld > 0; }
+
+int rows_tma_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld) {
+  PFN_cuTensorMapEncodeTiled fn = rt_encoder();
+  if (!fn) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: cuTensorMapEncodeTiled is not available from this driver");
+  if (!rows_tma_ok(ptr, ld) || rows < 1 || cols < 1 || cols > ld)
+    GNNFP_FAIL(GNNFP_E_INVALID, "rows_tma: matrix %p [%d x %d, ld %d] cannot be described by a tensor map (16-byte alignment)", (const void*)ptr, rows, cols, ld);
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {RT_CHUNK, RT_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GNNFP_FAIL(GNNFP_E_CUDA, "cuTensorMapEncodeTiled failed with %d ([%d x %d], ld %d)", (int)r, rows, cols, ld);
+  return GNNFP_OK;
+}
+
+static size_t rt_smem_cap() {
+  static size_t cap = 0;
+  if (!cap) {
+    cudaFuncAttributes fa;
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaFuncGetAttributes(&fa, rows_tma_kernel<RT_FWD>) != cudaSuccess ||
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    cudaFuncAttributes fb;
+    if (cudaFuncGetAttributes(&fb, rows_tma_kernel<RT_DX>) != cudaSuccess) return 0;
+    const size_t st = fa.sharedSizeBytes > fb.sharedSizeBytes ? fa.sharedSizeBytes : fb.sharedSizeBytes;
+    cap = (size_t)optin - st;
+  }
+  return cap;
+}
+size_t rows_tma_smem(const RowsTmaArgs& a) {
+  return (size_t)2 * a.n_kc * a.BN * 128 + (size_t)a.n_stages * 2 * RT_STAGE_BYTES + (size_t)a.n_ostages * RT_STAGE_BYTES + 1024;
+}
+int rows_tma_finish(RowsTmaArgs& a) {
+  if (a.n_kc < 1 || a.n_kc > RT_MAXKC || a.n_oc < 1 || a.n_oc > RT_MAXOC || a.BN < 16 || a.BN > RT_MAXBN || a.BN % 16 != 0)
+    GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: shape outside the kernel's limits (K chunks %d, output chunks %d, N %d)", a.n_kc, a.n_oc, a.BN);
+  const int need = 2 * a.BN + 32;
+  a.tmem_cols = need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512));
+  const size_t cap = rt_smem_cap();
+  if (!cap) GNNFP_FAIL(GNNFP_E_CUDA, "rows_tma: cannot query the shared-memory budget");
+  a.n_ostages = 2;
+  a.n_stages = 2;
+  if (rows_tma_smem(a) > cap) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: %zu bytes of shared memory needed, %zu available", rows_tma_smem(a), cap);
+  static const int st_max = getenv("GNNFP_RT_STAGES") ? atoi(getenv("GNNFP_RT_STAGES")) : 4;
+  while (a.n_stages < st_max && a.n_stages < 8) { ++a.n_stages; if (rows_tma_smem(a) > cap) { --a.n_stages; break; } }
+  while (a.n_ostages < 4) { ++a.n_ostages; if (rows_tma_smem(a) > cap) { --a.n_ostages; break; } }
+  return GNNFP_OK;
+}
+
+int launch_rows_tma(const RowsTmaArgs& a, cudaStream_t s, int prof_cat) {
+  if (a.n_rows <= 0) return GNNFP_OK;
+  if (a.mode == RT_FWD && a.BN > 112) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: forward mode takes at most 112 output columns (%d)", a.BN);
+  const size_t smem = rows_tma_smem(a);
+  static size_t attr[2] = {0, 0};
+  const int mi = a.mode == RT_DX ? 1 : 0;
+  if (smem > attr[mi]) {
+    if (mi) GNNFP_CHECK_CUDA(cudaFuncSetAttribute(rows_tma_kernel<RT_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else GNNFP_CHECK_CUDA(cudaFuncSetAttribute(rows_tma_kernel<RT_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[mi] = smem;
+  }
+  const int n_tiles = (a.n_rows + RT_ROWS - 1) / RT_ROWS;
+  const int nsm = gnnfp_num_sms();
+  const int grid = n_tiles < nsm ? n_tiles : nsm;
+  ProfScope ps(prof_cat, s);
+  if (mi) rows_tma_kernel<RT_DX><<<grid, RT_THREADS, smem, s>>>(a);
+  else rows_tma_kernel<RT_FWD><<<grid, RT_THREADS, smem, s>>>(a);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
