@@ -63,9 +63,16 @@ __device__ __forceinline__ void rt_tmem_ld32(uint32_t addr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// phase time stamps of the last launch (CTA x [entry, constants, weights ready, main loop done, exit], %globaltimer ns):
+// read back by gnnfp_debug_rt_times (scratch/profiling only; five 8-byte stores per CTA)
+__device__ long long g_rt_times[2][160][8];
+__device__ __forceinline__ long long rt_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define RT_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_rt_times[MODE][blockIdx.x][i] = rt_now(); } while (0)
+
 template <int MODE>
 __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_constant__ RowsTmaArgs a) {
   if (a.gate && *a.gate == 0) return;
+  RT_STAMP(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int BN = a.BN, NKC = a.n_kc, NOC = a.n_oc, NST = a.n_stages, NOS = a.n_ostages;
@@ -80,6 +87,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   __shared__ __align__(16) float s_c[4][RT_MAXIN];     // FWD: BN a | b | mean | var per input column
   __shared__ __align__(16) float s_tab[RT_MAXOC][4][32];   // per output chunk: FWD bias;  DX c0 | c1 | A | B
   __shared__ float s_part[4][128];
+  __shared__ short s_wrow[RT_MAXKC * RT_CHUNK];        // copy of the chunks' W-row tables: lane-varying indices into kernel
+                                                       // parameters serialise in the constant cache (~1 us per access)
   __shared__ double s_stat[4][RT_STAT_SLOTS][2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n_rows;
@@ -96,6 +105,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
     for (int i = 0; i < NOS; ++i) { mbar_init(&aux_full[i], 1); mbar_init(&out_full[i], 128); mbar_init(&col_done[i], 128); }
     notconv_s = 0;
   }
+  for (int e = tid; e < NKC * RT_CHUNK; e += RT_THREADS) s_wrow[e] = a.kc[e >> 5].wrow[e & 31];
   // ---- per-column constants ------------------------------------------------------------------------------------------
   if (MODE == RT_FWD) {
     if (a.net.bn_mode) {
@@ -114,6 +124,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
     }
   }
   __syncthreads();
+  RT_STAMP(1);
   // ---- resident weights: TF32 hi / lo, K-major SWIZZLE_128B tiles per K chunk -------------------------------------------
   const int H = a.H;
   if (MODE == RT_FWD) {
@@ -126,23 +137,53 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
         a.net.mvar[c] -= (a.net.mvar[c] - s_c[3][c]) * decay;
       }
     }
-    for (int e = tid; e < NKC * 32 * BN; e += RT_THREADS) {
-      const int kc = e / (32 * BN), r = e - kc * 32 * BN;
-      const int k = r / BN, nn = r - k * BN;
-      const int c = a.kc[kc].wrow[k];
-      float w = 0.f;
-      if (c >= 0 && nn < H) { w = Wg[(size_t)c * H + nn]; if (bn) w *= s_c[0][c]; }
-      const int off = kc * wtile + tc_sw128_off(nn, k);
-      *reinterpret_cast<uint32_t*>(Whi + off) = __float_as_uint(w);
-      *reinterpret_cast<uint32_t*>(Wlo + off) = tc_lo(__float_as_uint(w));
+    {
+      // 8 independent global loads in flight per thread (a one-at-a-time loop costs a full L2 round trip per element:
+      // measured 28 us for the widest layer)
+      // branch-free batches: addresses first (invalid elements read W[0] and are scaled by 0), then all loads, then the math
+      const int E = NKC * 32 * BN;
+      for (int e0 = tid; e0 < E; e0 += 8 * RT_THREADS) {
+        float w[8], sc[8];
+        int off[8], src[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = min(e0 + u * RT_THREADS, E - 1);
+          const int kc = e / (32 * BN), r = e - kc * 32 * BN;
+          const int k = r / BN, nn = r - k * BN;
+          const int c = s_wrow[kc * RT_CHUNK + k];
+          const bool ok = c >= 0 && nn < H;
+          off[u] = (e0 + u * RT_THREADS < E) ? kc * wtile + tc_sw128_off(nn, k) : -1;
+          src[u] = ok ? c * H + nn : 0;
+          sc[u] = ok ? (bn ? s_c[0][c >= 0 ? c : 0] : 1.0f) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(Wg + src[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (off[u] >= 0) {
+            const float v = w[u] * sc[u];
+            *reinterpret_cast<uint32_t*>(Whi + off[u]) = __float_as_uint(v);
+            *reinterpret_cast<uint32_t*>(Wlo + off[u]) = tc_lo(__float_as_uint(v));
+          }
+      }
     }
     // folded bias b_j + sum_c B_c W[c][j]: 4 fixed groups of input columns per output column, combined in a fixed order
     // (the launcher keeps BN <= 112 in this mode: 4 * BN <= RT_THREADS)
     if (tid < 4 * BN) {
       const int g = tid / BN, nn = tid - g * BN;
       float part = 0.f;
-      if (bn && nn < H)
-        for (int c = g; c < a.net.in_dim; c += 4) part = fmaf(s_c[1][c], Wg[(size_t)c * H + nn], part);
+      if (bn && nn < H) {
+        const int in = a.net.in_dim;
+        int c = g;
+        for (; c + 28 < in; c += 32) {                 // 8 loads in flight, summed in a fixed order
+          float wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = __ldg(Wg + (size_t)(c + 4 * u) * H + nn);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) part = fmaf(s_c[1][c + 4 * u], wv[u], part);
+        }
+        for (; c < in; c += 4) part = fmaf(s_c[1][c], __ldg(Wg + (size_t)c * H + nn), part);
+      }
       s_part[g][nn] = part;
     }
     __syncthreads();
@@ -157,29 +198,52 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
       s_tab[o][0][j] = b;
     }
   } else {
-    for (int e = tid; e < NKC * 32 * BN; e += RT_THREADS) {
-      const int kc = e / (32 * BN), r = e - kc * 32 * BN;
-      const int nn = r >> 5, k = r & 31;
-      const int j = a.kc[kc].wrow[k];
-      float w = 0.f;
-      if (j >= 0 && j < H) {
-        for (int b = 0; b < a.n_blk; ++b)
-          if (nn >= a.blk_acc0[b] && nn < a.blk_acc0[b] + a.blk_w[b]) {
-            const int c = a.blk_in0[b] + (nn - a.blk_acc0[b]);
-            w = a.W[(size_t)c * H + j];
-            if (a.colscale) w *= a.colscale[c];
+    // accumulator column nn -> input column (row of W) and its scale gamma * rstd; then the tiles with 8 loads in flight
+    int* s_ncol = reinterpret_cast<int*>(ring);        // scratch in the (still unused) operand ring
+    float* s_nscale = reinterpret_cast<float*>(ring) + 256;
+    for (int nn = tid; nn < BN; nn += RT_THREADS) {
+      int c = -1;
+      for (int b = 0; b < a.n_blk; ++b)
+        if (nn >= a.blk_acc0[b] && nn < a.blk_acc0[b] + a.blk_w[b]) c = a.blk_in0[b] + (nn - a.blk_acc0[b]);
+      s_ncol[nn] = c;
+      s_nscale[nn] = (c >= 0 && a.colscale) ? a.colscale[c] : 1.0f;
+    }
+    __syncthreads();
+    {
+      const int E = NKC * 32 * BN;
+      for (int e0 = tid; e0 < E; e0 += 8 * RT_THREADS) {
+        float w[8], sc[8];
+        int off[8], src[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = min(e0 + u * RT_THREADS, E - 1);
+          const int kc = e / (32 * BN), r = e - kc * 32 * BN;
+          const int nn = r >> 5, k = r & 31;
+          const int j = s_wrow[kc * RT_CHUNK + k], c = s_ncol[nn];
+          const bool ok = j >= 0 && j < H && c >= 0;
+          off[u] = (e0 + u * RT_THREADS < E) ? kc * wtile + tc_sw128_off(nn, k) : -1;
+          src[u] = ok ? c * H + j : 0;
+          sc[u] = ok ? s_nscale[nn] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(a.W + src[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (off[u] >= 0) {
+            const float v = w[u] * sc[u];
+            *reinterpret_cast<uint32_t*>(Whi + off[u]) = __float_as_uint(v);
+            *reinterpret_cast<uint32_t*>(Wlo + off[u]) = tc_lo(__float_as_uint(v));
           }
       }
-      const int off = kc * wtile + tc_sw128_off(nn, k);
-      *reinterpret_cast<uint32_t*>(Whi + off) = __float_as_uint(w);
-      *reinterpret_cast<uint32_t*>(Wlo + off) = tc_lo(__float_as_uint(w));
     }
+    __syncthreads();                                   // the scratch in the ring is dead before the first TMA load lands
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
+  RT_STAMP(2);
 
   if (warp == RT_W_PROD) {
     // =================== TMA producer: operand "hi" tiles ==========================================================
@@ -232,9 +296,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   } else if (warp == RT_W_OUT) {
     // =================== out thread: side-input preload + store of the finished output stages ============================
     if (lane == 0) {
-      const int total = my_tiles * NOC;
-      for (int g = 0; g < total + NOS - 1; ++g) {
+      // chunk g's stage is released once the store of chunk g - NOS has read it: stores are issued NOS - 2 chunks behind the
+      // releases, so "all but the latest store group have been read" is enough and one store is always in flight
+      const int total = my_tiles * NOC, lag = NOS - 2;
+      for (int g = 0; g < total + lag; ++g) {
         if (g < total) {
+          if (g >= NOS) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           const int s = g % NOS, tq = g / NOC, o = g - tq * NOC;
           if (a.oc[o].aux_map >= 0) {
             mbar_expect_tx(&aux_full[s], RT_STAGE_BYTES);
@@ -243,13 +310,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
             mbar_arrive(&aux_full[s]);
           }
         }
-        const int h = g - (NOS - 1);
-        if (h >= 0) {
+        const int h = g - lag;
+        if (h >= 0 && h < total) {
           const int s = h % NOS, tq = h / NOC, o = h - tq * NOC;
           mbar_wait_bounded(use_col ? &col_done[s] : &out_full[s], (uint32_t)(h / NOS) & 1u);
           rt_tma_store(&a.maps[a.oc[o].out_map], a.oc[o].out_col0, (tile0 + tq) * RT_ROWS, outst + (size_t)s * RT_STAGE_BYTES);
           bulk_commit();
-          bulk_wait_read0();                           // the stage may be refilled by the next preload
         }
       }
       bulk_wait0();
@@ -385,6 +451,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  RT_STAMP(3);
   if (MODE == RT_FWD) {
     if (a.flag_next && tid == 0 && notconv_s) atomicOr(a.flag_next, 1);
     if (use_col) {
@@ -399,6 +466,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
     }
   }
   if (warp == RT_W_MMA) tmem_dealloc(tmem_d, (uint32_t)a.tmem_cols);
+  RT_STAMP(4);
+}
+
+extern "C" int gnnfp_debug_rt_times(long long* out, int mode) {      // out[160][8] of the last launch of `mode`
+  GNNFP_CHECK_CUDA(cudaDeviceSynchronize());
+  GNNFP_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_rt_times, (size_t)160 * 8 * sizeof(long long), (size_t)(mode ? 1 : 0) * 160 * 8 * sizeof(long long)));
+  return GNNFP_OK;
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
@@ -436,19 +510,18 @@ int rows_tma_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld) {
   return GNNFP_OK;
 }
 
-static size_t rt_smem_cap() {
-  static size_t cap = 0;
-  if (!cap) {
+static size_t rt_smem_cap(int mode) {              // dynamic shared memory a launch of this mode may use next to the kernel's static arrays
+  static size_t cap[2] = {0, 0};
+  const int mi = mode == RT_DX ? 1 : 0;
+  if (!cap[mi]) {
     cudaFuncAttributes fa;
     int dev = 0, optin = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaFuncGetAttributes(&fa, rows_tma_kernel<RT_FWD>) != cudaSuccess ||
+    const cudaError_t e = mi ? cudaFuncGetAttributes(&fa, rows_tma_kernel<RT_DX>) : cudaFuncGetAttributes(&fa, rows_tma_kernel<RT_FWD>);
+    if (e != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
-    cudaFuncAttributes fb;
-    if (cudaFuncGetAttributes(&fb, rows_tma_kernel<RT_DX>) != cudaSuccess) return 0;
-    const size_t st = fa.sharedSizeBytes > fb.sharedSizeBytes ? fa.sharedSizeBytes : fb.sharedSizeBytes;
-    cap = (size_t)optin - st;
+    cap[mi] = (size_t)optin - fa.sharedSizeBytes;
   }
-  return cap;
+  return cap[mi];
 }
 size_t rows_tma_smem(const RowsTmaArgs& a) {
   return (size_t)2 * a.n_kc * a.BN * 128 + (size_t)a.n_stages * 2 * RT_STAGE_BYTES + (size_t)a.n_ostages * RT_STAGE_BYTES + 1024;
@@ -458,14 +531,16 @@ int rows_tma_finish(RowsTmaArgs& a) {
     GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: shape outside the kernel's limits (K chunks %d, output chunks %d, N %d)", a.n_kc, a.n_oc, a.BN);
   const int need = 2 * a.BN + 32;
   a.tmem_cols = need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512));
-  const size_t cap = rt_smem_cap();
+  const size_t cap = rt_smem_cap(a.mode);
   if (!cap) GNNFP_FAIL(GNNFP_E_CUDA, "rows_tma: cannot query the shared-memory budget");
   a.n_ostages = 2;
   a.n_stages = 2;
   if (rows_tma_smem(a) > cap) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: %zu bytes of shared memory needed, %zu available", rows_tma_smem(a), cap);
   static const int st_max = getenv("GNNFP_RT_STAGES") ? atoi(getenv("GNNFP_RT_STAGES")) : 4;
-  while (a.n_stages < st_max && a.n_stages < 8) { ++a.n_stages; if (rows_tma_smem(a) > cap) { --a.n_stages; break; } }
+  // output stages first: the side-input preload -> epilogue -> statistics -> store chain of a chunk is ~2 us long, a deeper
+  // operand ring measured no gain beyond 2 stages
   while (a.n_ostages < 4) { ++a.n_ostages; if (rows_tma_smem(a) > cap) { --a.n_ostages; break; } }
+  while (a.n_stages < st_max && a.n_stages < 8) { ++a.n_stages; if (rows_tma_smem(a) > cap) { --a.n_stages; break; } }
   return GNNFP_OK;
 }
 
