@@ -69,6 +69,26 @@ __device__ long long g_rt_times[2][160][8];
 __device__ __forceinline__ long long rt_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define RT_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_rt_times[MODE][blockIdx.x][i] = rt_now(); } while (0)
 
+// D[tmem] (+)= A[tmem] . B[smem desc]^T: the A operand (M = 128 lanes x 8 TF32 columns) comes from tensor memory
+__device__ __forceinline__ void rt_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void rt_tmem_st8(uint32_t addr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// one lane of a converged warp (the single-thread roles run their loops warp-uniformly and predicate only the
+// instruction itself: under `if (lane == 0)` every operand is a per-thread value and each tcgen05.mma / TMA instruction is
+// wrapped in a ~20-instruction R2UR "waterfall" loop - measured ~3 us per 128-row tile for the MMA issuer alone)
+__device__ __forceinline__ bool rt_elect() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+__device__ __forceinline__ void rt_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int MODE>
 __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_constant__ RowsTmaArgs a) {
   if (a.gate && *a.gate == 0) return;
@@ -79,8 +99,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   const int wtile = BN * 128;                          // bytes of one [BN x 32] weight tile
   uint8_t* Whi = base;                                 // [NKC][BN x 32] hi, then lo
   uint8_t* Wlo = Whi + (size_t)NKC * wtile;
-  uint8_t* ring = Wlo + (size_t)NKC * wtile;           // [NST][hi | lo]
-  uint8_t* outst = ring + (size_t)NST * 2 * RT_STAGE_BYTES;   // [NOS]
+  uint8_t* ring = Wlo + (size_t)NKC * wtile;           // [NST] raw fp32 operand tiles = a_hi (a_lo lives in tensor memory)
+  uint8_t* outst = ring + (size_t)NST * RT_STAGE_BYTES;       // [NOS]
+  const uint32_t lo_col0 = (uint32_t)(2 * BN + 32);    // TMEM columns [lo_col0 + 32 * slot, +32): a_lo of ring slot `slot`
   __shared__ __align__(8) uint64_t slot_empty[8], hi_full[8], ops_full[8], tm_full[2], tm_empty[2], aux_full[4], out_full[4], col_done[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ int notconv_s;
@@ -247,22 +268,25 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
 
   if (warp == RT_W_PROD) {
     // =================== TMA producer: operand "hi" tiles ==========================================================
-    if (lane == 0) {
+    {
       int slot = 0;
       uint32_t use = 0;
       for (int tq = 0; tq < my_tiles; ++tq) {
         const int row0 = (tile0 + tq) * RT_ROWS;
         for (int kc = 0; kc < NKC; ++kc) {
           if (use > 0) mbar_wait_bounded(&slot_empty[slot], (use - 1) & 1);
-          mbar_expect_tx(&hi_full[slot], RT_STAGE_BYTES);
-          rt_tma_load(ring + (size_t)slot * 2 * RT_STAGE_BYTES, &a.maps[a.kc[kc].map], a.kc[kc].col0, row0, &hi_full[slot]);
+          if (rt_elect()) {
+            mbar_expect_tx(&hi_full[slot], RT_STAGE_BYTES);
+            rt_tma_load(ring + (size_t)slot * RT_STAGE_BYTES, &a.maps[a.kc[kc].map], a.kc[kc].col0, row0, &hi_full[slot]);
+          }
+          __syncwarp();
           if (++slot == NST) { slot = 0; ++use; }
         }
       }
     }
   } else if (warp == RT_W_MMA) {
     // =================== MMA issuer ================================================================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(RT_ROWS >> 4) << 24);
       const uint32_t whi_addr = smem_u32(Whi), wlo_addr = smem_u32(Wlo), ring_addr = smem_u32(ring);
       int slot = 0;
@@ -275,74 +299,87 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
         for (int kc = 0; kc < NKC; ++kc) {
           mbar_wait_bounded(&ops_full[slot], ph);
           tc_fence_after();
-          const uint64_t dah = tc_desc_sw128(ring_addr + slot * 2 * RT_STAGE_BYTES);
-          const uint64_t dal = tc_desc_sw128(ring_addr + slot * 2 * RT_STAGE_BYTES + RT_STAGE_BYTES);
+          const uint64_t dah = tc_desc_sw128(ring_addr + slot * RT_STAGE_BYTES);
+          const uint32_t alo = tmem_d + lo_col0 + (uint32_t)(32 * slot);
           const uint64_t dbh = tc_desc_sw128(whi_addr + kc * wtile);
           const uint64_t dbl = tc_desc_sw128(wlo_addr + kc * wtile);
           const int k8n = a.kc[kc].k8;
-          for (int k8 = 0; k8 < k8n; ++k8) {           // 8 fp32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
-            const uint64_t adv = (uint64_t)(2 * k8);
-            tc_mma_tf32(dcol, dal + adv, dbh + adv, idesc, acc);
-            acc = 1u;
-            tc_mma_tf32(dcol, dah + adv, dbl + adv, idesc, 1u);
-            tc_mma_tf32(dcol, dah + adv, dbh + adv, idesc, 1u);
+          if (rt_elect()) {
+            for (int k8 = 0; k8 < k8n; ++k8) {         // 8 fp32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
+              const uint64_t adv = (uint64_t)(2 * k8);
+              rt_mma_tf32_ts(dcol, alo + (uint32_t)(8 * k8), dbh + adv, idesc, acc);
+              acc = 1u;
+              tc_mma_tf32(dcol, dah + adv, dbl + adv, idesc, 1u);
+              tc_mma_tf32(dcol, dah + adv, dbh + adv, idesc, 1u);
+            }
+            tc_commit(&slot_empty[slot]);
+            if (kc == NKC - 1) tc_commit(&tm_full[tb]);
           }
-          tc_commit(&slot_empty[slot]);
-          if (kc == NKC - 1) tc_commit(&tm_full[tb]);
+          __syncwarp();
+          acc = 1u;
           if (++slot == NST) { slot = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == RT_W_OUT) {
     // =================== out thread: side-input preload + store of the finished output stages ============================
-    if (lane == 0) {
+    {
       // chunk g's stage is released once the store of chunk g - NOS has read it: stores are issued NOS - 2 chunks behind the
       // releases, so "all but the latest store group have been read" is enough and one store is always in flight
       const int total = my_tiles * NOC, lag = NOS - 2;
       for (int g = 0; g < total + lag; ++g) {
+        const bool leader = rt_elect();              // the same lane every time: bulk-store groups are per thread
         if (g < total) {
-          if (g >= NOS) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           const int s = g % NOS, tq = g / NOC, o = g - tq * NOC;
-          if (a.oc[o].aux_map >= 0) {
-            mbar_expect_tx(&aux_full[s], RT_STAGE_BYTES);
-            rt_tma_load(outst + (size_t)s * RT_STAGE_BYTES, &a.maps[a.oc[o].aux_map], a.oc[o].aux_col0, (tile0 + tq) * RT_ROWS, &aux_full[s]);
-          } else {
-            mbar_arrive(&aux_full[s]);
+          if (leader) {
+            if (g >= NOS) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (a.oc[o].aux_map >= 0) {
+              mbar_expect_tx(&aux_full[s], RT_STAGE_BYTES);
+              rt_tma_load(outst + (size_t)s * RT_STAGE_BYTES, &a.maps[a.oc[o].aux_map], a.oc[o].aux_col0, (tile0 + tq) * RT_ROWS, &aux_full[s]);
+            } else {
+              mbar_arrive(&aux_full[s]);
+            }
           }
+          __syncwarp();
         }
         const int h = g - lag;
         if (h >= 0 && h < total) {
           const int s = h % NOS, tq = h / NOC, o = h - tq * NOC;
           mbar_wait_bounded(use_col ? &col_done[s] : &out_full[s], (uint32_t)(h / NOS) & 1u);
-          rt_tma_store(&a.maps[a.oc[o].out_map], a.oc[o].out_col0, (tile0 + tq) * RT_ROWS, outst + (size_t)s * RT_STAGE_BYTES);
-          bulk_commit();
+          if (leader) {
+            rt_tma_store(&a.maps[a.oc[o].out_map], a.oc[o].out_col0, (tile0 + tq) * RT_ROWS, outst + (size_t)s * RT_STAGE_BYTES);
+            bulk_commit();
+          }
+          __syncwarp();
         }
       }
-      bulk_wait0();
+      if (rt_elect()) bulk_wait0();
     }
   } else if (warp >= RT_W_CONV && warp < RT_W_CONV + 4) {
     // =================== converters: thread = row, lo tile of the landed stage ==============================================
-    const int r = tid - 32 * RT_W_CONV;
+    const int r = tid - 32 * RT_W_CONV;                 // row of the tile = TMEM lane (warp w may touch lanes 32 (w & 3) ..)
     const int rbase = (r >> 3) * 1024 + (r & 7) * 128, rx = r & 7;
+    const uint32_t lo_lane = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + lo_col0;
     int slot = 0;
     uint32_t ph = 0;
     for (int tq = 0; tq < my_tiles; ++tq) {
       for (int kc = 0; kc < NKC; ++kc) {
         mbar_wait_bounded(&hi_full[slot], ph);
-        uint8_t* hi = ring + (size_t)slot * 2 * RT_STAGE_BYTES + rbase;
-        uint8_t* lo = hi + RT_STAGE_BYTES;
-        const int nl = 2 * a.kc[kc].k8;                // 16-byte chunks that carry data
+        const uint8_t* hi = ring + (size_t)slot * RT_STAGE_BYTES + rbase;
+        const int k8n = a.kc[kc].k8;                   // 8-column K steps that carry data
 #pragma unroll
-        for (int l = 0; l < 8; ++l) {
-          if (l < nl) {
-            const int off = (l ^ rx) << 4;
-            const uint4 v = *reinterpret_cast<const uint4*>(hi + off);
-            uint4 w;
-            w.x = tc_lo(v.x); w.y = tc_lo(v.y); w.z = tc_lo(v.z); w.w = tc_lo(v.w);
-            *reinterpret_cast<uint4*>(lo + off) = w;
+        for (int q = 0; q < 4; ++q) {
+          if (q < k8n) {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(hi + (((2 * q) ^ rx) << 4));
+            const uint4 v1 = *reinterpret_cast<const uint4*>(hi + (((2 * q + 1) ^ rx) << 4));
+            uint32_t w[8];
+            w[0] = tc_lo(v0.x); w[1] = tc_lo(v0.y); w[2] = tc_lo(v0.z); w[3] = tc_lo(v0.w);
+            w[4] = tc_lo(v1.x); w[5] = tc_lo(v1.y); w[6] = tc_lo(v1.z); w[7] = tc_lo(v1.w);
+            rt_tmem_st8(lo_lane + (uint32_t)(32 * slot + 8 * q), w);
           }
         }
-        fence_proxy_async();
+        rt_tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(&ops_full[slot]);
         if (++slot == NST) { slot = 0; ph ^= 1u; }
       }
@@ -524,23 +561,27 @@ static size_t rt_smem_cap(int mode) {              // dynamic shared memory a la
   return cap[mi];
 }
 size_t rows_tma_smem(const RowsTmaArgs& a) {
-  return (size_t)2 * a.n_kc * a.BN * 128 + (size_t)a.n_stages * 2 * RT_STAGE_BYTES + (size_t)a.n_ostages * RT_STAGE_BYTES + 1024;
+  return (size_t)2 * a.n_kc * a.BN * 128 + (size_t)a.n_stages * RT_STAGE_BYTES + (size_t)a.n_ostages * RT_STAGE_BYTES + 1024;
 }
 int rows_tma_finish(RowsTmaArgs& a) {
   if (a.n_kc < 1 || a.n_kc > RT_MAXKC || a.n_oc < 1 || a.n_oc > RT_MAXOC || a.BN < 16 || a.BN > RT_MAXBN || a.BN % 16 != 0)
     GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: shape outside the kernel's limits (K chunks %d, output chunks %d, N %d)", a.n_kc, a.n_oc, a.BN);
-  const int need = 2 * a.BN + 32;
-  a.tmem_cols = need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512));
   const size_t cap = rt_smem_cap(a.mode);
   if (!cap) GNNFP_FAIL(GNNFP_E_CUDA, "rows_tma: cannot query the shared-memory budget");
   a.n_ostages = 2;
   a.n_stages = 2;
   if (rows_tma_smem(a) > cap) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: %zu bytes of shared memory needed, %zu available", rows_tma_smem(a), cap);
-  static const int st_max = getenv("GNNFP_RT_STAGES") ? atoi(getenv("GNNFP_RT_STAGES")) : 4;
+  static const int st_max = getenv("GNNFP_RT_STAGES") ? atoi(getenv("GNNFP_RT_STAGES")) : 6;
   // output stages first: the side-input preload -> epilogue -> statistics -> store chain of a chunk is ~2 us long, a deeper
   // operand ring measured no gain beyond 2 stages
   while (a.n_ostages < 4) { ++a.n_ostages; if (rows_tma_smem(a) > cap) { --a.n_ostages; break; } }
-  while (a.n_stages < st_max && a.n_stages < 8) { ++a.n_stages; if (rows_tma_smem(a) > cap) { --a.n_stages; break; } }
+  // ring depth: bounded by shared memory (16 KB per stage) and by tensor memory (32 columns of a_lo per stage)
+  while (a.n_stages < st_max && a.n_stages < 8 && 2 * a.BN + 32 + 32 * (a.n_stages + 1) <= 512) {
+    ++a.n_stages;
+    if (rows_tma_smem(a) > cap) { --a.n_stages; break; }
+  }
+  const int need = 2 * a.BN + 32 + 32 * a.n_stages;
+  a.tmem_cols = need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512));
   return GNNFP_OK;
 }
 
