@@ -10,6 +10,8 @@
 #define GNNFP_MAXP 6        // max input pieces of one net application
 #define GNNFP_JC 16         // output columns per thread chunk in the tile MLP
 #define GNNFP_NSM_FALLBACK 148
+#define GNNFP_TILE_ROWS 128       // row tile of the TMA kernels (rows_tma.cu) and of the tile-local CSR view (graph.cu)
+#define GNNFP_TILE_ARCS 1024      // in-arcs of one tile the fused gather can stage; tiles above are handled by the row-list pass
 
 // ---- error plumbing (never throw across the C ABI) -------------------------------------------
 void gnnfp_set_error(const char* fmt, ...);
@@ -212,6 +214,7 @@ int launch_dz(const DzArgs& a, cudaStream_t s);
 
 struct AggArgs {            // AGG = Adj^T . S (dst-CSR gather) as a streaming kernel + fp64 column statistics
   int n_rows;
+  const int* n_rows_dev;   // optional device scalar overriding n_rows (then n_rows is only the upper bound that sizes the grid)
   const int* rowlist;
   int D;
   const float* S; int ld;

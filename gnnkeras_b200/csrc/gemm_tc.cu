@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
     tc_cp_wait<0>();
   } else if (warp == 4 + TC_EPI_WARPS) {
     // =================== MMA issuer: one thread drives the tensor core ====================================================
-    if (lane == 0) {
+    {   // warp-uniform loop, one elected lane issues (a lane-0 branch wraps every tcgen05.mma in an R2UR waterfall loop)
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t whi_addr = smem_u32(Whi), wlo_addr = smem_u32(Wlo), aop_addr = smem_u32(Aop);
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           tc_fence_after();
           const uint64_t dah = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES);
           const uint64_t dal = tc_desc_sw128(aop_addr + ob * 2 * TC_TILE_BYTES + TC_TILE_BYTES);
+          if (tc_elect()) {
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
             const uint32_t dcol = dcol0 + (uint32_t)(b * BN);
@@ -221,6 +222,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_rows_tc_kernel(const __gri
           }
           tc_commit(&ops_empty[ob]);                   // operand buffer free once these MMAs have completed
           if (kb == NKB - 1) tc_commit(&tm_full[tb]);  // accumulator tile complete
+          }
+          __syncwarp();
           if (++ob == NST) { ob = 0; oph ^= 1u; }
         }
       }
@@ -674,8 +677,8 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
       mbar_arrive(&ops_full[slot]);
     }
     tc_cp_wait<0>();
-  } else if (lane == 0) {
-    // ---- MMA issuer -------------------------------------------------------------------------------------------------------
+  } else {
+    // ---- MMA issuer (warp-uniform loop, one elected lane issues) ----------------------------------------------------------
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t ops_addr = smem_u32(ops);
     for (int it = 0; it < total; ++it) {
@@ -685,16 +688,20 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
       const uint32_t sa = ops_addr + slot * slot_bytes;
       const uint64_t dah = tc_desc_sw128(sa), dal = tc_desc_sw128(sa + TC_TILE_BYTES);
       const uint64_t dbh = tc_desc_sw128(sa + 2 * TC_TILE_BYTES), dbl = tc_desc_sw128(sa + 2 * TC_TILE_BYTES + btile);
+      if (tc_elect()) {
 #pragma unroll
-      for (int k8 = 0; k8 < DW_TC_ROWS / 8; ++k8) {
-        const uint64_t adv = (uint64_t)(2 * k8);
-        tc_mma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (it | k8) ? 1u : 0u);
-        tc_mma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-        tc_mma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+        for (int k8 = 0; k8 < DW_TC_ROWS / 8; ++k8) {
+          const uint64_t adv = (uint64_t)(2 * k8);
+          tc_mma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (it | k8) ? 1u : 0u);
+          tc_mma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+          tc_mma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+        }
+        tc_commit(&ops_empty[slot]);
       }
-      tc_commit(&ops_empty[slot]);
+      __syncwarp();
     }
-    tc_commit(&done_bar);
+    if (tc_elect()) tc_commit(&done_bar);
+    __syncwarp();
   }
   // ---- flush: accumulator -> shared memory (sD[c][j]) -> BN algebra -> this CTA's partial slot -------------------------
   constexpr int HS = 129;                              // leading dimension of sD (rows of D = 128 TMEM lanes)

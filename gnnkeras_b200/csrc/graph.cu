@@ -94,6 +94,31 @@ static __global__ void k_nodegraph_values(const int* node2graph, const int* cnt,
   if (i < n) val[i] = (float)(1.0 * (1.0 / (double)cnt[node2graph[i]]));   // graph_class.py:136
 }
 
+// ---- tile-local view of the dst-CSR (fused forward iteration, rows_tma.cu) ------------------------------------------
+// entry p of row j: lidx = src - 128 * (j / 128) if the source lies in j's 128-row tile, else -1
+static __global__ void k_tile_lidx(const int* rowptr, const int* csr_src, int n, short* lidx, uint8_t* bnd) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int t0 = j & ~(GNNFP_TILE_ROWS - 1);
+  const int tend = t0 + GNNFP_TILE_ROWS < n ? t0 + GNNFP_TILE_ROWS : n;
+  bool out = rowptr[tend] - rowptr[t0] > GNNFP_TILE_ARCS;     // too many arcs for the staged gather: the whole tile goes to the row-list pass
+  for (int p = rowptr[j]; p < rowptr[j + 1]; ++p) {
+    const int l = csr_src[p] - t0;
+    const bool in = l >= 0 && l < GNNFP_TILE_ROWS;
+    lidx[p] = in ? (short)l : (short)-1;
+    out = out || !in;
+  }
+  bnd[j] = out ? 1 : 0;
+}
+static __global__ void k_tile_arc0(const int* rowptr, int n, int n_tiles, int* arc0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tiles + 2) { const int r = i * GNNFP_TILE_ROWS; arc0[i] = rowptr[r < n ? r : n]; }
+}
+static __global__ void k_fill_i(int* p, int n, const int* value) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = *value;
+}
+
 #define GRID(n) (((n) + 255) / 256), 256
 
 // Stream-ordered allocations from the device's default memory pool (kept warm: release threshold
@@ -120,9 +145,9 @@ struct DevAlloc {
 
 // stable sort of arc ids by key -> CSR (rowptr, permutation)
 static int build_csr(DevAlloc& A, const int* key, int n_arcs, int n_rows, int** rowptr, int** perm, void** tmp,
-                     size_t* tmp_bytes, int* d_bad, cudaStream_t s) {
+                     size_t* tmp_bytes, int* d_bad, cudaStream_t s, int rowptr_pad = 0) {
   int rc;
-  if ((rc = A.get(rowptr, (size_t)n_rows + 1))) return rc;
+  if ((rc = A.get(rowptr, (size_t)n_rows + 1 + rowptr_pad))) return rc;
   if ((rc = A.get(perm, (size_t)n_arcs))) return rc;
   int *cnt = nullptr, *iota = nullptr, *key_out = nullptr;
   GNNFP_CHECK_CUDA(cudaMallocAsync(&cnt, sizeof(int) * ((size_t)n_rows + 1), s));
@@ -229,12 +254,16 @@ extern "C" int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* d, v
     BUILD_CUDA(cudaMemcpyAsync(g->src, d->src, sizeof(int) * NA, cudaMemcpyDeviceToDevice, s));
     BUILD_CUDA(cudaMemcpyAsync(g->dst, d->dst, sizeof(int) * NA, cudaMemcpyDeviceToDevice, s));
   }
-  BUILD_TRY(build_csr(A, g->dst, NA, N, &g->dst_rowptr, &g->dst_arc, &tmp, &tmp_bytes, d_bad, s));
+  // (the row pointer and the weights carry padding: the fused forward iteration stages fixed-size, 16-byte aligned slices)
+  const int RP_PAD = 2 * GNNFP_TILE_ROWS + 8, ARC_PAD = GNNFP_TILE_ARCS + 32;
+  BUILD_TRY(build_csr(A, g->dst, NA, N, &g->dst_rowptr, &g->dst_arc, &tmp, &tmp_bytes, d_bad, s, RP_PAD));
+  k_fill_i<<<GRID(RP_PAD), 0, s>>>(g->dst_rowptr + N + 1, RP_PAD, g->dst_rowptr + N);
   BUILD_TRY(build_csr(A, g->src, NA, N, &g->src_rowptr, &g->src_arc, &tmp, &tmp_bytes, d_bad, s));
   BUILD_TRY(A.get(&g->dst_src, (size_t)NA));
   BUILD_TRY(A.get(&g->src_dst, (size_t)NA));
   BUILD_TRY(A.get(&g->arc_val, (size_t)NA));
-  BUILD_TRY(A.get(&g->dst_w, (size_t)NA));
+  BUILD_TRY(A.get(&g->dst_w, (size_t)NA + ARC_PAD));
+  BUILD_CUDA(cudaMemsetAsync(g->dst_w + NA, 0, sizeof(float) * ARC_PAD, s));
   BUILD_TRY(A.get(&g->src_w, (size_t)NA));
   if (NA) {
     k_gather_i<<<GRID(NA), 0, s>>>(g->src, g->dst_arc, g->dst_src, NA);
@@ -256,6 +285,29 @@ extern "C" int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* d, v
     BUILD_CUDA(cudaFreeAsync(indeg, s));
     k_gather_f<<<GRID(NA), 0, s>>>(g->arc_val, g->dst_arc, g->dst_w, NA);
     k_gather_f<<<GRID(NA), 0, s>>>(g->arc_val, g->src_arc, g->src_w, NA);
+  }
+  // tile-local CSR view + boundary row list (count stays on the device: no host synchronisation)
+  {
+    const int n_tiles = (N + GNNFP_TILE_ROWS - 1) / GNNFP_TILE_ROWS;
+    uint8_t* bflag = nullptr;
+    BUILD_TRY(A.get(&g->tile_lidx, (size_t)NA + ARC_PAD));
+    BUILD_TRY(A.get(&g->tile_arc0, (size_t)n_tiles + 2));
+    BUILD_TRY(A.get(&g->bnd_rows, (size_t)N));
+    BUILD_TRY(A.get(&g->bnd_count, (size_t)1));
+    BUILD_TRY(A.get(&bflag, (size_t)N));
+    BUILD_CUDA(cudaMemsetAsync(g->tile_lidx + NA, 0xFF, sizeof(short) * ARC_PAD, s));
+    k_tile_lidx<<<GRID(N), 0, s>>>(g->dst_rowptr, g->dst_src, N, g->tile_lidx, bflag);
+    k_tile_arc0<<<GRID(n_tiles + 2), 0, s>>>(g->dst_rowptr, N, n_tiles, g->tile_arc0);
+    thrust::counting_iterator<int> it(0);
+    size_t need = 0;
+    cub::DeviceSelect::Flagged(nullptr, need, it, bflag, g->bnd_rows, g->bnd_count, N, s);
+    if (need > tmp_bytes) {
+      if (tmp) BUILD_CUDA(cudaFreeAsync(tmp, s));
+      BUILD_CUDA(cudaMallocAsync(&tmp, need, s));
+      tmp_bytes = need;
+    }
+    size_t tb = tmp_bytes;
+    BUILD_CUDA(cub::DeviceSelect::Flagged(tmp, tb, it, bflag, g->bnd_rows, g->bnd_count, N, s));
   }
   // masks -> index list
   if (!d->set_mask && !d->output_mask) {

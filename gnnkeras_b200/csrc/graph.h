@@ -24,6 +24,11 @@ struct gnnfp_graph {
   int type_count[GNNFP_MAX_TYPES] = {};
   float* typed_w[GNNFP_MAX_TYPES] = {};     // dst-CSR weights of CompositeAdjacencies[t]
   int types_ok = 1;                         // every node in exactly one type
+  // tile-local view of the dst-CSR for the fused forward iteration (rows_tma.cu): 128-row tiles
+  short* tile_lidx = nullptr;  // [A + pad] source row inside the destination's tile (dst_src - 128 * (row / 128)), -1 = outside
+  int* tile_arc0 = nullptr;    // [ceil(N/128) + 2] dst_rowptr[128 i]
+  int* bnd_rows = nullptr;     // rows with an in-arc from outside their tile (or whose tile holds too many arcs), ascending
+  int* bnd_count = nullptr;    // device scalar: entries of bnd_rows
   int* node2graph = nullptr;   // [N]
   float* ng_val = nullptr;     // [N]
   int* graph_ptr = nullptr;    // [G+1]

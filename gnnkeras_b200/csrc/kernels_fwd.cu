@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(BT) agg_stats_kernel(const __grid_constant__ A
     // arc order inside a row is kept (sequential fmaf), absent arcs are predicated off.  DIRECT (no CSR: the row's
     // only entry is S[row], weight 1) is the column-statistics / copy pass of a plain matrix.
     constexpr int NR = DIRECT ? 8 : 4;
-    const int n_rows = a.n_rows;
+    const int n_rows = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
     const int* __restrict__ rowlist = a.rowlist;
     const float* __restrict__ Sq = a.S + qx * VEC;
     const size_t ld = (size_t)a.ld;

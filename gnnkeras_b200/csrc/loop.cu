@@ -399,10 +399,15 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
       RowsTmaArgs pf, pd;
       memset(&pf, 0, sizeof(pf));
       memset(&pd, 0, sizeof(pd));
-      pf.mode = RT_FWD; pf.n_kc = nkc; pf.n_oc = (L->D + 31) / 32; pf.BN = ceil_to(L->D, 16);
+      // fused aggregation (rows_tma.cu): measured a net loss when the aggregate's BN batch statistics have to be reduced in
+      // the same kernel (column sums across thread = row partials), a gain otherwise; GNNFP_FUSE_AGG=0|1 overrides
+      const bool bn_stats = cfg->training && L->snet[0].has_bn;
+      const char* fenv = getenv("GNNFP_FUSE_AGG");
+      const int no_fuse = fenv ? (atoi(fenv) == 0) : (bn_stats ? 1 : 0);
+      pf.mode = RT_FWD; pf.n_kc = nkc; pf.n_oc = (L->D + 31) / 32; pf.BN = ceil_to(L->D, 16); pf.fuse_agg = !no_fuse;
       pd.mode = RT_DX; pd.n_kc = (L->D + 31) / 32; pd.n_oc = 2 * ((L->D + 31) / 32); pd.BN = 2 * ceil_to(L->D, 16);
       if (nkc <= RT_MAXKC && rows_tma_finish(pf) == GNNFP_OK && (!cfg->training || rows_tma_finish(pd) == GNNFP_OK)) {
-        L->xlay = 1; L->xs_inline = inl;
+        L->xlay = 1; L->xs_inline = inl; L->fuse_agg = !no_fuse;
         L->ldX = ceil_to(w0, 4); L->ldG = ceil_to(L->D, 4); L->ldXs = ceil_to(L->LsM, 4);
       }
     }
@@ -621,6 +626,14 @@ static int rt_build_fwd(const Ctx& c, int t, const gnnfp_net_params* sp, RowsTma
     if (L->bn_train_state) { ra.ost_sum = c.stS(0, t); ra.ost_sq = ra.ost_sum + D; }
   }
   ra.gate = c.flags() + (t - 1);
+  if (L->fuse_agg && t < MI) {   // Adj^T S_t for iteration t + 1, gathered from the output stages (rows local to their tile)
+    const gnnfp_graph* g = L->g;
+    ra.fuse_agg = 1;
+    ra.g_rowptr = g->dst_rowptr; ra.g_lidx = g->tile_lidx; ra.g_arc0 = g->tile_arc0;
+    ra.g_w = g->mode == GNNFP_AGG_SUM ? nullptr : g->dst_w;
+    ra.agg_out = c.AGG(t + 1); ra.ld_agg = c.ldA();
+    if (L->bn_train_state) { ra.agg_sum = c.stA(0, t); ra.agg_sq = ra.agg_sum + D; }
+  }
   return rows_tma_finish(ra);
 }
 
@@ -639,6 +652,7 @@ static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp
     const int* gate = c.flags() + (t - 1);
     for (int ty = 0; ty < L->nt; ++ty) {     // Adj^T.state of this iteration (+ BN batch statistics); saved in training
       if (!L->bn_train_state && !L->gemm_ok[ty]) continue;
+      if (L->fuse_agg && t > 1) continue;    // produced by iteration t - 1 (fused gather + the row-list pass below)
       AggArgs aa;
       memset(&aa, 0, sizeof(aa));
       TileSrc rows;
@@ -656,6 +670,19 @@ static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp
       RowsTmaArgs ra;
       if ((rc = rt_build_fwd(c, t, sp, ra))) return rc;
       if ((rc = launch_rows_tma(ra, s, PC_FWD_ITER))) return rc;
+      if (L->fuse_agg && t < MI) {
+        // rows with an in-neighbour outside their 128-row tile (graphs straddling a tile boundary): the streaming kernel over
+        // the graph's boundary row list (its length stays on the device), only if iteration t + 1 runs
+        AggArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.n_rows = N; aa.n_rows_dev = g->bnd_count; aa.rowlist = g->bnd_rows; aa.D = D;
+        aa.S = c.S(t); aa.ld = c.ldS(t);
+        aa.rowptr = g->dst_rowptr; aa.idx = g->dst_src; aa.wgt = wgt;
+        aa.out = c.AGG(t + 1); aa.ld_out = c.ldA();
+        if (L->bn_train_state) { aa.st_sum = c.stA(0, t); aa.st_sq = aa.st_sum + D; }
+        aa.gate = c.flags() + t;
+        if ((rc = launch_agg_stats(aa, s))) return rc;
+      }
     }
     for (int ty = 0; ty < L->nt; ++ty) {
       if (!L->gemm_ok[ty] || L->xlay) continue;

@@ -49,6 +49,7 @@ struct gnnfp_loop {
   int ldX = 0;           // floats per row of an X slot
   int ldG = 0;           // leading dimension of dz / dOwn / dAgg / dSfin  (D unless xlay)
   int ldXs = 0;          // leading dimension of the static block Xs / dXs  (LsM unless xlay)
+  int fuse_agg = 0;      // the forward iteration kernel also produces Adj^T S_t for the next iteration (in-tile gather)
   int xs_inline = 0;     // static columns are copied into every X slot (few columns: saves one operand chunk per tile)
   int cap_per_row = 4;   // CSR scratch capacity per tile row (from A/N)
   int grid_cap = 0;      // upper bound of any backward tile kernel grid (partials are sized by it)

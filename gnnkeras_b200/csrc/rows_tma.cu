@@ -32,14 +32,19 @@
 #include "rows_tma.h"
 #include "tc.cuh"
 
-#define RT_THREADS 480
+#define RT_THREADS 512
 #define RT_W_EPI 0
 #define RT_W_CONV 4
 #define RT_W_COL 8
 #define RT_W_PROD 12
 #define RT_W_MMA 13
 #define RT_W_OUT 14
-#define RT_STAT_SLOTS 4
+#define RT_W_CSR 15
+#define RT_CSR_RP_BYTES 528                                   // 132 row pointers
+#define RT_CSR_LI_BYTES ((GNNFP_TILE_ARCS + 8) * 2)           // local source indices (16-byte aligned window)
+#define RT_CSR_W_BYTES ((GNNFP_TILE_ARCS + 8) * 4)            // weights
+#define RT_CSR_BUF (544 + 2080 + RT_CSR_W_BYTES)              // one staged CSR slice
+#define RT_STAT_SLOTS 3
 
 __device__ __forceinline__ void rt_tma_load(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -101,8 +106,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   uint8_t* Wlo = Whi + (size_t)NKC * wtile;
   uint8_t* ring = Wlo + (size_t)NKC * wtile;           // [NST] raw fp32 operand tiles = a_hi (a_lo lives in tensor memory)
   uint8_t* outst = ring + (size_t)NST * RT_STAGE_BYTES;       // [NOS]
+  uint8_t* csrb = outst + (size_t)NOS * RT_STAGE_BYTES;       // [2] CSR slices of the fused aggregation (fuse_agg only)
   const uint32_t lo_col0 = (uint32_t)(2 * BN + 32);    // TMEM columns [lo_col0 + 32 * slot, +32): a_lo of ring slot `slot`
-  __shared__ __align__(8) uint64_t slot_empty[8], hi_full[8], ops_full[8], tm_full[2], tm_empty[2], aux_full[4], out_full[4], col_done[4];
+  __shared__ __align__(8) uint64_t slot_empty[8], hi_full[8], ops_full[8], tm_full[2], tm_empty[2], aux_full[4], out_full[4], col_done[4], csr_full[2], csr_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int notconv_s;
   __shared__ __align__(16) float s_c[4][RT_MAXIN];     // FWD: BN a | b | mean | var per input column
@@ -110,20 +116,22 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   __shared__ float s_part[4][128];
   __shared__ short s_wrow[RT_MAXKC * RT_CHUNK];        // copy of the chunks' W-row tables: lane-varying indices into kernel
                                                        // parameters serialise in the constant cache (~1 us per access)
-  __shared__ double s_stat[4][RT_STAT_SLOTS][2][32];
+  __shared__ double s_stat[4][RT_STAT_SLOTS][4][32];    // per column warp: sum / sum of squares of S_t and of Adj^T S_t
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n_rows;
   const int n_tiles = (n + RT_ROWS - 1) / RT_ROWS;
   const int tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int tile0 = blockIdx.x * tiles_per_cta;
   const int my_tiles = max(0, min(n_tiles, tile0 + tiles_per_cta) - tile0);
-  const bool use_col = MODE == RT_FWD && a.ost_sum != nullptr;
+  const bool fuse = MODE == RT_FWD && a.fuse_agg != 0;
+  const bool use_col = MODE == RT_FWD && (a.ost_sum != nullptr || fuse);
 
   if (warp == RT_W_MMA) { tmem_alloc(&tmem_base_s, (uint32_t)a.tmem_cols); tmem_relinquish(); }
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&slot_empty[i], 1); mbar_init(&hi_full[i], 1); mbar_init(&ops_full[i], 128); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128); }
     for (int i = 0; i < NOS; ++i) { mbar_init(&aux_full[i], 1); mbar_init(&out_full[i], 128); mbar_init(&col_done[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&csr_full[i], 1); mbar_init(&csr_empty[i], 128); }
     notconv_s = 0;
   }
   for (int e = tid; e < NKC * RT_CHUNK; e += RT_THREADS) s_wrow[e] = a.kc[e >> 5].wrow[e & 31];
@@ -355,6 +363,23 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
       }
       if (rt_elect()) bulk_wait0();
     }
+  } else if (warp == RT_W_CSR) {
+    // =================== CSR loader: the tile's slice of the dst-CSR (row pointers, tile-local sources, weights) ==============
+    if (fuse) {
+      for (int tq = 0; tq < my_tiles; ++tq) {
+        const int b = tq & 1, tile = tile0 + tq;
+        if (tq >= 2) mbar_wait_bounded(&csr_empty[b], (uint32_t)((tq >> 1) - 1) & 1u);
+        const int start = a.g_arc0[tile] & ~7;         // 16-byte aligned window start (shorts and floats)
+        if (rt_elect()) {
+          uint8_t* buf = csrb + (size_t)b * RT_CSR_BUF;
+          mbar_expect_tx(&csr_full[b], RT_CSR_RP_BYTES + RT_CSR_LI_BYTES + (a.g_w ? RT_CSR_W_BYTES : 0));
+          bulk_g2s(buf, a.g_rowptr + (size_t)tile * RT_ROWS, RT_CSR_RP_BYTES, &csr_full[b]);
+          bulk_g2s(buf + 544, a.g_lidx + start, RT_CSR_LI_BYTES, &csr_full[b]);
+          if (a.g_w) bulk_g2s(buf + 544 + 2080, a.g_w + start, RT_CSR_W_BYTES, &csr_full[b]);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp >= RT_W_CONV && warp < RT_W_CONV + 4) {
     // =================== converters: thread = row, lo tile of the landed stage ==============================================
     const int r = tid - 32 * RT_W_CONV;                 // row of the tile = TMEM lane (warp w may touch lanes 32 (w & 3) ..)
@@ -423,10 +448,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
               for (int jj = 0; jj < 4; ++jj) {
                 const float z = acc[4 * l + jj] + ba[jj];
                 float y = selu ? tc_selu(z) : act_fwd(a.act, z);
+                const float pj = 4 * l + jj < width ? pa[jj] : 0.f;
                 if (4 * l + jj >= width) y = 0.f;
-                const float d = y - pa[jj];
+                const float d = y - pj;
                 sd = fmaf(d, d, sd);
-                sp = fmaf(pa[jj], pa[jj], sp);
+                sp = fmaf(pj, pj, sp);
                 v[jj] = y;
               }
             } else {
@@ -452,21 +478,42 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   } else if (warp >= RT_W_COL && warp < RT_W_COL + 4) {
     // =================== column warps: lane = column, statistics of the finished output stage ================================
     const int cw = warp - RT_W_COL;
-    double s1[RT_STAT_SLOTS], s2[RT_STAT_SLOTS];
+    double s1[RT_STAT_SLOTS], s2[RT_STAT_SLOTS], g1[RT_STAT_SLOTS], g2[RT_STAT_SLOTS];
+    float padv[3] = {0.f, 0.f, 0.f};                   // this row's first Adj^T S_t columns (see the pad patch below)
 #pragma unroll
-    for (int q = 0; q < RT_STAT_SLOTS; ++q) { s1[q] = 0.0; s2[q] = 0.0; }
+    for (int q = 0; q < RT_STAT_SLOTS; ++q) { s1[q] = 0.0; s2[q] = 0.0; g1[q] = 0.0; g2[q] = 0.0; }
     if (use_col) {
       int os = 0;
       uint32_t oph = 0;
       const int coff = ((lane >> 2) << 4), cin = (lane & 3) << 2;
+      const bool want_s = a.ost_sum != nullptr;
       for (int tq = 0; tq < my_tiles; ++tq) {
-        const int rfirst = (tile0 + tq) * RT_ROWS + 32 * cw;
+        const int row0 = (tile0 + tq) * RT_ROWS;
+        const int rfirst = row0 + 32 * cw;
         const int nv = min(32, max(0, n - rfirst));
+        // staged CSR slice of this tile (fused aggregation)
+        const int* rp = nullptr;
+        const short* li = nullptr;
+        const float* wv = nullptr;
+        int arcs0 = 0;
+        bool over = false;
+        if (fuse) {
+          const int b = tq & 1;
+          mbar_wait_bounded(&csr_full[b], (uint32_t)(tq >> 1) & 1u);
+          const uint8_t* buf = csrb + (size_t)b * RT_CSR_BUF;
+          rp = reinterpret_cast<const int*>(buf) + 32 * cw;
+          arcs0 = reinterpret_cast<const int*>(buf)[0];
+          li = reinterpret_cast<const short*>(buf + 544) + (arcs0 & 7);
+          wv = a.g_w ? reinterpret_cast<const float*>(buf + 544 + 2080) + (arcs0 & 7) : nullptr;
+          over = reinterpret_cast<const int*>(buf)[RT_ROWS] - arcs0 > GNNFP_TILE_ARCS;   // graph.cu put the whole tile on the row list
+        }
         for (int o = 0; o < NOC; ++o) {
           mbar_wait_bounded(&out_full[os], oph);
-          float p1 = 0.f, p2 = 0.f;
-          if (lane < a.oc[o].width) {
-            const uint8_t* st = outst + (size_t)os * RT_STAGE_BYTES + (4 * cw) * 1024;
+          const uint8_t* stg = outst + (size_t)os * RT_STAGE_BYTES;
+          const bool colok = lane < a.oc[o].width;
+          float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;
+          if (want_s && colok) {
+            const uint8_t* st = stg + (4 * cw) * 1024;
 #pragma unroll 8
             for (int rr = 0; rr < nv; ++rr) {
               const float x = *reinterpret_cast<const float*>(st + (rr >> 3) * 1024 + (rr & 7) * 128 + (coff ^ ((rr & 7) << 4)) + cin);
@@ -474,16 +521,85 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
               p2 = fmaf(x, x, p2);
             }
           }
+          if (fuse && !over) {
+            // Adj^T S_t, thread = row (row rfirst + lane): the row's in-arcs in dst-CSR order (ascending arc id, sequential
+            // fmaf = the summation order of agg_stats_kernel and of TF's SparseTensorDenseMatMul); 128-bit swizzled reads of
+            // the neighbours' rows.  (lane = column, as in the statistics pass, costs the index / pointer work once per row
+            // and WARP instead of once per row and lane: measured 4x the whole kernel's time.)
+            const bool rowok = lane < nv;
+            const int a0 = rp[rowok ? lane : 0] - arcs0;
+            const int na = rowok ? rp[lane + 1] - rp[lane] : 0;
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            bool good = true;
+            for (int q = 0; q < na; ++q) {
+              int l = li[a0 + q];
+              const float w = wv ? wv[a0 + q] : 1.0f;
+              good = good && l >= 0;
+              l = l < 0 ? 0 : l;
+              const uint8_t* rowp = stg + (l >> 3) * 1024 + (l & 7) * 128;
+              const int key = l & 7;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                const float4 v = *reinterpret_cast<const float4*>(rowp + ((ch ^ key) << 4));
+                acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
+                acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
+                acc[4 * ch + 2] = fmaf(w, v.z, acc[4 * ch + 2]);
+                acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
+              }
+            }
+            const bool wr = rowok && good;
+            const int width = a.oc[o].width;
+            // The TMA store of S_t works in 16-byte units: when D is not a multiple of 4 the last unit of an S_t row also
+            // covers the first (4 - D % 4) columns of the neighbouring Adj^T S_t block of the X slot and would overwrite them
+            // with the stage's padding.  The row's own values are therefore patched into the stage's padding columns before
+            // the store (rows left to the row-list pass get zeros here and their full row there, later in stream order).
+            if (o == 0) { padv[0] = wr ? acc[0] : 0.f; padv[1] = wr ? acc[1] : 0.f; padv[2] = wr ? acc[2] : 0.f; }
+            if (o == NOC - 1 && (width & 3) != 0 && rowok) {
+              float* strow = reinterpret_cast<float*>(const_cast<uint8_t*>(stg) + ((4 * cw + (lane >> 3)) * 1024) + (lane & 7) * 128 +
+                                                     (((width >> 2) ^ (lane & 7)) << 4));
+              const int p0 = width & 3;
+#pragma unroll
+              for (int p = 1; p < 4; ++p) if (p >= p0) strow[p] = padv[p - p0];
+              fence_proxy_async();
+            }
+            float* outp = a.agg_out + (size_t)(rfirst + lane) * a.ld_agg + a.oc[o].out_col0;
+            const bool v2 = a.ld_agg % 2 == 0 && ((reinterpret_cast<uintptr_t>(a.agg_out) + 4 * (size_t)a.oc[o].out_col0) & 7) == 0;
+            if (wr) {
+              if (v2) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  if (j + 1 < width) *reinterpret_cast<float2*>(outp + j) = make_float2(acc[j], acc[j + 1]);
+                  else if (j < width) outp[j] = acc[j];
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < width) outp[j] = acc[j];
+              }
+            }
+            if (a.agg_sum) {                           // column sums over the warp's rows: lane j ends up with column j
+              float sq[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { acc[j] = (wr && j < width) ? acc[j] : 0.f; sq[j] = acc[j] * acc[j]; }
+              q1 = warp_colsum32(acc, lane);
+              q2 = warp_colsum32(sq, lane);
+            }
+          }
           mbar_arrive(&col_done[os]);
           const int slot = a.oc[o].st_slot;
 #pragma unroll
           for (int q = 0; q < RT_STAT_SLOTS; ++q)
-            if (q == slot) { s1[q] += (double)p1; s2[q] += (double)p2; }
+            if (q == slot) { s1[q] += (double)p1; s2[q] += (double)p2; g1[q] += (double)q1; g2[q] += (double)q2; }
           if (++os == NOS) { os = 0; oph ^= 1u; }
         }
+        if (fuse) mbar_arrive(&csr_empty[tq & 1]);
       }
 #pragma unroll
-      for (int q = 0; q < RT_STAT_SLOTS; ++q) { s_stat[cw][q][0][lane] = s1[q]; s_stat[cw][q][1][lane] = s2[q]; }
+      for (int q = 0; q < RT_STAT_SLOTS; ++q) {
+        s_stat[cw][q][0][lane] = s1[q]; s_stat[cw][q][1][lane] = s2[q];
+        s_stat[cw][q][2][lane] = g1[q]; s_stat[cw][q][3][lane] = g2[q];
+      }
     }
   }
   tc_fence_before();
@@ -496,8 +612,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
         const int o = e >> 5, j = e & 31;
         if (j < a.oc[o].width) {
           const int q = a.oc[o].st_slot, c = a.oc[o].cidx0 + j;
-          atomicAdd(a.ost_sum + c, (s_stat[0][q][0][j] + s_stat[1][q][0][j]) + (s_stat[2][q][0][j] + s_stat[3][q][0][j]));
-          atomicAdd(a.ost_sq + c, (s_stat[0][q][1][j] + s_stat[1][q][1][j]) + (s_stat[2][q][1][j] + s_stat[3][q][1][j]));
+          if (a.ost_sum) {
+            atomicAdd(a.ost_sum + c, (s_stat[0][q][0][j] + s_stat[1][q][0][j]) + (s_stat[2][q][0][j] + s_stat[3][q][0][j]));
+            atomicAdd(a.ost_sq + c, (s_stat[0][q][1][j] + s_stat[1][q][1][j]) + (s_stat[2][q][1][j] + s_stat[3][q][1][j]));
+          }
+          if (fuse && a.agg_sum) {
+            atomicAdd(a.agg_sum + c, (s_stat[0][q][2][j] + s_stat[1][q][2][j]) + (s_stat[2][q][2][j] + s_stat[3][q][2][j]));
+            atomicAdd(a.agg_sq + c, (s_stat[0][q][3][j] + s_stat[1][q][3][j]) + (s_stat[2][q][3][j] + s_stat[3][q][3][j]));
+          }
         }
       }
     }
@@ -561,7 +683,8 @@ static size_t rt_smem_cap(int mode) {              // dynamic shared memory a la
   return cap[mi];
 }
 size_t rows_tma_smem(const RowsTmaArgs& a) {
-  return (size_t)2 * a.n_kc * a.BN * 128 + (size_t)a.n_stages * RT_STAGE_BYTES + (size_t)a.n_ostages * RT_STAGE_BYTES + 1024;
+  return (size_t)2 * a.n_kc * a.BN * 128 + (size_t)a.n_stages * RT_STAGE_BYTES + (size_t)a.n_ostages * RT_STAGE_BYTES +
+         (a.fuse_agg ? (size_t)2 * RT_CSR_BUF : 0) + 1024;
 }
 int rows_tma_finish(RowsTmaArgs& a) {
   if (a.n_kc < 1 || a.n_kc > RT_MAXKC || a.n_oc < 1 || a.n_oc > RT_MAXOC || a.BN < 16 || a.BN > RT_MAXBN || a.BN % 16 != 0)

@@ -48,6 +48,13 @@ struct RowsTmaArgs {
   float thr;                 // convergence test against the aux (previous state) chunk; flag_next NULL = no test
   int* flag_next;
   double* ost_sum; double* ost_sq;    // column statistics of the output (next iteration's BN) or NULL
+  // fused aggregation (reference GNN.py:228 of the NEXT iteration): Adj^T S_t of every row whose in-neighbours all lie in
+  // its 128-row tile is gathered from the finished output stage in shared memory (the graph handle's tile-local CSR view);
+  // the remaining rows (graph.cu: bnd_rows) are left to the row-list pass of agg_stats_kernel
+  int fuse_agg;
+  const int* g_rowptr; const short* g_lidx; const float* g_w; const int* g_arc0;
+  float* agg_out; int ld_agg;         // Adj^T S_t [row][c] = agg_out[row * ld_agg + c]
+  double* agg_sum; double* agg_sq;    // its column statistics or NULL
   // ---- RT_DX: dX = dz (W^T * colscale) - BN-training correction ------------------------------------------------------
   const float* W;            // [in][H] Dense kernel
   const float* colscale;     // [in] gamma * rstd (NULL = 1)

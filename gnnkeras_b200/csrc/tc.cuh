@@ -37,6 +37,12 @@ __device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinq
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
+// one lane of a converged warp (elect.sync): the issue roles keep their loops warp-uniform and predicate only the instruction
+__device__ __forceinline__ bool tc_elect() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
