@@ -214,6 +214,7 @@ int launch_dz(const DzArgs& a, cudaStream_t s);
 
 struct AggArgs {            // AGG = Adj^T . S (dst-CSR gather) as a streaming kernel + fp64 column statistics
   int n_rows;
+  int pad4;                // set by the launcher: padded float4 walk (D % 4 == 2)
   const int* n_rows_dev;   // optional device scalar overriding n_rows (then n_rows is only the upper bound that sizes the grid)
   const int* rowlist;
   int D;

@@ -723,11 +723,14 @@ __global__ void reduce_params_kernel(const __grid_constant__ ReduceArgs a) {
 // ------------------------------------------------------------------------------------------------
 // dz = act'(s_t) * G_t as a streaming kernel (single-layer state nets): the gather over the source-grouped
 // CSR runs with thousands of independent threads instead of inside the persistent GEMM kernel.
-template <int VEC>
+// PAD (VEC == 4, D % 4 == 2, every leading dimension a multiple of 4): rows are walked as ceil(D / 4) float4 slots; the last
+// slot reads two columns of padding / of the neighbouring block (finite values) and writes zeros into dz's padding - half
+// the threads and index arithmetic of the float2 walk.  agg_next (the Adj^T S block of an X slot) starts 8-byte aligned.
+template <int VEC, bool PAD>
 __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzArgs a) {
   if (a.gate && *a.gate == 0) return;
   const bool last = a.always_last || a.last_flag == nullptr || *a.last_flag == 0;
-  const int nq = a.D / VEC;
+  const int nq = PAD ? (a.D + 3) / 4 : a.D / VEC;
   const int ldg = a.ldg ? a.ldg : a.D, lda = a.ld_agg ? a.ld_agg : a.D, ldz = a.ld_dz ? a.ld_dz : ldg;
   const long long items = (long long)a.n_rows * nq;
   for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
@@ -747,7 +750,8 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
         const int in = a.in_dim;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          const int oc = a.own_col0 + q * VEC + v, ac = a.agg_col0 + q * VEC + v;
+          const int cv = (PAD && q * VEC + v >= a.D) ? a.D - 1 : q * VEC + v;
+          const int oc = a.own_col0 + cv, ac = a.agg_col0 + cv;
           g[v] -= cn[oc] + fmaf(yv[v], cn[2 * in + oc], cn[3 * in + oc]) * cn[in + oc];
           k0a[v] = cn[ac]; k1a[v] = cn[in + ac]; Aa[v] = cn[2 * in + ac]; Ba[v] = cn[3 * in + ac];
         }
@@ -768,7 +772,14 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
           wv[u] = ok ? (a.wgt ? a.wgt[pi] : 1.0f) : 0.0f;
           const size_t so = (size_t)a.idx[pi] * ldg + q * VEC;
           load_vec<VEC>(a.dAgg + so, t[u]);
-          if (cn) load_vec<VEC>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC, xg[u]);
+          if (cn) {
+            if (PAD) {
+              load_vec<2>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC, xg[u]);
+              load_vec<2>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC + 2, xg[u] + (VEC > 2 ? 2 : 0));
+            } else {
+              load_vec<VEC>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC, xg[u]);
+            }
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -783,10 +794,11 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
       }
     }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) a.dz[(size_t)gr * ldz + q * VEC + v] = act_bwd(a.act, yv[v], g[v]);
+    for (int v = 0; v < VEC; ++v) a.dz[(size_t)gr * ldz + q * VEC + v] = (PAD && q * VEC + v >= a.D) ? 0.f : act_bwd(a.act, yv[v], g[v]);
   }
 }
 
+static bool dz_pad4_enabled() { static const bool on = getenv("GNNFP_DZ_PAD4") != nullptr; return on; }
 int launch_dz(const DzArgs& a, cudaStream_t s) {
   if (a.n_rows <= 0) return GNNFP_OK;
   auto al = [&](const void* p, int m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
@@ -795,25 +807,32 @@ int launch_dz(const DzArgs& a, cudaStream_t s) {
   const int ldz = a.ld_dz ? a.ld_dz : ldg;
   const bool g4 = ldg % 4 == 0 && ldz % 4 == 0 && (!a.agg_next || (lda % 4 == 0 && al(a.agg_next, 16))) && (!a.pre || al(a.pre, 16));
   const bool g2 = ldg % 2 == 0 && ldz % 2 == 0 && (!a.agg_next || (lda % 2 == 0 && al(a.agg_next, 8))) && (!a.pre || al(a.pre, 8));
-  if (g4 && a.D % 4 == 0 && a.ld_s % 4 == 0 && al(a.s_t, 16) && al(a.dSfin, 16) && al(a.dOwn, 16) && al(a.dAgg, 16) && al(a.dz, 16)) vec = 4;
+  bool pad = false;
+  const bool a16 = a.ld_s % 4 == 0 && al(a.s_t, 16) && al(a.dSfin, 16) && al(a.dOwn, 16) && al(a.dAgg, 16) && al(a.dz, 16);
+  if (g4 && a.D % 4 == 0 && a16) vec = 4;
+  // (the padded float4 walk measured 1.5x SLOWER than the float2 walk on B200 - the kernel is bound by loads in flight, not
+  //  by instruction issue - so it is only taken on request: GNNFP_DZ_PAD4=1)
+  else if (dz_pad4_enabled() && a.D % 4 == 2 && a16 && ldg % 4 == 0 && ldz % 4 == 0 && (!a.pre || al(a.pre, 16)) &&
+           (!a.agg_next || (lda % 2 == 0 && al(a.agg_next, 8)))) { vec = 4; pad = true; }
   else if (g2 && a.D % 2 == 0 && a.ld_s % 2 == 0 && al(a.s_t, 8) && al(a.dSfin, 8) && al(a.dOwn, 8) && al(a.dAgg, 8) && al(a.dz, 8)) vec = 2;
-  const long long items = (long long)a.n_rows * (a.D / vec);
+  const long long items = (long long)a.n_rows * (pad ? (a.D + 3) / 4 : a.D / vec);
   long long blocks = (items + 255) / 256;
   static int occ[3] = {0, 0, 0};                      // resident blocks per SM: the grid is a whole number of waves
   const int oi = vec == 4 ? 2 : (vec == 2 ? 1 : 0);
   if (!occ[oi]) {
     int o = 0;
-    if (vec == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<4>, 256, 0);
-    else if (vec == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<2>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<1>, 256, 0);
+    if (vec == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<4, false>, 256, 0);
+    else if (vec == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<2, false>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dz_kernel<1, false>, 256, 0);
     occ[oi] = o > 0 ? o : 4;
   }
   const long long cap = (long long)gnnfp_num_sms() * occ[oi] * 3;
   if (blocks > cap) blocks = cap;
   ProfScope ps(PC_DZ, s);
-  if (vec == 4) dz_kernel<4><<<(int)blocks, 256, 0, s>>>(a);
-  else if (vec == 2) dz_kernel<2><<<(int)blocks, 256, 0, s>>>(a);
-  else dz_kernel<1><<<(int)blocks, 256, 0, s>>>(a);
+  if (pad) dz_kernel<4, true><<<(int)blocks, 256, 0, s>>>(a);
+  else if (vec == 4) dz_kernel<4, false><<<(int)blocks, 256, 0, s>>>(a);
+  else if (vec == 2) dz_kernel<2, false><<<(int)blocks, 256, 0, s>>>(a);
+  else dz_kernel<1, false><<<(int)blocks, 256, 0, s>>>(a);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;

@@ -132,20 +132,33 @@ static __global__ void k_pool(const float* out_nodes, const int* graph_ptr, cons
   out[e] = acc;
 }
 
-// interleaved layout: slot 0 columns [0, D) = initial state; columns [2D, 2D + LsM) of the first n_slots slots = static block
+// interleaved layout, one warp per row (coalesced): slot 0 columns [0, D) = the caller's initial state, columns
+// [2D, 2D + LsM) of the first n_slots slots = the static block; the same pass evaluates condition() before the first
+// iteration (state_old = ones, GNN.py:261 - otherwise k_cond0)
 static __global__ void k_xlay_init(const float* s0, int ld0, const float* Xs, int ldXs, int LsM, float* slots, size_t stride,
-                                   int n_slots, int ldX, int D, int n) {
-  const int W = D + n_slots * LsM;
-  const size_t total = (size_t)n * W;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = e / W;
-    const int j = (int)(e - r * W);
-    if (j < D) slots[r * ldX + j] = s0[r * ld0 + j];
-    else {
-      const int q = (j - D) / LsM, x = (j - D) - q * LsM;
-      slots[(size_t)q * stride + r * ldX + 2 * D + x] = Xs[r * ldXs + x];
+                                   int n_slots, int ldX, int D, int n, float thr, int max_iter, int* flag0) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float normp = thr * sqrtf((float)D);
+  int notconv = 0;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
+    const float* src = s0 + (size_t)r * ld0;
+    float* dst = slots + (size_t)r * ldX;
+    float sd = 0.f;
+    for (int j = lane; j < D; j += 32) {
+      const float v = src[j];
+      dst[j] = v;
+      sd = fmaf(v - 1.0f, v - 1.0f, sd);
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, of);
+    if (sqrtf(sd) > normp) notconv = 1;
+    for (int e = lane; e < n_slots * LsM; e += 32) {
+      const int q = e / LsM, x = e - q * LsM;
+      slots[(size_t)q * stride + (size_t)r * ldX + 2 * D + x] = Xs[(size_t)r * ldXs + x];
     }
   }
+  const int any = __syncthreads_or(notconv);
+  if (threadIdx.x == 0 && any && max_iter > 0) atomicOr(flag0, 1);
 }
 
 // ---- piece builders -----------------------------------------------------------------------------
@@ -553,14 +566,14 @@ static int fwd_begin(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_p
   }
   if (L->xlay) {   // X_0[:, 0:D] = the caller's initial state; inline static columns into every slot
     const int ns = L->xs_inline ? L->slot_count : 0;
-    const size_t tot = (size_t)N * (D + (size_t)ns * L->LsM);
-    int blocks = (int)((tot + 255) / 256);
+    int blocks = (N + 7) / 8;
     if (blocks > 2368) blocks = 2368;
-    k_xlay_init<<<blocks, 256, 0, s>>>(c.S0user(), c.ldS0user(), c.Xs(), L->ldXs, L->LsM, c.slots(), c.slot_stride(), ns, L->ldX, D, N);
+    k_xlay_init<<<blocks, 256, 0, s>>>(c.S0user(), c.ldS0user(), c.Xs(), L->ldXs, L->LsM, c.slots(), c.slot_stride(), ns, L->ldX, D, N,
+                                       L->cfg.state_threshold, MI, c.flags());
     GNNFP_COUNT_LAUNCH();
   }
   // ---- condition before the first iteration ------------------------------------------------------
-  {
+  if (!L->xlay) {
     const int blocks = (L->Nact + 255) / 256 < 1184 ? (L->Nact + 255) / 256 : 1184;
     k_cond0<<<blocks, 256, 0, s>>>(c.S(0), c.ldS(0), L->Nact, D, L->cfg.state_threshold, MI, c.flags());
     GNNFP_COUNT_LAUNCH();
