@@ -21,11 +21,14 @@ X_DST_ROWPTR, X_DST_SRC, X_DST_ARC, X_SRC_ROWPTR, X_SRC_DST, X_SRC_ARC, X_ARC_VA
 _vp = C.c_void_p
 
 
+GRAPH_DEFER_CHECK = 1
+
+
 class GraphDesc(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_arcs", C.c_int32), ("n_graphs", C.c_int32), ("n_types", C.c_int32),
                 ("aggregation_mode", C.c_int32), ("mask_len", C.c_int32),
                 ("src", _vp), ("dst", _vp), ("arc_values", _vp), ("type_mask", _vp), ("node2graph", _vp),
-                ("nodegraph_values", _vp), ("set_mask", _vp), ("output_mask", _vp)]
+                ("nodegraph_values", _vp), ("set_mask", _vp), ("output_mask", _vp), ("flags", C.c_int32)]
 
 
 class GraphInfo(C.Structure):
@@ -71,11 +74,11 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnnfp.so
 
 # every symbol include/gnnfp.h declares
 SYMBOLS = ["gnnfp_last_error", "gnnfp_abi_version", "gnnfp_graph_build", "gnnfp_graph_free", "gnnfp_graph_get_info",
-           "gnnfp_graph_export", "gnnfp_loop_create", "gnnfp_loop_free", "gnnfp_loop_workspace_bytes",
+           "gnnfp_graph_export", "gnnfp_graph_check", "gnnfp_loop_create", "gnnfp_loop_free", "gnnfp_loop_workspace_bytes",
            "gnnfp_loop_out_rows", "gnnfp_loop_state_dim", "gnnfp_loop_forward", "gnnfp_loop_forward_begin", "gnnfp_loop_forward_iter",
            "gnnfp_loop_forward_end", "gnnfp_loop_ws_offsets", "gnnfp_loop_backward",
            "gnnfp_loop_backward_step", "gnnfp_loop_bwd_offsets",
-           "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step",
+           "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step", "gnnfp_adam_step_dev", "gnnfp_adam_advance",
            "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect"]
 
 
@@ -91,6 +94,7 @@ def lib():
     L.gnnfp_last_error.restype = C.c_char_p
     L.gnnfp_abi_version.restype = C.c_int
     L.gnnfp_graph_build.argtypes = [C.POINTER(_vp), C.POINTER(GraphDesc), _vp]
+    L.gnnfp_graph_check.argtypes = [_vp]
     L.gnnfp_graph_free.argtypes = [_vp]
     L.gnnfp_graph_free.restype = None
     L.gnnfp_graph_get_info.argtypes = [_vp, C.POINTER(GraphInfo)]
@@ -122,13 +126,16 @@ def lib():
     L.gnnfp_update_graph_backward.argtypes = [_vp, C.c_int32, _vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32,
                                               C.c_int32, _vp]
     L.gnnfp_cce_loss.argtypes = [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, _vp, _vp, _vp]
+    L.gnnfp_adam_step_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      _vp, C.c_float, _vp]
+    L.gnnfp_adam_advance.argtypes = [_vp, _vp]
     L.gnnfp_adam_step.argtypes = [_vp, _vp, _vp, _vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int32, C.c_float, _vp]
     L.gnnfp_launch_count.argtypes = [C.c_int]
     L.gnnfp_launch_count.restype = C.c_longlong
     L.gnnfp_profile_enable.argtypes = [C.c_int]
     L.gnnfp_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
-    if L.gnnfp_abi_version() != 1:
+    if L.gnnfp_abi_version() != 2:
         raise GnnfpError("libgnnfp.so ABI version mismatch")
     _LIB = L
     return L

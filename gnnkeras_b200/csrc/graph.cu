@@ -245,7 +245,8 @@ extern "C" int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* d, v
   int h_bad = 0;
 #define BUILD_TRY(x) do { rc = (x); if (rc) { gnnfp_graph_free(g); return rc; } } while (0)
 #define BUILD_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { gnnfp_set_error("CUDA error in graph_build: %s", cudaGetErrorString(_e)); gnnfp_graph_free(g); return GNNFP_E_CUDA; } } while (0)
-  BUILD_CUDA(cudaMallocAsync(&d_bad, sizeof(int), s));
+  BUILD_TRY(A.get(&d_bad, (size_t)1));
+  g->d_bad = d_bad;
   BUILD_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
   // keep our own copy of src/dst (the caller's buffers may go away)
   BUILD_TRY(A.get(&g->src, (size_t)NA));
@@ -364,14 +365,24 @@ extern "C" int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* d, v
       k_nodegraph_values<<<GRID(N), 0, s>>>(g->node2graph, cnt, N, g->ng_val);
     BUILD_CUDA(cudaFreeAsync(cnt, s));
   }
-  BUILD_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
-  BUILD_CUDA(cudaStreamSynchronize(s));
-  BUILD_CUDA(cudaFreeAsync(d_bad, s));
   if (tmp) BUILD_CUDA(cudaFreeAsync(tmp, s));
   BUILD_CUDA(cudaGetLastError());
+  if (d->flags & GNNFP_GRAPH_DEFER_CHECK) { *out = g; return GNNFP_OK; }      // verdict read by gnnfp_graph_check
+  BUILD_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BUILD_CUDA(cudaStreamSynchronize(s));
   if (h_bad == 1) { gnnfp_graph_free(g); GNNFP_FAIL(GNNFP_E_INVALID, "graph_build: node / graph id out of range"); }
   if (h_bad == 2) { gnnfp_graph_free(g); GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "graph_build: nodes of a graph must be contiguous and in graph order (GraphObject.merge layout)"); }
   *out = g;
+  return GNNFP_OK;
+}
+
+extern "C" int gnnfp_graph_check(const gnnfp_graph* g) {
+  if (!g) GNNFP_FAIL(GNNFP_E_INVALID, "graph_check: null handle");
+  int h_bad = 0;
+  GNNFP_CHECK_CUDA(cudaMemcpyAsync(&h_bad, g->d_bad, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+  GNNFP_CHECK_CUDA(cudaStreamSynchronize(g->stream));
+  if (h_bad == 1) GNNFP_FAIL(GNNFP_E_INVALID, "graph_build: node / graph id out of range");
+  if (h_bad == 2) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "graph_build: nodes of a graph must be contiguous and in graph order (GraphObject.merge layout)");
   return GNNFP_OK;
 }
 

@@ -32,6 +32,7 @@ struct gnnfp_graph {
   int* node2graph = nullptr;   // [N]
   float* ng_val = nullptr;     // [N]
   int* graph_ptr = nullptr;    // [G+1]
+  int* d_bad = nullptr;        // device word of the id validation (0 ok, 1 id out of range, 2 nodes of a graph not contiguous)
   cudaStream_t stream = nullptr;   // stream the device arrays were allocated on (stream-ordered pool)
   std::vector<void*> allocs;
   size_t device_bytes = 0;

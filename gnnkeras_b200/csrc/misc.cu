@@ -155,6 +155,45 @@ static __global__ void k_adam(float* p, const float* g, float* m, float* v, size
     p[i] -= (mi * alpha) / (sqrtf(vi) + eps);
   }
 }
+// The same update with the step count on the device (int32 counter, incremented by gnnfp_adam_advance after the last span of
+// an optimisation step): nothing of the step is baked into kernel arguments, so a whole train step can be captured into one
+// CUDA graph and replayed.
+static __global__ void k_adam_dev(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
+                                  float eps, float gscale, const int* step_dev) {
+  __shared__ float s_alpha;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_dev + 1);
+    s_alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  }
+  __syncthreads();
+  const float alpha = s_alpha;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.0f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (mi * alpha) / (sqrtf(vi) + eps);
+  }
+}
+static __global__ void k_adam_advance(int* step_dev) { *step_dev += 1; }
+extern "C" int gnnfp_adam_step_dev(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                                   float beta2, float eps, const int32_t* step_dev, float grad_scale, void* stream) {
+  if (!params || !grads || !m || !v || !step_dev) GNNFP_FAIL(GNNFP_E_INVALID, "adam_step_dev: bad arguments");
+  if (n == 0) return GNNFP_OK;
+  k_adam_dev<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, grad_scale, step_dev);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+extern "C" int gnnfp_adam_advance(int32_t* step_dev, void* stream) {
+  if (!step_dev) GNNFP_FAIL(GNNFP_E_INVALID, "adam_advance: null counter");
+  k_adam_advance<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
 extern "C" int gnnfp_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
                                float beta2, float eps, int32_t step, float grad_scale, void* stream) {
   if (!params || !grads || !m || !v || step < 1) GNNFP_FAIL(GNNFP_E_INVALID, "adam_step: bad arguments");

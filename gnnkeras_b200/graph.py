@@ -183,7 +183,7 @@ class GraphTensor:
     @classmethod
     def from_host_arrays(cls, nodes, arcs, targets, sample_weight, set_mask, output_mask, dim_node_label, focus,
                          aggregation_mode, node2graph, nodegraph_values, n_graphs, type_mask=None, arc_values=None,
-                         device="cuda", non_blocking=False, masks_all_true=None):
+                         device="cuda", non_blocking=False, masks_all_true=None, defer_check=False):
         """Upload one merged batch and build its integer structures on the device."""
         up = lambda a, dt=None: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a if dt is None else np.asarray(a).astype(dt)))).to(device, non_blocking=non_blocking)
         d_nodes = up(nodes, np.float32)
@@ -206,7 +206,7 @@ class GraphTensor:
             tm = up(np.ascontiguousarray(np.asarray(type_mask).transpose()), np.uint8)      # [n_types, N]
         av = up(arc_values, np.float32) if arc_values is not None else None
         graph = DeviceGraph(src, dst, d_nodes.shape[0], aggregation_mode, n2g, int(n_graphs), ngv, sm, om, tm, av,
-                            mask_len=len(set_mask))
+                            mask_len=len(set_mask), defer_check=defer_check)
         return cls(d_nodes, d_arcs, d_targets, d_sw, sm, om, dim_node_label, graph, aggregation_mode, focus, tm)
 
 

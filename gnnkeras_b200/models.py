@@ -60,6 +60,7 @@ class ParamStore:
             n.set_trainable(views)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)   # optimizer.iterations on the device (graph capture)
         occ_sizes = [sizes[seen[id(n)]] for n in self.occurrences]
         self.g_off = np.concatenate([[0], np.cumsum(occ_sizes)]).astype(np.int64)
         self.grad_flat = torch.zeros(int(self.g_off[-1]), dtype=torch.float32, device=device)
@@ -85,10 +86,43 @@ class ParamStore:
         for po, go, n in spans:
             if n == 0:
                 continue
-            B.check(L.gnnfp_adam_step(C.c_void_p(self.flat.data_ptr() + 4 * po), C.c_void_p(self.grad_flat.data_ptr() + 4 * go),
-                                      C.c_void_p(self.m.data_ptr() + 4 * po), C.c_void_p(self.v.data_ptr() + 4 * po),
-                                      C.c_size_t(n), opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon,
-                                      opt.iterations, grad_scale, _stream()))
+            B.check(L.gnnfp_adam_step_dev(C.c_void_p(self.flat.data_ptr() + 4 * po), C.c_void_p(self.grad_flat.data_ptr() + 4 * go),
+                                          C.c_void_p(self.m.data_ptr() + 4 * po), C.c_void_p(self.v.data_ptr() + 4 * po),
+                                          C.c_size_t(n), opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon,
+                                          _ptr(self.step_dev), grad_scale, _stream()))
+        B.check(L.gnnfp_adam_advance(_ptr(self.step_dev), _stream()))
+
+
+class GraphedTrainStep:
+    """ONE CUDA graph for a whole train step on a fixed batch (forward with its device-side loop control, loss, BPTT,
+    Adam): replaying it costs one launch on the host instead of a few hundred.  Everything the step needs lives on
+    the device (iteration flags, k, optimizer step count), so the captured graph stays valid from step to step.
+
+    ``warmup`` REAL optimisation steps run first (plans, workspaces and kernel attributes are created there), then
+    the step is captured (capture records, it does not execute)."""
+
+    def __init__(self, model, data, warmup: int = 2):
+        if getattr(model, "state_vect_dim", 0) and getattr(model, "fixed_state0", None) is None:
+            raise ValueError("graph capture needs a fixed initial state (state_vect_dim > 0 draws it per call)")
+        self.model, self.data = model, data
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                model.train_step(data)
+        torch.cuda.current_stream().wait_stream(side)
+        gnns = getattr(model, "gnns", [model])
+        self._keep = [g._ws.get("buf") for g in gnns]          # workspaces the captured kernels point into
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = model.train_step(data)
+        opt = model.optimizer
+        opt.iterations -= 1                                    # the capture pass did not execute
+
+    def __call__(self):
+        self.graph.replay()
+        self.model.optimizer.iterations += 1
+        return self.result
 
 
 def cce_loss(y_true, y_pred, sample_weight, scale, loss_acc, want_grad=True):

@@ -43,7 +43,7 @@ class DeviceGraph:
                  node2graph: Optional[torch.Tensor] = None, n_graphs: int = 0,
                  nodegraph_values: Optional[torch.Tensor] = None, set_mask: Optional[torch.Tensor] = None,
                  output_mask: Optional[torch.Tensor] = None, type_mask: Optional[torch.Tensor] = None,
-                 arc_values: Optional[torch.Tensor] = None, mask_len: Optional[int] = None):
+                 arc_values: Optional[torch.Tensor] = None, mask_len: Optional[int] = None, defer_check: bool = False):
         L = B.lib()
         if aggregation_mode not in B.AGG:
             raise ValueError("ERROR: Unknown aggregation mode")      # graph_class.py:97
@@ -83,6 +83,7 @@ class DeviceGraph:
                 keep.append(m)
                 setattr(d, nm, _ptr(m))
         d.mask_len = ml
+        d.flags = B.GRAPH_DEFER_CHECK if defer_check else 0      # True: no host synchronisation here, call check() later
         h = C.c_void_p()
         B.check(L.gnnfp_graph_build(C.byref(h), C.byref(d), _stream()))
         self._h = h
@@ -96,6 +97,10 @@ class DeviceGraph:
         self.device = src.device
         self.device_bytes = info.device_bytes
         self.aggregation_mode = aggregation_mode
+
+    def check(self):
+        """Report the id validation of a build with ``defer_check=True`` (waits for the build's stream work)."""
+        B.check(self._L.gnnfp_graph_check(self._h))
 
     def export(self, which: int) -> np.ndarray:
         sizes = {B.X_DST_ROWPTR: (self.n_nodes + 1, np.int32), B.X_DST_SRC: (self.n_arcs, np.int32),

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GNNFP_ABI_VERSION 1
+#define GNNFP_ABI_VERSION 2
 #define GNNFP_MAX_LAYERS 8
 #define GNNFP_MAX_TYPES 8
 
@@ -88,9 +88,18 @@ typedef struct gnnfp_graph_desc {
   const float* nodegraph_values; /* [N] NodeGraph.data (1/n_g, graph_class.py:136); NULL = compute 1/n_g */
   const uint8_t* set_mask;   /* [mask_len] or NULL (= all true)                                */
   const uint8_t* output_mask;/* [mask_len] or NULL (= all true)                                */
+  int32_t flags;             /* GNNFP_GRAPH_*                                                  */
 } gnnfp_graph_desc;
 
+/* flags.  DEFER_CHECK: gnnfp_graph_build does not wait for the device-side validation of the ids (node / graph id out of
+ * range, nodes of a graph not contiguous): the verdict stays in the handle until gnnfp_graph_check.  With no masks and no
+ * node types the build then enqueues its work and returns WITHOUT any host synchronisation (the per-step input path of a
+ * training loop); the structures of an invalid graph are never dereferenced out of bounds, its results are undefined. */
+#define GNNFP_GRAPH_DEFER_CHECK 1
+
 int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* desc, void* stream);
+/* waits for the build's stream work and reports the deferred validation (GNNFP_OK, GNNFP_E_INVALID, GNNFP_E_UNSUPPORTED) */
+int gnnfp_graph_check(const gnnfp_graph* g);
 void gnnfp_graph_free(gnnfp_graph* g);
 
 typedef struct gnnfp_graph_info {
@@ -263,6 +272,12 @@ int gnnfp_cce_loss(const float* y_true, const float* y_pred, const float* sample
                    float* d_pred /* [rows, cols] or NULL */, void* stream);
 int gnnfp_adam_step(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
                     float beta2, float eps, int32_t step, float grad_scale, void* stream);
+/* The same update with the step count in device memory (t = *step_dev + 1): no per-step value is baked into a kernel
+ * argument, so a whole train step (forward, loss, BPTT, update) can be captured into ONE CUDA graph and replayed
+ * (optimizer.apply_gradients, GNN.py:297).  gnnfp_adam_advance increments the counter after the step's last span. */
+int gnnfp_adam_step_dev(float* params, const float* grads, float* m, float* v, size_t n, float lr, float beta1,
+                        float beta2, float eps, const int32_t* step_dev, float grad_scale, void* stream);
+int gnnfp_adam_advance(int32_t* step_dev, void* stream);
 
 /* Counters for bench.py's `gpu_launches` (kernels this library launched since the last reset). */
 long long gnnfp_launch_count(int reset);

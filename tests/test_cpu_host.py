@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = B.lib()                       # dlopen only; no CUDA call is made
     for sym in B.SYMBOLS:
         assert hasattr(lib, sym), sym
-    assert lib.gnnfp_abi_version() == 1
+    assert lib.gnnfp_abi_version() == 2
 
 
 def test_compute_entry_points_fail_loudly_without_gpu():
