@@ -677,6 +677,11 @@ static int fwd_iter(const Ctx& c, int t, const gnnfp_net_params* sp, const gnnfp
       aa.out = c.AGG(t); aa.ld_out = c.ldA();
       if (L->bn_train_state) { aa.st_sum = c.stA(ty, t - 1); aa.st_sq = aa.st_sum + D; }
       aa.gate = gate;
+      if (L->xlay && rows.rowlist == nullptr && agg_tile_supported(aa.S, aa.ld, D)) {
+        if ((rc = launch_agg_tile(aa.S, aa.ld, aa.n_rows, D, g->dst_rowptr, g->dst_src, wgt, g->tile_lidx, g->tile_arc0, aa.out, aa.ld_out,
+                                  aa.st_sum, aa.st_sq, gate, s, PC_AGG))) return rc;
+        continue;
+      }
       if ((rc = launch_agg_stats(aa, s))) return rc;
     }
     if (L->xlay) {

@@ -70,3 +70,8 @@ int rows_tma_ok(const float* ptr, int ld);                       // 16-byte alig
 size_t rows_tma_smem(const RowsTmaArgs& a);
 int rows_tma_finish(RowsTmaArgs& a);                             // derive tmem_cols / ring depths from the shared-memory budget; error if it does not fit
 int launch_rows_tma(const RowsTmaArgs& a, cudaStream_t s, int prof_cat);
+// agg_tile.cu: Adj^T . S as a TMA-pipelined tile kernel over the graph's tile-local CSR view
+int agg_tile_supported(const float* S, int ld_s, int D);
+int launch_agg_tile(const float* S, int ld_s, int n_rows, int D, const int* rowptr, const int* src, const float* wgt,
+                    const short* lidx, const int* arc0, float* out, int ld_out, double* st_sum, double* st_sq,
+                    const int* gate, cudaStream_t s, int prof_cat);
