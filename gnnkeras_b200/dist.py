@@ -45,18 +45,49 @@ class DataParallel:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if self.world > 1:
             dist.broadcast(model._store.flat, src=0, group=group)
+            for t in self._bn_buffers():
+                dist.broadcast(t, src=0, group=group)
             model.grad_hook = lambda flat: allreduce_mean_(flat, group)
             model.grad_scale = 1.0 / self.world
 
+    def _bn_buffers(self):
+        """BatchNormalization moving statistics of every net: non-trainable, so not in the flat parameter buffer; each rank
+        updates them from its own batches (k times per Loop)."""
+        out = []
+        for n in self.model._store.uniq:
+            if n.has_bn:
+                out += [n.moving_mean, n.moving_var]
+        return out
+
+    def sync_bn_buffers(self):
+        """Average the moving statistics over the ranks (call before evaluate / predict / save: otherwise inference gives
+        rank-dependent results).  One small all-reduce per buffer."""
+        if self.world > 1:
+            for t in self._bn_buffers():
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.mul_(1.0 / self.world)
+
     def train_step(self, data):
         return self.model.train_step(data)
+
+    def evaluate(self, sequencer):
+        self.sync_bn_buffers()
+        return self.model.evaluate(sequencer)
+
+    def predict(self, sequencer):
+        self.sync_bn_buffers()
+        return self.model.predict(sequencer)
 
     def __getattr__(self, name):
         return getattr(self.model, name)
 
 
-def shard_batches(n_batches: int, rank: int, world: int) -> List[int]:
-    """Round-robin assignment of whole reference batches to ranks."""
+def shard_batches(n_batches: int, rank: int, world: int, drop_tail: bool = True) -> List[int]:
+    """Round-robin assignment of whole reference batches to ranks.  Every train_step contains a collective (the gradient
+    all-reduce), so all ranks must run the SAME number of steps: by default the n_batches % world left-over batches of
+    an epoch are dropped (``drop_tail=False`` keeps them - only for collective-free passes such as predict)."""
+    if drop_tail:
+        n_batches = (n_batches // world) * world
     return list(range(rank, n_batches, world))
 
 

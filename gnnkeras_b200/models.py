@@ -170,9 +170,21 @@ class GNNnodeBased:
         return cls(**config)
 
     def copy(self, copy_weights: bool = True):
-        import copy as _copy
+        """GNN.py:66-76: a new model with cloned nets; ``copy_weights=False`` re-draws the Dense kernels and biases
+        (the reference re-initialises through the Keras initializers; here glorot-normal kernels, zero biases,
+        BatchNormalization reset to its defaults - the initializer NAMES are not kept on op.Net)."""
         cfg = self.get_config()
-        clone = lambda n: Net.from_dict(n.to_dict(), n.W[0].device)
+
+        def clone(n):
+            m = Net.from_dict(n.to_dict(), n.W[0].device)
+            if not copy_weights:
+                for i, W in enumerate(m.W):
+                    std = float(np.sqrt(2.0 / (W.shape[0] + W.shape[1])))
+                    W.copy_(torch.randn(W.shape, device=W.device) * std)
+                    m.b[i].zero_()
+                if m.has_bn:
+                    m.gamma.fill_(1.0); m.beta.zero_(); m.moving_mean.zero_(); m.moving_var.fill_(1.0)
+            return m
         cfg["net_state"] = [clone(n) for n in self.net_state] if self.composite else clone(self.net_state)
         cfg["net_output"] = clone(self.net_output)
         return self.from_config(cfg)
@@ -381,10 +393,13 @@ class LGNN:
     def compile(self, optimizer=None, loss="categorical_crossentropy", *args, training_mode: str = 'parallel',
                 average_st_grads: bool = False, metrics=None, **kwargs):
         """LGNN.py:133-152."""
+        if training_mode not in ('serial', 'parallel', 'residual'):
+            raise ValueError("param <training_mode> must be one of 'serial', 'parallel', 'residual'")     # LGNN.py:139
         self.optimizer = optimizer if optimizer is not None else Adam()
         self.loss = loss
-        for gnn in self.gnns:
-            gnn.loss, gnn.average_st_grads = loss, average_st_grads
+        for gnn in self.gnns:     # LGNN.py:143-144 compiles every layer too; a net's variables live in ONE flat buffer at a time,
+            gnn.loss, gnn.average_st_grads = loss, average_st_grads      # so the per-layer stores are made by the serial fit
+            gnn.optimizer = Adam(self.optimizer.learning_rate, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon)
         self.training_mode = training_mode
         self.average_st_grads = average_st_grads
         # apply_gradients order of LGNN.py:270-278: all state nets (layer by layer), then all output nets
@@ -495,9 +510,67 @@ class LGNN:
         acc = (y_pred.argmax(dim=1) == y.argmax(dim=1)).float().mean()
         return {"loss": loss, "accuracy": acc}
 
-    fit = GNNnodeBased.fit
+    _fit_joint = GNNnodeBased.fit
     evaluate = GNNnodeBased.evaluate
     predict = GNNnodeBased.predict
+
+    # ---- serial training mode (LGNN.py:290-362) -----------------------------------------------------------------------
+    def _relabel(self, gnn, seq, seq_t0, relabel_batch_size: int = 1):
+        """Labels for the next layer (LGNN.py:318-338): run the trained layer's un-pooled node Loop over the sequence
+        (batch size 1 and training=True as the reference does - BatchNormalization then uses every single graph's own
+        statistics and keeps updating its moving averages), and prepend its state / scattered output to
+        the ORIGINAL labels of every graph with the device update_graph kernel (gnnfp_update_graph_forward).
+        ``relabel_batch_size > 1`` processes several graphs per launch: identical labels when the nets have no
+        BatchNormalization and every graph runs max_iteration iterations, else a documented deviation."""
+        seq.shuffle = False
+        seq.set_batch_size(relabel_batch_size)
+        new = seq_t0.copy()
+        pos = 0
+        dev = gnn.net_output.W[0].device
+        for i in range(len(seq)):
+            x = seq[i][0]
+            res = gnn.Loop(*x, training=True, pool=False)
+            state, out = res[1], res[2]
+            graph = x[-1]
+            members = new.data[pos: pos + relabel_batch_size]
+            nodes0 = torch.as_tensor(np.concatenate([g.nodes for g in members], axis=0)).to(dev)
+            nodes1, sw, ow = self.update_graph(graph, nodes0, state, out)
+            nodes1 = nodes1.cpu().numpy()
+            off = 0
+            for g in members:
+                n = g.nodes.shape[0]
+                g.nodes = nodes1[off: off + n].astype(g.dtype)
+                g.DIM_NODE_LABEL = g.DIM_NODE_LABEL + sw + ow
+                off += n
+            pos += len(members)
+        new.build_batches()
+        return new
+
+    def fit(self, sequencer, epochs: int = 1, validation_data=None, verbose: int = 0, relabel_batch_size: int = 1):
+        """'parallel' / 'residual': the joint train_step over all layers.  'serial' (the mode starter.py:41 selects,
+        LGNN.py:290-362): every layer is trained on its own, then the whole dataset is re-labelled on the device for the
+        next layer."""
+        if self.training_mode != 'serial':
+            return self._fit_joint(sequencer, epochs=epochs, validation_data=validation_data, verbose=verbose)
+        t0, seq = sequencer, sequencer.copy()
+        v0 = validation_data
+        vseq = v0.copy() if v0 is not None else None
+        dev = self.gnns[0].net_output.W[0].device
+        histories = []
+        for idx, gnn in enumerate(self.gnns):
+            if verbose:
+                print(f"\n\n --- GNN {idx + 1}/{self.LAYERS} ---")
+            gnn._store = ParamStore(gnn._state_nets() + [gnn.net_output], dev)     # this layer's variables in their own flat buffer
+            histories.append(gnn.fit(seq.copy(), epochs=epochs, validation_data=vseq.copy() if vseq is not None else None,
+                                     verbose=verbose))
+            if idx < self.LAYERS - 1:
+                seq = self._relabel(gnn, seq, t0, relabel_batch_size)
+                if vseq is not None:
+                    vseq = self._relabel(gnn, vseq, v0, relabel_batch_size)
+        # back to one flat buffer for the whole model (evaluate / predict / a later joint training)
+        occ = [n for g in self.gnns for n in g._state_nets()] + [g.net_output for g in self.gnns]
+        self._store = ParamStore(occ, dev)
+        return histories
 
 
 class CompositeLGNN(LGNN):

@@ -273,9 +273,12 @@ class LoopPlan:
         """(k, state, out[, out_nodes]) = Loop(...).  k is a device int32 tensor (no host sync)."""
         g = self.graph
         dev = g.device
-        _require_cuda(nodes, "nodes", torch.float32) if nodes.is_contiguous() else None
-        if nodes.stride(1) != 1:
-            raise ValueError("nodes must be row-major")
+        if not nodes.is_cuda:
+            raise B.GnnfpError("nodes must live on the GPU: the fixed-point loop has no CPU path")
+        if nodes.dtype != torch.float32:
+            raise TypeError(f"nodes must be torch.float32, got {nodes.dtype}")
+        if nodes.dim() != 2 or nodes.stride(1) != 1 or nodes.shape[0] != g.n_nodes:
+            raise ValueError("nodes must be a row-major [n_nodes, width] matrix (a row stride is allowed)")
         ld_arcs = int(arc_labels.stride(0)) if ld_arcs is None and arc_labels is not None and arc_labels.dim() == 2 and arc_labels.shape[0] > 0 else (ld_arcs or max(self.AL, 1))
         if self.S > 0:
             if state0 is None:

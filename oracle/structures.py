@@ -192,3 +192,30 @@ def src_csr(src: np.ndarray, dst: np.ndarray, n_nodes: int):
     np.add.at(rowptr, src + 1, 1)
     rowptr = np.cumsum(rowptr)
     return rowptr.astype(np.int32), dst[order].astype(np.int32), order.astype(np.int32)
+
+
+def transduction(nodes, arcs, targets, set_mask, output_mask, transductive_rate, focus="n", rng=None):
+    """TransductiveGraphSequencers.py:62-95 `get_transduction`: a homogeneous graph becomes a 2-type composite graph.
+    Targeted nodes (set_mask & output_mask) are shuffled (:68, NumPy's global generator unless ``rng`` is given); the first
+    ceil(n (1 - rate)) stay non-transductive (:70-71), the others become transductive: their target is appended to their
+    label (:77-81), they leave the output mask (:90-91) and form node type 1 (:86-88).
+    Returns nodes_new, targets_new, type_mask [N, 2], output_mask_new, dim_node_label_new (2 entries)."""
+    nodes, targets = np.asarray(nodes), np.asarray(targets)
+    set_mask, output_mask = np.asarray(set_mask, bool), np.asarray(output_mask, bool)
+    tmask = np.logical_and(set_mask, output_mask)
+    idx = np.argwhere(tmask).squeeze()
+    (np.random if rng is None else rng).shuffle(idx)
+    n_non = int(np.ceil(np.sum(tmask) * (1 - transductive_rate)))
+    tmask[idx[:n_non]] = False
+    t_target = tmask[output_mask]
+    length = arcs.shape[0] if focus == "a" else nodes.shape[0]
+    plus = np.zeros((length, targets.shape[1]), dtype=nodes.dtype)
+    plus[tmask] = targets[t_target]
+    nodes_new = np.concatenate([nodes, plus], axis=1)
+    targets_new = targets[np.logical_not(t_target)]
+    type_mask = np.zeros((nodes.shape[0], 2), dtype=bool)
+    type_mask[tmask, 1] = True
+    type_mask[:, 0] = np.logical_not(type_mask[:, 1])
+    out_new = output_mask.copy()
+    out_new[tmask] = False
+    return nodes_new, targets_new, type_mask, out_new, np.array([nodes.shape[1], nodes.shape[1] + targets.shape[1]])
