@@ -21,8 +21,8 @@ def _worker(rank, world, port, ret):
         D.allreduce_mean_(g)
         assert torch.allclose(g, torch.arange(10, dtype=torch.float32) * sum(range(1, world + 1)))
         # every train_step holds a collective: all ranks get the same number of batches (the tail of the epoch is dropped)
-    assert D.shard_batches(7, rank, world) == list(range(rank, (7 // world) * world, world))
-    assert D.shard_batches(7, rank, world, drop_tail=False) == list(range(rank, 7, world))
+        assert D.shard_batches(7, rank, world) == list(range(rank, (7 // world) * world, world))
+        assert D.shard_batches(7, rank, world, drop_tail=False) == list(range(rank, 7, world))
         # ---- partitioned graph: one aggregation Adj^T.state with halo exchange == the global result -------
         b = random_graph(500, 4000, seed=3, locality=0.5, band=50)
         src, dst = b.src.astype(np.int64), b.dst.astype(np.int64)
