@@ -28,9 +28,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LAYERS, MAX_ITER, THR, NL, AL, T = 5, 5, 0.01, 14, 3, 2
-WIDTHS = [NL + l * (NL + T) for l in range(LAYERS)]            # 14, 30, 46, 62, 78 (MLP.py:114, DS=0)
+MAX_ITER, THR, NL, AL, T = 5, 0.01, 14, 3, 2
 METRIC = "fixed-point node-updates/sec (fwd+bwd)"
+
+
+def workload_spec(key):
+    """The metric's configurations (BASELINE.json configs): per layer the state width D and the loop-invariant
+    input columns Ls (Ls = 2 NL + AL if state_vect_dim > 0 else AL; composite: d_t + sum NL + AL)."""
+    if key == "c2":      # configs[1]: LGNN 5 layers, parallel (the configuration the metric is quoted on)
+        L = 5
+        D = [NL + l * (NL + T) for l in range(L)]             # 14, 30, 46, 62, 78 (MLP.py:114, DS = 0)
+        return dict(key=key, layers=L, S=0, D=D, Ls=[AL] * L, graphs=8192, composite=False, cpu_graphs=1024,
+                    title=f"C2: LGNN {L} GNNgraphBased layers (state widths {D}), parallel mode, MUTAG-shaped synthetic")
+    if key == "c1":      # configs[0]: GNNgraphBased via starter.py (batch 1000, starter.py:45)
+        return dict(key=key, layers=1, S=0, D=[NL], Ls=[AL], graphs=1000, composite=False, cpu_graphs=1000,
+                    title="C1: GNNgraphBased (starter.py: state width 14, batch 1000), MUTAG-shaped synthetic")
+    if key == "c3":      # configs[2]: CompositeLGNN via starter_composite.py (dim_state 10, batch 500, 5 layers, shared net_output)
+        L, S = 5, 10
+        lab = [NL] + [NL + S + T] * (L - 1)                   # labels of layer l: [state | out | original] (LGNN.py:195-210)
+        return dict(key=key, layers=L, S=S, D=[S] * L, Ls=[2 * w + AL for w in lab], labels=lab, graphs=500, composite=True,
+                    cpu_graphs=500, title=f"C3: CompositeLGNN {L} CompositeGNNgraphBased layers (dim_state {S}, one node type, "
+                                          "ONE net_output shared by all layers), parallel mode, MUTAG-shaped synthetic")
+    raise SystemExit(f"unknown workload {key!r} (c1, c2, c3; c5 = bench_c5.py)")
 
 
 def algorithmic_bytes(D, Ls, deg, fwd=True, w=0):
@@ -41,7 +60,7 @@ def algorithmic_bytes(D, Ls, deg, fwd=True, w=0):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_step_factory(n_graphs, seed, threads):
+def cpu_reference_step_factory(spec, n_graphs, seed, threads):
     """The restated reference (oracle/loop_torch.py: op-for-op PyTorch-CPU eager, autograd backward,
     torch Adam) on a bounded sample of the same workload.  TensorFlow is not installable here."""
     import torch
@@ -49,31 +68,43 @@ def cpu_reference_step_factory(n_graphs, seed, threads):
     from oracle import loop_torch as LT
     from oracle.adapt import ograph_from_batch
     torch.set_num_threads(threads)
-    b = mutag_shaped_batch(n_graphs, seed=seed)
-    g = ograph_from_batch(b, "g", "average")
+    comp = spec["composite"]
+    b = mutag_shaped_batch(n_graphs, seed=seed, n_types=1 if comp else 0)
+    g = ograph_from_batch(b, "g", "composite_average" if comp else "average", dim_node_label=[NL] if comp else None)
     tg = LT.TorchGraph(g, torch.float32, fast=True)
     rng = np.random.default_rng(seed)
-    specs = []
-    for l in range(LAYERS):
-        D = WIDTHS[l]
-        ns = LT.net_to_torch(make_net(rng, 2 * D + AL, [D], ["selu"], True))
-        no = LT.net_to_torch(make_net(rng, D, [T], ["softmax"], True))
-        specs.append({"net_state": ns, "net_output": no, "state_vect_dim": 0, "max_iteration": MAX_ITER,
+    S, specs = spec["S"], []
+    shared_out = LT.net_to_torch(make_net(rng, S, [T], ["softmax"], True)) if comp else None
+    for l in range(spec["layers"]):
+        D, Ls = spec["D"][l], spec["Ls"][l]
+        ns = LT.net_to_torch(make_net(rng, 2 * D + Ls, [D], ["selu"], True))
+        no = shared_out if comp else LT.net_to_torch(make_net(rng, D, [T], ["softmax"], True))
+        specs.append({"net_state": [ns] if comp else ns, "net_output": no, "state_vect_dim": S, "max_iteration": MAX_ITER,
                       "state_threshold": THR, "kind": "graph"})
-    params = [p for s in specs for p in LT.trainable(s["net_state"])] + [p for s in specs for p in LT.trainable(s["net_output"])]
+    st_nets = [n for s_ in specs for n in (s_["net_state"] if comp else [s_["net_state"]])]
+    out_nets = [shared_out] if comp else [s_["net_output"] for s_ in specs]
+    params = [p for n in st_nets for p in LT.trainable(n)] + [p for n in out_nets for p in LT.trainable(n)]
     opt = torch.optim.Adam(params, lr=0.01, eps=1e-7)
     nodes, arcs = torch.tensor(g.nodes), torch.tensor(g.arcs)
     y, sw = torch.tensor(g.targets), torch.tensor(g.sample_weight, dtype=torch.float32)
+    single = spec["layers"] == 1
 
     def step():
         opt.zero_grad(set_to_none=True)
-        K, states, outs = LT.loop_lgnn(tg, nodes, arcs, specs, True, True, True, None)
+        s0 = [0.1 * torch.randn((g.n_nodes, S)) for _ in specs] if S else None
+        if single:
+            k, _, out = LT.loop_homogeneous(tg, nodes, arcs, specs[0]["net_state"], specs[0]["net_output"], S, MAX_ITER, THR, True,
+                                            s0[0] if S else None, "graph")
+            K, outs = [k], [out]
+        else:
+            K, _, outs = LT.loop_lgnn(tg, nodes, arcs, specs, True, True, True, s0, composite=comp)
         loss = torch.stack([LT.categorical_crossentropy(y, o, sw) for o in outs]).mean()
         loss.backward()
-        for li, s in enumerate(specs):                       # average_st_grads (LGNN.py:272)
-            for p in LT.trainable(s["net_state"]):
-                if K[li] > 0:
-                    p.grad /= K[li]
+        for li, s_ in enumerate(specs):                      # average_st_grads (LGNN.py:272)
+            for n in (s_["net_state"] if comp else [s_["net_state"]]):
+                for p in LT.trainable(n):
+                    if K[li] > 0 and p.grad is not None:
+                        p.grad /= K[li]
         opt.step()
         return sum(K) * g.n_nodes, float(loss)
     return step, g.n_nodes, n_graphs
@@ -143,30 +174,45 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-def build_model(device, seed):
+def build_model(device, seed, spec=None):
     import torch
     from gnnkeras_b200 import models as M
     from gnnkeras_b200.nets import MLP, get_inout_dims
-    gnns = []
-    for l in range(LAYERS):
-        (i_st,), lay_st = get_inout_dims('state', NL, AL, T, 'g', 0, layer=l, get_state=True, get_output=True)
-        (i_out,), lay_out = get_inout_dims('output', NL, AL, T, 'g', 0, layer=l, get_state=True, get_output=True)
-        ns = MLP(input_dim=i_st, layers=lay_st, activations='selu', kernel_initializer='lecun_normal',
+    spec = spec or workload_spec("c2")
+    S, comp = spec["S"], spec["composite"]
+    gnns, shared = [], None
+    if comp:       # starter_composite.py:82-86: one output net object for every layer
+        shared = MLP(input_dim=(S,), layers=[T], activations='softmax', kernel_initializer='glorot_normal',
+                     bias_initializer='glorot_normal', name='Out', device=device, seed=seed * 100 + 50)
+    for l in range(spec["layers"]):
+        D, Ls = spec["D"][l], spec["Ls"][l]
+        ns = MLP(input_dim=(2 * D + Ls,), layers=[D], activations='selu', kernel_initializer='lecun_normal',
                  bias_initializer='lecun_normal', name=f'State_{l}', device=device, seed=seed * 100 + l)
-        no = MLP(input_dim=i_out, layers=lay_out, activations='softmax', kernel_initializer='glorot_normal',
-                 bias_initializer='glorot_normal', name=f'Out_{l}', device=device, seed=seed * 100 + 50 + l)
-        gnns.append(M.GNNgraphBased(ns, no, 0, MAX_ITER, THR))
-    lgnn = M.LGNN(gnns, True, True)
-    lgnn.compile(optimizer=M.Adam(learning_rate=0.01), loss="categorical_crossentropy", average_st_grads=True,
-                 training_mode='parallel')
-    return lgnn
+        if comp:
+            gnns.append(M.CompositeGNNgraphBased([ns], shared, S, MAX_ITER, THR))
+        else:
+            (i_st,), lay_st = get_inout_dims('state', NL, AL, T, 'g', 0, layer=l, get_state=True, get_output=True)
+            assert int(i_st[0]) == 2 * D + Ls and [int(v) for v in lay_st] == [D]
+            no = MLP(input_dim=(D,), layers=[T], activations='softmax', kernel_initializer='glorot_normal',
+                     bias_initializer='glorot_normal', name=f'Out_{l}', device=device, seed=seed * 100 + 50 + l)
+            gnns.append(M.GNNgraphBased(ns, no, 0, MAX_ITER, THR))
+    if spec["layers"] == 1:
+        model = gnns[0]
+        model.compile(optimizer=M.Adam(learning_rate=0.01), loss="categorical_crossentropy", average_st_grads=True)
+        return model
+    model = (M.CompositeLGNN if comp else M.LGNN)(gnns, True, True)
+    model.compile(optimizer=M.Adam(learning_rate=0.01), loss="categorical_crossentropy", average_st_grads=True,
+                  training_mode='parallel')
+    return model
 
 
 class HostBatch:
     """One merged batch in pinned host memory (what a GraphSequencer hands to fit())."""
 
-    def __init__(self, b):
+    def __init__(self, b, composite=False):
         import torch
+        self.composite = composite
+        self.type_mask = np.ascontiguousarray(b.type_mask) if composite else None
         pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).pin_memory()
         self.nodes, self.arcs, self.targets = pin(b.nodes, np.float32), pin(b.arcs, np.float32), pin(b.targets, np.float32)
         self.sw = pin(np.ones(b.n_graphs), np.float32)
@@ -178,12 +224,17 @@ class HostBatch:
     def upload(self, device, defer_check=False):
         from gnnkeras_b200.graph import GraphTensor
         return GraphTensor.from_host_arrays(self.nodes, self.arcs, self.targets, self.sw, self.mask, self.mask, [NL], 'g',
-                                            'average', self.node2graph, None, self.n_graphs, None, None, device,
+                                            'composite_average' if self.composite else 'average', self.node2graph, None,
+                                            self.n_graphs, self.type_mask, None, device,
                                             non_blocking=True, masks_all_true=True, defer_check=defer_check)
 
 
 def sequencer_item(gt):
-    return [gt.nodes, gt.arcs, gt.DIM_NODE_LABEL, gt.set_mask, gt.output_mask, gt.Adjacency, gt.ArcNode, gt.NodeGraph], gt.targets, gt.sample_weight
+    out = [gt.nodes, gt.arcs, gt.DIM_NODE_LABEL, gt.set_mask, gt.output_mask, gt.Adjacency, gt.ArcNode, gt.NodeGraph]
+    if gt.type_mask is not None:                     # composite tuple layout (GraphSequencers.py:240-244)
+        out.insert(3, gt.type_mask)
+        out.insert(-3, gt.CompositeAdjacencies)
+    return out, gt.targets, gt.sample_weight
 
 
 def main():
@@ -192,30 +243,36 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--graphs", type=int, default=8192, help="graphs per batch per GPU")
-    ap.add_argument("--cpu-graphs", type=int, default=1024, help="graphs in the CPU-baseline sample batch")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"], help="c2 = the configuration the metric is quoted on (default)")
+    ap.add_argument("--graphs", type=int, default=0, help="graphs per batch per GPU (0 = the workload's own batch size)")
+    ap.add_argument("--cpu-graphs", type=int, default=0, help="graphs in the CPU-baseline sample batch (0 = the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="resident-input leg: launch every kernel from the host instead of replaying one CUDA graph per batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    spec = workload_spec(args.workload)
+    args.graphs = args.graphs or spec["graphs"]
+    args.cpu_graphs = args.cpu_graphs or spec["cpu_graphs"]
+    WIDTHS, LS, LAYERS = spec["D"], spec["Ls"], spec["layers"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    workload = (f"C2: LGNN {LAYERS} GNNgraphBased layers (state widths {WIDTHS}), parallel mode, MUTAG-shaped synthetic, "
-                f"batch={args.graphs} graphs/GPU, BN+Dense(selu)/BN+Dense(softmax), max_iteration={MAX_ITER}, thr={THR}, average")
+    workload = (f"{spec['title']}, batch={args.graphs} graphs/GPU, BN+Dense(selu)/BN+Dense(softmax), max_iteration={MAX_ITER}, "
+                f"thr={THR}, {'composite_average' if spec['composite'] else 'average'}")
 
     # ---------------- reference arm: the restated reference on the host cores ----------------------------
     if args.impl == "reference":
         if rank != 0:
             return
-        step, n_nodes, n_g = cpu_reference_step_factory(args.cpu_graphs, 0, cores)
+        step, n_nodes, n_g = cpu_reference_step_factory(spec, args.cpu_graphs, 0, cores)
         ups, s_per_step, n = time_cpu(step, args.steps, args.warmup, budget_s=60.0)
         line = {"impl": "reference", "metric": METRIC, "value": ups, "unit": "node-updates/s", "n_gpus": args.gpus,
                 "steps": n, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "training_graphs_per_s": n_g / s_per_step,
-                "config": {"workload": workload, "sample": f"{n_g} graphs ({n_nodes} nodes) per step"},
+                "config": {"workload": workload, "sample": f"{n_g} graphs ({n_nodes} nodes) per step (the GPU arm's batch is "
+                                                             f"{spec['graphs']} graphs; the metric is per node-update)"},
                 "cpu_baseline": {"value": ups, "unit": "node-updates/s", "cores": cores, "kind": "port",
                                  "sample": f"oracle/loop_torch.py (op-for-op PyTorch-CPU eager restatement of the reference; "
                                            f"TensorFlow is not installable in this image), LGNN train step on a {n_g}-graph batch"},
@@ -236,7 +293,7 @@ def main():
         import datetime
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     Lib = B.lib()
-    model = build_model(device, seed=1)
+    model = build_model(device, 1, spec)
     if world > 1:     # data parallel: one merged batch per GPU per step, flat-gradient all-reduce
         model.grad_hook = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         model.grad_scale = 1.0 / world
@@ -244,10 +301,13 @@ def main():
             dist.broadcast(p, src=0)
 
     n_res = 3
-    host_batches = [HostBatch(mutag_shaped_batch(args.graphs, seed=1000 * rank + i)) for i in range(n_res)]
+    host_batches = [HostBatch(mutag_shaped_batch(args.graphs, seed=1000 * rank + i, n_types=1 if spec["composite"] else 0),
+                              spec["composite"]) for i in range(n_res)]
     dev_batches = [hb.upload(device) for hb in host_batches]
     items = [sequencer_item(gt) for gt in dev_batches]
     torch.cuda.synchronize()
+
+    klist = lambda r: list(r["k"]) if isinstance(r["k"], (list, tuple)) else [r["k"]]     # per layer (LGNN) or one (GNN)
 
     def barrier():
         torch.cuda.synchronize()
@@ -299,7 +359,7 @@ def main():
             loss_host[i:i + 1].copy_(r["loss"].reshape(1), non_blocking=True)   # D2H read of this step's loss
             done = torch.cuda.Event()
             done.record()
-            out_ks.append((r["k"], host_batches[i % n_res].n_nodes))
+            out_ks.append((klist(r), host_batches[i % n_res].n_nodes))
             inflight.append((gt, done))
             if i + 1 < n:                         # next batch: H2D + structure build on the side stream while step i runs
                 nxt = upload_async(host_batches[(i + 1) % n_res])
@@ -329,6 +389,8 @@ def main():
         model.train_step(items[i % n_res])
     barrier()
     graphed, launches_per_step = None, None
+    if spec["S"] > 0:
+        args.no_graph = True      # state_vect_dim > 0 draws the initial state per call (GNN.py:257): launched from the host
     if not args.no_graph:
         from gnnkeras_b200.models import GraphedTrainStep
         graphed, launches_per_step = [], []
@@ -349,7 +411,7 @@ def main():
     ev0.record()
     for i in range(args.steps):
         r = graphed[i % n_res]() if graphed else model.train_step(items[i % n_res])
-        ks.append((r["k"], i % n_res))
+        ks.append((klist(r), i % n_res))
     ev1.record()
     barrier()
     launches = int(Lib.gnnfp_launch_count(0))
@@ -377,8 +439,8 @@ def main():
         cnt = (C.c_longlong * NC)()
         Lib.gnnfp_profile_collect(msc, cnt, NC)
         Lib.gnnfp_profile_enable(0)
-        names = ["other", "state_fwd_iter(gemm_rows_tc fwd)", "state_bwd_dW(gemm_dw_tc)", "tile_pass(prologue, BN statistics)",
-                 "out_fwd", "out_bwd", "bn_fix", "state_bwd_dz(dz_kernel)", "state_bwd_dX(gemm_rows_tc bwd)",
+        names = ["other", "state_fwd_iter(rows_tma FWD)", "state_bwd_dW(gemm_dw_tc)", "tile_pass(prologue, BN statistics)",
+                 "out_fwd", "out_bwd", "bn_fix", "state_bwd_dz(dz_kernel)", "state_bwd_dX(rows_tma DX)",
                  "aggregate(agg_stats)"]
         shares = {names[i]: {"ms": msc[i], "launches": int(cnt[i])} for i in range(len(names))}
         nsteps_p = min(args.steps, 6)
@@ -392,12 +454,18 @@ def main():
         #   gemm_rows dX  : reads dz (D) once, writes dOwn and dAgg (D each) - one launch for both where the two
         #                   accumulator blocks fit (D <= 64), else one launch per destination
         cand = {
-            "gemm_rows_tc_kernel<fwd>": (msc[1], int(cnt[1]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
-                                      sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
-            "gemm_dw_tc_kernel": (msc[2], int(cnt[2]), sum(4 * (3 * D + AL) for D in WIDTHS) * iters,
-                               sum(2 * (2 * D + AL) * D for D in WIDTHS) * iters),
-            "gemm_rows_tc_kernel<bwd dX>": (msc[8], int(cnt[8]), sum(4 * (3 * D) for D in WIDTHS) * iters,
-                                         sum(2 * (2 * D) * D for D in WIDTHS) * iters),
+            "forward iteration (rows_tma_kernel<FWD> / tile_fwd)": (msc[1], int(cnt[1]), sum(4 * (3 * D + l_) for D, l_ in zip(WIDTHS, LS)) * iters,
+                                                                   sum(2 * (2 * D + l_) * D for D, l_ in zip(WIDTHS, LS)) * iters),
+            "dW (gemm_dw_tc_kernel / tile_bwd)": (msc[2], int(cnt[2]), sum(4 * (3 * D + l_) for D, l_ in zip(WIDTHS, LS)) * iters,
+                                                 sum(2 * (2 * D + l_) * D for D, l_ in zip(WIDTHS, LS)) * iters),
+            "dX (rows_tma_kernel<DX>)": (msc[8], int(cnt[8]), sum(4 * (3 * D) for D in WIDTHS) * iters,
+                                        sum(2 * (2 * D) * D for D in WIDTHS) * iters),
+            # dz = act'(s_t) (dOwn + Adj dAgg): read s_t, dOwn, dAgg once each, write dz, + the src-CSR (row pointer, index, weight)
+            "dz (dz_kernel)": (msc[7], int(cnt[7]), sum(4 * (4 * D) + 4 + 8 * deg for D in WIDTHS) * iters,
+                               sum(2 * deg * D for D in WIDTHS) * iters),
+            # Adj^T s: read s once, write the aggregate, + the dst-CSR
+            "Adj^T s (agg_stats_kernel)": (msc[9], int(cnt[9]), sum(4 * (2 * D) + 4 + 8 * deg for D in WIDTHS) * iters,
+                                           sum(2 * deg * D for D in WIDTHS) * iters),
         }
         dom = max(cand, key=lambda k_: cand[k_][0])
         dom_ms, dom_n, dom_bytes, flops = cand[dom]
@@ -412,9 +480,9 @@ def main():
         tf32_peak = 1100.0                                  # dense TF32 tensor peak (B200_PROFILING.md); each product = 3 MMAs
         # whole fixed-point iteration against SURVEY 8(d)'s per-node-update figure B = B_f + B_b
         it_ms = msc[1] + msc[2] + msc[7] + msc[8] + msc[9]
-        it_bytes = sum(algorithmic_bytes(D, AL, deg, True) + algorithmic_bytes(D, AL, deg, False) for D in WIDTHS) * iters
+        it_bytes = sum(algorithmic_bytes(D, l_, deg, True) + algorithmic_bytes(D, l_, deg, False) for D, l_ in zip(WIDTHS, LS)) * iters
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):                          # dram__bytes_read+write per launch, one ncu capture of this workload
             tj = json.load(open(tpath))
             if dom in tj:
@@ -426,13 +494,12 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes / max(1, dom_n),
                 "useful_tflops_achieved": tfl, "tf32_mma_tflops_issued": 3 * tfl, "tf32_tensor_peak_tflops": tf32_peak,
                 "tensor_frac": 3 * tfl / tf32_peak, "fp32_pipe_nominal_peak_tflops": fp32_peak,
-                "binding": "the GEMM kernels run on tcgen05 (3xTF32: 3 MMAs per product); with the math on the tensor pipe the "
-                           "33 flop/B workload is HBM-bound by the roofline (ridge ~57 flop/B at 1.1 PF/3), so frac is against the "
-                           "measured HBM peak; what limits the kernels today is operand conversion / epilogue instruction issue "
-                           "and L2 latency at one CTA per SM (DESIGN.md 6)",
+                "binding": "the three GEMMs of an iteration run on tcgen05 (3xTF32: 3 MMAs per product), so the 33 flop/B workload is "
+                           "HBM-bound by the roofline (ridge ~57 flop/B at 1.1 PF/3) and frac is against the measured HBM peak; the "
+                           "dominant kernel is whichever category took the most time in the profiled steps (DESIGN.md 5, 6)",
                 "fixed_point_iteration": {"ms": it_ms, "algorithmic_GBps": it_bytes / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0,
                                           "frac_of_hbm_peak": (it_bytes / (it_ms * 1e-3) / 1e9) / peak if it_ms > 0 else 0.0,
-                                          "kernels": "gemm_rows_tc fwd (tcgen05 3xTF32) + agg_stats + dz + gemm_dw_tc + gemm_rows_tc dX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
+                                          "kernels": "rows_tma FWD (TMA + tcgen05 3xTF32) + agg_stats + dz + gemm_dw_tc + rows_tma DX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
                 "kernel_time_by_category_ms": shares,
                 "note": "achieved = algorithmic bytes of the kernel's launches / their CUDA-event durations "
                         "(events recorded by the library on the launch stream, separate profiled pass of the same steps)"}
@@ -440,14 +507,14 @@ def main():
     # ---- CPU baseline (rank 0, bounded sample) -------------------------------------------------------------------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        step, n_nodes_c, n_g = cpu_reference_step_factory(args.cpu_graphs, 0, cores)
+        step, n_nodes_c, n_g = cpu_reference_step_factory(spec, args.cpu_graphs, 0, cores)
         ups, s_per, n = time_cpu(step, 40, 2, budget_s=20.0)
         cpu = {"value": ups, "unit": "node-updates/s", "cores": cores, "kind": "port",
                "training_graphs_per_s": n_g / s_per,
-               "sample": f"oracle/loop_torch.py restated reference (PyTorch-CPU eager, TF unavailable), LGNN train step, "
-                         f"{n_g}-graph batch ({n_nodes_c} nodes), {n} steps"}
+               "sample": f"oracle/loop_torch.py restated reference (PyTorch-CPU eager, TF unavailable), train step of this workload on a "
+                         f"{n_g}-graph batch ({n_nodes_c} nodes; the GPU arm's batch is {args.graphs} graphs), {n} steps"}
     if rank == 0:
-        ws_bytes = sum(g._ws["buf"].numel() for g in model.gnns if "buf" in g._ws)
+        ws_bytes = sum(g._ws["buf"].numel() for g in getattr(model, "gnns", [model]) if "buf" in g._ws)
         line = {"metric": METRIC, "value": value, "unit": "node-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
