@@ -66,35 +66,38 @@ def MLP(input_dim: tuple, layers: list, activations, kernel_initializer, bias_in
 
 def get_inout_dims(net_name: str, dim_node_label, dim_arc_label: int, dim_target: int, focus: str, dim_state: int,
                    hidden_units=None, *, layer: int = 0, get_state: bool = False, get_output: bool = False):
-    """Input and output dimensions of the state / output MLPs (MLP.py:82-140)."""
-    assert layer >= 0
-    assert focus in ['a', 'n', 'g']
-    assert dim_state >= 0
-    assert isinstance(hidden_units, (int, type(None))) or (isinstance(hidden_units, list) and all(isinstance(x, int) for x in hidden_units))
-    NL, AL, T = np.array(dim_node_label, ndmin=1), dim_arc_label, dim_target
-    DS, GS, GO = dim_state, get_state, get_output
+    """Input shapes and layer widths of the state / output MLPs of LGNN layer ``layer`` (drop-in for MLP.py:82-140).
+
+    What the loop feeds: a node of type t carries ``labels_t`` label columns; net_state[t] sees
+    [own labels | state | neighbour states | aggregated labels of every type | aggregated arc labels], i.e.
+    ``labels_t + sum(labels) + arc_labels + 2 * dim_state`` columns, and emits ``dim_state`` (or the label width when the
+    labels ARE the state, dim_state == 0).  net_output sees [state | labels] per node - twice that plus the arc labels for
+    arc focus - and emits ``dim_target``; composite models (several label widths) feed the state only.  From the second
+    LGNN layer on the labels grow by what update_graph prepends: the previous state and / or output."""
+    if layer < 0 or focus not in ('a', 'n', 'g') or dim_state < 0:
+        raise AssertionError("layer >= 0, focus in 'a' / 'n' / 'g', dim_state >= 0")
+    if not (hidden_units is None or isinstance(hidden_units, int) or
+            (isinstance(hidden_units, list) and all(isinstance(x, int) for x in hidden_units))):
+        raise AssertionError("hidden_units: None, an int or a list of ints")
+    labels = np.array(dim_node_label, ndmin=1).astype(int)
+    arc_labels = int(dim_arc_label)
+    out_to_arcs = focus == 'a'
     if layer > 0:
-        if DS != 0:
-            NL = NL + DS * GS + T * (focus != 'a') * GO
-            AL = AL + T * (focus == 'a') * GO
-        else:
-            NL = NL + layer * NL * GS + ((layer - 1) * GS + 1) * T * (focus != 'a') * GO
-            AL = AL + T * (focus == 'a') * GO
+        grown_out = int(dim_target) if get_output else 0
+        if dim_state > 0:          # constant growth: [state | out | original labels]
+            labels = labels + (dim_state if get_state else 0) + (0 if out_to_arcs else grown_out)
+        else:                      # the state IS the previous layer's labels: the width compounds layer by layer
+            labels = labels + (layer * labels if get_state else 0) + (0 if out_to_arcs else ((layer - 1 if get_state else 0) + 1) * grown_out)
+        if out_to_arcs:
+            arc_labels += grown_out
     if net_name == 'state':
-        NLgen = np.sum(NL)
-        input_shape = list(NL + NLgen + AL + 2 * DS)
-        output_shape = DS if DS else NL
+        inputs = [int(w) for w in labels + int(labels.sum()) + arc_labels + 2 * dim_state]
+        out_width = int(dim_state) if dim_state else (int(labels[0]) if labels.size == 1 else labels)
     elif net_name == 'output':
-        if len(NL) > 1: NL = np.array([0])
-        input_shape = list((focus == 'a') * (NL + AL + DS) + NL + DS)
-        output_shape = T
+        lab = 0 if labels.size > 1 else int(labels[0])
+        inputs = [(lab + arc_labels + dim_state if out_to_arcs else 0) + lab + dim_state]
+        out_width = int(dim_target)
     else:
         raise ValueError(':param net_name: not in [\'state\', \'output\']')
-    input_shape = [(int(i),) for i in input_shape]
-    if not hidden_units: hidden_units = list()
-    if isinstance(hidden_units, int): hidden_units = [hidden_units]
-    out = output_shape
-    if isinstance(out, np.ndarray):
-        out = int(out[0]) if out.size == 1 else out
-    layers = hidden_units + [out]
-    return input_shape, layers
+    hidden = [] if not hidden_units else ([hidden_units] if isinstance(hidden_units, int) else list(hidden_units))
+    return [(int(i),) for i in inputs], hidden + [out_width]

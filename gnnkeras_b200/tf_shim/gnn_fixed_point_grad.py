@@ -1,4 +1,7 @@
-"""Registered gradient of the GnnFixedPoint custom op (SOURCE ONLY here - TensorFlow is not installable in the
+"""*** SKETCH, NOT WORKING CODE: the op it calls (gnn_fixed_point_grad) is registered nowhere - see the header of
+gnn_fixed_point_op.cc.  The tested binding of this repository is ctypes (gnnkeras_b200/_lib.py). ***
+
+Registered gradient of the GnnFixedPoint custom op (SOURCE ONLY here - TensorFlow is not installable in the
 build image).  Where TF exists, `GNNnodeBased.Loop` becomes:
 
     k, state, out, ws = _mod.gnn_fixed_point(nodes, arcs[:, 2:], state0, src, dst, node2graph, set_mask,

@@ -1,3 +1,7 @@
+// *** SKETCH, NOT A WORKING OP ***  Key bodies below are elided ("... (elided) ..."), the gradient op the Python file refers
+// to is not registered, and Compute() frees the plan the gradient would need.  It documents WHERE the C ABI plugs into a
+// TF custom op; the working, tested binding in this image is ctypes (gnnkeras_b200/_lib.py).
+//
 // gnn_fixed_point_op.cc - TensorFlow custom op over the gnnfp C ABI (SOURCE ONLY in this repository:
 // the build image has no TensorFlow headers, so this file is neither compiled nor tested here; it shows the
 // exact binding a maintainer adds where `import tensorflow` works).
