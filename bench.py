@@ -237,19 +237,122 @@ def sequencer_item(gt):
     return out, gt.targets, gt.sample_weight
 
 
+def run_c5(args, rank, world, local_rank, cores):
+    """BASELINE.json configs[4]: GNNnodeBased on ONE large synthetic graph, 1-D block (edge-cut) partition over the ranks,
+    per-iteration halo exchange of boundary states + max-reduce of the convergence flag over NCCL / NVLink, BPTT with the
+    reverse halo reduction, parameter gradients all-reduced.  Every rank generates ITS block locally (dist.py:
+    synthetic_partition / build_local_halo_plan), so 10 M nodes / 100 M arcs never exist in one host array."""
+    import torch
+    import torch.distributed as dist
+    from gnnkeras_b200 import dist as D
+    from gnnkeras_b200.op import Net
+    from gnnkeras_b200.synthetic import make_net
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=600))
+    S, NLc, ALc, Tc = 32, 16, 4, 4
+    n_total = args.c5_nodes * world
+    arcs_total = 10 * n_total
+    lo, hi, src, dst, al = D.synthetic_partition(rank, world, n_total, arcs_total, seed=7, locality=args.c5_locality,
+                                                 band=args.c5_band, dim_arc_label=ALc)
+    plan = D.build_local_halo_plan(rank, world, n_total, src, dst, device=device)
+    ids_local = np.concatenate([np.arange(lo, hi, dtype=np.int64), plan.halo_global])
+    nodes_local = D.node_labels_of(ids_local, NLc, seed=1)
+    rng = np.random.default_rng(3)                     # the same weights on every rank
+    ns = make_net(rng, 2 * S + 2 * NLc + ALc, [S], ["tanh"], False, 0.5)
+    no = make_net(rng, S + NLc, [Tc], ["softmax"], False)
+    loop = D.PartitionedLoop(plan, nodes_local, al, Net.from_dict(ns, device), Net.from_dict(no, device), S, MAX_ITER, 0.0,
+                             "average", device=device, training=True, local=True)
+    state0 = torch.as_tensor(0.1 * D.node_labels_of(ids_local, S, seed=99)).to(device)
+    n_own = plan.n_own
+    d_out = torch.full((n_own, Tc), 1.0 / max(1, n_total), dtype=torch.float32, device=device)
+
+    def step():
+        k, st, out = loop.forward(state0)
+        loop.backward(d_out, None, False)              # incl. the all-reduce of the parameter gradients over the ranks
+        return k
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        k = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        k = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stats = torch.tensor([ms, float(plan.n_halo), float(len(src)), float((src < lo).sum() + (src >= hi).sum())], dtype=torch.float64, device=device)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        ms = float(mx[0].item())
+    kk = int(k.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        halo_rows, arcs_all, cut = float(stats[1].item()), float(stats[2].item()), float(stats[3].item())
+        value = n_total * kk * args.steps / (ms * 1e-3)
+        deg = arcs_all / n_total
+        b_node = algorithmic_bytes(S, 2 * NLc + ALc, deg, True) + algorithmic_bytes(S, 2 * NLc + ALc, deg, False)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        ach = value * b_node / 1e9 / world
+        line = {"metric": METRIC, "value": value, "unit": "node-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"C5: GNNnodeBased on one synthetic graph, {n_total} nodes / {int(arcs_all)} arcs, state_dim {S}, "
+                                       f"node labels {NLc}, arc labels {ALc}, net_state Dense({2 * S + 2 * NLc + ALc}->{S}, tanh) without "
+                                       f"BatchNormalization, max_iteration {MAX_ITER}, threshold 0 (k = {kk}), average aggregation, "
+                                       f"1-D block partition over {world} rank(s), locality {args.c5_locality} (band {args.c5_band})",
+                           "nodes_per_gpu": args.c5_nodes, "cut_arc_fraction": cut / max(1.0, arcs_all),
+                           "halo_rows_total": int(halo_rows),
+                           "nvlink_bytes_per_iteration": int(halo_rows * S * 4) if world > 1 else 0,
+                           "exchange": "index_select of the boundary rows + NCCL all_to_all_single per iteration (forward), reverse "
+                                       "all_to_all + index_add per iteration (backward), 1-word flag all-reduce(max), gradient all-reduce",
+                           "parallelism": f"edge-cut partition over {world}" if world > 1 else "single"},
+                "e2e": None, "gpu_launches": None, "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "whole fixed-point iteration (forward + BPTT)", "achieved": ach, "peak": peak,
+                             "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "note": f"per GPU: node-updates/s x SURVEY 8(d) B_f + B_b = {b_node:.0f} bytes per node-update"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"], help="c2 = the configuration the metric is quoted on (default)")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"], help="c2 = the configuration the metric is quoted on (default)")
+    ap.add_argument("--c5-nodes", type=int, default=1250000, help="c5: nodes per GPU (x10 arcs); 8 GPUs = 10 M nodes / 100 M arcs")
+    ap.add_argument("--c5-locality", type=float, default=0.95, help="c5: fraction of arcs whose source lies within --c5-band ids of the destination")
+    ap.add_argument("--c5-band", type=int, default=8192)
     ap.add_argument("--graphs", type=int, default=0, help="graphs per batch per GPU (0 = the workload's own batch size)")
     ap.add_argument("--cpu-graphs", type=int, default=0, help="graphs in the CPU-baseline sample batch (0 = the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="resident-input leg: launch every kernel from the host instead of replaying one CUDA graph per batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "c5":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "c5 has no CPU arm in this harness (see --workload c2 for the metric's reference arm)"}))
+            return
+        return run_c5(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+                      int(os.environ.get("LOCAL_RANK", "0")), os.cpu_count() or 1)
     spec = workload_spec(args.workload)
     args.graphs = args.graphs or spec["graphs"]
     args.cpu_graphs = args.cpu_graphs or spec["cpu_graphs"]

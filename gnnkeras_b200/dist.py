@@ -148,12 +148,91 @@ def build_halo_plans(src: np.ndarray, dst: np.ndarray, n_nodes: int, world: int)
     return plans
 
 
+def _send_idx(plan: HaloPlan, device) -> torch.Tensor:
+    """Rows this rank sends, concatenated per peer - built and uploaded ONCE per plan and device (it used to be rebuilt from
+    NumPy on every exchange)."""
+    cache = plan.__dict__.setdefault("_send_idx_cache", {})
+    key = str(device)
+    if key not in cache:
+        rows = np.concatenate(plan.send_rows) if len(plan.send_rows) else np.zeros(0, np.int64)
+        cache[key] = torch.as_tensor(rows.astype(np.int64)).to(device)
+    return cache[key]
+
+
+def node_labels_of(ids: np.ndarray, width: int, seed: int = 0) -> np.ndarray:
+    """Deterministic pseudo-random labels in [-0.5, 0.5) as a pure function of (node id, column): every rank can produce the
+    labels of any node (its own block and its halo) without a global array."""
+    ids = np.asarray(ids, dtype=np.uint64)[:, None]
+    cols = np.arange(width, dtype=np.uint64)[None, :]
+    h = (ids * np.uint64(0x9E3779B97F4A7C15) + cols * np.uint64(0xBF58476D1CE4E5B9) + np.uint64(seed)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    h ^= h >> np.uint64(31)
+    h = (h * np.uint64(0x94D049BB133111EB)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    h ^= h >> np.uint64(29)
+    return ((h >> np.uint64(40)).astype(np.float64) / float(1 << 24) - 0.5).astype(np.float32)
+
+
+def synthetic_partition(rank: int, world: int, n_total: int, arcs_total: int, seed: int = 0, locality: float = 0.9,
+                        band: int = 4096, dim_arc_label: int = 4):
+    """This rank's share of one large synthetic graph (BASELINE.json configs[4]), generated locally: the rank owns the node
+    block [lo, hi) and draws arcs_total / world arcs INTO it - the source within ``band`` ids of the destination with
+    probability ``locality`` (block-banded: few cut arcs), uniform over the whole graph otherwise.  Arcs are unique and
+    sorted by (src, dst) - the reference's arc order (graph_class.py:47) restricted to this rank's destinations.
+    Returns lo, hi, src (global ids, int64), dst (global ids, int64), arc_labels [A_loc, AL]."""
+    bounds = block_ranges(n_total, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    rng = np.random.default_rng(seed * 1000003 + rank)
+    a_loc = arcs_total // world
+    dst = rng.integers(lo, hi, size=a_loc, dtype=np.int64)
+    near = np.clip(dst + rng.integers(-band, band + 1, size=a_loc), 0, n_total - 1)
+    far = rng.integers(0, n_total, size=a_loc, dtype=np.int64)
+    src = np.where(rng.random(a_loc) < locality, near, far)
+    keep = src != dst
+    key = np.unique(src[keep] * np.int64(n_total) + dst[keep])        # unique, sorted by (src, dst)
+    src, dst = key // n_total, key % n_total
+    arc_labels = rng.standard_normal((len(src), dim_arc_label), dtype=np.float32)
+    return lo, hi, src, dst, arc_labels
+
+
+def build_local_halo_plan(rank: int, world: int, n_total: int, src: np.ndarray, dst: np.ndarray, group=None,
+                          device=None) -> HaloPlan:
+    """HaloPlan of this rank from ITS arcs only (all destinations in its block); the rows every peer must send are agreed
+    by one all-to-all of the needed node ids at plan time (NCCL on ``device`` tensors, gloo on CPU tensors)."""
+    bounds = block_ranges(n_total, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    remote = (src < lo) | (src >= hi)
+    halo = np.unique(src[remote])
+    slot = np.searchsorted(halo, src[remote])
+    local_src = np.where(remote, 0, src - lo)
+    local_src[remote] = (hi - lo) + slot
+    owner = np.searchsorted(bounds, halo, side="right") - 1
+    recv = np.bincount(owner, minlength=world).astype(np.int64) if len(halo) else np.zeros(world, np.int64)
+    send_rows = [np.zeros(0, np.int64) for _ in range(world)]
+    if world > 1:
+        dev = torch.device(device) if device is not None else torch.device("cpu")
+        want_counts = torch.as_tensor(recv).to(dev)                  # ids I need from every owner
+        give_counts = torch.empty_like(want_counts)
+        if dist.get_backend(group) == "gloo":                        # CPU tests: gloo has no all_to_all
+            all_halos = [None] * world
+            dist.all_gather_object(all_halos, halo, group=group)
+            send_rows = [(h[(h >= lo) & (h < hi)] - lo).astype(np.int64) for h in all_halos]
+        else:
+            dist.all_to_all_single(give_counts, want_counts, group=group)
+            give = [int(x) for x in give_counts.tolist()]
+            ids_out = torch.as_tensor(halo).to(dev)                  # grouped by owner (halo is sorted)
+            ids_in = torch.empty(sum(give), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(ids_in, ids_out, give, [int(x) for x in recv], group=group)
+            parts = ids_in.cpu().numpy()
+            offs = np.concatenate([[0], np.cumsum(give)])
+            send_rows = [(parts[offs[p]:offs[p + 1]] - lo).astype(np.int64) for p in range(world)]
+    return HaloPlan(rank, world, lo, hi, local_src.astype(np.int32), (dst - lo).astype(np.int32),
+                    np.arange(len(src), dtype=np.int64), halo, recv, send_rows)
+
+
 def exchange_halo(plan: HaloPlan, own_rows: torch.Tensor, group=None) -> torch.Tensor:
     """Send the owned rows every peer needs and receive this rank's halo rows ([n_halo, D], halo-slot order).
     One all-to-all-v per call (NCCL on device tensors, gloo on CPU tensors)."""
     D = own_rows.shape[1]
-    send_idx = torch.as_tensor(np.concatenate(plan.send_rows) if plan.world else np.zeros(0, np.int64),
-                               device=own_rows.device)
+    send_idx = _send_idx(plan, own_rows.device)
     send = own_rows.index_select(0, send_idx) if send_idx.numel() else own_rows.new_zeros((0, D))
     recv = own_rows.new_empty((plan.n_halo, D))
     in_splits = [int(len(x)) for x in plan.send_rows]
@@ -200,7 +279,7 @@ def reduce_halo_grads(plan: HaloPlan, d_halo: torch.Tensor, d_own: torch.Tensor,
                 q.wait()
         else:
             dist.all_to_all_single(recv, d_halo.contiguous(), out_splits, in_splits, group=group)
-    idx = torch.as_tensor(np.concatenate(plan.send_rows), device=d_own.device)
+    idx = _send_idx(plan, d_own.device)
     if idx.numel():
         d_own.index_add_(0, idx, recv)
     return d_own
@@ -223,7 +302,7 @@ class PartitionedLoop:
 
     def __init__(self, plan: HaloPlan, nodes, arcs, net_state, net_output, state_vect_dim, max_iteration,
                  state_threshold, aggregation_mode="sum", set_mask=None, output_mask=None, device="cuda",
-                 exchange=None, reduce_flag=None, group=None, training=False, reduce_halo=None):
+                 exchange=None, reduce_flag=None, group=None, training=False, reduce_halo=None, local=False):
         from .op import DeviceGraph, LoopPlan
         if aggregation_mode not in ("sum", "average"):
             raise ValueError("partitioned loop supports aggregation modes 'sum' and 'average' "
@@ -234,13 +313,19 @@ class PartitionedLoop:
         n_loc = plan.n_own + plan.n_halo
         nodes = np.asarray(nodes, dtype=np.float32)
         arcs = np.asarray(arcs, dtype=np.float32)
-        # local node labels: owned rows then halo rows (labels of halo nodes are needed by Adj^T.nodes)
-        self.nodes = t(np.concatenate([nodes[plan.lo:plan.hi], nodes[plan.halo_global]], axis=0), np.float32)
-        self.arc_labels = t(arcs[plan.arc_ids][:, 2:], np.float32)
         sm = np.zeros(n_loc, np.uint8)
         om = np.zeros(n_loc, np.uint8)
-        sm[:plan.n_own] = 1 if set_mask is None else np.asarray(set_mask)[plan.lo:plan.hi]
-        om[:plan.n_own] = 1 if output_mask is None else np.asarray(output_mask)[plan.lo:plan.hi]
+        if local:     # the caller hands over THIS rank's arrays: labels of [owned | halo] rows, labels of its arcs, masks of owned rows
+            self.nodes = t(nodes, np.float32)
+            self.arc_labels = t(arcs, np.float32)
+            sm[:plan.n_own] = 1 if set_mask is None else np.asarray(set_mask)
+            om[:plan.n_own] = 1 if output_mask is None else np.asarray(output_mask)
+        else:
+            # local node labels: owned rows then halo rows (labels of halo nodes are needed by Adj^T.nodes)
+            self.nodes = t(np.concatenate([nodes[plan.lo:plan.hi], nodes[plan.halo_global]], axis=0), np.float32)
+            self.arc_labels = t(arcs[plan.arc_ids][:, 2:], np.float32)
+            sm[:plan.n_own] = 1 if set_mask is None else np.asarray(set_mask)[plan.lo:plan.hi]
+            om[:plan.n_own] = 1 if output_mask is None else np.asarray(output_mask)[plan.lo:plan.hi]
         self.graph = DeviceGraph(t(plan.local_src, np.int32), t(plan.local_dst, np.int32), n_loc, aggregation_mode,
                                  set_mask=t(sm, np.uint8), output_mask=t(om, np.uint8))
         self.loop = LoopPlan(self.graph, [net_state], net_output, "node", state_vect_dim, max_iteration, state_threshold,

@@ -23,6 +23,18 @@ def _worker(rank, world, port, ret):
         # every train_step holds a collective: all ranks get the same number of batches (the tail of the epoch is dropped)
         assert D.shard_batches(7, rank, world) == list(range(rank, (7 // world) * world, world))
         assert D.shard_batches(7, rank, world, drop_tail=False) == list(range(rank, 7, world))
+        # ---- locally generated partition (bench --workload c5): the plan built from this rank's arcs only, send lists agreed
+        # ---- by a collective, equals the plan of the global builder on the gathered arcs ---------------------------------
+        lo_, hi_, ls, ld, lal = D.synthetic_partition(rank, world, 900, 7200, seed=4, locality=0.6, band=60)
+        lp = D.build_local_halo_plan(rank, world, 900, ls, ld)
+        allarcs = [None] * world
+        dist.all_gather_object(allarcs, (ls, ld))
+        gs_, gd_ = np.concatenate([a[0] for a in allarcs]), np.concatenate([a[1] for a in allarcs])
+        o_ = np.lexsort((gd_, gs_))
+        gp = D.build_halo_plans(gs_[o_], gd_[o_], 900, world)[rank]
+        assert np.array_equal(lp.halo_global, gp.halo_global) and np.array_equal(lp.local_src, gp.local_src)
+        assert np.array_equal(lp.local_dst, gp.local_dst) and np.array_equal(lp.recv_counts, gp.recv_counts)
+        assert all(np.array_equal(a, b_) for a, b_ in zip(lp.send_rows, gp.send_rows))
         # ---- partitioned graph: one aggregation Adj^T.state with halo exchange == the global result -------
         b = random_graph(500, 4000, seed=3, locality=0.5, band=50)
         src, dst = b.src.astype(np.int64), b.dst.astype(np.int64)
