@@ -263,16 +263,28 @@ def run_c5(args, rank, world, local_rank, cores):
     rng = np.random.default_rng(3)                     # the same weights on every rank
     ns = make_net(rng, 2 * S + 2 * NLc + ALc, [S], ["tanh"], False, 0.5)
     no = make_net(rng, S + NLc, [Tc], ["softmax"], False)
-    loop = D.PartitionedLoop(plan, nodes_local, al, Net.from_dict(ns, device), Net.from_dict(no, device), S, MAX_ITER, 0.0,
-                             "average", device=device, training=True, local=True)
     state0 = torch.as_tensor(0.1 * D.node_labels_of(ids_local, S, seed=99)).to(device)
     n_own = plan.n_own
     d_out = torch.full((n_own, Tc), 1.0 / max(1, n_total), dtype=torch.float32, device=device)
+    if world > 1:
+        loop = D.PartitionedLoop(plan, nodes_local, al, Net.from_dict(ns, device), Net.from_dict(no, device), S, MAX_ITER, 0.0,
+                                 "average", device=device, training=True, local=True)
 
-    def step():
-        k, st, out = loop.forward(state0)
-        loop.backward(d_out, None, False)              # incl. the all-reduce of the parameter gradients over the ranks
-        return k
+        def step():
+            k, st, out = loop.forward(state0)
+            loop.backward(d_out, None, False)          # incl. the all-reduce of the parameter gradients over the ranks
+            return k
+    else:          # one rank owns the whole graph: the plain (unpartitioned) loop
+        from gnnkeras_b200.op import DeviceGraph, LoopPlan
+        t32 = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a.astype(dt))).to(device)
+        dg = DeviceGraph(t32(plan.local_src, np.int32), t32(plan.local_dst, np.int32), n_own, "average")
+        nodes_d, al_d = t32(nodes_local, np.float32), t32(al, np.float32)
+        lp = LoopPlan(dg, [Net.from_dict(ns, device)], Net.from_dict(no, device), "node", S, MAX_ITER, 0.0, True, NLc, ALc)
+
+        def step():
+            k, st, out = lp.forward(nodes_d, al_d, state0, ld_arcs=al_d.stride(0))
+            lp.backward(d_out, None, None, False)
+            return k
 
     def barrier():
         torch.cuda.synchronize()
@@ -497,13 +509,17 @@ def main():
     if not args.no_graph:
         from gnnkeras_b200.models import GraphedTrainStep
         graphed, launches_per_step = [], []
-        for it in items:
-            c0 = int(Lib.gnnfp_launch_count(0))
-            g = GraphedTrainStep(model, it, warmup=1)
-            launches_per_step.append((int(Lib.gnnfp_launch_count(0)) - c0) // 2)    # one warm-up step + the capture pass
-            graphed.append(g)
-        for i in range(n_res):
-            graphed[i]()
+        try:
+            for it in items:
+                c0 = int(Lib.gnnfp_launch_count(0))
+                g = GraphedTrainStep(model, it, warmup=1)
+                launches_per_step.append((int(Lib.gnnfp_launch_count(0)) - c0) // 2)    # one warm-up step + the capture pass
+                graphed.append(g)
+            for i in range(n_res):
+                graphed[i]()
+        except Exception as e:      # never lose the measurement to a capture problem: launch from the host instead
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); launching kernels from the host", file=sys.stderr)
+            graphed = None
         barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:

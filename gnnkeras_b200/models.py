@@ -113,14 +113,32 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         gnns = getattr(model, "gnns", [model])
         self._keep = [g._ws.get("buf") for g in gnns]          # workspaces the captured kernels point into
+        self.hook = model.grad_hook
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.result = model.train_step(data)
-        opt = model.optimizer
-        opt.iterations -= 1                                    # the capture pass did not execute
+        self.update_graph = None
+        if self.hook is None:
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.result = model.train_step(data)
+            model.optimizer.iterations -= 1                    # the capture pass did not execute
+        else:
+            # data parallel: the gradient all-reduce stays OUTSIDE the graphs (a NCCL collective captured next to the
+            # process group's watchdog thread is fragile) - graph 1 = forward + loss + BPTT, then the hook, graph 2 = Adam
+            model._defer_update = True
+            try:
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                    self.result = model.train_step(data)
+            finally:
+                model._defer_update = False
+            self.update_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.update_graph, capture_error_mode="thread_local"):
+                model._store.adam_step(model.optimizer, model.grad_scale)
+            model.optimizer.iterations -= 1
 
     def __call__(self):
         self.graph.replay()
+        if self.update_graph is not None:
+            self.hook(self.model._store.grad_flat)
+            self.update_graph.replay()
         self.model.optimizer.iterations += 1
         return self.result
 
@@ -274,9 +292,10 @@ class GNNnodeBased:
         gs = [self._store.grad_views(i) for i in range(ns)]
         go = self._store.grad_views(ns)
         self._last_plan.backward(d_out, None, None, self.average_st_grads, grad_state=gs, grad_out=go)
-        if self.grad_hook is not None:
-            self.grad_hook(self._store.grad_flat)
-        self._store.adam_step(self.optimizer, self.grad_scale)
+        if not getattr(self, "_defer_update", False):          # GraphedTrainStep applies hook + update itself
+            if self.grad_hook is not None:
+                self.grad_hook(self._store.grad_flat)
+            self._store.adam_step(self.optimizer, self.grad_scale)
         return {"loss": loss, "k": k}
 
     def test_step(self, data):
@@ -496,9 +515,10 @@ class LGNN:
                 d_out_nodes = torch.empty((graph.n_masked, ow), dtype=torch.float32, device=nodes0.device) if ow else None
                 B.check(B.lib().gnnfp_update_graph_backward(graph._h, nodes0.shape[0], _ptr(d_nodes), _ptr(d_state), sw,
                                                             _ptr(d_out_nodes), ow, None, nodes0.shape[1], 0, _stream()))
-        if self.grad_hook is not None:
-            self.grad_hook(self._store.grad_flat)
-        self._store.adam_step(self.optimizer, self.grad_scale)
+        if not getattr(self, "_defer_update", False):
+            if self.grad_hook is not None:
+                self.grad_hook(self._store.grad_flat)
+            self._store.adam_step(self.optimizer, self.grad_scale)
         return {"loss": loss, "k": k}
 
     def test_step(self, data):
