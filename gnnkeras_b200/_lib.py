@@ -65,6 +65,18 @@ class LoopGrads(C.Structure):
                 ("d_state0", _vp), ("average_st_grads", C.c_int32)]
 
 
+class StoreDesc(C.Structure):
+    _fields_ = [("nodes", _vp), ("nodes_width", C.c_int32), ("arcs", _vp), ("arcs_width", C.c_int32), ("targets", _vp),
+                ("targets_width", C.c_int32), ("sample_weight", _vp), ("set_mask", _vp), ("output_mask", _vp),
+                ("node2graph", _vp), ("nodegraph_values", _vp), ("type_mask", _vp), ("n_types", C.c_int32),
+                ("node_ptr", _vp), ("arc_ptr", _vp), ("tgt_ptr", _vp), ("mask_ptr", _vp), ("n_sub", _vp)]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [("nodes", _vp), ("arcs", _vp), ("src", _vp), ("dst", _vp), ("targets", _vp), ("sample_weight", _vp),
+                ("set_mask", _vp), ("output_mask", _vp), ("node2graph", _vp), ("nodegraph_values", _vp), ("type_mask", _vp)]
+
+
 class GnnfpError(RuntimeError):
     pass
 
@@ -78,7 +90,7 @@ SYMBOLS = ["gnnfp_last_error", "gnnfp_abi_version", "gnnfp_graph_build", "gnnfp_
            "gnnfp_loop_out_rows", "gnnfp_loop_state_dim", "gnnfp_loop_forward", "gnnfp_loop_forward_begin", "gnnfp_loop_forward_iter",
            "gnnfp_loop_forward_end", "gnnfp_loop_ws_offsets", "gnnfp_loop_backward",
            "gnnfp_loop_backward_step", "gnnfp_loop_bwd_offsets",
-           "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step", "gnnfp_adam_step_dev", "gnnfp_adam_advance",
+           "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step", "gnnfp_adam_step_dev", "gnnfp_adam_advance", "gnnfp_batch_assemble",
            "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect"]
 
 
@@ -129,6 +141,7 @@ def lib():
     L.gnnfp_adam_step_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                       _vp, C.c_float, _vp]
     L.gnnfp_adam_advance.argtypes = [_vp, _vp]
+    L.gnnfp_batch_assemble.argtypes = [C.POINTER(StoreDesc), _vp, C.c_int32, C.c_int64, _vp, C.POINTER(BatchOut), _vp]
     L.gnnfp_adam_step.argtypes = [_vp, _vp, _vp, _vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int32, C.c_float, _vp]
     L.gnnfp_launch_count.argtypes = [C.c_int]

@@ -86,11 +86,63 @@ class GraphStore:
         pos = torch.arange(total, device=self.device) - first[seg]
         return self._dev_ptrs[which][ids_dev][seg] + pos, seg
 
-    def assemble(self, ids) -> dict:
-        """The arrays of ``merge([graphs[i] for i in ids])`` as tensors on the store's device."""
+    def _assemble_lib(self, ids: np.ndarray) -> dict:
+        """``assemble`` by libgnnfp (gnnfp_batch_assemble: prefix sums of the selected members + one block per member) -
+        two kernel launches for the whole batch; the sizes of the outputs are known on the host."""
+        import ctypes as C
+        from . import _lib as B
+        from .op import _ptr, _stream
+        dev = self.device
+        nn, na, nt = int(self.n_nodes[ids].sum()), int(self.n_arcs[ids].sum()), int(self.n_tgt[ids].sum())
+        nm = int(self.n_mask[ids].sum())
+        all_true = bool(np.all(self.masks_true[ids]))
+        if not hasattr(self, "_lib_ptrs"):
+            self._lib_ptrs = {"n_sub": torch.from_numpy(self.n_sub.astype(np.int32)).to(dev)}
+        e = lambda *shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=dev)
+        out = {"nodes": e(nn, self.nodes.shape[1]), "arcs": e(na, self.arcs.shape[1]), "targets": e(nt, self.targets.shape[1]),
+               "sample_weight": e(nt), "set_mask": e(nm, dt=torch.uint8), "output_mask": e(nm, dt=torch.uint8),
+               "node2graph": None, "nodegraph_values": None, "n_graphs": 0, "type_mask": None,
+               "masks_all_true": all_true, "n_nodes": nn, "n_arcs": na,
+               "src": e(na, dt=torch.int32), "dst": e(na, dt=torch.int32)}
+        if self.has_nodegraph:
+            out["node2graph"], out["nodegraph_values"] = e(nn, dt=torch.int32), e(nn)
+            out["n_graphs"] = int(self.n_sub[ids].sum())
+        tm_t = e(self.type_mask.shape[1], nn, dt=torch.uint8) if self.composite else None
+        st = B.StoreDesc()
+        st.nodes, st.nodes_width = _ptr(self.nodes), self.nodes.shape[1]
+        st.arcs, st.arcs_width = _ptr(self.arcs), self.arcs.shape[1]
+        st.targets, st.targets_width = _ptr(self.targets), self.targets.shape[1]
+        st.sample_weight = _ptr(self.sample_weight)
+        st.set_mask, st.output_mask = _ptr(self.set_mask), _ptr(self.output_mask)
+        st.node2graph, st.nodegraph_values = _ptr(self.node2graph), _ptr(self.nodegraph_values)
+        st.type_mask, st.n_types = _ptr(self.type_mask), (self.type_mask.shape[1] if self.composite else 0)
+        st.node_ptr, st.arc_ptr = _ptr(self._dev_ptrs["node"]), _ptr(self._dev_ptrs["arc"])
+        st.tgt_ptr, st.mask_ptr = _ptr(self._dev_ptrs["tgt"]), _ptr(self._dev_ptrs["mask"])
+        st.n_sub = _ptr(self._lib_ptrs["n_sub"]) if self.has_nodegraph else None
+        bo = B.BatchOut()
+        for k in ("nodes", "arcs", "src", "dst", "targets", "sample_weight", "set_mask", "output_mask", "node2graph", "nodegraph_values"):
+            setattr(bo, k, _ptr(out[k]))
+        bo.type_mask = _ptr(tm_t)
+        ids_dev = torch.from_numpy(ids).to(dev)
+        scratch = torch.empty(5 * (len(ids) + 1), dtype=torch.int64, device=dev)
+        B.check(B.lib().gnnfp_batch_assemble(C.byref(st), _ptr(ids_dev), len(ids), nn, _ptr(scratch), C.byref(bo), _stream()))
+        if self.composite:
+            out["type_mask_t"] = tm_t                      # [n_types, N] as it reaches the model
+        return out
+
+    def assemble(self, ids, use_lib: Optional[bool] = None) -> dict:
+        """The arrays of ``merge([graphs[i] for i in ids])`` as tensors on the store's device.  On a CUDA store the gathers
+        run in libgnnfp (``gnnfp_batch_assemble``); the torch formulation below is the CPU-testable statement of the same
+        index arithmetic (``use_lib=False`` forces it)."""
         ids = np.asarray(ids, dtype=np.int64).reshape(-1)
         if ids.size == 0 or ids.min() < 0 or ids.max() >= self.n:
             raise IndexError("graph ids out of range")
+        if use_lib is None:
+            use_lib = self.device.type == "cuda"
+        if use_lib:
+            mask_len_ok = np.array_equal(self.n_mask[ids], self.n_arcs[ids] if self.focus == "a" else self.n_nodes[ids])
+            if mask_len_ok:
+                return self._assemble_lib(ids)
         ids_dev = torch.from_numpy(ids).to(self.device)
         nn, na = self.n_nodes[ids], self.n_arcs[ids]
         row_n, seg_n = self._ranges("node", ids_dev, nn)
@@ -123,12 +175,17 @@ class GraphStore:
         """Assembled batch + its device-built integer structures (needs the CUDA library)."""
         from .op import DeviceGraph
         a = self.assemble(ids)
-        ij = a["arcs"][:, :2].to(torch.int32)      # node ids are stored as float32 in arcs (graph_class.py:47)
-        src, dst = ij[:, 0].contiguous(), ij[:, 1].contiguous()
+        if "src" in a:                             # libgnnfp batcher: ids already split off as int32
+            src, dst = a["src"], a["dst"]
+        else:
+            ij = a["arcs"][:, :2].to(torch.int32)  # node ids are stored as float32 in arcs (graph_class.py:47)
+            src, dst = ij[:, 0].contiguous(), ij[:, 1].contiguous()
         sm = om = None
         if not a["masks_all_true"]:
             sm, om = a["set_mask"], a["output_mask"]
-        tm = a["type_mask"].t().contiguous() if self.composite else None          # [n_types, N] as it reaches the model
+        tm = None
+        if self.composite:                         # [n_types, N] as it reaches the model
+            tm = a["type_mask_t"] if "type_mask_t" in a else a["type_mask"].t().contiguous()
         graph = DeviceGraph(src, dst, a["n_nodes"], aggregation_mode, a["node2graph"], a["n_graphs"],
                             a["nodegraph_values"], sm, om, tm, None, mask_len=int(a["set_mask"].numel()))
         cls = CompositeGraphTensor if self.composite else GraphTensor

@@ -204,3 +204,103 @@ extern "C" int gnnfp_adam_step(float* params, const float* grads, float* m, floa
   GNNFP_CHECK_CUDA(cudaGetLastError());
   return GNNFP_OK;
 }
+
+// ---- device-side batcher (reference GraphObject.merge, graph_class.py:385-413, called for EVERY batch at
+// ---- construction and at every epoch end by GraphSequencers.py:42-46, 123-127) -------------------------------------------
+// The dataset lives flat on the device (gnnfp_store_desc: members back to back, arc ids LOCAL to their member); a batch is
+// the list of member ids.  Two launches: the exclusive prefix sums of the selected members' sizes (one block), then ONE
+// block per member that copies its rows to their place in the batch - node rows, arc rows with the node-id offset added
+// to columns 0-1 (graph_class.py:391-394) and split off as int32 src / dst, targets, sample weights, masks, NodeGraph
+// entries with the sub-graph offset (block-diagonal NodeGraph, :407), type masks transposed to [n_types, N].
+static __global__ void __launch_bounds__(1024) k_batch_offsets(const gnnfp_store_desc st, const int64_t* ids, int n_ids, int64_t* off) {
+  // off: [5][n_ids + 1] = nodes | arcs | targets | masks | sub-graphs
+  __shared__ long long carry[5];
+  __shared__ long long part[5][1024];
+  if (threadIdx.x < 5) carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (int base = 0; base < n_ids; base += 1024) {
+    const int i = base + threadIdx.x;
+    long long v[5] = {0, 0, 0, 0, 0};
+    if (i < n_ids) {
+      const int64_t m = ids[i];
+      v[0] = st.node_ptr[m + 1] - st.node_ptr[m];
+      v[1] = st.arc_ptr[m + 1] - st.arc_ptr[m];
+      v[2] = st.tgt_ptr[m + 1] - st.tgt_ptr[m];
+      v[3] = st.mask_ptr ? st.mask_ptr[m + 1] - st.mask_ptr[m] : 0;
+      v[4] = st.n_sub ? st.n_sub[m] : 0;
+    }
+    for (int q = 0; q < 5; ++q) part[q][threadIdx.x] = v[q];
+    __syncthreads();
+    for (int s = 1; s < 1024; s <<= 1) {               // Hillis-Steele inclusive scan of the chunk
+      long long t[5];
+      for (int q = 0; q < 5; ++q) t[q] = threadIdx.x >= s ? part[q][threadIdx.x - s] : 0;
+      __syncthreads();
+      for (int q = 0; q < 5; ++q) part[q][threadIdx.x] += t[q];
+      __syncthreads();
+    }
+    if (i < n_ids)
+      for (int q = 0; q < 5; ++q) off[(size_t)q * (n_ids + 1) + i] = carry[q] + part[q][threadIdx.x] - v[q];
+    __syncthreads();
+    if (threadIdx.x == 1023)
+      for (int q = 0; q < 5; ++q) carry[q] += part[q][1023];
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) off[(size_t)threadIdx.x * (n_ids + 1) + n_ids] = carry[threadIdx.x];
+}
+
+static __global__ void __launch_bounds__(256) k_batch_assemble(const gnnfp_store_desc st, const int64_t* ids, int n_ids,
+                                                                const int64_t* off, const gnnfp_batch_out out, int64_t n_nodes_batch) {
+  const int b = blockIdx.x;
+  const int64_t m = ids[b];
+  const int64_t* on = off, *oa = off + (n_ids + 1), *ot = off + 2 * (size_t)(n_ids + 1), *om = off + 3 * (size_t)(n_ids + 1),
+               *os = off + 4 * (size_t)(n_ids + 1);
+  const int64_t n0 = st.node_ptr[m], nn = st.node_ptr[m + 1] - n0, dn = on[b];
+  const int64_t a0 = st.arc_ptr[m], na = st.arc_ptr[m + 1] - a0, da = oa[b];
+  const int64_t t0 = st.tgt_ptr[m], nt = st.tgt_ptr[m + 1] - t0, dt = ot[b];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int NW = st.nodes_width, AW = st.arcs_width, TW = st.targets_width;
+  for (int64_t e = tid; e < nn * NW; e += nth) out.nodes[dn * NW + e] = st.nodes[n0 * NW + e];
+  const float foff = (float)dn;                         // node ids are stored as float32 in arcs (exact below 2^24)
+  for (int64_t e = tid; e < na * AW; e += nth) {
+    const int64_t r = e / AW;
+    const int c = (int)(e - r * AW);
+    float v = st.arcs[a0 * AW + e];
+    if (c < 2) {
+      v += foff;
+      (c == 0 ? out.src : out.dst)[da + r] = (int32_t)v;
+    }
+    out.arcs[da * AW + e] = v;
+  }
+  for (int64_t e = tid; e < nt * TW; e += nth) out.targets[dt * TW + e] = st.targets[t0 * TW + e];
+  for (int64_t e = tid; e < nt; e += nth) out.sample_weight[dt + e] = st.sample_weight[t0 + e];
+  if (st.set_mask && out.set_mask) {
+    const int64_t m0 = st.mask_ptr[m], nm = st.mask_ptr[m + 1] - m0, dm = om[b];
+    for (int64_t e = tid; e < nm; e += nth) { out.set_mask[dm + e] = st.set_mask[m0 + e]; out.output_mask[dm + e] = st.output_mask[m0 + e]; }
+  }
+  if (st.node2graph && out.node2graph) {
+    const int32_t so = (int32_t)os[b];
+    for (int64_t e = tid; e < nn; e += nth) { out.node2graph[dn + e] = st.node2graph[n0 + e] + so; out.nodegraph_values[dn + e] = st.nodegraph_values[n0 + e]; }
+  }
+  if (st.type_mask && out.type_mask)
+    for (int64_t e = tid; e < nn * st.n_types; e += nth) {
+      const int64_t i = e / st.n_types;
+      const int t = (int)(e - i * st.n_types);
+      out.type_mask[(size_t)t * n_nodes_batch + dn + i] = st.type_mask[(n0 + i) * st.n_types + t];
+    }
+}
+
+extern "C" int gnnfp_batch_assemble(const gnnfp_store_desc* st, const int64_t* ids_dev, int32_t n_ids, int64_t n_nodes_batch,
+                                    int64_t* offsets_scratch, const gnnfp_batch_out* out, void* stream) {
+  if (!st || !ids_dev || !out || !offsets_scratch || n_ids < 1) GNNFP_FAIL(GNNFP_E_INVALID, "batch_assemble: bad arguments");
+  if (!st->nodes || !st->targets || !st->sample_weight || !st->node_ptr || !st->arc_ptr || !st->tgt_ptr)
+    GNNFP_FAIL(GNNFP_E_INVALID, "batch_assemble: store arrays missing");
+  if (!out->nodes || !out->targets || !out->sample_weight)      // (arc arrays may be empty: a batch of arc-less members)
+    GNNFP_FAIL(GNNFP_E_INVALID, "batch_assemble: output arrays missing");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_batch_offsets<<<1, 1024, 0, s>>>(*st, ids_dev, n_ids, offsets_scratch);
+  GNNFP_COUNT_LAUNCH();
+  k_batch_assemble<<<n_ids, 256, 0, s>>>(*st, ids_dev, n_ids, offsets_scratch, *out, n_nodes_batch);
+  GNNFP_COUNT_LAUNCH();
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}

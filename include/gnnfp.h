@@ -279,6 +279,35 @@ int gnnfp_adam_step_dev(float* params, const float* grads, float* m, float* v, s
                         float beta2, float eps, const int32_t* step_dev, float grad_scale, void* stream);
 int gnnfp_adam_advance(int32_t* step_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-side batcher ("next" row f1): replaces GraphObject.merge (graph_class.py:385-413) + the per-batch host work of
+ * MultiGraphSequencer.build_batches / on_epoch_end (GraphSequencers.py:42-46, 123-127).  The dataset is resident on the
+ * device as flat arrays (members back to back; arc id columns LOCAL to their member, rows sorted and unique as
+ * GraphObject.__init__ leaves them, graph_class.py:47); a batch is a list of member ids.  All pointers are device
+ * pointers owned by the caller; sizes of the outputs are the sums of the selected members' sizes (known on the host).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct gnnfp_store_desc {
+  const float* nodes; int32_t nodes_width;            /* [sum N, nodes_width]                                  */
+  const float* arcs; int32_t arcs_width;              /* [sum A, 2 + AL], columns 0-1 = local src, dst ids      */
+  const float* targets; int32_t targets_width;        /* [sum T, targets_width]                                */
+  const float* sample_weight;                         /* [sum T]                                               */
+  const uint8_t* set_mask; const uint8_t* output_mask;/* [sum Mk] or NULL                                      */
+  const int32_t* node2graph; const float* nodegraph_values;   /* [sum N] or NULL (no NodeGraph)                */
+  const uint8_t* type_mask; int32_t n_types;          /* [sum N, n_types] or NULL                              */
+  const int64_t* node_ptr; const int64_t* arc_ptr; const int64_t* tgt_ptr; const int64_t* mask_ptr;   /* [n + 1] prefix sums */
+  const int32_t* n_sub;                               /* [n] NodeGraph columns of each member, or NULL         */
+} gnnfp_store_desc;
+typedef struct gnnfp_batch_out {
+  float* nodes; float* arcs; int32_t* src; int32_t* dst; float* targets; float* sample_weight;
+  uint8_t* set_mask; uint8_t* output_mask;            /* or NULL                                               */
+  int32_t* node2graph; float* nodegraph_values;       /* or NULL                                               */
+  uint8_t* type_mask;                                 /* [n_types, N_batch] (as it reaches the model) or NULL  */
+} gnnfp_batch_out;
+/* offsets_scratch: 5 * (n_ids + 1) int64 (device); after the call it holds the exclusive prefix sums of the selected
+ * members' node / arc / target / mask / sub-graph counts.  Two kernel launches on `stream`, no synchronisation. */
+int gnnfp_batch_assemble(const gnnfp_store_desc* store, const int64_t* ids_dev, int32_t n_ids, int64_t n_nodes_batch,
+                         int64_t* offsets_scratch, const gnnfp_batch_out* out, void* stream);
+
 /* Counters for bench.py's `gpu_launches` (kernels this library launched since the last reset). */
 long long gnnfp_launch_count(int reset);
 

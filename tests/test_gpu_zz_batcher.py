@@ -37,3 +37,36 @@ def test_device_batch_equals_host_merge(focus, composite, masked):
         a, b = gt.graph.export(which), ref.graph.export(which)
         assert a.dtype == b.dtype and a.shape == b.shape, which
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), which
+
+
+@pytest.mark.parametrize("focus,composite,masked", [("g", False, False), ("n", False, True), ("a", False, True), ("n", True, True)])
+def test_lib_batcher_matches_oracle_merge(focus, composite, masked):
+    """gnnfp_batch_assemble (libgnnfp, two launches per batch) against the ORACLE's restatement of GraphObject.merge
+    (oracle/structures.py::merge, pinned to the reference's merge on MUTAG by tests/test_oracle_golden.py): every array of
+    the merged batch bit for bit, repeated and permuted member ids included."""
+    from oracle import structures as S
+    graphs = make_graphs(focus, 30, seed=77, composite=composite, masked=masked)
+    store = GraphStore(graphs, device="cuda")
+    og = [S.make_graph(g.nodes, g.arcs, g.targets, focus=focus, set_mask=g.set_mask, output_mask=g.output_mask,
+                       sample_weight=g.sample_weight, aggregation_mode="sum",
+                       node2graph=g.node2graph if g.n_graphs else None, nodegraph_values=g.nodegraph_values if g.n_graphs else None,
+                       n_graphs=g.n_graphs if g.n_graphs else None, type_mask=g.type_mask if composite else None,
+                       dim_node_label=g.DIM_NODE_LABEL if composite else None) for g in graphs]
+    rng = np.random.default_rng(5)
+    for ids in (np.arange(30), rng.permutation(30)[:11], np.array([2]), np.array([7, 7, 2, 19])):
+        a = store.assemble(ids)
+        assert "src" in a, "the library batcher did not run"
+        ref = S.merge([og[i] for i in ids], focus, "sum")
+        torch.cuda.synchronize()
+        for key, want in (("nodes", ref.nodes), ("arcs", ref.arcs), ("targets", ref.targets),
+                          ("sample_weight", ref.sample_weight.astype(np.float32)),
+                          ("set_mask", ref.set_mask.astype(np.uint8)), ("output_mask", ref.output_mask.astype(np.uint8))):
+            got = a[key].cpu().numpy()
+            assert got.dtype == want.dtype and np.array_equal(got, want), key
+        assert np.array_equal(a["src"].cpu().numpy(), ref.arcs[:, 0].astype(np.int32))
+        assert np.array_equal(a["dst"].cpu().numpy(), ref.arcs[:, 1].astype(np.int32))
+        if focus == "g":
+            assert np.array_equal(a["node2graph"].cpu().numpy(), ref.node2graph.astype(np.int32))
+            assert np.array_equal(a["nodegraph_values"].cpu().numpy(), ref.nodegraph_values)
+        if composite:
+            assert np.array_equal(a["type_mask_t"].cpu().numpy().astype(bool), ref.type_mask.transpose())
