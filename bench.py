@@ -343,13 +343,103 @@ def run_c5(args, rank, world, local_rank, cores):
         dist.destroy_process_group()
 
 
+def run_c4(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: the batch sweep over a large MUTAG-shaped dataset.  The rank's shard of the dataset is
+    RESIDENT on the device (batcher.GraphStore); every step assembles its batch there (libgnnfp gnnfp_batch_assemble),
+    builds the batch's integer structures (gnnfp_graph_build, no host synchronisation) and runs the train step; an epoch
+    end only re-draws the permutation (GraphSequencers.py:123-127 re-merges every batch on the host).  Reports training
+    graphs/s over whole epochs including the reshuffle."""
+    import torch
+    import torch.distributed as dist
+    from gnnkeras_b200 import _lib as B
+    from gnnkeras_b200.batcher import DeviceMultiGraphSequencer, GraphStore
+    from gnnkeras_b200.synthetic import mutag_shaped_batch
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=600))
+    spec = workload_spec("c1" if args.c4_model == "gnn" else "c2")
+    model = build_model(device, 1, spec)
+    if world > 1:
+        model.grad_hook = lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        model.grad_scale = 1.0 / world
+        dist.broadcast(model._store.flat, src=0)
+    n_local = args.c4_graphs // world
+    parts, off = [], 0                                   # generated 100k graphs at a time (the stub matching sorts)
+    for c0 in range(0, n_local, 100000):
+        b = mutag_shaped_batch(min(100000, n_local - c0), seed=1000 * (rank + 1) + c0 // 100000)
+        parts.append((b.nodes, b.src.astype(np.int64) + off, b.dst.astype(np.int64) + off, b.arcs[:, 2:], b.targets, b.graph_sizes))
+        off += int(b.n_nodes)
+    cat = [np.concatenate([p[i] for p in parts]) for i in range(6)]
+    store = GraphStore.from_merged(*cat, "g", device)
+    seq = DeviceMultiGraphSequencer(store, 'g', 'average', batch_size=args.c4_batch, shuffle=True, device=device)
+    n_batches = len(store) // args.c4_batch            # full batches only: every rank runs the same number of steps
+    total_nodes = off
+    del b, parts, cat
+    klist = lambda r: list(r["k"]) if isinstance(r["k"], (list, tuple)) else [r["k"]]
+
+    def epoch():
+        ks = []
+        for i in range(n_batches):
+            ks.append(klist(model.train_step(seq[i])))
+            seq._cache[i] = None                       # the batch is dropped after its step: nothing is kept from epoch to epoch
+        seq.on_epoch_end()
+        return ks
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    epoch() if n_batches <= 40 else [model.train_step(seq[i]) for i in range(5)]
+    barrier()
+    B.lib().gnnfp_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ks = []
+    for _ in range(args.c4_epochs):
+        ks += epoch()
+    e1.record()
+    barrier()
+    launches = int(B.lib().gnnfp_launch_count(0))
+    ms = e0.elapsed_time(e1)
+    kmean = float(np.mean([sum(int(k.item()) for k in kk) for kk in ks]))     # iterations summed over the model's layers, per step
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        steps = n_batches * args.c4_epochs
+        graphs = steps * args.c4_batch * world
+        upd = kmean * (total_nodes * (n_batches * args.c4_batch) / max(1, len(store))) * args.c4_epochs * world
+        line = {"metric": METRIC, "value": upd / (ms * 1e-3), "unit": "node-updates/s", "n_gpus": world, "steps": steps, "warmup": 5,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "training_graphs_per_s": graphs / (ms * 1e-3),
+                "config": {"workload": f"C4: {args.c4_graphs} MUTAG-shaped graphs resident on the device(s), batches of {args.c4_batch} assembled "
+                                       f"on the device (gnnfp_batch_assemble + gnnfp_graph_build) and trained ({spec['title']}), "
+                                       f"{args.c4_epochs} epoch(s) incl. the per-epoch reshuffle",
+                           "graphs_per_gpu": n_local, "batches_per_epoch_per_gpu": n_batches, "parallelism": f"dp{world}" if world > 1 else "single"},
+                "e2e": {"value": upd / (ms * 1e-3), "unit": "node-updates/s", "h2d_bytes_per_step": 8 * args.c4_batch, "d2h_bytes_per_step": 0,
+                        "note": "the dataset is resident: per step only the batch's member ids cross the bus"},
+                "gpu_launches": launches, "clocks": None, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"], help="c2 = the configuration the metric is quoted on (default)")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"], help="c2 = the configuration the metric is quoted on (default)")
+    ap.add_argument("--c4-graphs", type=int, default=1000000, help="c4: graphs in the dataset (all ranks together)")
+    ap.add_argument("--c4-batch", type=int, default=1000, help="c4: graphs per batch (starter.py:45)")
+    ap.add_argument("--c4-epochs", type=int, default=1)
+    ap.add_argument("--c4-model", default="gnn", choices=["gnn", "lgnn"], help="c4: GNNgraphBased (C1 model) or the 5-layer LGNN (C2 model)")
     ap.add_argument("--c5-nodes", type=int, default=1250000, help="c5: nodes per GPU (x10 arcs); 8 GPUs = 10 M nodes / 100 M arcs")
     ap.add_argument("--c5-locality", type=float, default=0.95, help="c5: fraction of arcs whose source lies within --c5-band ids of the destination")
     ap.add_argument("--c5-band", type=int, default=8192)
@@ -359,6 +449,11 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="resident-input leg: launch every kernel from the host instead of replaying one CUDA graph per batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "c4":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "c4 has no CPU arm in this harness (see --workload c1 / c2)"}))
+            return
+        return run_c4(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0")))
     if args.workload == "c5":
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "c5 has no CPU arm in this harness (see --workload c2 for the metric's reference arm)"}))

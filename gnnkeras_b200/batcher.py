@@ -73,6 +73,48 @@ class GraphStore:
         self._dev_ptrs = {k: torch.from_numpy(v).to(self.device) for k, v in
                           (("node", self.node_ptr), ("arc", self.arc_ptr), ("tgt", self.tgt_ptr), ("mask", self.mask_ptr))}
 
+    @classmethod
+    def from_merged(cls, nodes, src, dst, arc_labels, targets, graph_sizes, focus="g", device="cuda"):
+        """Store of graph-focused members given in MERGED form (what ``GraphObject.merge`` of all of them holds: global node
+        ids, members back to back) - the million-graph synthetic datasets never exist as Python objects.  All masks true,
+        one target row and one NodeGraph column (value 1 / n) per member.  ``src`` / ``dst`` are INTEGER global ids (a float32
+        arcs matrix, the reference's format, cannot hold ids above 2**24); the store keeps member-local ids."""
+        if focus != "g":
+            raise NotImplementedError("from_merged builds graph-focused stores")
+        self = cls.__new__(cls)
+        sizes = np.asarray(graph_sizes, dtype=np.int64)
+        src, dst = np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
+        self.focus, self.composite = focus, False
+        self.dim_node_label = np.array([nodes.shape[1]], dtype=int)
+        self.device = torch.device(device)
+        self.n = len(sizes)
+        node_ptr = _ptr(sizes)
+        owner = np.searchsorted(node_ptr, dst, side="right") - 1      # member of every arc (by its destination)
+        self.n_nodes, self.n_arcs = sizes, np.bincount(owner, minlength=self.n).astype(np.int64)
+        self.n_tgt, self.n_mask = np.ones(self.n, np.int64), sizes.copy()
+        self.n_sub = np.ones(self.n, np.int64)
+        self.has_nodegraph = True
+        self.masks_true = np.ones(self.n, bool)
+        self.node_ptr, self.arc_ptr = node_ptr, _ptr(self.n_arcs)
+        self.tgt_ptr, self.mask_ptr = _ptr(self.n_tgt), _ptr(self.n_mask)
+        order = np.argsort(owner, kind="stable")              # arcs grouped by member, (src, dst) order kept inside a member
+        local = np.empty((len(src), 2 + arc_labels.shape[1]), np.float32)
+        base = node_ptr[owner[order]]
+        local[:, 0], local[:, 1], local[:, 2:] = src[order] - base, dst[order] - base, np.asarray(arc_labels)[order]
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(dt))).to(self.device)
+        self.nodes, self.arcs = up(nodes, np.float32), up(local, np.float32)
+        self.targets = up(targets, np.float32)
+        self.sample_weight = torch.ones(self.n, dtype=torch.float32, device=self.device)
+        tot = int(sizes.sum())
+        self.set_mask = torch.ones(tot, dtype=torch.uint8, device=self.device)
+        self.output_mask = torch.ones(tot, dtype=torch.uint8, device=self.device)
+        self.node2graph = torch.zeros(tot, dtype=torch.int32, device=self.device)
+        self.nodegraph_values = up(np.repeat((1.0 / sizes).astype(np.float32), sizes), np.float32)   # graph_class.py:136
+        self.type_mask = None
+        self._dev_ptrs = {k: torch.from_numpy(v).to(self.device) for k, v in
+                          (("node", self.node_ptr), ("arc", self.arc_ptr), ("tgt", self.tgt_ptr), ("mask", self.mask_ptr))}
+        return self
+
     def __len__(self):
         return self.n
 

@@ -70,3 +70,31 @@ def test_lib_batcher_matches_oracle_merge(focus, composite, masked):
             assert np.array_equal(a["nodegraph_values"].cpu().numpy(), ref.nodegraph_values)
         if composite:
             assert np.array_equal(a["type_mask_t"].cpu().numpy().astype(bool), ref.type_mask.transpose())
+
+
+def test_store_from_merged_reassembles_the_flat_batch():
+    """GraphStore.from_merged (datasets given flat, ids as integers): assembling all members in order gives back the flat
+    batch it was built from; a permuted draw equals the store built from per-graph objects."""
+    from gnnkeras_b200.synthetic import mutag_shaped_batch
+    b = mutag_shaped_batch(64, seed=9)
+    store = GraphStore.from_merged(b.nodes, b.src, b.dst, b.arcs[:, 2:], b.targets, b.graph_sizes, "g", "cuda")
+    gt = store.batch(np.arange(64), "average")
+    assert torch.equal(gt.nodes.cpu(), torch.from_numpy(b.nodes))
+    assert torch.equal(gt.arcs.cpu(), torch.from_numpy(b.arcs))
+    assert torch.equal(gt.targets.cpu(), torch.from_numpy(b.targets))
+    assert np.array_equal(gt.graph.export(B.X_GRAPH_PTR), np.concatenate([[0], np.cumsum(b.graph_sizes)]).astype(np.int32))
+    # a shuffled draw: same as merging the picked members as GraphObjects
+    off = np.concatenate([[0], np.cumsum(b.graph_sizes)])
+    objs = []
+    for g in range(64):
+        m = (b.src >= off[g]) & (b.src < off[g + 1])
+        a = b.arcs[m].copy()
+        a[:, :2] -= off[g]
+        objs.append(GraphObject(b.nodes[off[g]:off[g + 1]], a, b.targets[g:g + 1], focus="g", aggregation_mode="average"))
+    ids = np.random.default_rng(3).permutation(64)[:40]
+    gt = store.batch(ids, "average")
+    ref = GraphTensor.fromGraphObject(GraphObject.merge([objs[i] for i in ids], "g", "average"), "cuda")
+    for name in ("nodes", "arcs", "targets", "sample_weight"):
+        assert torch.equal(getattr(gt, name), getattr(ref, name)), name
+    for which in (B.X_DST_ROWPTR, B.X_DST_SRC, B.X_ARC_VALUE, B.X_GRAPH_PTR, B.X_NODEGRAPH_VALUE):
+        assert np.array_equal(gt.graph.export(which).view(np.uint32), ref.graph.export(which).view(np.uint32)), which
