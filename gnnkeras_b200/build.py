@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libgnnfp.so")
-SOURCES = ["graph.cu", "kernels_fwd.cu", "kernels_bwd.cu", "gemm.cu", "gemm_tc.cu", "rows_tma.cu", "agg_tile.cu", "loop.cu", "loop_bwd.cu", "misc.cu"]
+SOURCES = ["graph.cu", "kernels_fwd.cu", "kernels_bwd.cu", "gemm.cu", "gemm_tc.cu", "rows_tma.cu", "agg_tile.cu", "dw_tma.cu", "narrow.cu", "loop.cu", "loop_bwd.cu", "misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 

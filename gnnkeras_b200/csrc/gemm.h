@@ -57,6 +57,25 @@ struct GemmDwArgs {
 };
 
 
+// narrow.cu: net_output with a single Dense layer of H <= 4 columns as streaming kernels (warp per row, lane = input column)
+struct NarrowArgs {
+  int n_rows; const int* rowlist;
+  int n_pieces; GemmPiece p[GEMM_MAXP];    // input pieces (k8 = row offset inside the padded weights Wp)
+  int K, H;                                // input columns, output columns
+  // forward: out[r] = act(x . Wp + bias), rows compact
+  const float* Wp; int ldw; const float* bias; int act; float* out; int ld_out;
+  // backward: dz compact [n_rows, H]
+  const float* dz;
+  float* partial; int n_params, bias_off;  // dW: as GemmDwArgs
+  const float* W; const float* bnA; const float* bnB; const float* gamma; const float* beta; float* bn_partial;
+  const float* colscale; const float* corr; int corr_in;       // dX: per input column gamma * rstd, BN constants [c0|c1|A|B] x corr_in
+  float* gout[GEMM_MAXP]; int gld[GEMM_MAXP]; int gadd[GEMM_MAXP];   // per piece: gradient destination (NULL = none), leading dimension, += or =
+};
+int narrow_supported(const NarrowArgs& a);
+int launch_narrow_fwd(const NarrowArgs& a, cudaStream_t s, int prof_cat);
+int launch_narrow_dw(const NarrowArgs& a, cudaStream_t s, int prof_cat, int* grid_out);
+int launch_narrow_dx(const NarrowArgs& a, cudaStream_t s, int prof_cat);
+
 struct FoldArgs {            // padded, BN-folded weights of a single Dense layer for gemm_rows (forward)
   TileSrc src;               // the net's input pieces (their st_sum/st_sq feed the BN batch statistics)
   NetDev net;

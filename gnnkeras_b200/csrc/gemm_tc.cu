@@ -727,25 +727,14 @@ __global__ void __launch_bounds__(DW_TC_THREADS, 1) gemm_dw_tc_kernel(const __gr
     float* part = a.partial + (size_t)blockIdx.x * a.n_params;
     const float* sdb = sD + Kp * HS;                   // db_j = D[j][Kp] (the column of ones)
     const int KH = K * H;
-    for (int e0 = tid; e0 < KH; e0 += 4 * DW_TC_CONV_THREADS) {          // 4 read-modify-writes in flight per thread
-      float old[4], v[4];
-      int idx[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * DW_TC_CONV_THREADS;
-        idx[u] = e < KH ? e : -1;
-        old[u] = 0.f; v[u] = 0.f;
-        if (e < KH) {
-          const int c = e / H, j = e - c * H;
-          old[u] = part[e];
-          const float x = sD[s_kp[c] * HS + j];
-          v[u] = a.bnA ? s_gam[c] * fmaf(s_bA[c], x, s_bB[c] * sdb[j]) + s_bet[c] * sdb[j] : x;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) if (idx[u] >= 0) part[idx[u]] = old[u] + v[u];
+    // one reduction per element and launch into this CTA's slot: fire-and-forget RED.ADD (no read latency); the order of the
+    // additions to one address is the launch order, so the sums stay deterministic
+    for (int e = tid; e < KH; e += DW_TC_CONV_THREADS) {
+      const int c = e / H, j = e - c * H;
+      const float x = sD[s_kp[c] * HS + j];
+      atomicAdd(part + e, a.bnA ? s_gam[c] * fmaf(s_bA[c], x, s_bB[c] * sdb[j]) + s_bet[c] * sdb[j] : x);
     }
-    for (int j = tid; j < H; j += DW_TC_CONV_THREADS) part[a.bias_off + j] += sdb[j];
+    for (int j = tid; j < H; j += DW_TC_CONV_THREADS) atomicAdd(part + a.bias_off + j, sdb[j]);
     if (a.bn_partial) {
       float* bp = a.bn_partial + (size_t)blockIdx.x * 2 * K;
       for (int c = tid; c < K; c += DW_TC_CONV_THREADS) {

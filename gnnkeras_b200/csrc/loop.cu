@@ -820,7 +820,16 @@ static int fwd_end(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_par
       ga.Wp = fo.Wp; ga.ldw = fo.ldw; ga.N = H; ga.bias = fo.biasp; ga.act = L->onet.acts[0];
       ga.out = on; ga.ld_out = L->T; ga.out_compact = 1; ga.fwd = 1;
       ga.vec2 = L->T % 2 == 0 && ((uintptr_t)on & 7) == 0;
-      if ((rc = launch_gemm_rows(ga, s, PC_FWD_OUT))) return rc;
+      // narrow Dense (H <= 4, the starters' Dense(2, softmax)): streaming kernel, warp per row (narrow.cu)
+      static const int no_narrow = getenv("GNNFP_NO_NARROW") ? 1 : 0;
+      NarrowArgs na;
+      memset(&na, 0, sizeof(na));
+      na.n_rows = ga.n_rows; na.rowlist = ga.rowlist; na.n_pieces = ga.n_pieces;
+      for (int p = 0; p < ga.n_pieces; ++p) na.p[p] = ga.p[p];
+      na.K = L->out_in; na.H = H; na.Wp = fo.Wp; na.ldw = fo.ldw; na.bias = fo.biasp; na.act = ga.act; na.out = on; na.ld_out = L->T;
+      if (!no_narrow && narrow_supported(na)) {
+        if ((rc = launch_narrow_fwd(na, s, PC_FWD_OUT))) return rc;
+      } else if ((rc = launch_gemm_rows(ga, s, PC_FWD_OUT))) return rc;
     } else {
       fa.tc.cap_per_row = L->cap_per_row;
       if ((rc = tile_cfg_fwd(fa.net, fa.src.n_rows, &fa.tc))) return rc;

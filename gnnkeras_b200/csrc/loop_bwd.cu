@@ -327,14 +327,36 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
       dw.partial = part_out; dw.n_params = L->nparam_o; dw.bias_off = in * H;
       dw.W = ond.W[0];
       if (bn) { dw.bnA = coef; dw.bnB = coef + in; dw.gamma = ond.gamma; dw.beta = ond.beta; dw.bn_partial = bn_part; }
-      if ((rc = launch_gemm_dw(dw, s, PC_BWD_OUT, &grid_out))) return rc;
+      // narrow Dense (H <= 4): streaming kernels, warp per row (narrow.cu) - no transposed weight copies, no GEMM tiles
+      static const int no_narrow = getenv("GNNFP_NO_NARROW") ? 1 : 0;
+      NarrowArgs na;
+      memset(&na, 0, sizeof(na));
+      na.n_rows = dw.n_rows; na.rowlist = dw.rowlist; na.n_pieces = dw.n_pieces;
+      for (int p = 0; p < dw.n_pieces; ++p) na.p[p] = dw.p[p];
+      na.K = in; na.H = H; na.dz = dzo;
+      na.partial = dw.partial; na.n_params = dw.n_params; na.bias_off = dw.bias_off;
+      na.W = dw.W; na.bnA = dw.bnA; na.bnB = dw.bnB; na.gamma = dw.gamma; na.beta = dw.beta; na.bn_partial = dw.bn_partial;
+      const bool narrow = !no_narrow && narrow_supported(na);
+      if (narrow) { if ((rc = launch_narrow_dw(na, s, PC_BWD_OUT, &grid_out))) return rc; }
+      else if ((rc = launch_gemm_dw(dw, s, PC_BWD_OUT, &grid_out))) return rc;
       if (bn) {
         ba.net = ond; ba.bn_partial = bn_part; ba.tc.grid = grid_out;
         if ((rc = launch_bn_tail(ba, bn_grad + bg_off[L->nt], bn_const, s, 1, nullptr))) return rc;
       }
+      if (narrow) {
+        bool any = false;
+        for (int p = 0; p < ba.src.n_pieces; ++p) {
+          const Piece& pc = ba.src.p[p];
+          na.gout[p] = pc.gptr; na.gld[p] = pc.gld; na.gadd[p] = pc.gmode == GM_ADD;
+          any = any || pc.gptr != nullptr;
+        }
+        na.colscale = bn ? coef + 2 * in : nullptr;
+        na.corr = bn ? bn_const : nullptr; na.corr_in = in;
+        if (any && (rc = launch_narrow_dx(na, s, PC_BWD_OUT))) return rc;
+      }
       float* wt = (float*)(c.ws + L->ws.wtb) + (size_t)L->nt * L->ws.wtb_stride;
       const int KH = gemm_rows_kpad(H);
-      for (int p = 0; p < ba.src.n_pieces; ++p) {
+      for (int p = 0; !narrow && p < ba.src.n_pieces; ++p) {
         const Piece& pc = ba.src.p[p];
         if (!pc.gptr) continue;
         const int ldw = gemm_rows_ldw(pc.width);
@@ -546,7 +568,45 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
           dw.W = ndfull.W[0];
           if (bn) { dw.bnA = coef; dw.bnB = coef + in; dw.gamma = ndfull.gamma; dw.beta = ndfull.beta; dw.bn_partial = bn_part; }
           dw.gate = gate;
-          if ((rc = launch_gemm_dw(dw, s, PC_BWD_ITER, &grid_dw))) return rc;
+          static const int no_dw_tma = getenv("GNNFP_NO_DW_TMA") ? 1 : 0;
+          bool dw_done = false;
+          if (L->xlay && !no_dw_tma && full.rowlist == nullptr && H0 <= 128 && rows_tma_ok(dzbuf, ldG)) {
+            // TMA path (dw_tma.cu): the X slot and dz are read as MN-major boxes, no transposing split
+            DwTmaArgs da;
+            memset(&da, 0, sizeof(da));
+            const int LsM = L->LsM, NLq = L->S > 0 ? L->NLw : 0;
+            const int w0 = 2 * D + (L->xs_inline ? LsM : 0);
+            da.n_rows = full.n_rows; da.H = H0; da.K = in;
+            da.n_zc = (H0 + 31) / 32;
+            da.rows = dw_tma_rows((w0 + 31) / 32 + (L->xs_inline ? 0 : (LsM + 31) / 32), da.n_zc);
+            bool ok = rows_tma_map(&da.xmap[0], c.S(t - 1), L->N, w0, L->ldX, da.rows, 1) == GNNFP_OK &&
+                      rows_tma_map(&da.zmap, dzbuf, L->N, H0, ldG, da.rows, 1) == GNNFP_OK;
+            if (ok && !L->xs_inline && LsM > 0) ok = rows_tma_map(&da.xmap[1], c.Xs(), L->N, LsM, L->ldXs, da.rows, 1) == GNNFP_OK;
+            for (int c0_ = 0; ok && c0_ < w0; c0_ += 32) {
+              if (da.n_xc >= DT_MAXXC) { ok = false; break; }
+              da.xc_map[da.n_xc] = 0; da.xc_col0[da.n_xc] = c0_; ++da.n_xc;
+            }
+            const int sbase = L->xs_inline ? 2 * D : 32 * da.n_xc;          // accumulator column of static column 0
+            if (ok && !L->xs_inline)
+              for (int c0_ = 0; c0_ < LsM; c0_ += 32) {
+                if (da.n_xc >= DT_MAXXC) { ok = false; break; }
+                da.xc_map[da.n_xc] = 1; da.xc_col0[da.n_xc] = c0_; ++da.n_xc;
+              }
+            auto piece = [&](int in0, int w, int acc0) {
+              if (w <= 0) return;
+              da.p_in0[da.n_pieces] = in0; da.p_w[da.n_pieces] = w; da.p_acc0[da.n_pieces] = acc0; ++da.n_pieces;
+            };
+            // the net sees [S | nodes? | Adj^T S | agg_nodes | agg_arcs]; the slot holds [S | Adj^T S | static columns]
+            piece(0, D, 0); piece(D + NLq, D, D); piece(D, NLq, sbase); piece(2 * D + NLq, LsM - NLq, sbase + NLq);
+            da.partial = dw.partial; da.n_params = dw.n_params; da.bias_off = dw.bias_off;
+            da.W = dw.W; da.bnA = dw.bnA; da.bnB = dw.bnB; da.gamma = dw.gamma; da.beta = dw.beta; da.bn_partial = dw.bn_partial;
+            da.gate = gate;
+            if (ok && in == 2 * D + LsM && dw_tma_finish(da) == GNNFP_OK) {
+              if ((rc = launch_dw_tma(da, s, PC_BWD_ITER, &grid_dw))) return rc;
+              dw_done = true;
+            }
+          }
+          if (!dw_done && (rc = launch_gemm_dw(dw, s, PC_BWD_ITER, &grid_dw))) return rc;
           grid_state[ty] = grid_dw > grid_state[ty] ? grid_dw : grid_state[ty];
           if (bn) {   // batch sums are complete after dW: constants c0 | c1 | rstd | -mean*rstd of this iteration, BEFORE dX, so that
                       // the dX epilogue can apply dx = a dy - (c0 + x~ c1) while it writes (no correction pass, no gathers later)

@@ -628,8 +628,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
   RT_STAMP(4);
 }
 
-extern "C" int gnnfp_debug_rt_times(long long* out, int mode) {      // out[160][8] of the last launch of `mode`
+int dw_tma_times(long long* out);
+extern "C" int gnnfp_debug_rt_times(long long* out, int mode) {      // out[160][8] of the last launch of `mode` (2 = dw_tma.cu)
   GNNFP_CHECK_CUDA(cudaDeviceSynchronize());
+  if (mode == 2) return dw_tma_times(out);
   GNNFP_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_rt_times, (size_t)160 * 8 * sizeof(long long), (size_t)(mode ? 1 : 0) * 160 * 8 * sizeof(long long)));
   return GNNFP_OK;
 }
@@ -653,17 +655,17 @@ int rows_tma_available() {
 }
 int rows_tma_ok(const float* ptr, int ld) { return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0 && ld > 0; }
 
-int rows_tma_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld) {
+int rows_tma_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int box_rows, int atom32) {
   PFN_cuTensorMapEncodeTiled fn = rt_encoder();
   if (!fn) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: cuTensorMapEncodeTiled is not available from this driver");
   if (!rows_tma_ok(ptr, ld) || rows < 1 || cols < 1 || cols > ld)
     GNNFP_FAIL(GNNFP_E_INVALID, "rows_tma: matrix %p [%d x %d, ld %d] cannot be described by a tensor map (16-byte alignment)", (const void*)ptr, rows, cols, ld);
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {RT_CHUNK, RT_ROWS};
+  const cuuint32_t box[2] = {RT_CHUNK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) GNNFP_FAIL(GNNFP_E_CUDA, "cuTensorMapEncodeTiled failed with %d ([%d x %d], ld %d)", (int)r, rows, cols, ld);
   return GNNFP_OK;

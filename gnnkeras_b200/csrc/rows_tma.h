@@ -64,8 +64,29 @@ struct RowsTmaArgs {
   const int* gate;
 };
 
+// dw_tma.cu: dW = X^T dz with both operands read as MN-major TMA boxes (no transposing pass)
+#define DT_MAXXC 8
+#define DT_MAXP 4
+struct DwTmaArgs {
+  CUtensorMap xmap[2];       // X sources: [n_rows x cols] row-major, box 32 columns x 32 rows
+  CUtensorMap zmap;          // dz [n_rows x H]
+  int n_rows, H, K;          // K = input columns of the net (rows of W)
+  int n_xc; int xc_map[DT_MAXXC], xc_col0[DT_MAXXC];   // X chunk i = columns [col0, col0 + 32) of xmap[map] -> accumulator columns [32 i, 32 i + 32)
+  int n_zc;                  // dz chunks = ceil(H / 32)
+  int n_pieces; int p_in0[DT_MAXP], p_w[DT_MAXP], p_acc0[DT_MAXP];   // input columns [in0, in0 + w) sit in accumulator columns [acc0, ..)
+  int n_stages, n_lo;        // hi ring depth, lo slots
+  int rows;                  // rows per stage / TMA box (32, 64, 128): dw_tma_rows()
+  float* partial; int n_params, bias_off;               // as GemmDwArgs
+  const float* W; const float* bnA; const float* bnB; const float* gamma; const float* beta;
+  float* bn_partial;
+  const int* gate;
+};
+int dw_tma_rows(int n_xc, int n_zc);
+int dw_tma_finish(DwTmaArgs& a);                                 // ring depth from the shared-memory budget; error if the shape does not fit
+int launch_dw_tma(const DwTmaArgs& a, cudaStream_t s, int prof_cat, int* grid_out);
+
 int rows_tma_available();                                        // the driver exports cuTensorMapEncodeTiled
-int rows_tma_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld);   // [rows, cols] fp32 row-major, box 32 x 128, SWIZZLE_128B
+int rows_tma_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int box_rows = RT_ROWS, int atom32 = 0);   // atom32: SWIZZLE_128B_ATOM_32B   // [rows, cols] fp32 row-major, box 32 x 128, SWIZZLE_128B
 int rows_tma_ok(const float* ptr, int ld);                       // 16-byte aligned base and row pitch
 size_t rows_tma_smem(const RowsTmaArgs& a);
 int rows_tma_finish(RowsTmaArgs& a);                             // derive tmem_cols / ring depths from the shared-memory budget; error if it does not fit

@@ -36,10 +36,10 @@ for NL in widths:
     print(f"NL={NL} N={N} step {e0.elapsed_time(e1)/5:.3f} ms k={int(r['k'].item())} | " +
           " ".join(f"{names[i]}={1e3*ms[i]/max(cnt[i],1):.1f}us x{cnt[i]//3}" for i in range(10) if cnt[i]), flush=True)
     if os.environ.get("RT_TIMES"):
-        for mode, nm in ((0, "FWD (last iteration)"), (1, "DX (iteration 1)")):
+        for mode, nm in ((0, "FWD (last iteration)"), (1, "DX (iteration 1)"), (2, "dW (iteration 1)")):
             buf = (C.c_longlong * (160 * 8))()
             Lb.gnnfp_debug_rt_times(buf, mode)
             a = np.array(buf[:]).reshape(160, 8)[:148, :5]
             t0 = a[:, 0].min()
             rel = (a - t0) / 1e3
-            print(f"   {nm} phases us (min/median/max over CTAs): " + " | ".join(f"{n}: {rel[:, i].min():.1f}/{np.median(rel[:, i]):.1f}/{rel[:, i].max():.1f}" for i, n in enumerate(["entry", "consts", "weights", "main", "exit"])))
+            print(f"   {nm} phases us (min/median/max over CTAs): " + " | ".join(f"{n}: {rel[:, i].min():.1f}/{np.median(rel[:, i]):.1f}/{rel[:, i].max():.1f}" for i, n in enumerate(["entry", "consts", "weights", "main", "exit"] if mode < 2 else ["entry", "prologue", "main", "staged", "exit"])))
