@@ -726,15 +726,36 @@ __global__ void reduce_params_kernel(const __grid_constant__ ReduceArgs a) {
 // PAD (VEC == 4, D % 4 == 2, every leading dimension a multiple of 4): rows are walked as ceil(D / 4) float4 slots; the last
 // slot reads two columns of padding / of the neighbouring block (finite values) and writes zeros into dz's padding - half
 // the threads and index arithmetic of the float2 walk.  agg_next (the Adj^T S block of an X slot) starts 8-byte aligned.
+#ifndef DZ_MINB
+#define DZ_MINB 5
+#endif
 template <int VEC, bool PAD>
-__global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzArgs a) {
+__global__ void __launch_bounds__(256, DZ_MINB) dz_kernel(const __grid_constant__ DzArgs a) {
   if (a.gate && *a.gate == 0) return;
   const bool last = a.always_last || a.last_flag == nullptr || *a.last_flag == 0;
   const int nq = PAD ? (a.D + 3) / 4 : a.D / VEC;
   const int ldg = a.ldg ? a.ldg : a.D, lda = a.ld_agg ? a.ld_agg : a.D, ldz = a.ld_dz ? a.ld_dz : ldg;
-  const long long items = (long long)a.n_rows * nq;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(it / nq), q = (int)(it - (long long)r * nq);
+  // thread = (column chunk q, rows r0, r0 + rows_per_pass, ...): the chunk is fixed per thread, so the BN constants of its
+  // columns are loaded ONCE (the kernel is bound by the L1 data path: ncu l1tex 76 % busy, 80 % hits - reloading 8 constants
+  // per item was a third of its sectors)
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows_per_pass = (int)(((long long)gridDim.x * blockDim.x) / nq);
+  const int q = gtid % nq, r0 = gtid / nq;
+  if (r0 >= rows_per_pass) return;
+  float k0o[VEC], k1o[VEC], Ao[VEC], Bo[VEC], k0a[VEC], k1a[VEC], Aa[VEC], Ba[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { k0o[v] = k1o[v] = Ao[v] = Bo[v] = k0a[v] = k1a[v] = Aa[v] = Ba[v] = 0.f; }
+  if (a.cn && !last) {
+    const int in = a.in_dim;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int cv = (PAD && q * VEC + v >= a.D) ? a.D - 1 : q * VEC + v;
+      const int oc = a.own_col0 + cv, ac = a.agg_col0 + cv;
+      k0o[v] = a.cn[oc]; k1o[v] = a.cn[in + oc]; Ao[v] = a.cn[2 * in + oc]; Bo[v] = a.cn[3 * in + oc];
+      k0a[v] = a.cn[ac]; k1a[v] = a.cn[in + ac]; Aa[v] = a.cn[2 * in + ac]; Ba[v] = a.cn[3 * in + ac];
+    }
+  }
+  for (int r = r0; r < a.n_rows; r += rows_per_pass) {
     const int gr = a.rowlist ? a.rowlist[r] : r;
     const size_t o = (size_t)gr * ldg + q * VEC;
     float g[VEC], yv[VEC];
@@ -744,17 +765,10 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
     } else {
       load_vec<VEC>(a.dOwn + o, g);
       const float* cn = a.cn;
-      float k0a[VEC], k1a[VEC], Aa[VEC], Ba[VEC];
       if (cn) {   // BN-training correction of iteration t+1's raw gradients, applied where they are consumed:
                   // dx = a dy - (c0 + x~ c1),  x~ = x*rstd - mean*rstd
-        const int in = a.in_dim;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const int cv = (PAD && q * VEC + v >= a.D) ? a.D - 1 : q * VEC + v;
-          const int oc = a.own_col0 + cv, ac = a.agg_col0 + cv;
-          g[v] -= cn[oc] + fmaf(yv[v], cn[2 * in + oc], cn[3 * in + oc]) * cn[in + oc];
-          k0a[v] = cn[ac]; k1a[v] = cn[in + ac]; Aa[v] = cn[2 * in + ac]; Ba[v] = cn[3 * in + ac];
-        }
+        for (int v = 0; v < VEC; ++v) g[v] -= k0o[v] + fmaf(yv[v], Ao[v], Bo[v]) * k1o[v];
       }
       if (a.pre) {
         float pv[VEC];
@@ -768,16 +782,21 @@ __global__ void __launch_bounds__(256, 5) dz_kernel(const __grid_constant__ DzAr
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const bool ok = p + u < a1;
-          const int pi = ok ? p + u : p;
-          wv[u] = ok ? (a.wgt ? a.wgt[pi] : 1.0f) : 0.0f;
-          const size_t so = (size_t)a.idx[pi] * ldg + q * VEC;
-          load_vec<VEC>(a.dAgg + so, t[u]);
-          if (cn) {
-            if (PAD) {
-              load_vec<2>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC, xg[u]);
-              load_vec<2>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC + 2, xg[u] + (VEC > 2 ? 2 : 0));
-            } else {
-              load_vec<VEC>(a.agg_next + (size_t)a.idx[pi] * lda + q * VEC, xg[u]);
+          wv[u] = 0.0f;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) { t[u][v] = 0.f; xg[u][v] = 0.f; }
+          if (ok) {   // predicated loads: an absent arc must not cost L1 sectors (the kernel is bound by the L1 data path)
+            const int pi = p + u;
+            const int di = a.idx[pi];
+            wv[u] = a.wgt ? a.wgt[pi] : 1.0f;
+            load_vec<VEC>(a.dAgg + (size_t)di * ldg + q * VEC, t[u]);
+            if (cn) {
+              if (PAD) {
+                load_vec<2>(a.agg_next + (size_t)di * lda + q * VEC, xg[u]);
+                load_vec<2>(a.agg_next + (size_t)di * lda + q * VEC + 2, xg[u] + (VEC > 2 ? 2 : 0));
+              } else {
+                load_vec<VEC>(a.agg_next + (size_t)di * lda + q * VEC, xg[u]);
+              }
             }
           }
         }

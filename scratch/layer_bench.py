@@ -13,7 +13,7 @@ widths = [int(a) for a in sys.argv[1:]] or [14, 30, 46, 62, 78]
 Lb = B.lib()
 for NL in widths:
     b = mutag_shaped_batch(8192, seed=0, dim_node_label=NL)
-    ns = MLP((2 * NL + 3,), [NL], 'selu', 'lecun_normal', 'lecun_normal', device=dev, seed=1)
+    ns = MLP((2 * NL + 3,), [NL], 'selu', 'lecun_normal', 'lecun_normal', device=dev, seed=1, batch_normalization=not os.environ.get('NOBN'))
     no = MLP((NL,), [2], 'softmax', 'glorot_normal', 'glorot_normal', device=dev, seed=2)
     gnn = M.GNNgraphBased(ns, no, 0, 5, 0.0)
     gnn.compile(optimizer=M.Adam(0.01), loss="categorical_crossentropy", average_st_grads=True)
