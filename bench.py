@@ -653,7 +653,7 @@ def main():
         cnt = (C.c_longlong * NC)()
         Lib.gnnfp_profile_collect(msc, cnt, NC)
         Lib.gnnfp_profile_enable(0)
-        names = ["other", "state_fwd_iter(rows_tma FWD)", "state_bwd_dW(gemm_dw_tc)", "tile_pass(prologue, BN statistics)",
+        names = ["other", "state_fwd_iter(rows_tma FWD)", "state_bwd_dW(dw_tma)", "tile_pass(prologue, BN statistics)",
                  "out_fwd", "out_bwd", "bn_fix", "state_bwd_dz(dz_kernel)", "state_bwd_dX(rows_tma DX)",
                  "aggregate(agg_stats)"]
         shares = {names[i]: {"ms": msc[i], "launches": int(cnt[i])} for i in range(len(names))}
@@ -663,14 +663,13 @@ def main():
         kmean = float(np.mean([int(k.item()) for kk, _ in ks for k in kk]))
         iters = Nn * kmean * nsteps_p                     # node-updates per layer in the profiled steps
         # per-kernel algorithmic traffic (fp32 words that must move once, SURVEY 8(d) convention: raw inputs, no re-reads)
-        #   gemm_rows_tc fwd : read s (D) + Adj^T s (D) + invariant columns (AL), write s' (D)
-        #   gemm_dw_tc    : read the same inputs (2D + AL) + dz (D); dW/db stay on chip
-        #   gemm_rows dX  : reads dz (D) once, writes dOwn and dAgg (D each) - one launch for both where the two
-        #                   accumulator blocks fit (D <= 64), else one launch per destination
+        #   rows_tma FWD : read s (D) + Adj^T s (D) + invariant columns (AL), write s' (D)
+        #   dw_tma       : read the same inputs (2D + AL) + dz (D); dW/db stay on chip
+        #   rows_tma DX  : reads dz (D) once, writes dOwn and dAgg (D each) in one launch
         cand = {
             "forward iteration (rows_tma_kernel<FWD> / tile_fwd)": (msc[1], int(cnt[1]), sum(4 * (3 * D + l_) for D, l_ in zip(WIDTHS, LS)) * iters,
                                                                    sum(2 * (2 * D + l_) * D for D, l_ in zip(WIDTHS, LS)) * iters),
-            "dW (gemm_dw_tc_kernel / tile_bwd)": (msc[2], int(cnt[2]), sum(4 * (3 * D + l_) for D, l_ in zip(WIDTHS, LS)) * iters,
+            "dW (dw_tma_kernel)": (msc[2], int(cnt[2]), sum(4 * (3 * D + l_) for D, l_ in zip(WIDTHS, LS)) * iters,
                                                  sum(2 * (2 * D + l_) * D for D, l_ in zip(WIDTHS, LS)) * iters),
             "dX (rows_tma_kernel<DX>)": (msc[8], int(cnt[8]), sum(4 * (3 * D) for D in WIDTHS) * iters,
                                         sum(2 * (2 * D) * D for D in WIDTHS) * iters),
@@ -697,10 +696,14 @@ def main():
         it_bytes = sum(algorithmic_bytes(D, l_, deg, True) + algorithmic_bytes(D, l_, deg, False) for D, l_ in zip(WIDTHS, LS)) * iters
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
-        if os.path.exists(tpath):                          # dram__bytes_read+write per launch, one ncu capture of this workload
-            tj = json.load(open(tpath))
-            if dom in tj:
-                traffic, traffic_src = tj[dom]["avg_dram_bytes_per_launch"], "profiles/r1_gemm_traffic.json (" + tj["source"] + ")"
+        if os.path.exists(tpath) and args.workload == "c2" and args.graphs in (0, 8192):   # dram__bytes_read+write per launch, one ncu capture of THIS workload
+            try:
+                tj = json.load(open(tpath))
+                if dom in tj:
+                    traffic = float(tj[dom]["avg_dram_bytes_per_launch"])
+                    traffic_src = "profiles/r2_traffic.json (" + str(tj[dom].get("source", "ncu")) + ")"
+            except (OSError, ValueError, KeyError, TypeError):
+                traffic, traffic_src = None, None
         roof = {"bound": "hbm", "kernel": dom,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
@@ -713,7 +716,7 @@ def main():
                            "dominant kernel is whichever category took the most time in the profiled steps (DESIGN.md 5, 6)",
                 "fixed_point_iteration": {"ms": it_ms, "algorithmic_GBps": it_bytes / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0,
                                           "frac_of_hbm_peak": (it_bytes / (it_ms * 1e-3) / 1e9) / peak if it_ms > 0 else 0.0,
-                                          "kernels": "rows_tma FWD (TMA + tcgen05 3xTF32) + agg_stats + dz + gemm_dw_tc + rows_tma DX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
+                                          "kernels": "rows_tma FWD (TMA + tcgen05 3xTF32) + agg_stats + dz + dw_tma + rows_tma DX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
                 "kernel_time_by_category_ms": shares,
                 "note": "achieved = algorithmic bytes of the kernel's launches / their CUDA-event durations "
                         "(events recorded by the library on the launch stream, separate profiled pass of the same steps)"}
