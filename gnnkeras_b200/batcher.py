@@ -282,3 +282,91 @@ class DeviceMultiGraphSequencer:
         if self.shuffle:
             np.random.shuffle(self.order)                                # GraphSequencers.py:123-127, without the re-merge
             self._cache = [None] * len(self)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Transductive re-draw on the device (reference TransductiveGraphSequencers.py:56-95)
+# ------------------------------------------------------------------------------------------------------------------------
+def transduce_batch(nodes, targets, sample_weight, set_mask, output_mask, member, n_members, transductive_rate,
+                    generator=None, keys=None):
+    """``get_transduction`` (TransductiveGraphSequencers.py:62-95) applied to every member of a MERGED node-focused batch at
+    once, as tensor operations on the batch's device: per member, the targeted nodes (set_mask & output_mask) are ranked by a
+    random key (the reference's ``np.random.shuffle``, :68), the first ceil(n (1 - rate)) stay non-transductive (:70-71), the
+    others get their target appended to their label (:77-81), leave the output set (:90-91) and form node type 1 (:86-88).
+    ``member`` [N] = index of the node's graph in the batch.  ``keys`` (optional, [N] in [0, 1)) fixes the draw (tests).
+    Returns nodes_new [N, NL + T], targets_new, sample_weight_new, type_mask [2, N] uint8, output_mask_new uint8, tmask bool."""
+    dev = nodes.device
+    sm, om = set_mask.bool(), output_mask.bool()
+    tmask = sm & om
+    member = member.long()
+    cnt = torch.zeros(n_members, dtype=torch.float64, device=dev).index_add_(0, member, tmask.double())
+    n_non = torch.ceil(cnt * (1.0 - float(transductive_rate))).long()        # np.ceil(np.sum(mask) * (1 - rate)), float64 as NumPy
+    if keys is None:
+        keys = torch.rand(nodes.shape[0], device=dev, generator=generator, dtype=torch.float64)
+    idx_t = torch.nonzero(tmask).reshape(-1)
+    order = torch.argsort(member[idx_t].double() + keys[idx_t].double().clamp(0.0, 1.0 - 1e-12))   # by member, then by key
+    sorted_idx = idx_t[order]
+    start = torch.cumsum(cnt.long(), 0) - cnt.long()                          # first position of every member in the sorted list
+    pos = torch.arange(sorted_idx.numel(), device=dev) - start[member[sorted_idx]]
+    stay = pos < n_non[member[sorted_idx]]
+    tmask = tmask.clone()
+    tmask[sorted_idx[stay]] = False                                           # :71
+    t_target = tmask[om]                                                      # :74, rows of `targets` that turn into labels
+    plus = torch.zeros((nodes.shape[0], targets.shape[1]), dtype=nodes.dtype, device=dev)
+    plus[tmask] = targets[t_target]                                           # :78-79
+    nodes_new = torch.cat([nodes, plus], dim=1)                               # :81
+    keep = ~t_target
+    type_mask = torch.stack([~tmask, tmask]).to(torch.uint8)                  # :86-88, [n_types, N] as the model takes it
+    out_new = (om & ~tmask).to(torch.uint8)                                   # :90-91
+    return nodes_new, targets[keep], sample_weight[keep], type_mask, out_new, tmask
+
+
+class DeviceTransductiveSequencer(DeviceMultiGraphSequencer):
+    """``TransductiveMultiGraphSequencer`` (TransductiveGraphSequencers.py:13-95) over a device-resident ``GraphStore`` of
+    HOMOGENEOUS node-focused graphs: every batch is assembled on the device and turned into a 2-type composite batch by
+    ``transduce_batch``; an epoch end redraws the permutation, and the transductive split is drawn afresh whenever a batch is
+    built (the reference re-runs ``get_transduction`` over every graph on the host at every epoch end, :56-59)."""
+
+    def __init__(self, graphs, focus: str, aggregation_mode: str, transductive_rate: float = 0.5, batch_size: int = 32,
+                 shuffle: bool = True, device="cuda", seed: Optional[int] = None):
+        if focus != "n":
+            raise NotImplementedError("the device-side transductive transform covers node-focused graphs")
+        super().__init__(graphs, focus, aggregation_mode, batch_size, shuffle, device)
+        if self.store.composite:
+            raise ValueError("transduction starts from homogeneous graphs (TransductiveGraphSequencers.py:62)")
+        self.transductive_rate = float(transductive_rate)
+        self.generator = torch.Generator(device=self.store.device)
+        if seed is not None:
+            self.generator.manual_seed(int(seed))
+
+    def get_batch(self, index):
+        if self._cache[index] is None:
+            from .op import DeviceGraph
+            st = self.store
+            ids = np.asarray(self.batch_ids(index), dtype=np.int64)
+            a = st.assemble(ids)
+            member = torch.repeat_interleave(torch.arange(len(ids), device=st.device),
+                                             torch.from_numpy(st.n_nodes[ids]).to(st.device))
+            nodes, targets, sw, tm, om, _ = transduce_batch(a["nodes"], a["targets"], a["sample_weight"], a["set_mask"],
+                                                            a["output_mask"], member, len(ids), self.transductive_rate, self.generator)
+            if "src" in a:
+                src, dst = a["src"], a["dst"]
+            else:
+                ij = a["arcs"][:, :2].to(torch.int32)
+                src, dst = ij[:, 0].contiguous(), ij[:, 1].contiguous()
+            sm = a["set_mask"]
+            graph = DeviceGraph(src, dst, a["n_nodes"], self.aggregation_mode, None, 0, None, sm, om, tm.contiguous(), None,
+                                mask_len=int(sm.numel()))
+            nl = int(np.asarray(st.dim_node_label).reshape(-1)[0])
+            dnl = np.array([nl, nl + int(targets.shape[1])], dtype=int)
+            self._cache[index] = CompositeGraphTensor(nodes, a["arcs"], targets, sw, sm, om, dnl, graph, self.aggregation_mode,
+                                                      self.focus, tm.contiguous())
+        g = self._cache[index]
+        return g, g.set_mask
+
+    def __getitem__(self, index):
+        g, set_mask = self.get_batch(index)
+        out = [g.nodes, g.arcs, g.DIM_NODE_LABEL, g.type_mask, g.set_mask, g.output_mask, g.CompositeAdjacencies, g.Adjacency,
+               g.ArcNode, g.NodeGraph]                       # GraphSequencers.py:240-244
+        mask = set_mask.bool()[g.output_mask.bool()]
+        return out, g.targets[mask], g.sample_weight[mask]

@@ -549,6 +549,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
                 acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
               }
             }
+            // (compute-sanitizer racecheck reports the 128-bit reads above against the padding patch below, which another
+            //  column warp may apply to ITS rows of the same stage meanwhile: the overlap is confined to the padding columns
+            //  of the last chunk, whose gathered values land in acc[j >= width] and are never stored or counted)
             const bool wr = rowok && good;
             const int width = a.oc[o].width;
             // The TMA store of S_t works in 16-byte units: when D is not a multiple of 4 the last unit of an S_t row also

@@ -98,3 +98,44 @@ def test_store_from_merged_reassembles_the_flat_batch():
         assert torch.equal(getattr(gt, name), getattr(ref, name)), name
     for which in (B.X_DST_ROWPTR, B.X_DST_SRC, B.X_ARC_VALUE, B.X_GRAPH_PTR, B.X_NODEGRAPH_VALUE):
         assert np.array_equal(gt.graph.export(which).view(np.uint32), ref.graph.export(which).view(np.uint32)), which
+
+
+def test_device_transductive_sequencer_feeds_a_two_type_cgnn():
+    """SURVEY 8(f) row 4 on the device: homogeneous node-focused graphs resident in a GraphStore become 2-type composite
+    batches per draw (TransductiveGraphSequencers.py:56-95); the batch trains a CompositeGNNnodeBased, and the transform obeys
+    the reference's rules (exact equality with the reference's own code: tests/test_cpu_transductive.py on CPU tensors)."""
+    from gnnkeras_b200 import models as M
+    from gnnkeras_b200.batcher import DeviceTransductiveSequencer
+    from gnnkeras_b200.nets import MLP
+    graphs = make_graphs("n", 30, seed=77, masked=True)
+    rate = 0.5
+    seq = DeviceTransductiveSequencer(graphs, "n", "average", transductive_rate=rate, batch_size=12, shuffle=False, seed=3)
+    x, y, sw = seq[0]
+    g, _ = seq.get_batch(0)
+    nodes, tm, om, sm = g.nodes.cpu().numpy(), g.type_mask.cpu().numpy().astype(bool), g.output_mask.cpu().numpy().astype(bool), g.set_mask.cpu().numpy().astype(bool)
+    ref = GraphObject.merge(graphs[:12], "n", "average")
+    assert nodes.shape[1] == 4 + 2 and np.array_equal(nodes[:, :4], ref.nodes)
+    assert np.array_equal(tm[0], ~tm[1]) and not np.any(tm[1] & ~(ref.set_mask & ref.output_mask))
+    assert np.array_equal(om, ref.output_mask & ~tm[1])
+    # transductive nodes carry their own target as extra label, the others zeros
+    row_of = np.cumsum(ref.output_mask) - 1
+    assert np.array_equal(nodes[tm[1], 4:], ref.targets[row_of[tm[1]]]) and not np.any(nodes[~tm[1], 4:])
+    assert np.array_equal(g.targets.cpu().numpy(), ref.targets[~tm[1][ref.output_mask]])
+    off = 0
+    for go in graphs[:12]:                               # per member: ceil(n (1 - rate)) targeted nodes stay non-transductive
+        n = go.nodes.shape[0]
+        targeted = go.set_mask & go.output_mask
+        assert int(tm[1][off:off + n].sum()) == int(targeted.sum()) - int(np.ceil(targeted.sum() * (1 - rate)))
+        off += n
+    # a second draw of the same batch differs (re-drawn whenever the batch is rebuilt), same counts
+    seq.on_epoch_end()
+    g2, _ = seq.get_batch(0)
+    assert int(g2.type_mask[1].sum()) == int(tm[1].sum())
+    # trains
+    ns = [MLP((4 + 2 * 5 + 4 + 6 + 3,), [5], "tanh", "glorot_normal", "glorot_normal", device="cuda", seed=1, batch_normalization=False),
+          MLP((6 + 2 * 5 + 4 + 6 + 3,), [5], "tanh", "glorot_normal", "glorot_normal", device="cuda", seed=2, batch_normalization=False)]
+    no = MLP((5,), [2], "softmax", "glorot_normal", "glorot_normal", device="cuda", seed=3, batch_normalization=False)
+    model = M.CompositeGNNnodeBased(ns, no, 5, 3, 0.01)
+    model.compile(optimizer=M.Adam(0.01), loss="categorical_crossentropy")
+    r = model.train_step((x, y, sw))
+    assert np.isfinite(float(r["loss"]))
