@@ -259,8 +259,10 @@ __global__ void __launch_bounds__(BT) agg_stats_kernel(const __grid_constant__ A
   const int qx = threadIdx.x % QX, ry = threadIdx.x / QX;
   const int rpb = blockDim.x / QX;
   double su[VEC], sq[VEC];
+  float ts[VEC], tq[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { su[v] = 0.0; sq[v] = 0.0; }
+  for (int v = 0; v < VEC; ++v) { su[v] = 0.0; sq[v] = 0.0; ts[v] = 0.f; tq[v] = 0.f; }
+  const bool want_stats = a.st_sum != nullptr;
   if (qx < nq && ry < rpb) {
     // NR rows per trip: their rowptr -> idx -> state-row load chains overlap (the kernel is latency bound otherwise);
     // arc order inside a row is kept (sequential fmaf), absent arcs are predicated off.  DIRECT (no CSR: the row's
@@ -350,8 +352,14 @@ __global__ void __launch_bounds__(BT) agg_stats_kernel(const __grid_constant__ A
           else if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[j][0], acc[j][1 % VEC]);
           else o[0] = acc[j][0];
         }
+        if (want_stats) {                              // uniform branch: no fp64 work at all without statistics
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { su[v] += (double)acc[j][v]; sq[v] += (double)acc[j][v] * (double)acc[j][v]; }
+          for (int v = 0; v < VEC; ++v) { ts[v] += acc[j][v]; tq[v] = fmaf(acc[j][v], acc[j][v], tq[v]); }
+        }
+      }
+      if (want_stats) {                                // one conversion per trip (NR rows): fp32 partials of <= 8 values
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { su[v] += (double)ts[v]; sq[v] += (double)tq[v]; ts[v] = 0.f; tq[v] = 0.f; }
       }
     }
   }
