@@ -680,6 +680,10 @@ def main():
             "Adj^T s (agg_stats_kernel)": (msc[9], int(cnt[9]), sum(4 * (2 * D) + 4 + 8 * deg for D in WIDTHS) * iters,
                                            sum(2 * deg * D for D in WIDTHS) * iters),
         }
+        if spec["composite"]:       # composite nets run the FP32-pipe tile kernels (one launch per type and column split)
+            ren = {"forward iteration (rows_tma_kernel<FWD> / tile_fwd)": "forward iteration (tile_fwd_kernel, FP32 pipe)",
+                   "dW (dw_tma_kernel)": "backward iteration dW + dX (tile_bwd_kernel, FP32 pipe)"}
+            cand = {ren.get(k_, k_): v_ for k_, v_ in cand.items()}
         dom = max(cand, key=lambda k_: cand[k_][0])
         dom_ms, dom_n, dom_bytes, flops = cand[dom]
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -689,6 +693,21 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # nominal FFMA peak at the boost clock
+        # measured sustained FP32-pipe peak (FMA-only kernel of the library, CUDA events): the denominator for the FP32 tile kernels
+        fp32_meas = None
+        try:
+            sink = torch.zeros(4, dtype=torch.float32, device=device)
+            fl = C.c_double()
+            st_ = torch.cuda.current_stream().cuda_stream
+            Lib.gnnfp_debug_fma_peak(sink.data_ptr(), 2000, 8, C.byref(fl), st_)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            Lib.gnnfp_debug_fma_peak(sink.data_ptr(), 20000, 8, C.byref(fl), st_)
+            f1.record()
+            torch.cuda.synchronize()
+            fp32_meas = fl.value / (f0.elapsed_time(f1) * 1e-3) / 1e12
+        except Exception:
+            fp32_meas = None
         tfl = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0      # useful (fp32-equivalent) flops
         tf32_peak = 1100.0                                  # dense TF32 tensor peak (B200_PROFILING.md); each product = 3 MMAs
         # whole fixed-point iteration against SURVEY 8(d)'s per-node-update figure B = B_f + B_b
@@ -711,6 +730,8 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes / max(1, dom_n),
                 "useful_tflops_achieved": tfl, "tf32_mma_tflops_issued": 3 * tfl, "tf32_tensor_peak_tflops": tf32_peak,
                 "tensor_frac": 3 * tfl / tf32_peak, "fp32_pipe_nominal_peak_tflops": fp32_peak,
+                "fp32_pipe_measured_peak_tflops": fp32_meas,
+                "fp32_pipe_frac": (tfl / fp32_meas) if (fp32_meas and spec["composite"]) else None,
                 "binding": "the three GEMMs of an iteration run on tcgen05 (3xTF32: 3 MMAs per product), so the 33 flop/B workload is "
                            "HBM-bound by the roofline (ridge ~57 flop/B at 1.1 PF/3) and frac is against the measured HBM peak; the "
                            "dominant kernel is whichever category took the most time in the profiled steps (DESIGN.md 5, 6)",

@@ -91,7 +91,7 @@ SYMBOLS = ["gnnfp_last_error", "gnnfp_abi_version", "gnnfp_graph_build", "gnnfp_
            "gnnfp_loop_forward_end", "gnnfp_loop_ws_offsets", "gnnfp_loop_backward",
            "gnnfp_loop_backward_step", "gnnfp_loop_bwd_offsets",
            "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step", "gnnfp_adam_step_dev", "gnnfp_adam_advance", "gnnfp_batch_assemble",
-           "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect"]
+           "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect", "gnnfp_debug_fma_peak"]
 
 
 def lib():
@@ -144,6 +144,7 @@ def lib():
     L.gnnfp_batch_assemble.argtypes = [C.POINTER(StoreDesc), _vp, C.c_int32, C.c_int64, _vp, C.POINTER(BatchOut), _vp]
     L.gnnfp_adam_step.argtypes = [_vp, _vp, _vp, _vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int32, C.c_float, _vp]
+    L.gnnfp_debug_fma_peak.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_void_p]
     L.gnnfp_launch_count.argtypes = [C.c_int]
     L.gnnfp_launch_count.restype = C.c_longlong
     L.gnnfp_profile_enable.argtypes = [C.c_int]

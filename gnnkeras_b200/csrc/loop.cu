@@ -113,11 +113,16 @@ static __global__ void k_finalize(const int* flags, int max_iter, const float* s
   int ld;
   if (k == 0) { src = s0; ld = ld0; }
   else { src = slots + (slot_mode == 0 ? (size_t)(k - 1) : (slot_mode == 1 ? (size_t)(k & 1) : (size_t)k)) * slot_stride; ld = ld_slot; }
-  const size_t total = (size_t)n * D;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = e / D;
-    const int j = (int)(e - r * D);
-    state_out[e] = src[r * ld + j];
+  // one warp per row, 4 rows in flight (a per-element division by the runtime width ran on the conversion pipe)
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = wid * 4; r0 < n; r0 += nw * 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= n) break;
+      for (int j = lane; j < D; j += 32) state_out[(size_t)r * D + j] = src[(size_t)r * ld + j];
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && k_out) *k_out = k;
 }
@@ -774,9 +779,9 @@ static int fwd_end(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_par
   (void)MI; (void)D; (void)N; (void)training; (void)wgt; (void)io; (void)op; (void)sp;
   // ---- converged state, iteration count --------------------------------------------------------------
   {
-    const size_t total = (size_t)N * D;
-    int blocks = (int)((total + 255) / 256);
+    int blocks = (N + 31) / 32;                          // 8 warps x 4 rows per block
     if (blocks > 2368) blocks = 2368;
+    if (blocks < 1) blocks = 1;
     k_finalize<<<blocks, 256, 0, s>>>(c.flags(), MI, c.S0user(), c.ldS0user(), c.slots(), c.slot_stride(),
                                       training ? (L->xlay ? 2 : 0) : 1, L->xlay ? L->ldX : D, N, D, io->state_out, io->k_out);
     GNNFP_COUNT_LAUNCH();

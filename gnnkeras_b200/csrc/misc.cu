@@ -2,48 +2,58 @@
 // fused train-step tail (Keras categorical_crossentropy + Adam).
 #include "graph.h"
 
+// Row-wise kernels: one warp per row (lane = column, 4 rows in flight) instead of one thread per element - a per-element
+// 64-bit division by the runtime row width costs ~50 instructions on the conversion (XU) pipe and made these copies 2x
+// slower than their traffic.
 static __global__ void k_update_graph_fwd(int n, const float* state, int sw, int ow, const float* base, int bw, int ldb, float* dst) {
   const int W = sw + ow + bw;
-  const size_t total = (size_t)n * W;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = e / W;
-    const int c = (int)(e - r * W);
-    float v;
-    if (c < sw) v = state[r * sw + c];
-    else if (c < sw + ow) v = 0.0f;                       // tf.scatter_nd zero fill (LGNN.py:203)
-    else v = base[r * ldb + (c - sw - ow)];
-    dst[e] = v;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = wid * 4; r0 < n; r0 += nw * 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= n) break;
+      for (int c = lane; c < W; c += 32) {
+        float v;
+        if (c < sw) v = state[(size_t)r * sw + c];
+        else if (c < sw + ow) v = 0.0f;                     // tf.scatter_nd zero fill (LGNN.py:203)
+        else v = base[(size_t)r * ldb + (c - sw - ow)];
+        dst[(size_t)r * W + c] = v;
+      }
+    }
   }
 }
 static __global__ void k_scatter_rows(int m, const int* idx, const float* rows, int ow, float* dst, int W, int col0) {
-  const size_t total = (size_t)m * ow;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = e / ow;
-    const int c = (int)(e - r * ow);
-    const size_t row = idx ? (size_t)idx[r] : r;
-    dst[row * W + col0 + c] = rows[e];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    const size_t row = idx ? (size_t)idx[r] : (size_t)r;
+    for (int c = 0; c < ow; ++c) dst[row * W + col0 + c] = rows[(size_t)r * ow + c];
   }
 }
 static __global__ void k_update_graph_bwd(int n, const float* d_dst, float* d_state, int sw, int ow, float* d_base, int bw, int accumulate) {
   const int W = sw + ow + bw;
-  const size_t total = (size_t)n * W;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = e / W;
-    const int c = (int)(e - r * W);
-    const float v = d_dst[e];
-    if (c < sw) { if (d_state) d_state[r * sw + c] = v; }
-    else if (c >= sw + ow) {
-      if (d_base) { float* d = d_base + r * bw + (c - sw - ow); if (accumulate) *d += v; else *d = v; }
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = wid * 4; r0 < n; r0 += nw * 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= n) break;
+      for (int c = lane; c < W; c += 32) {
+        if (c >= sw && c < sw + ow) continue;
+        if (c < sw && !d_state) continue;
+        if (c >= sw + ow && !d_base) continue;
+        const float v = d_dst[(size_t)r * W + c];
+        if (c < sw) d_state[(size_t)r * sw + c] = v;
+        else { float* d = d_base + (size_t)r * bw + (c - sw - ow); if (accumulate) *d += v; else *d = v; }
+      }
     }
   }
 }
 static __global__ void k_gather_rows(int m, const int* idx, const float* src, int W, int col0, int ow, float* rows) {
-  const size_t total = (size_t)m * ow;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = e / ow;
-    const int c = (int)(e - r * ow);
-    const size_t row = idx ? (size_t)idx[r] : r;
-    rows[e] = src[row * W + col0 + c];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    const size_t row = idx ? (size_t)idx[r] : (size_t)r;
+    for (int c = 0; c < ow; ++c) rows[(size_t)r * ow + c] = src[row * W + col0 + c];
   }
 }
 
@@ -62,11 +72,11 @@ extern "C" int gnnfp_update_graph_forward(const gnnfp_graph* g, int32_t n_rows, 
   if ((state_w > 0 && !state) || (out_w > 0 && !out_rows)) GNNFP_FAIL(GNNFP_E_INVALID, "update_graph: state / out rows missing");
   cudaStream_t s = (cudaStream_t)stream;
   const int W = state_w + out_w + base_w;
-  k_update_graph_fwd<<<blocks_for((size_t)n_rows * W), 256, 0, s>>>(n_rows, state, state_w, out_w, base, base_w, ld_base, dst);
+  k_update_graph_fwd<<<blocks_for((size_t)n_rows * 8), 256, 0, s>>>(n_rows, state, state_w, out_w, base, base_w, ld_base, dst);
   GNNFP_COUNT_LAUNCH();
   if (out_w > 0 && g->M > 0) {
     const int* idx = g->M == g->mask_len ? nullptr : g->mask_idx;
-    k_scatter_rows<<<blocks_for((size_t)g->M * out_w), 256, 0, s>>>(g->M, idx, out_rows, out_w, dst, W, state_w);
+    k_scatter_rows<<<blocks_for((size_t)g->M), 256, 0, s>>>(g->M, idx, out_rows, out_w, dst, W, state_w);
     GNNFP_COUNT_LAUNCH();
   }
   GNNFP_CHECK_CUDA(cudaGetLastError());
@@ -80,11 +90,11 @@ extern "C" int gnnfp_update_graph_backward(const gnnfp_graph* g, int32_t n_rows,
   if (n_rows != g->mask_len) GNNFP_FAIL(GNNFP_E_INVALID, "update_graph_backward: n_rows must equal the mask length");
   cudaStream_t s = (cudaStream_t)stream;
   const int W = state_w + out_w + base_w;
-  k_update_graph_bwd<<<blocks_for((size_t)n_rows * W), 256, 0, s>>>(n_rows, d_dst, d_state, state_w, out_w, d_base, base_w, accumulate_base);
+  k_update_graph_bwd<<<blocks_for((size_t)n_rows * 8), 256, 0, s>>>(n_rows, d_dst, d_state, state_w, out_w, d_base, base_w, accumulate_base);
   GNNFP_COUNT_LAUNCH();
   if (out_w > 0 && d_out_rows && g->M > 0) {
     const int* idx = g->M == g->mask_len ? nullptr : g->mask_idx;
-    k_gather_rows<<<blocks_for((size_t)g->M * out_w), 256, 0, s>>>(g->M, idx, d_dst, W, state_w, out_w, d_out_rows);
+    k_gather_rows<<<blocks_for((size_t)g->M), 256, 0, s>>>(g->M, idx, d_dst, W, state_w, out_w, d_out_rows);
     GNNFP_COUNT_LAUNCH();
   }
   GNNFP_CHECK_CUDA(cudaGetLastError());
@@ -302,5 +312,30 @@ extern "C" int gnnfp_batch_assemble(const gnnfp_store_desc* st, const int64_t* i
   k_batch_assemble<<<n_ids, 256, 0, s>>>(*st, ids_dev, n_ids, offsets_scratch, *out, n_nodes_batch);
   GNNFP_COUNT_LAUNCH();
   GNNFP_CHECK_CUDA(cudaGetLastError());
+  return GNNFP_OK;
+}
+
+
+// ---- measurement aid: sustained FP32 FMA rate of this GPU (the roofline denominator of the FP32-pipe tile kernels) -------------
+// 8 independent FMA chains per thread, no memory traffic; bench.py times one launch with CUDA events.
+static __global__ void __launch_bounds__(256) k_fma_peak(float* sink, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 12345.678f) sink[0] = r;                    // never true: keeps the chains alive
+}
+// launches blocks_per_sm x SMs blocks of 256 threads; *flops_out = FLOPs of the launch (2 per FMA)
+extern "C" int gnnfp_debug_fma_peak(float* sink, int32_t iters, int32_t blocks_per_sm, double* flops_out, void* stream) {
+  if (!sink || iters < 1 || blocks_per_sm < 1) GNNFP_FAIL(GNNFP_E_INVALID, "fma_peak: bad arguments");
+  const int grid = gnnfp_num_sms() * blocks_per_sm;
+  k_fma_peak<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters, 0.999f, 0.001f);
+  GNNFP_CHECK_CUDA(cudaGetLastError());
+  if (flops_out) *flops_out = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)grid;
   return GNNFP_OK;
 }

@@ -310,6 +310,9 @@ int gnnfp_batch_assemble(const gnnfp_store_desc* store, const int64_t* ids_dev, 
 
 /* Counters for bench.py's `gpu_launches` (kernels this library launched since the last reset). */
 long long gnnfp_launch_count(int reset);
+/* measurement aid (bench.py): one launch of an FMA-only kernel (8 chains per thread, blocks_per_sm x SMs blocks of 256
+ * threads); *flops_out = its FLOPs.  Timed by the caller: the sustained FP32-pipe peak the tile kernels are held against. */
+int gnnfp_debug_fma_peak(float* sink, int32_t iters, int32_t blocks_per_sm, double* flops_out, void* stream);
 
 /* Optional per-category kernel timing (CUDA events recorded on the launch stream around every tile
  * kernel; off by default).  Categories: 0 other, 1 state-net forward iteration, 2 state-net backward
