@@ -145,6 +145,13 @@ class GraphedTrainStep:
 
 def cce_loss(y_true, y_pred, sample_weight, scale, loss_acc, want_grad=True):
     """Keras categorical_crossentropy + SUM_OVER_BATCH_SIZE, fused with its gradient (gnnfp_cce_loss)."""
+    for nm, t in (("y_true", y_true), ("y_pred", y_pred), ("sample_weight", sample_weight)):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError(f"{nm} must be a contiguous float32 CUDA tensor")
+    if y_pred.dim() != 2 or tuple(y_true.shape) != tuple(y_pred.shape):
+        raise ValueError(f"y_true {tuple(y_true.shape)} and y_pred {tuple(y_pred.shape)} must be equal [rows, classes] matrices")
+    if sample_weight.numel() != y_pred.shape[0]:
+        raise ValueError(f"sample_weight has {sample_weight.numel()} entries for {y_pred.shape[0]} rows")
     d = torch.empty_like(y_pred) if want_grad else None
     B.check(B.lib().gnnfp_cce_loss(_ptr(y_true), _ptr(y_pred), _ptr(sample_weight), y_pred.shape[0], y_pred.shape[1],
                                    float(scale), _ptr(loss_acc), _ptr(d), _stream()))

@@ -88,6 +88,7 @@ class DeviceGraph:
         B.check(L.gnnfp_graph_build(C.byref(h), C.byref(d), _stream()))
         self._h = h
         self._L = L
+        self._build_stream = torch.cuda.current_stream(src.device)   # the handle's memory is freed in THIS stream's order
         info = B.GraphInfo()
         B.check(L.gnnfp_graph_get_info(h, C.byref(info)))
         self.n_nodes, self.n_arcs, self.n_graphs, self.n_types = info.n_nodes, info.n_arcs, info.n_graphs, info.n_types
@@ -118,6 +119,16 @@ class DeviceGraph:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
+            # gnnfp_graph_free releases the arrays in the order of the stream the handle was built on: when the plans ran on
+            # another stream (bench.py builds on a side stream), that stream's work must come first - a device-side wait, no
+            # host synchronisation
+            try:
+                cur = torch.cuda.current_stream(self.device)
+                bs = getattr(self, "_build_stream", None)
+                if bs is not None and cur != bs:
+                    bs.wait_stream(cur)
+            except Exception:
+                pass                                   # interpreter shutdown: CUDA may be gone, the driver reclaims the memory
             self._L.gnnfp_graph_free(h)
             self._h = None
 

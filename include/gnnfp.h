@@ -100,6 +100,8 @@ typedef struct gnnfp_graph_desc {
 int gnnfp_graph_build(gnnfp_graph** out, const gnnfp_graph_desc* desc, void* stream);
 /* waits for the build's stream work and reports the deferred validation (GNNFP_OK, GNNFP_E_INVALID, GNNFP_E_UNSUPPORTED) */
 int gnnfp_graph_check(const gnnfp_graph* g);
+/* releases the handle's arrays in the order of the stream it was built on (cudaFreeAsync): work that uses the handle on
+ * OTHER streams must have been ordered before that stream by the caller (event / stream wait) */
 void gnnfp_graph_free(gnnfp_graph* g);
 
 typedef struct gnnfp_graph_info {
