@@ -88,7 +88,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnnfp.so
 SYMBOLS = ["gnnfp_last_error", "gnnfp_abi_version", "gnnfp_graph_build", "gnnfp_graph_free", "gnnfp_graph_get_info",
            "gnnfp_graph_export", "gnnfp_graph_check", "gnnfp_loop_create", "gnnfp_loop_free", "gnnfp_loop_workspace_bytes",
            "gnnfp_loop_out_rows", "gnnfp_loop_state_dim", "gnnfp_loop_forward", "gnnfp_loop_forward_begin", "gnnfp_loop_forward_iter",
-           "gnnfp_loop_forward_end", "gnnfp_loop_ws_offsets", "gnnfp_loop_backward",
+           "gnnfp_loop_forward_end", "gnnfp_loop_ws_offsets", "gnnfp_loop_ws_layout", "gnnfp_loop_backward",
            "gnnfp_loop_backward_step", "gnnfp_loop_bwd_offsets",
            "gnnfp_update_graph_forward", "gnnfp_update_graph_backward", "gnnfp_cce_loss", "gnnfp_adam_step", "gnnfp_adam_step_dev", "gnnfp_adam_advance", "gnnfp_batch_assemble",
            "gnnfp_launch_count", "gnnfp_profile_enable", "gnnfp_profile_collect", "gnnfp_debug_fma_peak"]
@@ -124,6 +124,7 @@ def lib():
     L.gnnfp_loop_forward_end.argtypes = L.gnnfp_loop_forward.argtypes
     L.gnnfp_loop_forward_iter.argtypes = [_vp, C.c_int32, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(LoopIO), _vp,
                                           C.c_size_t, _vp]
+    L.gnnfp_loop_ws_layout.argtypes = [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.gnnfp_loop_ws_offsets.argtypes = [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                         C.POINTER(C.c_int32)]
     L.gnnfp_loop_backward.argtypes = [_vp, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(LoopIO),

@@ -410,7 +410,11 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
   L->ldG = L->D; L->ldXs = L->LsM; L->ldX = L->D;
   {
     static const int no_rt = getenv("GNNFP_NO_RT") ? 1 : 0;
-    if (!no_rt && !L->composite && L->gemm_ok[0] && L->Nact == L->N && cfg->max_iteration > 0 && L->D <= 96 && rows_tma_available()) {
+    // (partitioned plans - n_active_rows < N, the rest are halo copies - take it too: no BatchNormalization there, and no
+    //  fused aggregation, whose tile-local CSR view assumes that every row of a tile is computed by this launch)
+    const bool part = L->Nact < L->N;
+    const bool part_ok = !part || !(L->snet[0].has_bn || L->onet.has_bn);
+    if (!no_rt && !L->composite && L->gemm_ok[0] && part_ok && cfg->max_iteration > 0 && L->D <= 96 && rows_tma_available()) {
       const int inl = L->LsM > 0 && L->LsM <= 8;
       const int w0 = 2 * L->D + (inl ? L->LsM : 0);
       const int nkc = (w0 + 31) / 32 + (inl ? 0 : (L->LsM + 31) / 32);
@@ -421,7 +425,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
       // the same kernel (column sums across thread = row partials), a gain otherwise; GNNFP_FUSE_AGG=0|1 overrides
       const bool bn_stats = cfg->training && L->snet[0].has_bn;
       const char* fenv = getenv("GNNFP_FUSE_AGG");
-      const int no_fuse = fenv ? (atoi(fenv) == 0) : (bn_stats ? 1 : 0);
+      const int no_fuse = part ? 1 : (fenv ? (atoi(fenv) == 0) : (bn_stats ? 1 : 0));
       pf.mode = RT_FWD; pf.n_kc = nkc; pf.n_oc = (L->D + 31) / 32; pf.BN = ceil_to(L->D, 16); pf.fuse_agg = !no_fuse;
       pd.mode = RT_DX; pd.n_kc = (L->D + 31) / 32; pd.n_oc = 2 * ((L->D + 31) / 32); pd.BN = 2 * ceil_to(L->D, 16);
       if (nkc <= RT_MAXKC && rows_tma_finish(pf) == GNNFP_OK && (!cfg->training || rows_tma_finish(pd) == GNNFP_OK)) {
@@ -616,7 +620,7 @@ static int rt_build_fwd(const Ctx& c, int t, const gnnfp_net_params* sp, RowsTma
   if ((rc = rows_tma_map(&ra.maps[0], c.S(t - 1), N, w0, L->ldX))) return rc;
   if (!L->xs_inline && LsM > 0 && (rc = rows_tma_map(&ra.maps[1], c.Xs(), N, LsM, L->ldXs))) return rc;
   if ((rc = rows_tma_map(&ra.maps[2], c.S(t - 1), N, D, L->ldX))) return rc;
-  if ((rc = rows_tma_map(&ra.maps[3], c.S(t), N, D, L->ldX))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[3], c.S(t), L->Nact, D, L->ldX))) return rc;   // stores clip at the computed rows (halo rows below stay the exchange's)
   // input column (row of W) of X-slot column m / static column x: the net sees [S | nodes? | Adj^T S | agg_nodes | agg_arcs]
   auto stat_col = [&](int x) { return x < NLp ? D + x : 2 * D + x; };
   auto slot_col = [&](int m) { return m < D ? m : (m < 2 * D ? D + NLp + (m - D) : stat_col(m - 2 * D)); };
@@ -900,6 +904,13 @@ extern "C" int gnnfp_loop_forward_end(gnnfp_loop* L, const gnnfp_net_params* sp,
   if ((rc = fwd_check(L, sp, op, io, workspace, workspace_bytes))) return rc;
   Ctx c{L, io, (char*)workspace, (cudaStream_t)stream};
   return fwd_end(c, sp, op);
+}
+extern "C" int gnnfp_loop_ws_layout(const gnnfp_loop* L, int32_t* ld_state, int32_t* state1_slot, int32_t* ld_grad) {
+  if (!L) GNNFP_FAIL(GNNFP_E_INVALID, "loop_ws_layout: null plan");
+  if (ld_state) *ld_state = L->xlay ? L->ldX : L->D;
+  if (state1_slot) *state1_slot = (L->xlay && L->cfg.training) ? 1 : 0;
+  if (ld_grad) *ld_grad = L->ldG;
+  return GNNFP_OK;
 }
 extern "C" int gnnfp_loop_ws_offsets(const gnnfp_loop* L, size_t* flags_off, size_t* slots_off, size_t* slot_stride_floats,
                                      int32_t* slot_count) {

@@ -157,11 +157,11 @@ static int rt_build_dx(const Ctx& c, int t, const gnnfp_net_params* sp, const fl
   int rc;
   memset(&ra, 0, sizeof(ra));
   ra.mode = RT_DX; ra.n_rows = L->Nact; ra.H = H0;
-  if ((rc = rows_tma_map(&ra.maps[0], dz, N, H0, L->ldG))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[0], dz, L->Nact, H0, L->ldG))) return rc;       // rows past the computed ones read as zeros
   if ((rc = rows_tma_map(&ra.maps[1], c.S(t - 1), N, D, L->ldX))) return rc;
   if ((rc = rows_tma_map(&ra.maps[2], c.S(t - 1), N, 2 * D, L->ldX))) return rc;
-  if ((rc = rows_tma_map(&ra.maps[3], dOwn, N, D, L->ldG))) return rc;
-  if ((rc = rows_tma_map(&ra.maps[4], dAgg, N, D, L->ldG))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[3], dOwn, L->Nact, D, L->ldG))) return rc;
+  if ((rc = rows_tma_map(&ra.maps[4], dAgg, L->Nact, D, L->ldG))) return rc;
   for (int c0 = 0; c0 < H0; c0 += RT_CHUNK) {
     RtKChunk& k = ra.kc[ra.n_kc++];
     k.map = 0; k.col0 = c0; k.width = H0 - c0 < RT_CHUNK ? H0 - c0 : RT_CHUNK; k.k8 = (k.width + 7) / 8;
@@ -494,7 +494,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     aa.n_rows = N; aa.rowlist = nullptr; aa.D = D;
     aa.S = dAgg[(t_only + 1) & 1]; aa.ld = ldG;
     aa.rowptr = g->src_rowptr; aa.idx = g->src_dst; aa.wgt = src_w;
-    aa.out = pgather;
+    aa.out = pgather; aa.ld_out = ldG;
     aa.gate = c.flags() + t_only;               // only if iteration t+1 ran
     if ((rc = launch_agg_stats(aa, s))) return rc;
   }
@@ -579,9 +579,9 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
             da.n_rows = full.n_rows; da.H = H0; da.K = in;
             da.n_zc = (H0 + 31) / 32;
             da.rows = dw_tma_rows((w0 + 31) / 32 + (L->xs_inline ? 0 : (LsM + 31) / 32), da.n_zc);
-            bool ok = rows_tma_map(&da.xmap[0], c.S(t - 1), L->N, w0, L->ldX, da.rows, 1) == GNNFP_OK &&
-                      rows_tma_map(&da.zmap, dzbuf, L->N, H0, ldG, da.rows, 1) == GNNFP_OK;
-            if (ok && !L->xs_inline && LsM > 0) ok = rows_tma_map(&da.xmap[1], c.Xs(), L->N, LsM, L->ldXs, da.rows, 1) == GNNFP_OK;
+            bool ok = rows_tma_map(&da.xmap[0], c.S(t - 1), full.n_rows, w0, L->ldX, da.rows, 1) == GNNFP_OK &&   // rows past n_rows: zero-filled
+                      rows_tma_map(&da.zmap, dzbuf, full.n_rows, H0, ldG, da.rows, 1) == GNNFP_OK;
+            if (ok && !L->xs_inline && LsM > 0) ok = rows_tma_map(&da.xmap[1], c.Xs(), full.n_rows, LsM, L->ldXs, da.rows, 1) == GNNFP_OK;
             for (int c0_ = 0; ok && c0_ < w0; c0_ += 32) {
               if (da.n_xc >= DT_MAXXC) { ok = false; break; }
               da.xc_map[da.n_xc] = 0; da.xc_col0[da.n_xc] = c0_; ++da.n_xc;

@@ -355,13 +355,14 @@ class PartitionedLoop:
     def begin(self, state0=None):
         self.loop.forward_begin(self.nodes, self.arc_labels, state0, ld_arcs=self.arc_labels.stride(0))
         self.flags, self.slots = self.loop.ws_views()
+        self.state1_slot = self.loop.ws_layout()[1]
         self.reduce_flag(self.flags[0:1])
 
     def iterate(self, t):
         self.loop.forward_iter(t)
 
     def _slot(self, t):
-        return self.slots[t - 1] if self.training else self.slots[t & 1]   # gnnfp.h: slot index of state t
+        return self.slots[t - 1 + self.state1_slot] if self.training else self.slots[t & 1]   # gnnfp.h: slot index of state t
 
     def own_rows(self, t):
         return self._slot(t)[: self.plan.n_own]

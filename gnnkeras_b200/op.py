@@ -345,11 +345,19 @@ class LoopPlan:
         n_flags = int(self.cfg.max_iteration) + 1
         flags = ws[fo.value: fo.value + 4 * n_flags].view(torch.int32)
         n, D = self.graph.n_nodes, self.D
+        ld, s1, _ = self.ws_layout()
         slots = []
         for i in range(sc.value):
             o = so.value + 4 * st.value * i
-            slots.append(ws[o: o + 4 * n * D].view(torch.float32).view(n, D))
+            slots.append(ws[o: o + 4 * n * ld].view(torch.float32).view(n, ld)[:, :D])    # a slot row may be wider than the state
         return flags, slots
+
+    def ws_layout(self):
+        """(row pitch of a state slot in floats, slot index of the state of iteration 1 in a training plan, row pitch of the
+        gather buffer): gnnfp_loop_ws_layout."""
+        ld, s1, lg = C.c_int32(), C.c_int32(), C.c_int32()
+        B.check(self._L.gnnfp_loop_ws_layout(self._h, C.byref(ld), C.byref(s1), C.byref(lg)))
+        return int(ld.value), int(s1.value), int(lg.value)
 
     def backward(self, d_out=None, d_out_nodes=None, d_state=None, average_st_grads=False,
                  state_tensors=None, out_tensors=None, grad_state=None, grad_out=None):
@@ -426,7 +434,8 @@ class LoopPlan:
         B.check(self._L.gnnfp_loop_bwd_offsets(self._h, C.byref(off)))
         base = (self.workspace.data_ptr() + 255) // 256 * 256 - self.workspace.data_ptr()
         n, D = self.graph.n_nodes, self.D
-        return self.workspace[base:][off.value: off.value + 4 * n * D].view(torch.float32).view(n, D)
+        lg = self.ws_layout()[2]
+        return self.workspace[base:][off.value: off.value + 4 * n * lg].view(torch.float32).view(n, lg)[:, :D]
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -219,6 +219,10 @@ int gnnfp_loop_forward_end(gnnfp_loop* L, const gnnfp_net_params* state_params, 
                            const gnnfp_loop_io* io, void* workspace, size_t workspace_bytes, void* stream);
 int gnnfp_loop_ws_offsets(const gnnfp_loop* L, size_t* flags_off, size_t* slots_off, size_t* slot_stride_floats,
                           int32_t* slot_count);
+/* row pitch (floats) of a state slot - the state occupies columns [0, D) of a slot row -, the slot index that holds the
+ * state of iteration 1 in a training plan (state t sits in slot state1_slot + t - 1; inference plans ping-pong: slot t & 1),
+ * and the row pitch of the Adj . dAgg gather buffer (gnnfp_loop_bwd_offsets) */
+int gnnfp_loop_ws_layout(const gnnfp_loop* plan, int32_t* ld_state, int32_t* state1_slot, int32_t* ld_grad);
 
 typedef struct gnnfp_loop_grads {
   const float* d_out;        /* [out_rows, T] dL/d out (may be NULL = zeros)                    */
