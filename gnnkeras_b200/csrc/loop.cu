@@ -470,6 +470,7 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     w.wfold = off; off = align_up(off + (L->nt + 1) * w.wfold_stride * sizeof(float));
     w.wtb = off; off = align_up(off + (L->nt + 1) * w.wtb_stride * sizeof(float));
     w.bncoef = off; off = align_up(off + (L->nt + 1) * w.bncoef_stride * sizeof(float));
+    w.bncoef_t = off; off = align_up(off + (size_t)(L->xlay ? MI : 0) * w.bncoef_stride * sizeof(float));
   }
   if (cfg->training) {
     const size_t ND = (((size_t)L->N * L->ldG + 31) / 32 * 32) * sizeof(float);
@@ -616,6 +617,9 @@ static int rt_build_fwd(const Ctx& c, int t, const gnnfp_net_params* sp, RowsTma
   build_state_src(c, 0, t, ra.src, 1);
   fill_netdev(L->snet[0], sp[0], L->cfg.training, ra.src.n_rows, ra.net);
   ra.update_moving = L->cfg.training; ra.act = L->snet[0].acts[0];
+  // training with batch statistics: CTA 0 leaves the backward's coefficients [rstd | -mean rstd | gamma rstd] of this iteration
+  if (L->cfg.training && L->snet[0].has_bn && L->ws.bncoef_stride)
+    ra.coef_out = (float*)(c.ws + L->ws.bncoef_t) + (size_t)(t - 1) * L->ws.bncoef_stride;
   const int w0 = 2 * D + (L->xs_inline ? LsM : 0);
   if ((rc = rows_tma_map(&ra.maps[0], c.S(t - 1), N, w0, L->ldX))) return rc;
   if (!L->xs_inline && LsM > 0 && (rc = rows_tma_map(&ra.maps[1], c.Xs(), N, LsM, L->ldXs))) return rc;

@@ -549,7 +549,9 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
           const int in = L->snet[ty].in_dim;
           float* coef = (float*)(c.ws + L->ws.bncoef) + (size_t)ty * L->ws.bncoef_stride;
           const bool bn = L->snet[ty].has_bn != 0;
-          if (bn) {
+          const bool coef_saved = bn && L->xlay;          // left by the forward kernel of iteration t (rows_tma.cu, CTA 0)
+          if (coef_saved) coef = (float*)(c.ws + L->ws.bncoef_t) + (size_t)(t - 1) * L->ws.bncoef_stride;
+          if (bn && !coef_saved) {
             BnCoefArgs bc;
             memset(&bc, 0, sizeof(bc));
             bc.src = full; bc.net = ndfull; bc.coef = coef; bc.gate = gate;

@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
     if (a.net.bn_mode) {
       const bool upd = a.update_moving && a.net.bn_mode == 1 && blockIdx.x == 0;
       bn_coefficients(a.src, a.net, 1, s_c[0], s_c[1], upd ? s_c[2] : nullptr, upd ? s_c[3] : nullptr);
+      if (a.coef_out && blockIdx.x == 0 && a.net.bn_mode == 1) {   // the same function the backward's bn_coef_kernel ran
+        const int in = a.net.in_dim;
+        bn_coefficients(a.src, a.net, 0, a.coef_out, a.coef_out + in, nullptr, nullptr);
+        for (int c = tid; c < in; c += RT_THREADS) a.coef_out[2 * in + c] = a.net.gamma[c] * a.coef_out[c];   // own element: no barrier needed
+      }
     }
   } else {
     for (int e = tid; e < NOC * 32; e += RT_THREADS) {

@@ -44,6 +44,7 @@ struct RowsTmaArgs {
   TileSrc src;               // the net's input pieces (BN batch statistics per piece, column layout of W's rows)
   NetDev net;
   int update_moving;         // CTA 0 applies the Keras moving-average update
+  float* coef_out;           // CTA 0: [3][in] = rstd | -mean*rstd | gamma*rstd for the backward of this iteration (or NULL)
   int act;
   float thr;                 // convergence test against the aux (previous state) chunk; flag_next NULL = no test
   int* flag_next;
