@@ -541,7 +541,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
           da.own_col0 = 0; da.agg_col0 = D + NLp;
         }
         if ((rc = launch_dz(da, s))) return rc;
-        if (L->snet[ty].has_bn)
+        if (L->snet[ty].has_bn && !gemm_bwd[ty])     // (the GEMM dW kernels ASSIGN their CTA's slot; bn_reduce reads the written slots only)
           GNNFP_CHECK_CUDA(cudaMemsetAsync(bn_part, 0, (size_t)L->grid_cap * 2 * L->snet[ty].in_dim * sizeof(float), s));
         const int H0 = L->snet[ty].widths[0];
         int grid_dw = 0;
