@@ -462,6 +462,7 @@ def main():
                       int(os.environ.get("LOCAL_RANK", "0")), os.cpu_count() or 1)
     spec = workload_spec(args.workload)
     args.graphs = args.graphs or spec["graphs"]
+    args.cpu_graphs_given = bool(args.cpu_graphs)
     args.cpu_graphs = args.cpu_graphs or spec["cpu_graphs"]
     WIDTHS, LS, LAYERS = spec["D"], spec["Ls"], spec["layers"]
     rank = int(os.environ.get("RANK", "0"))
@@ -475,12 +476,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        explicit = args.cpu_graphs_given
         step, n_nodes, n_g = cpu_reference_step_factory(spec, args.cpu_graphs, 0, cores)
-        ups, s_per_step, n = time_cpu(step, args.steps, args.warmup, budget_s=60.0)
+        if not explicit and args.cpu_graphs < spec["graphs"]:
+            # same configuration as the GPU arm when it fits the time box: one probe step on the bounded sample, then the
+            # largest batch (up to the GPU arm's) whose K + W steps are estimated to end within ~150 s
+            step()
+            t0 = time.perf_counter(); step(); probe = time.perf_counter() - t0
+            per_graph = probe / n_g
+            fit = int(150.0 / (max(1, args.steps + args.warmup) * per_graph * 1.8))   # 1.8: measured super-linear cost of the 8x batch on the host
+            want_g = spec["graphs"] if fit >= spec["graphs"] else max(n_g, 1 << max(0, fit.bit_length() - 1))
+            if want_g > n_g:
+                try:
+                    step, n_nodes, n_g = cpu_reference_step_factory(spec, want_g, 0, cores)
+                except MemoryError:
+                    pass
+        ups, s_per_step, n = time_cpu(step, args.steps, args.warmup, budget_s=170.0)
         line = {"impl": "reference", "metric": METRIC, "value": ups, "unit": "node-updates/s", "n_gpus": args.gpus,
                 "steps": n, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "training_graphs_per_s": n_g / s_per_step,
+                "same_config": bool(n_g == spec["graphs"]),
                 "config": {"workload": workload, "sample": f"{n_g} graphs ({n_nodes} nodes) per step (the GPU arm's batch is "
                                                              f"{spec['graphs']} graphs; the metric is per node-update)"},
                 "cpu_baseline": {"value": ups, "unit": "node-updates/s", "cores": cores, "kind": "port",
