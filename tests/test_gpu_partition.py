@@ -17,7 +17,7 @@ from util import DEV, relerr, run_cuda
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,mode,thr,dim", [(2, "average", 0.01, 8), (3, "sum", 0.05, 8), (2, "average", 0.01, 32)])
+@pytest.mark.parametrize("world,mode,thr,dim", [(2, "average", 0.01, 8), (3, "sum", 0.05, 8), (2, "average", 0.01, 32), (2, "average", 0.01, 6)])
 def test_partitioned_matches_global(world, mode, thr, dim):
     rng = np.random.default_rng(5)
     b = random_graph(3000, 24000, seed=7, dim_node_label=6, dim_arc_label=2, dim_target=3, locality=0.7, band=200)
@@ -73,7 +73,7 @@ def test_partitioned_matches_global(world, mode, thr, dim):
     assert relerr(np.concatenate(states), state.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("world,mode,dim", [(2, "average", 8), (3, "sum", 8), (2, "average", 32)])
+@pytest.mark.parametrize("world,mode,dim", [(2, "average", 8), (3, "sum", 8), (2, "average", 32), (3, "average", 6)])
 def test_partitioned_backward_matches_global(world, mode, dim):
     """BPTT on the partitioned graph (stepping backward C ABI + reverse halo reduction between iterations): the
     parameter gradients summed over the ranks equal the unpartitioned CUDA backward and the fp64 oracle."""
