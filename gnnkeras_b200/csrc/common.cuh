@@ -87,6 +87,7 @@ struct Piece {
   float* gptr;
   int gld;
   int gmode;               // GM_*
+  int gdirect;             // the gradient row is the row's own id even when the VALUES are read through `map`
 };
 
 struct TileSrc {

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
   const int lane = tid & 31, warp = tid >> 5;
   const int rg = warp % tc.RG, cg = warp / tc.RG;
   __shared__ BwdLayout y;
+  __shared__ float s_dbred[256];
   if (tid == 0) bwd_layout(net, tc.R, T, REGACC ? 1 : 0, tc.cap, a.dz_ready, tc.raw_per_row, tc.out_per_row, y);
   __syncthreads();
   const int L = y.L;
@@ -322,16 +323,23 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
           }
           if (groups > 1) break;
         }
-        // db_l += column sums of dz (all threads: column x row group, shared float atomics)
+        // db_l += column sums of dz (all threads: column x row group; the row groups are summed in a FIXED order through
+        // shared memory - shared float atomics made the bias gradient the one run-to-run varying output of this kernel)
         float* ab = smem + y.oAccb[l];
         if (a.skip_bias && !y.bn) {
         } else if (T >= H) {
           const int ngr = T / H, j = tid % H, gg = tid / H;
-          if (gg < ngr) {
-            float s2 = 0.f;
+          float s2 = 0.f;
+          if (gg < ngr)
             for (int r = gg; r < nr; r += ngr) s2 += cur[r * XSc + j];
-            atomicAdd(ab + j, s2);
+          s_dbred[tid] = s2;
+          __syncthreads();
+          if (tid < H) {
+            float t2 = 0.f;
+            for (int g2 = 0; g2 < ngr; ++g2) t2 += s_dbred[g2 * H + tid];
+            ab[tid] += t2;
           }
+          __syncthreads();
         } else {
           for (int j = tid; j < H; j += T) {
             float s2 = 0.f;
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(256, REGACC ? 1 : 2) tile_bwd_kernel(const __g
             v[u] = cur[r * XSc + pc.col0 + c];
             if (y.bn) v[u] *= bnS[pc.col0 + c];
             const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
-            const int drow = pc.map ? pc.map[gr] : gr;
+            const int drow = (pc.map && !pc.gdirect) ? pc.map[gr] : gr;
             d[u] = pc.gptr + (size_t)drow * pc.gld + c;
             if (pc.gmode == GM_ADD) old[u] = *d[u];
           }
@@ -656,7 +664,7 @@ __global__ void __launch_bounds__(256) tile_bnfix_kernel(const __grid_constant__
             const int cc = pc.col0 + c;
             corr[u] = c0[cc] + fmaf(X[r * tc.XS0 + cc], bnA[cc], bnB[cc]) * c1[cc];
             const int gr = a.src.rowlist ? a.src.rowlist[row0 + r] : row0 + r;
-            const int drow = pc.map ? pc.map[gr] : gr;
+            const int drow = (pc.map && !pc.gdirect) ? pc.map[gr] : gr;
             dp[u] = pc.gptr + (size_t)drow * pc.gld + c;
             if (pc.gmode != GM_ATOMIC) old[u] = *dp[u];
           }

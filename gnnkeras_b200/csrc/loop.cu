@@ -480,6 +480,8 @@ extern "C" int gnnfp_loop_create(gnnfp_loop** out, const gnnfp_graph* g, const g
     w.dz = off; off = align_up(off + ND);
     if (L->Nact < L->N) { w.pgather = off; off = align_up(off + ND); }
     w.dOutN = off; off = align_up(off + (size_t)L->M * L->T * sizeof(float));
+    if (cfg->kind == GNNFP_KIND_ARC)
+      { w.arc_tmp = off; off = align_up(off + (size_t)L->A * 2 * (L->D + ((!L->composite && L->S > 0) ? L->NLw : 0)) * sizeof(float) + 16); }
     size_t ps = 0, bg = 2 * (size_t)L->onet.in_dim;
     int din_max = L->onet.in_dim;
     for (int t = 0; t < L->nt; ++t) {

@@ -16,6 +16,7 @@ struct WsLayout {
   size_t part_state = 0, part_out = 0, bn_part = 0, bn_const = 0, bn_grad = 0;
   size_t wfold = 0, wtb = 0, bncoef = 0;    // GEMM path: folded weights per type, W^T blocks, per-iteration BN coefficients
   size_t wfold_stride = 0, wtb_stride = 0, bncoef_stride = 0;   // floats per type
+  size_t arc_tmp = 0;                       // arc focus: per-arc gradient of net_output's gathered input [A][2 (D + NL)]
   size_t bncoef_t = 0;                      // X-slot path: [max_iteration][bncoef_stride] backward BN coefficients left by the forward kernels
   size_t bn_const_t = 0, bn_static = 0;     // per-iteration BN constants, running static-column sums
   size_t bwd_zero = 0, bwd_zero_bytes = 0;   // region zeroed at the start of every backward

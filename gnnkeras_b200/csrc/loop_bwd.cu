@@ -101,6 +101,21 @@ static __global__ void k_input_grads_arcs(int A, int AL, int LsM, int col0, cons
   }
 }
 
+// arc focus: d(state)[i] (+ d(nodes)[i]) += sum over the out-arcs of i of the source-side block + sum over the in-arcs of i of the
+// destination-side block of the per-arc gradient tmp[A][2 aw]; arcs in CSR (= arc id) order, one thread per (node, column)
+static __global__ void k_arc_grad_gather(int N, int D, int cols, const int* src_rowptr, const int* src_arc, const int* dst_rowptr,
+                                         const int* dst_arc, const float* tmp, int aw, float* dS, int ldS, float* d_nodes, int ldn) {
+  for (int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); i < N; i += gridDim.x * (blockDim.x / 32)) {
+    for (int c = threadIdx.x & 31; c < cols; c += 32) {
+      float acc = 0.f;
+      for (int q = src_rowptr[i]; q < src_rowptr[i + 1]; ++q) acc += tmp[(size_t)src_arc[q] * 2 * aw + c];
+      for (int q = dst_rowptr[i]; q < dst_rowptr[i + 1]; ++q) acc += tmp[(size_t)dst_arc[q] * 2 * aw + aw + c];
+      if (c < D) dS[(size_t)i * ldS + c] += acc;
+      else if (d_nodes) d_nodes[(size_t)i * ldn + (c - D)] += acc;
+    }
+  }
+}
+
 // dz of net_output's single Dense layer, compact [M, T]:  g = un-pooled d_out (+ d_out_nodes),  dz = act'(y) g
 // (softmax: dz_j = y_j (g_j - sum_k g_k y_k), as TF's SoftmaxGrad)
 struct OutDzArgs {
@@ -273,10 +288,22 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     memset(&ba, 0, sizeof(ba));
     build_out_src(c, ba.src);
     const bool arc = L->cfg.kind == GNNFP_KIND_ARC;
+    // arc focus: net_output reads [state[src] | nodes[src]? | state[dst] | nodes[dst]? | arc labels] per arc (GNN.py:317-330).
+    // Its input gradient is first STORED per arc (row = arc id, no atomics), then summed per node over the node's out-arcs
+    // (source side) and in-arcs (destination side) in CSR order: deterministic, unlike a scatter with atomicAdd
+    float* arc_tmp = arc ? (float*)(c.ws + L->ws.arc_tmp) : nullptr;
+    const int aw = D + NLp;                           // columns per side
+    if (arc) GNNFP_CHECK_CUDA(cudaMemsetAsync(arc_tmp, 0, (size_t)L->A * 2 * aw * sizeof(float), s));   // unmasked arcs contribute nothing
+    int n_state_seen = 0, n_nodes_seen = 0;
     for (int p = 0; p < ba.src.n_pieces; ++p) {
       Piece& pc = ba.src.p[p];
-      if (pc.tag == TAG_STATE) { pc.gptr = dSfin; pc.gld = ldG; pc.gmode = arc ? GM_ATOMIC : GM_ADD; }
-      else if (pc.tag == TAG_NODES) { if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = arc ? GM_ATOMIC : GM_ADD; } }
+      if (pc.tag == TAG_STATE) {
+        if (arc) { pc.gptr = arc_tmp + (size_t)(n_state_seen++ ? aw : 0); pc.gld = 2 * aw; pc.gmode = GM_STORE; pc.gdirect = 1; }
+        else { pc.gptr = dSfin; pc.gld = ldG; pc.gmode = GM_ADD; }
+      } else if (pc.tag == TAG_NODES) {
+        if (arc) { if (want & 1) { pc.gptr = arc_tmp + (size_t)(n_nodes_seen ? aw : 0) + D; pc.gld = 2 * aw; pc.gmode = GM_STORE; pc.gdirect = 1; } ++n_nodes_seen; }
+        else if (want & 1) { pc.gptr = gr->d_nodes; pc.gld = L->NLw; pc.gmode = GM_ADD; }
+      }
       else if (pc.tag == TAG_ARC_LABELS) { if ((want & 2) && L->AL > 0) { pc.gptr = gr->d_arc_labels; pc.gld = L->AL; pc.gmode = GM_ADD; } }
     }
     bool og = L->out_gemm_ok && !arc && getenv("GNNFP_NO_GEMM_BWD") == nullptr && ba.src.n_pieces <= GEMM_MAXP;
@@ -398,6 +425,16 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     ba.prof_cat = PC_BWD_OUT;
     if ((rc = launch_tile_bwd(ba, s))) return rc;
     if (L->onet.has_bn && (rc = launch_bn_tail(ba, bn_grad + bg_off[L->nt], bn_const, s))) return rc;
+    if (arc) {
+      const int cols = D + ((want & 1) ? NLp : 0);
+      const size_t total = (size_t)N * cols;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > 4736) blocks = 4736;
+      if (blocks < 1) blocks = 1;
+      k_arc_grad_gather<<<blocks, 256, 0, s>>>(N, D, cols, g->src_rowptr, g->src_arc, g->dst_rowptr, g->dst_arc, arc_tmp, aw,
+                                               dSfin, ldG, (want & 1) ? gr->d_nodes : nullptr, L->NLw);
+      GNNFP_COUNT_LAUNCH();
+    }
     }
   }
 

@@ -5,7 +5,8 @@ streams and autograd plumbing only; all arithmetic happens in libgnnfp.so.
     DeviceGraph   <-> gnnfp_graph   (replaces GraphObject.buildArcNode/... + GraphTensor tensorisation)
     Net           <-> gnnfp_net_desc + gnnfp_net_params (a Keras Sequential [BN] + Dense* built by MLP())
     LoopPlan      <-> gnnfp_loop
-    fixed_point_loop(...)  = GNN*.Loop  (reference GNN/Models/GNN.py:245-274) with autograd
+    LoopPlan.forward / .backward = GNN*.Loop (reference GNN/Models/GNN.py:245-274) and the tape's gradient of it; the model
+    classes in models.py call the pair explicitly (there is no torch.autograd.Function wrapper)
 """
 from __future__ import annotations
 

@@ -103,10 +103,11 @@ def test_random_sweep_forward_backward(cfg):
     torch.cuda.synchronize()
     _, gs64, go64, *_ = oracle_grads(g, ns, no, S_, max_it, thr, s0, kind, r_out, None, torch.float64)
     _, gs32, go32, *_ = oracle_grads(g, ns, no, S_, max_it, thr, s0, kind, r_out, None, torch.float32)
-    # arc focus scatters d(net_output input) back to the nodes with float atomics (order-dependent rounding): badly
-    # conditioned sums (e.g. a bias gradient that cancels to ~1e-2 of its terms) then move run to run by a few times the
-    # fp32 oracle's own distance to fp64, so the conditioning factor is wider there (measured spread 3..12 x).
-    factor = 32 if kind == "arc" else 8
+    # (arc focus needed a 32x factor while two reductions on its path were order-dependent: the scatter of d(net_output input)
+    #  to the nodes (float atomicAdd) and the bias sums of the tile kernel (shared-memory atomics); both run in a fixed order
+    #  now - stored per arc and summed per node in CSR order / row groups summed through shared memory - and every focus gets
+    #  the same bound; 5 consecutive runs of the arc cases pass at 8x)
+    factor = 8
     for a, b64, b32 in zip(gs[0] + go, gs64[0] + go64, gs32[0] + go32):
         e, e32 = relerr(a.cpu().numpy(), b64), relerr(b32, b64)
         assert e <= max(2e-5, factor * e32), (e, e32, tuple(a.shape))
@@ -240,3 +241,27 @@ def test_random_sweep_composite(cfg):
     for a, b64, b32 in zip(flat(gs, go), flat(gs64, go64), flat(gs32, go32)):
         a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
         assert relerr(a, b64) <= max(2e-5, factor * relerr(b32, b64)), (relerr(a, b64), relerr(b32, b64), a.shape)
+
+
+def test_arc_focus_backward_is_bit_reproducible():
+    """Arc focus: the gradient of net_output's gathered [state[src] | state[dst]] input is stored per arc and summed per node
+    in CSR order (no float atomics), so two runs of the same backward give bit-identical parameter gradients."""
+    rng = np.random.default_rng(77)
+    NL, AL, T, S_ = 5, 2, 3, 4
+    b = random_batch(rng, 200, NL, AL, T, max_nodes=20)
+    b.set_mask = rng.random(b.n_arcs) < 0.9
+    b.output_mask = rng.random(b.n_arcs) < 0.8
+    b.targets = np.eye(T, dtype=np.float32)[rng.integers(0, T, b.n_arcs)]
+    g = ograph_from_batch(b, "a", "average")
+    ns, no = nets_for(rng, NL, AL, T, S_, "arc", False, "tanh", ())     # no BN: its batch statistics are fp64 atomics
+    s0 = (0.1 * rng.standard_normal((g.n_nodes, S_))).astype(np.float32)
+    runs = []
+    for _ in range(3):
+        plan, nets, onet, (k, state, out) = run_cuda(g, ns, no, S_, 4, 0.0, True, s0, "arc")
+        r_out = torch.as_tensor(np.random.default_rng(1).standard_normal(tuple(out.shape)).astype(np.float32)).to(DEV)
+        gs, go, *_ = plan.backward(r_out, None, None, False)
+        torch.cuda.synchronize()
+        runs.append([t.cpu().numpy().copy() for t in gs[0] + go])
+    for other in runs[1:]:
+        for a, c in zip(runs[0], other):
+            assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
