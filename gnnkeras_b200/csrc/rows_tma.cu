@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int e = min(e0 + u * RT_THREADS, E - 1);
-          const int kc = e / (32 * BN), r = e - kc * 32 * BN;
-          const int k = r / BN, nn = r - k * BN;
+          // e = (kc * 32 + k) * BN + nn: ONE division by BN, by multiplication (runtime integer divisions run on the
+          // conversion pipe and were a third of this prologue)
+          const int R = (int)__umulhi((unsigned)e, a.bn_magic);
+          const int nn = e - R * BN, kc = R >> 5, k = R & 31;
           const int c = s_wrow[kc * RT_CHUNK + k];
           const bool ok = c >= 0 && nn < H;
           off[u] = (e0 + u * RT_THREADS < E) ? kc * wtile + tc_sw128_off(nn, k) : -1;
@@ -251,8 +253,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tma_kernel(const __grid_co
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int e = min(e0 + u * RT_THREADS, E - 1);
-          const int kc = e / (32 * BN), r = e - kc * 32 * BN;
-          const int nn = r >> 5, k = r & 31;
+          // e = ((kc * BN + nn) << 5) + k
+          const int q = e >> 5, k = e & 31;
+          const int kc = (int)__umulhi((unsigned)q, a.bn_magic);
+          const int nn = q - kc * BN;
           const int j = s_wrow[kc * RT_CHUNK + k], c = s_ncol[nn];
           const bool ok = j >= 0 && j < H && c >= 0;
           off[u] = (e0 + u * RT_THREADS < E) ? kc * wtile + tc_sw128_off(nn, k) : -1;
@@ -701,6 +705,7 @@ int rows_tma_finish(RowsTmaArgs& a) {
     GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: shape outside the kernel's limits (K chunks %d, output chunks %d, N %d)", a.n_kc, a.n_oc, a.BN);
   const size_t cap = rt_smem_cap(a.mode);
   if (!cap) GNNFP_FAIL(GNNFP_E_CUDA, "rows_tma: cannot query the shared-memory budget");
+  a.bn_magic = (unsigned)((0x100000000ull + (unsigned)a.BN - 1) / (unsigned)a.BN);   // exact for the < 2^17 indices of the weight build
   a.n_ostages = 2;
   a.n_stages = 2;
   if (rows_tma_smem(a) > cap) GNNFP_FAIL(GNNFP_E_UNSUPPORTED, "rows_tma: %zu bytes of shared memory needed, %zu available", rows_tma_smem(a), cap);

@@ -36,6 +36,7 @@ struct RowsTmaArgs {
   int n_oc; RtOChunk oc[RT_MAXOC];
   int mode;                  // RT_FWD | RT_DX
   int BN;                    // MMA N: accumulator columns per tile (multiple of 16)
+  unsigned bn_magic;         // ceil(2^32 / BN): division by BN as a multiplication (set by rows_tma_finish)
   int tmem_cols;             // power of two >= 2 * BN + 32
   int n_stages;              // operand ring depth (hi + lo tile per stage)
   int n_ostages;             // output stage ring depth
