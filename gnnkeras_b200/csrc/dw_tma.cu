@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dw_tma_kernel(const __grid_cons
     // one reduction per element and launch into this CTA's slot: fire-and-forget RED.ADD (no read latency); the order of the
     // additions to one address is the launch order, so the sums stay deterministic
     for (int e = tid; e < KH; e += DT_THREADS) {
-      const int c = e / H, j = e - c * H;
+      const int c = (int)__umulhi((unsigned)e, a.h_magic), j = e - c * H;     // e / H without the conversion pipe (e < 2^16)
       const float x = sD[s_kp[c] * HS + j];
       atomicAdd(part + e, a.bnA ? s_gam[c] * fmaf(s_bA[c], x, s_bB[c] * sdb[j]) + s_bet[c] * sdb[j] : x);
     }
@@ -291,6 +291,7 @@ int dw_tma_finish(DwTmaArgs& a) {
   const size_t cap = dt_smem_cap();
   if (!cap) GNNFP_FAIL(GNNFP_E_CUDA, "dw_tma: cannot query the shared-memory budget");
   static const int max_st = getenv("GNNFP_DW_STAGES") ? atoi(getenv("GNNFP_DW_STAGES")) : DT_MAXSTAGES;
+  a.h_magic = (unsigned)((0x100000000ull + (unsigned)a.H - 1) / (unsigned)a.H);
   static const int max_lo = getenv("GNNFP_DW_LO") ? atoi(getenv("GNNFP_DW_LO")) : 3;
   a.n_stages = 2; a.n_lo = 2;
   if (a.rows != 32 && a.rows != 64 && a.rows != 128) GNNFP_FAIL(GNNFP_E_INVALID, "dw_tma: %d rows per stage", a.rows);

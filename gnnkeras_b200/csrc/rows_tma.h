@@ -78,6 +78,7 @@ struct DwTmaArgs {
   int n_pieces; int p_in0[DT_MAXP], p_w[DT_MAXP], p_acc0[DT_MAXP];   // input columns [in0, in0 + w) sit in accumulator columns [acc0, ..)
   int n_stages, n_lo;        // hi ring depth, lo slots
   int rows;                  // rows per stage / TMA box (32, 64, 128): dw_tma_rows()
+  unsigned h_magic;          // ceil(2^32 / H) (set by dw_tma_finish)
   float* partial; int n_params, bias_off;               // as GemmDwArgs
   const float* W; const float* bnA; const float* bnB; const float* gamma; const float* beta;
   float* bn_partial;
