@@ -299,7 +299,7 @@ class LoopPlan:
         state = torch.empty((g.n_nodes, self.D), dtype=torch.float32, device=dev)
         out = torch.empty((self.out_rows, self.T), dtype=torch.float32, device=dev)
         out_nodes = torch.empty((g.n_masked, self.T), dtype=torch.float32, device=dev) if want_out_nodes else None
-        k = torch.zeros((), dtype=torch.int32, device=dev)
+        k = torch.empty((), dtype=torch.int32, device=dev)        # written by every forward (k_finalize): no fill launch
         io = self._io(nodes, arc_labels, ld_arcs, state0, state, out, out_nodes, k)
         sp, op = self._param_arrays(state_tensors, out_tensors)
         B.check(self._L.gnnfp_loop_forward(self._h, sp, C.byref(op), C.byref(io), self._ws_ptr(),
@@ -315,7 +315,7 @@ class LoopPlan:
         ld_arcs = int(arc_labels.stride(0)) if ld_arcs is None else ld_arcs
         state = torch.empty((g.n_nodes, self.D), dtype=torch.float32, device=dev)
         out = torch.empty((self.out_rows, self.T), dtype=torch.float32, device=dev)
-        k = torch.zeros((), dtype=torch.int32, device=dev)
+        k = torch.empty((), dtype=torch.int32, device=dev)        # written by every forward (k_finalize): no fill launch
         self._step_io = self._io(nodes, arc_labels, ld_arcs, state0, state, out, None, k)
         self._step_keep = (nodes, arc_labels, state0, state, out, k)
         self._step_ld_arcs = ld_arcs
