@@ -157,9 +157,9 @@ static __global__ void k_xlay_init(const float* s0, int ld0, const float* Xs, in
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, of);
     if (sqrtf(sd) > normp) notconv = 1;
-    for (int e = lane; e < n_slots * LsM; e += 32) {
-      const int q = e / LsM, x = e - q * LsM;
-      slots[(size_t)q * stride + (size_t)r * ldX + 2 * D + x] = Xs[(size_t)r * ldXs + x];
+    for (int e = lane; e < n_slots * 8; e += 32) {       // inline static blocks have LsM <= 8 columns: slot q = e / 8, column x = e % 8
+      const int q = e >> 3, x = e & 7;
+      if (x < LsM) slots[(size_t)q * stride + (size_t)r * ldX + 2 * D + x] = Xs[(size_t)r * ldXs + x];
     }
   }
   const int any = __syncthreads_or(notconv);

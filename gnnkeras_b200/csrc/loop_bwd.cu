@@ -518,7 +518,12 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
     const int KH = gemm_rows_kpad(H0);
     for (int p = 0; p < probe.n_pieces && (phases & PH_BEGIN); ++p) {
       const int ldw = gemm_rows_ldw(probe.p[p].width);
-      if ((rc = launch_transpose_block(sp[ty].W[0], H0, probe.p[p].col0, probe.p[p].width, KH, ldw, wt, s))) return rc;
+      // X-slot path: dOwn / dAgg come from rows_tma (it folds W itself), and a static block only has a consumer when input
+      // gradients are wanted - no transposed copy for blocks nobody reads
+      const bool via_rt = L->xlay && (probe.p[p].tag == TAG_STATE || probe.p[p].tag == TAG_AGG_STATE);
+      const bool unused_static = probe.p[p].tag == TAG_STATIC && !want;
+      if (!via_rt && !unused_static &&
+          (rc = launch_transpose_block(sp[ty].W[0], H0, probe.p[p].col0, probe.p[p].width, KH, ldw, wt, s))) return rc;
       wt += (size_t)KH * ldw;
     }
   }
