@@ -634,6 +634,10 @@ __global__ void __launch_bounds__(256) fold_w_kernel(const __grid_constant__ Fol
     float* mean = (a.update_moving && net.bn_mode == 1 && blockIdx.x == 0) ? sm + 2 * in : nullptr;
     float* var = mean ? sm + 3 * in : nullptr;
     bn_coefficients(a.src, net, 1, A, B, mean, var);
+    if (a.coef_out && blockIdx.x == 0 && net.bn_mode == 1) {   // what bn_coef_kernel would compute before the backward
+      bn_coefficients(a.src, net, 0, a.coef_out, a.coef_out + in, nullptr, nullptr);
+      for (int c = tid; c < in; c += blockDim.x) a.coef_out[2 * in + c] = net.gamma[c] * a.coef_out[c];   // own element
+    }
     __syncthreads();
     if (mean) {   // Keras BatchNormalization._assign_moving_average: var -= (var - value) * (1 - momentum)
       const float decay = (float)(1.0 - (double)net.bn_momentum);

@@ -84,6 +84,7 @@ struct FoldArgs {            // padded, BN-folded weights of a single Dense laye
   float* Wp;                 // [Kpad][ldw]
   float* biasp;              // [ldw]
   int update_moving;
+  float* coef_out;           // block 0 (training, batch statistics): [3][in] = rstd | -mean*rstd | gamma*rstd for the backward, or NULL
   const int* gate;
 };
 struct BnCoefArgs { TileSrc src; NetDev net; float* coef; const int* gate; };

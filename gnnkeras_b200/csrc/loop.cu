@@ -830,6 +830,8 @@ static int fwd_end(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_par
       float* wf = (float*)(c.ws + L->ws.wfold) + (size_t)L->nt * L->ws.wfold_stride;
       fo.Kpad = gemm_rows_kpad(k2); fo.ldw = gemm_rows_ldw(H); fo.Wp = wf; fo.biasp = wf + (size_t)fo.Kpad * fo.ldw;
       fo.update_moving = training;
+      if (training && L->onet.has_bn && L->ws.bncoef_stride)      // the backward's coefficients of net_output, left here
+        fo.coef_out = (float*)(c.ws + L->ws.bncoef) + (size_t)L->nt * L->ws.bncoef_stride;
       if ((rc = launch_fold_w(fo, s))) return rc;
       ga.n_rows = fa.src.n_rows; ga.rowlist = fa.src.rowlist; ga.n_pieces = fa.src.n_pieces; ga.Kpad = fo.Kpad;
       ga.Wp = fo.Wp; ga.ldw = fo.ldw; ga.N = H; ga.bias = fo.biasp; ga.act = L->onet.acts[0];

@@ -336,7 +336,7 @@ static int backward_impl(gnnfp_loop* L, const gnnfp_net_params* sp, const gnnfp_
         GNNFP_COUNT_LAUNCH();
       }
       float* coef = (float*)(c.ws + L->ws.bncoef) + (size_t)L->nt * L->ws.bncoef_stride;
-      if (bn) {
+      if (bn && !L->out_gemm_ok) {                    // (the GEMM forward's fold_w_kernel left them: loop.cu fwd_end)
         BnCoefArgs bc;
         memset(&bc, 0, sizeof(bc));
         bc.src = ba.src; bc.net = ond; bc.coef = coef;
