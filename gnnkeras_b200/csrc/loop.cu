@@ -145,21 +145,43 @@ static __global__ void k_xlay_init(const float* s0, int ld0, const float* Xs, in
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const float normp = thr * sqrtf((float)D);
   int notconv = 0;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n; r += gridDim.x * wpb) {
-    const float* src = s0 + (size_t)r * ld0;
-    float* dst = slots + (size_t)r * ldX;
-    float sd = 0.f;
-    for (int j = lane; j < D; j += 32) {
-      const float v = src[j];
-      dst[j] = v;
-      sd = fmaf(v - 1.0f, v - 1.0f, sd);
+  // 4 rows in flight per warp (all loads first): one row at a time left the copy latency bound (74 us for 176 MB)
+  const int wid = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+  for (int r0 = wid * 4; r0 < n; r0 += nw * 4) {
+    float v[4][3], xs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int j = lane + 32 * i;
+        v[u][i] = (r < n && j < D) ? s0[(size_t)r * ld0 + j] : 1.0f;
+      }
+      xs[u] = (r < n && (lane & 7) < LsM && lane < 8 * n_slots) ? Xs[(size_t)r * ldXs + (lane & 7)] : 0.f;
     }
 #pragma unroll
-    for (int of = 16; of > 0; of >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, of);
-    if (sqrtf(sd) > normp) notconv = 1;
-    for (int e = lane; e < n_slots * 8; e += 32) {       // inline static blocks have LsM <= 8 columns: slot q = e / 8, column x = e % 8
-      const int q = e >> 3, x = e & 7;
-      if (x < LsM) slots[(size_t)q * stride + (size_t)r * ldX + 2 * D + x] = Xs[(size_t)r * ldXs + x];
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= n) break;
+      float* dst = slots + (size_t)r * ldX;
+      float sd = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int j = lane + 32 * i;
+        if (j < D) { dst[j] = v[u][i]; sd = fmaf(v[u][i] - 1.0f, v[u][i] - 1.0f, sd); }
+      }
+      for (int j = lane + 96; j < D; j += 32) {          // state widths above 96 (not on the TMA path today)
+        const float w = s0[(size_t)r * ld0 + j];
+        dst[j] = w;
+        sd = fmaf(w - 1.0f, w - 1.0f, sd);
+      }
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, of);
+      if (sqrtf(sd) > normp) notconv = 1;
+      // inline static blocks have LsM <= 8 columns: lane -> (slot q = lane / 8 (+ 4 per pass), column x = lane % 8)
+      const int x = lane & 7;
+      if (x < LsM)
+        for (int q = lane >> 3; q < n_slots; q += 4) slots[(size_t)q * stride + (size_t)r * ldX + 2 * D + x] = xs[u];
     }
   }
   const int any = __syncthreads_or(notconv);
@@ -578,7 +600,7 @@ static int fwd_begin(const Ctx& c, const gnnfp_net_params* sp, const gnnfp_net_p
   }
   if (L->xlay) {   // X_0[:, 0:D] = the caller's initial state; inline static columns into every slot
     const int ns = L->xs_inline ? L->slot_count : 0;
-    int blocks = (N + 7) / 8;
+    int blocks = (N + 31) / 32;                          // 8 warps x 4 rows per block and trip
     if (blocks > 2368) blocks = 2368;
     k_xlay_init<<<blocks, 256, 0, s>>>(c.S0user(), c.ldS0user(), c.Xs(), L->ldXs, L->LsM, c.slots(), c.slot_stride(), ns, L->ldX, D, N,
                                        L->cfg.state_threshold, MI, c.flags());
