@@ -755,6 +755,9 @@ def main():
                                           "frac_of_hbm_peak": (it_bytes / (it_ms * 1e-3) / 1e9) / peak if it_ms > 0 else 0.0,
                                           "kernels": "rows_tma FWD (TMA + tcgen05 3xTF32) + agg_stats + dz + dw_tma + rows_tma DX; bytes = SURVEY 8(d) B_f + B_b per node-update"},
                 "kernel_time_by_category_ms": shares,
+                "traffic_note": ("dz: the measured DRAM traffic exceeds the algorithmic bytes by the Adj^T S rows the kernel re-gathers to apply "
+                                 "the BatchNormalization-training correction where the raw gradients are consumed (one more D-wide stream; "
+                                 "DESIGN.md 4)") if dom.startswith("dz") else None,
                 "note": "achieved = algorithmic bytes of the kernel's launches / their CUDA-event durations "
                         "(events recorded by the library on the launch stream, separate profiled pass of the same steps)"}
 
